@@ -1,0 +1,131 @@
+#!/usr/bin/env python
+"""Generate tests/golden/*.npz from the UNMODIFIED reference (build container only).
+
+    python tests/golden/make_golden.py
+
+Inputs are the deterministic tapes of oracle/tapes.py (so the fixtures hold outputs only);
+outputs are what the reference's own ControlEnv / F16Model / F16Dynamics return on CPU.
+Also snapshots the head of the reference's recorded trajectory renders/result/*.npy
+(the only trajectory fixture the reference ships).
+"""
+import contextlib
+import io
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+sys.path.insert(0, os.path.join(HERE, "..", ".."))
+from ref_harness import REF_ROOT, RefEnv, import_reference  # noqa: E402
+from oracle import tapes  # noqa: E402
+
+CHECKPOINTS = [1, 2, 3, 5, 10, 20, 50, 100, 200, 300, 500, 700, 1000]
+
+
+def snap(ref, obs, rew, done, bad, exc):
+    sn = ref.snapshot()
+    tgt = [sn[k] for k in ("target_altitude", "target_heading", "target_vt") if k in sn] \
+        if "target_heading" in sn and "target_pitch" not in sn and "target_npos" not in sn else None
+    if "target_pitch" in sn:
+        tgt = [sn["target_pitch"], sn["target_heading"], sn["target_vt"]]
+    if "target_npos" in sn:
+        tgt = [sn["target_npos"], sn["target_epos"], sn["target_altitude"]]
+    return dict(s=sn["s"].numpy().copy(), u=sn["u"].numpy().copy(), tgt=torch.stack(tgt, 1).numpy(),
+                step_count=sn["step_count"].numpy().astype(np.int32), obs=obs.numpy().copy(),
+                reward=rew.numpy().copy(), done=done.numpy().copy(), bad=bad.numpy().copy(), exc=exc.numpy().copy())
+
+
+def trajectory(task, n, steps, scale, seed, name):
+    ref = RefEnv(n, task, "F16", seed=0, noise_scale=0.0)
+    obs0 = ref.reset(torch.from_numpy(tapes.reset_draw_tape(seed, 0, n)))
+    out = {"obs0": obs0.numpy().copy(), "meta": np.array([n, steps, seed], dtype=np.int64), "scale": np.float32(scale)}
+    n_bad, n_done, rsum = [], [], []
+    for k in range(1, steps + 1):
+        a = torch.from_numpy(tapes.action_tape(seed, k, n, scale))
+        d = torch.from_numpy(tapes.reset_draw_tape(seed, k, n))
+        obs, rew, done, bad, exc = ref.step(a, d)
+        n_bad.append(int(bad.sum())); n_done.append(int(done.sum())); rsum.append(float(rew.double().sum()))
+        if k in CHECKPOINTS:
+            for key, v in snap(ref, obs, rew, done, bad, exc).items():
+                out[f"k{k}_{key}"] = v
+    out["n_bad"] = np.array(n_bad, dtype=np.int32)
+    out["n_done"] = np.array(n_done, dtype=np.int32)
+    out["reward_sum"] = np.array(rsum, dtype=np.float64)
+    np.savez_compressed(os.path.join(HERE, name), **out)
+    print(name, "bad events", sum(n_bad), "done events", sum(n_done))
+
+
+def done_branch(name):
+    """Drive the target-reached (`done`) branch of UnreachHeading (unreach_heading.py:38-53), which random
+    actions never reach: after the initial reset put every target on the current state and jump step_count
+    to just below min_check_interval; record the next 4 steps (done fires, +200, then the reset)."""
+    n, seed = 32, 21
+    ref = RefEnv(n, "heading", "F16", seed=0, noise_scale=0.0)
+    ref.reset(torch.from_numpy(tapes.reset_draw_tape(seed, 0, n)))
+    e = ref.env
+    e.task.target_altitude[:] = e.model.s[:, 2]
+    e.task.target_heading[:] = e.model.s[:, 5]
+    e.task.target_vt[:] = e.model.s[:, 6]
+    e.task.target_altitude[::4] += 500.0          # a quarter stay off-target
+    e.step_count[:] = 298
+    e.step_count[1::8] = 2499                      # late but on-target: neither done nor bad_done
+    e.step_count[::8] = 2499                       # late and off-target: bad_done (unreach heading)
+    out = {"meta": np.array([n, 4, seed], dtype=np.int64)}
+    for k in range(1, 5):
+        a = torch.from_numpy(tapes.action_tape(seed, k, n, 0.02))
+        d = torch.from_numpy(tapes.reset_draw_tape(seed, k, n))
+        obs, rew, done, bad, exc = ref.step(a, d)
+        for key, v in snap(ref, obs, rew, done, bad, exc).items():
+            out[f"k{k}_{key}"] = v
+    np.savez_compressed(os.path.join(HERE, name), **out)
+    print(name, "done at k2:", int(out["k2_done"].sum()), "bad at k1:", int(out["k1_bad"].sum()))
+
+
+def nlplant_kat(name, n=2048, seed=5):
+    """Known answers of F16Dynamics.nlplant, the 43 coefficient nets and the derived getters on random states."""
+    import_reference()
+    from models.F16_model import F16Model
+    cfg = type("Cfg", (), {"init_state": {"init_T": 2000}})
+    m = F16Model(cfg, n, torch.device("cpu"), 0)
+    s, u = tapes.random_envelope_states(seed, n)
+    m.s = torch.from_numpy(s); m.u = torch.from_numpy(u)
+    with torch.no_grad():
+        xdot = m.get_extended_state()
+        ax, ay, az = m.get_acceleration()
+        h = m.dynamics.hifi_F16
+        alpha, beta, el = m.s[:, 7] * (180.0 / torch.pi), m.s[:, 8] * (180.0 / torch.pi), m.u[:, 1]
+        d = np.load(os.path.join(HERE, "..", "..", "neuralplane_b200", "data", "f16_aero.npz"))
+        meths = {a.lower(): a for a in dir(h) if a.startswith("_") and not a.startswith("__")}
+        coefs = []
+        for nm, row in zip(d["names"], d["desc"]):
+            nm = str(nm)
+            meth = meths["_" + nm.lower()]
+            args = [(alpha, beta, el)[int(c)] for c in row[1:1 + int(row[0])]]
+            coefs.append(getattr(h, meth)(*args).numpy())
+        out = dict(xdot=xdot[:, :12].numpy(), accel=torch.stack((ax, ay, az), 1).numpy(),
+                   coefs=np.stack(coefs, 1), eas2tas=m.get_EAS2TAS().numpy(), G=m.get_G().numpy(),
+                   meta=np.array([n, seed], dtype=np.int64))
+    np.savez_compressed(os.path.join(HERE, name), **out)
+    print(name, out["xdot"].shape, out["coefs"].shape)
+
+
+def recorded_trajectory(name, head=400):
+    """Head of the reference's recorded F-16 trajectory (writer: renders/render_ppo.py:37,98-102,153-186)."""
+    keys = ["npos", "epos", "altitude", "roll", "pitch", "yaw", "vt", "alpha", "beta", "G", "T", "el", "ail", "rud"]
+    out = {k: np.load(os.path.join(REF_ROOT, "renders", "result", k + ".npy"))[:head].astype(np.float32) for k in keys}
+    np.savez_compressed(os.path.join(HERE, name), **out)
+    print(name, {k: v.shape for k, v in out.items()}["npos"])
+
+
+if __name__ == "__main__":
+    torch.set_num_threads(8)
+    recorded_trajectory("ref_recorded_trajectory.npz")
+    nlplant_kat("f16_nlplant_kat.npz")
+    done_branch("heading_done_branch.npz")
+    trajectory("heading", 128, 1000, 0.3, 11, "heading_traj_a03.npz")
+    trajectory("heading", 128, 1000, 1.0, 12, "heading_traj_a10.npz")
+    trajectory("control", 64, 300, 1.0, 13, "control_traj.npz")
+    trajectory("tracking", 64, 300, 1.0, 14, "tracking_traj.npz")
