@@ -1,0 +1,138 @@
+/*
+ * nplane.h -- C ABI of libnplane.so: the B200 (sm_100a) implementation of NeuralPlane's
+ * vectorised F-16 flight-dynamics step (ControlEnv.step / reset and the F16Model plug-in getters).
+ *
+ * The reference (xuecy22/NeuralPlane) is pure Python/PyTorch and has no FFI; the entry points below
+ * are what a binding for this path replaces, cited as reference file:line (relative to the reference
+ * repo root).  A maintainer-side ctypes stub is shown in INTEGRATION.md.
+ *
+ * Conventions
+ *   - every function returns an int status (NP_OK == 0); np_last_error() gives the thread-local text.
+ *   - all pointers named *_dev are DEVICE pointers owned by the caller (PyTorch allocates them); the
+ *     library only borrows them.  The library owns the small aero blob it uploads in np_aero_create.
+ *   - per-aircraft state is SoA, field-major: row f of a [F][ld] array starts at base + f*ld, ld >= n,
+ *     ld % 4 == 0.  obs is row-major [n][22] (what GPUVecEnv hands to the runners, env_wrappers.py:97).
+ *   - `stream` is a cudaStream_t passed as void*; step/reset only ENQUEUE work on it, never synchronise,
+ *     and are CUDA-graph capturable.  Handles are not thread-safe; distinct handles are independent.
+ */
+#ifndef NPLANE_H_
+#define NPLANE_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NP_ABI_VERSION 1
+
+enum { NP_OK = 0, NP_EINVAL = 1, NP_ECUDA = 2, NP_ESTATE = 3 };
+
+enum { NP_TASK_HEADING = 0, NP_TASK_CONTROL = 1, NP_TASK_TRACKING = 2 };
+
+#define NP_NUM_NETS 43       /* hifi_F16_AeroData.py:44-129 */
+#define NP_NUM_STATE 12      /* F16_model.py:19 */
+#define NP_NUM_CTRL 5        /* F16_model.py:21 (T, el, ail, rud, lef; lef is always 0, F16_model.py:57) */
+#define NP_NUM_TGT 3         /* heading: alt,psi,vt | control: theta,psi,vt | tracking: npos,epos,alt */
+#define NP_NUM_OBS 22        /* heading_task.py:71-152 */
+#define NP_NUM_ACT 4         /* F16_model.py:52-56 */
+#define NP_NUM_DRAWS 5       /* uniforms a resetting aircraft consumes: alt, vt, 3 task draws */
+#define NP_NUM_COUNTERS 8
+
+typedef struct np_aero np_aero; /* the 43 MLP surrogates, device-resident */
+typedef struct np_env np_env;   /* one ControlEnv(model='F16') population */
+
+/* One row of the packed net table (neuralplane_b200/data/f16_aero.npz `desc`). */
+typedef struct np_net_desc {
+  int32_t n_in;      /* 1..3 */
+  int32_t sel[3];    /* which input feeds column j: 0 alpha_deg, 1 beta_deg, 2 el_deg, -1 unused */
+  int32_t n_layers;  /* Linear layers incl. the 1-wide output */
+  int32_t dims[5];   /* widths d0 (= n_in) .. d_n_layers (= 1), 0 padded */
+  int32_t w_off;     /* float offset into the blob: per layer W[out][in] row-major, then b[out] */
+  int32_t used;      /* 0: evaluated by the reference but never consumed (delta_Czq_lef) */
+} np_net_desc;
+
+/* yaml task parameters (envs/configs/{heading,control,tracking}.yaml), read via getattr(config, key, default)
+ * at F16_model.py:13-29, heading_task.py:29-32, the termination conditions' __init__ and env_base.py:22. */
+typedef struct np_env_cfg {
+  int32_t n;            /* aircraft on this rank = num_envs * num_agents (env_base.py:25) */
+  int32_t ld;           /* row pitch of the SoA arrays, >= n, multiple of 4 */
+  int32_t task;         /* NP_TASK_* (control_env.py:28-35) */
+  int32_t use_coef_cache; /* 1: reuse the (alpha,beta)-only coefficients of the Overload evaluation in the next step */
+  uint64_t seed;        /* Philox key for reset draws / observation noise when no tape is injected */
+  uint64_t index_base;  /* global index of local aircraft 0 (rank sharding; RNG streams are per global index) */
+  float dt, airspeed, noise_scale;
+  float altitude_limit, acceleration_limit, max_velocity, min_velocity;
+  float min_alpha, max_alpha, min_beta, max_beta;
+  float max_heading_increment, max_pitch_increment, max_velocities_u_increment;
+  float max_distance, min_distance;
+  int32_t max_check_interval, min_check_interval;
+  float init_T, max_altitude, min_altitude, max_vt, min_vt;
+} np_env_cfg;
+
+/* Device buffers the env works on (replace the tensors of F16_model.py:19-22, heading_task.py:26-28,
+ * env_base.py:30-33). */
+typedef struct np_buffers {
+  float* s_dev;            /* [12][ld] state rows: npos epos alt phi theta psi vt alpha beta P Q R */
+  float* u_dev;            /* [5][ld]  controls: T el ail rud lef (row 4 stays 0 and is never read) */
+  float* tgt_dev;          /* [3][ld]  task targets */
+  int32_t* step_count_dev; /* [ld] */
+  uint8_t* flags_dev;      /* [3][ld]  is_done, bad_done, exceed_time_limit (0/1) */
+  float* obs_dev;          /* [n][22] row-major */
+  float* reward_dev;       /* [n] */
+  void* workspace_dev;     /* np_env_workspace_bytes() bytes, zero-initialised by the caller */
+} np_buffers;
+
+int np_version(void);
+/* Copies the calling thread's last error text (NUL terminated) into buf; returns its length. */
+size_t np_last_error(char* buf, size_t cap);
+
+/* Upload the 43 nets.  blob/descs/norm are HOST pointers in the layout of f16_aero.npz:
+ * norm[k] = {in_mean[3], in_std[3], out_mean, out_std} (mean_std.csv; hifi_F16_AeroData.py:32-37,149-166). */
+int np_aero_create(const float* blob, size_t n_floats, const np_net_desc* descs, const double* norm,
+                   int n_nets, np_aero** out);
+int np_aero_destroy(np_aero* aero);
+
+size_t np_env_workspace_bytes(const np_env_cfg* cfg);
+int np_env_create(const np_env_cfg* cfg, const np_aero* aero, np_env** out);
+int np_env_bind(np_env* env, const np_buffers* bufs);
+/* Replace the task parameters (e.g. task.noise_scale = 0 for parity runs); n, ld and task must not change. */
+int np_env_set_cfg(np_env* env, const np_env_cfg* cfg);
+int np_env_destroy(np_env* env);
+
+/* BaseEnv.reset() (env_base.py:83-97): re-initialise flagged aircraft (F16Model.reset F16_model.py:33-45,
+ * task.reset e.g. heading_task.py:49-69), clear all flags, write obs.
+ * draws_dev: [n][5] uniforms in [0,1) consumed by resetting aircraft, or NULL -> in-kernel Philox.
+ * noise_dev: [n][22] standard normals (scaled by noise_scale), or NULL -> in-kernel Philox (skipped when
+ * noise_scale == 0). */
+int np_env_reset(np_env* env, const float* draws_dev, const float* noise_dev, void* stream);
+
+/* BaseEnv.step(action) (env_base.py:99-109) as ONE kernel launch: reset -> control low-pass + Euler step
+ * (F16_model.py:51-67, F16_dynamics.py:37-229) -> step_count -> obs -> terminations (task_base.py:75-96)
+ * -> reward (task_base.py:60-73).  action_dev: [n][4] row-major (env_wrappers.py:94-95). */
+int np_env_step(np_env* env, const float* action_dev, const float* draws_dev, const float* noise_dev,
+                void* stream);
+
+/* Termination-cause counters accumulated on device since creation (replaces the per-condition
+ * print(torch.sum(bad_done)) host syncs, e.g. overload.py:32-34).  Synchronises `stream`.
+ * out[0..7] = overload, low_altitude, high_speed, low_speed, extreme_state, unreach, reached(done), resets. */
+int np_env_counters(np_env* env, uint64_t* out, void* stream);
+
+/* F16Dynamics.nlplant (F16_dynamics.py:37-229) on SoA rows: xdot_dev [12][ld] from s_dev [12][ld], u_dev [5][ld].
+ * Backs F16Model.get_extended_state and the getters built on it (F16_model.py:47-49,75-91,132-182). */
+int np_f16_nlplant(const np_aero* aero, const float* s_dev, const float* u_dev, float* xdot_dev, int n, int ld,
+                   void* stream);
+
+/* The 43 coefficient nets (hifi_F16_AeroData.py:748-819): out_dev [43][ld] in f16_aero.npz order from
+ * alpha_deg/beta_deg/el_deg [n]. */
+int np_f16_coeffs(const np_aero* aero, const float* alpha_deg_dev, const float* beta_deg_dev, const float* el_deg_dev,
+                  float* out_dev, int n, int ld, void* stream);
+
+/* Launch geometry the step kernel uses for this env (diagnostics / bench reporting). */
+int np_env_launch_info(const np_env* env, int* grid, int* block, int* smem_bytes, int* num_sms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NPLANE_H_ */

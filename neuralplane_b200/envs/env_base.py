@@ -1,0 +1,210 @@
+"""Batched gym-style env (reference: envs/env_base.py:13-109) whose step() is one native kernel launch.
+
+Keeps the reference surface: n = num_envs * num_agents aircraft, `reset() -> obs[n,D]`,
+`step(action[n,A]) -> (obs, reward, done, bad_done, exceed_time_limit, info)`, attributes `model`, `task`,
+`step_count`, `is_done`, `bad_done`, `exceed_time_limit`, the gym spaces and `num_observation` / `num_actions`.
+Differences a caller can observe: returned tensors are the env's persistent device buffers (overwritten by the
+next step) and `step_count` is int32.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+import torch
+
+from .. import _native as nv
+from . import _soa
+from .utils.utils import parse_config
+
+_CFG_KEYS = (  # yaml key, default (the reference's getattr defaults), ctypes field
+    ("dt", 0.02), ("airspeed", 0), ("noise_scale", 0.01),
+    ("altitude_limit", 2500.0), ("acceleration_limit", 300.0), ("max_velocity", 3), ("min_velocity", 0.01),
+    ("min_alpha", -20), ("max_alpha", 45), ("min_beta", -30), ("max_beta", 30),
+    ("max_heading_increment", 0.3), ("max_pitch_increment", 0.3), ("max_velocities_u_increment", 100),
+    ("max_distance", 2000), ("min_distance", 2000),
+    ("max_check_interval", 1500), ("min_check_interval", 300),
+    ("max_altitude", 20000), ("min_altitude", 19000), ("max_vt", 1200), ("min_vt", 1000),
+)
+
+
+class BaseEnv:
+    metadata = {}
+
+    def __init__(self, num_envs=10, config='heading', model='F16', random_seed=None, device="cuda:0",
+                 index_base=0, use_coef_cache=True):
+        self.config = parse_config(config)
+        self.num_envs = num_envs
+        self.num_agents = getattr(self.config, 'num_agents', 100)
+        self.n = self.num_agents * self.num_envs
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise RuntimeError(f"neuralplane_b200 envs run on CUDA devices only (got {device}); no CPU fallback exists")
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
+        self.random_seed = random_seed
+        self._seed = int(random_seed) if random_seed is not None else int.from_bytes(os.urandom(8), "little")
+        self.index_base = int(index_base)
+        self.use_coef_cache = bool(use_coef_cache)
+        self.ld = _soa.pitch(self.n)
+        self._handle = C.c_void_p()
+
+        n, ld, dev = self.n, self.ld, self.device
+        self._tgt = torch.zeros((3, ld), device=dev)
+        self._step_count = torch.zeros(ld, dtype=torch.int32, device=dev)
+        self._flags = torch.ones((3, ld), dtype=torch.uint8, device=dev)   # everyone resets first (env_base.py:31-33)
+        self.load(random_seed, config, model)                              # builds self.model / self.task
+        self._obs = torch.zeros((n, self.num_observation), device=dev)
+        self._reward = torch.zeros(n, device=dev)
+        self.step_count = self._step_count[:n]
+        self._flag_views = [self._flags[j, :n].view(torch.bool) for j in range(3)]
+        self.create_records = False
+        self._native_create()
+
+    # ---- construction ------------------------------------------------------------------------------------
+    def load(self, random_seed, config, model):
+        raise NotImplementedError
+
+    def _cfg_struct(self):
+        c = nv.EnvCfg()
+        c.n, c.ld, c.task = self.n, self.ld, self.task.task_id
+        c.use_coef_cache = 1 if self.use_coef_cache else 0
+        c.seed, c.index_base = self._seed & (2 ** 64 - 1), self.index_base
+        for key, default in _CFG_KEYS:
+            setattr(c, key, getattr(self.config, key, default))
+        c.noise_scale = self.task.noise_scale
+        c.airspeed = self.model.airspeed
+        c.init_T = self.config.init_state['init_T']
+        return c
+
+    def _native_create(self):
+        if self.num_observation != nv.NUM_OBS:
+            raise NotImplementedError("the native tasks produce 22-D observations")
+        L = nv.lib()
+        self._cfg = self._cfg_struct()
+        with torch.cuda.device(self.device):
+            nv.check(L.np_env_create(C.byref(self._cfg), self.model.aero.handle, C.byref(self._handle)), "np_env_create")
+            nbytes = L.np_env_workspace_bytes(C.byref(self._cfg))
+            self._workspace = torch.zeros(nbytes, dtype=torch.uint8, device=self.device)
+            b = nv.Buffers(self.model._s.data_ptr(), self.model._u.data_ptr(), self._tgt.data_ptr(),
+                           self._step_count.data_ptr(), self._flags.data_ptr(), self._obs.data_ptr(),
+                           self._reward.data_ptr(), self._workspace.data_ptr())
+            nv.check(L.np_env_bind(self._handle, C.byref(b)), "np_env_bind")
+
+    def _sync_cfg(self):
+        ns = float(self.task.noise_scale)
+        if ns != self._cfg.noise_scale:
+            self._cfg.noise_scale = ns
+            nv.check(nv.lib().np_env_set_cfg(self._handle, C.byref(self._cfg)), "np_env_set_cfg")
+
+    def __del__(self):
+        try:
+            if getattr(self, "_handle", None):
+                nv.lib().np_env_destroy(self._handle)
+        except Exception:
+            pass
+
+    def seed(self, random_seed):
+        self._seed = int(random_seed)
+        self._cfg.seed = self._seed & (2 ** 64 - 1)
+        nv.check(nv.lib().np_env_set_cfg(self._handle, C.byref(self._cfg)), "np_env_set_cfg")
+
+    # ---- reference attribute surface ----------------------------------------------------------------------
+    @property
+    def is_done(self):
+        return self._flag_views[0]
+
+    @property
+    def bad_done(self):
+        return self._flag_views[1]
+
+    @property
+    def exceed_time_limit(self):
+        return self._flag_views[2]
+
+    @property
+    def observation_space(self):
+        return self.task.observation_space
+
+    @property
+    def action_space(self):
+        return self.task.action_space
+
+    @property
+    def num_observation(self):
+        return self.task.num_observation
+
+    @property
+    def num_actions(self):
+        return self.task.num_actions
+
+    @property
+    def last_obs(self):
+        return self._obs
+
+    @property
+    def last_reward(self):
+        return self._reward
+
+    def obs(self):
+        return self._obs
+
+    def reward(self):
+        return self._reward
+
+    def info(self):
+        return {}
+
+    def get_number_of_agents(self):
+        return self.n
+
+    def termination_counters(self):
+        """Per-cause termination counts since construction (device counters; one sync)."""
+        out = (C.c_uint64 * nv.NUM_COUNTERS)()
+        nv.check(nv.lib().np_env_counters(self._handle, out, self._stream()), "np_env_counters")
+        return dict(zip(nv.COUNTER_NAMES, [int(x) for x in out]))
+
+    # ---- reset / step ---------------------------------------------------------------------------------------
+    def _stream(self):
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    @staticmethod
+    def _ptr(t, shape, what):
+        if t is None:
+            return None
+        if t.dtype != torch.float32 or not t.is_cuda or tuple(t.shape) != tuple(shape) or not t.is_contiguous():
+            raise ValueError(f"{what} must be a contiguous float32 CUDA tensor of shape {tuple(shape)}")
+        return t.data_ptr()
+
+    def reset(self, reset_draws=None, noise=None):
+        """BaseEnv.reset (env_base.py:83-97).  reset_draws [n,5] / noise [n,22] inject the random numbers
+        (parity runs); by default they come from the in-kernel Philox stream keyed by (seed, global index)."""
+        self._sync_cfg()
+        st = nv.lib().np_env_reset(self._handle, self._ptr(reset_draws, (self.n, nv.NUM_DRAWS), "reset_draws"),
+                                   self._ptr(noise, (self.n, nv.NUM_OBS), "noise"), self._stream())
+        nv.check(st, "np_env_reset")
+        return self._obs
+
+    def step(self, action, render=False, count=0, reset_draws=None, noise=None):
+        """BaseEnv.step (env_base.py:99-109): one kernel launch, no host synchronisation."""
+        if not torch.is_tensor(action):
+            action = torch.as_tensor(np.asarray(action), dtype=torch.float32, device=self.device)
+        if action.dim() != 2 or action.shape[0] != self.n or action.shape[1] < 4:
+            raise ValueError(f"action must have shape [{self.n}, >=4], got {tuple(action.shape)}")
+        if action.shape[1] != 4 or action.dtype != torch.float32 or not action.is_contiguous() or action.device != self.device:
+            action = action[:, :4].to(device=self.device, dtype=torch.float32).contiguous()
+        self._sync_cfg()
+        st = nv.lib().np_env_step(self._handle, action.data_ptr(),
+                                  self._ptr(reset_draws, (self.n, nv.NUM_DRAWS), "reset_draws"),
+                                  self._ptr(noise, (self.n, nv.NUM_OBS), "noise"), self._stream())
+        nv.check(st, "np_env_step")
+        if render:
+            self.render(count=count)
+        return self._obs, self._reward, self.is_done, self.bad_done, self.exceed_time_limit, {}
+
+    def launch_info(self):
+        g, b, s, m = C.c_int(), C.c_int(), C.c_int(), C.c_int()
+        nv.check(nv.lib().np_env_launch_info(self._handle, C.byref(g), C.byref(b), C.byref(s), C.byref(m)), "np_env_launch_info")
+        return {"grid": g.value, "block": b.value, "smem_bytes": s.value, "num_sms": m.value}
+
+    def render(self, count, filename='./tracks/F16SimRecording-'):
+        raise NotImplementedError("Tacview .acmi rendering (env_base.py:111-151) is host file I/O outside the hot path")

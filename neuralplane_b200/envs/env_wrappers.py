@@ -1,0 +1,76 @@
+"""GPUVecEnv (reference: envs/env_wrappers.py:84-124): the numpy boundary the runners call.
+
+Same shapes as the reference: actions (num_envs, agents, A) in; obs (num_envs, agents, D), rewards / dones /
+bad_dones / exceed_time_limits (num_envs, agents, 1) out.  Host<->device traffic goes through pinned staging
+buffers on the env's stream (one H2D, four D2H, one synchronise per step).  The returned arrays alias pinned
+buffers that are reused every OTHER step (double-buffered), so a result stays valid until the step after next.
+"""
+import numpy as np
+import torch
+
+
+class GPUVecEnv:
+    def __init__(self, env_fns):
+        assert len(env_fns) == 1, "Number of create env funcitions must be 1!"
+        self.gpu_vec_env = env_fns[0]()
+        assert hasattr(self.gpu_vec_env, "num_envs"), "Parameter of env must contain num_envs!"
+        e = self.gpu_vec_env
+        self.num_envs = e.num_envs
+        self.observation_space = e.observation_space
+        self.action_space = e.action_space
+        self.agents = e.num_agents
+        self.closed = False
+        n, D = e.n, e.num_observation
+        self._act_h = torch.empty((n, 4), dtype=torch.float32).pin_memory()
+        self._act_d = torch.empty((n, 4), dtype=torch.float32, device=e.device)
+        self._out = [dict(obs=torch.empty((n, D), dtype=torch.float32).pin_memory(),
+                          rew=torch.empty(n, dtype=torch.float32).pin_memory(),
+                          flags=torch.empty((3, n), dtype=torch.uint8).pin_memory()) for _ in range(2)]
+        self._flip = 0
+        self.h2d_bytes_per_step = self._act_h.numel() * 4
+        self.d2h_bytes_per_step = n * D * 4 + n * 4 + 3 * n
+
+    def _download(self, with_rest=True):
+        e = self.gpu_vec_env
+        o = self._out[self._flip]
+        self._flip ^= 1
+        o["obs"].copy_(e.last_obs, non_blocking=True)
+        if with_rest:
+            o["rew"].copy_(e.last_reward, non_blocking=True)
+            o["flags"].copy_(e._flags[:, :e.n], non_blocking=True)
+        torch.cuda.current_stream(e.device).synchronize()
+        return o
+
+    def step(self, actions):
+        e = self.gpu_vec_env
+        a = np.asarray(actions, dtype=np.float32).reshape(self.num_envs * self.agents, -1)
+        self._act_h.copy_(torch.from_numpy(a[:, :4]))
+        self._act_d.copy_(self._act_h, non_blocking=True)
+        e.step(self._act_d)
+        o = self._download()
+        shp = (self.num_envs, self.agents, 1)
+        obs = o["obs"].numpy().reshape(self.num_envs, self.agents, e.num_observation)
+        flags = o["flags"].numpy().view(np.bool_)
+        return (obs, o["rew"].numpy().reshape(shp), flags[0].reshape(shp), flags[1].reshape(shp),
+                flags[2].reshape(shp), {})
+
+    def reset(self):
+        e = self.gpu_vec_env
+        e.reset()
+        o = self._download(with_rest=False)
+        return o["obs"].numpy().reshape(self.num_envs, self.agents, e.num_observation)
+
+    def step_async(self, actions):
+        pass
+
+    def step_wait(self):
+        pass
+
+    def close_extras(self):
+        pass
+
+    def close(self):
+        if self.closed:
+            return
+        self.close_extras()
+        self.closed = True

@@ -33,8 +33,8 @@ NETS = [
     # (name, inputs)                      el-dependent
     ("Cx", (A, B, E)), ("Cz", (A, B, E)), ("Cm", (A, B, E)), ("Cn", (A, B, E)), ("Cl", (A, B, E)),
     ("eta_el", (E,)),
-    # (alpha, beta), hidden [20,10]
-    ("Cy", (A, B)), ("delta_Cx_lef", (A, B)), ("delta_Cl_lef", (A, B)), ("delta_Cl_a20", (A, B)),
+    # (alpha, beta), hidden [20,10]: two with the "r30/a20" input normalisation, two with the "lef" one
+    ("Cy", (A, B)), ("delta_Cl_a20", (A, B)), ("delta_Cx_lef", (A, B)), ("delta_Cl_lef", (A, B)),
     # (alpha, beta), hidden [20,10,5]
     ("delta_Cz_lef", (A, B)), ("delta_Cm_lef", (A, B)), ("delta_Cy_lef", (A, B)), ("delta_Cn_lef", (A, B)),
     ("delta_Cy_r30", (A, B)), ("delta_Cn_r30", (A, B)), ("delta_Cl_r30", (A, B)), ("delta_Cn_a20", (A, B)),
