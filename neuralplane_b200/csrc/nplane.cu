@@ -576,7 +576,7 @@ __global__ void __launch_bounds__(128) f16_c0_kernel(float* aero) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   float* blob = reinterpret_cast<float*>(smem_raw);
   float* coef = blob + kAeroFloats;
-  uint64_t* bar = reinterpret_cast<uint64_t*>(coef + kNumNets);
+  uint64_t* bar = reinterpret_cast<uint64_t*>(coef + pad4(kNumNets));  // 8-byte aligned
   stage_aero(blob, aero, bar);
   const uint32_t wb = aero_base_after_staging(blob);
   if (threadIdx.x == 0) {
@@ -659,7 +659,7 @@ int np_aero_create(const float* blob, size_t n_floats, const np_net_desc* descs,
   cudaGetDevice(&a->device);
   NP_CUDA(cudaMalloc(&a->blob_dev, kAeroBytes));
   NP_CUDA(cudaMemcpy(a->blob_dev, host.data(), kAeroBytes, cudaMemcpyHostToDevice));
-  constexpr int c0_smem = kAeroBytes + kNumNets * 4 + 16;
+  constexpr int c0_smem = kAeroBytes + pad4(kNumNets) * 4 + 16;
   NP_CUDA(cudaFuncSetAttribute(f16_c0_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, c0_smem));
   f16_c0_kernel<<<1, 128, c0_smem>>>(a->blob_dev);
   NP_CUDA(cudaGetLastError());

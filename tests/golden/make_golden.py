@@ -39,14 +39,28 @@ def snap(ref, obs, rew, done, bad, exc):
 
 
 def trajectory(task, n, steps, scale, seed, name):
+    """Reference trajectory + the reference's own sensitivity: a twin run whose state is perturbed by 1 ulp
+    (s * (1 + 2^-23)) after every episodic reset; the twin's distance to the unperturbed run at each checkpoint is
+    the fp32 noise level any re-implementation should be judged against."""
+    sys.path.insert(0, os.path.join(HERE, ".."))
+    from _metrics import state_rel_err
     ref = RefEnv(n, task, "F16", seed=0, noise_scale=0.0)
-    obs0 = ref.reset(torch.from_numpy(tapes.reset_draw_tape(seed, 0, n)))
+    twin = RefEnv(n, task, "F16", seed=0, noise_scale=0.0)
+    d0 = torch.from_numpy(tapes.reset_draw_tape(seed, 0, n))
+    obs0 = ref.reset(d0)
+    twin.reset(d0)
+    twin.env.model.s = twin.env.model.s * (1.0 + 2.0 ** -23)
     out = {"obs0": obs0.numpy().copy(), "meta": np.array([n, steps, seed], dtype=np.int64), "scale": np.float32(scale)}
     n_bad, n_done, rsum = [], [], []
     for k in range(1, steps + 1):
         a = torch.from_numpy(tapes.action_tape(seed, k, n, scale))
         d = torch.from_numpy(tapes.reset_draw_tape(seed, k, n))
         obs, rew, done, bad, exc = ref.step(a, d)
+        twin.step(a, d, perturb_after_reset=1.0 + 2.0 ** -23)
+        if k in CHECKPOINTS:
+            same = (twin.env.step_count == ref.env.step_count).numpy()
+            e = state_rel_err(twin.env.model.s.numpy()[same], ref.env.model.s.numpy()[same])
+            out[f"k{k}_selfnoise"] = np.array([np.median(e), e.max(), same.mean()], dtype=np.float64)
         n_bad.append(int(bad.sum())); n_done.append(int(done.sum())); rsum.append(float(rew.double().sum()))
         if k in CHECKPOINTS:
             for key, v in snap(ref, obs, rew, done, bad, exc).items():
@@ -56,6 +70,32 @@ def trajectory(task, n, steps, scale, seed, name):
     out["reward_sum"] = np.array(rsum, dtype=np.float64)
     np.savez_compressed(os.path.join(HERE, name), **out)
     print(name, "bad events", sum(n_bad), "done events", sum(n_done))
+
+
+def add_truth(name, task):
+    """Append the float64 'truth' trajectory to a trajectory fixture: the oracle restatement (bit-identical to the
+    reference in float32, tests/test_oracle_golden.py) run in double on the same tapes.  Stored per checkpoint:
+    k{k}_s64 and k{k}_ref_vs_truth = (median, max) of the reference-fp32 state error against it."""
+    sys.path.insert(0, os.path.join(HERE, ".."))
+    from _metrics import state_rel_err
+    from oracle.f16_oracle import F16EnvOracle
+    path = os.path.join(HERE, name)
+    g = dict(np.load(path))
+    n, steps, seed = [int(x) for x in g["meta"]]
+    scale = float(g["scale"])
+    o64 = F16EnvOracle(n, task, dtype=torch.float64)
+    o64.reset(torch.from_numpy(tapes.reset_draw_tape(seed, 0, n)).double())
+    for k in range(1, steps + 1):
+        o64.step(torch.from_numpy(tapes.action_tape(seed, k, n, scale)).double(),
+                 torch.from_numpy(tapes.reset_draw_tape(seed, k, n)).double())
+        if f"k{k}_s" in g:
+            same = o64.step_count.numpy() == g[f"k{k}_step_count"]
+            e = state_rel_err(g[f"k{k}_s"][same], o64.s.numpy()[same])
+            g[f"k{k}_s64"] = o64.s.numpy().copy()
+            g[f"k{k}_step_count64"] = o64.step_count.numpy().astype(np.int32)
+            g[f"k{k}_ref_vs_truth"] = np.array([np.median(e), e.max(), same.mean()])
+    np.savez_compressed(path, **g)
+    print(name, "truth added; ref-vs-truth median at last checkpoint %.2e" % g[f"k{max(c for c in CHECKPOINTS if c <= steps)}_ref_vs_truth"][0])
 
 
 def done_branch(name):
@@ -125,7 +165,9 @@ if __name__ == "__main__":
     recorded_trajectory("ref_recorded_trajectory.npz")
     nlplant_kat("f16_nlplant_kat.npz")
     done_branch("heading_done_branch.npz")
-    trajectory("heading", 128, 1000, 0.3, 11, "heading_traj_a03.npz")
-    trajectory("heading", 128, 1000, 1.0, 12, "heading_traj_a10.npz")
-    trajectory("control", 64, 300, 1.0, 13, "control_traj.npz")
-    trajectory("tracking", 64, 300, 1.0, 14, "tracking_traj.npz")
+    for task, n, steps, scale, seed, name in (("heading", 128, 1000, 0.3, 11, "heading_traj_a03.npz"),
+                                              ("heading", 128, 1000, 1.0, 12, "heading_traj_a10.npz"),
+                                              ("control", 64, 300, 1.0, 13, "control_traj.npz"),
+                                              ("tracking", 64, 300, 1.0, 14, "tracking_traj.npz")):
+        trajectory(task, n, steps, scale, seed, name)
+        add_truth(name, task)

@@ -88,13 +88,18 @@ class RefEnv:
         with contextlib.redirect_stdout(io.StringIO()), self._inject(draws):
             return self.env.reset()
 
-    def step(self, action, draws=None):
-        """One reference step; `draws` feeds the reset at the top of step()."""
+    def step(self, action, draws=None, perturb_after_reset=None):
+        """One reference step; `draws` feeds the reset at the top of step().  `perturb_after_reset` (a factor such
+        as 1 + 2^-23) scales the state of aircraft that have just been re-initialised: used to measure the
+        reference's own sensitivity to a 1-ulp perturbation."""
         env = self.env
         with contextlib.redirect_stdout(io.StringIO()):
             # BaseEnv.step = reset(); update; count; obs; done; reward (env_base.py:99-109)
+            mask = (env.is_done.bool() | env.bad_done.bool()) | env.exceed_time_limit.bool()
             with self._inject(draws):
                 env.reset()
+            if perturb_after_reset is not None:
+                env.model.s[mask] = env.model.s[mask] * perturb_after_reset
             env.model.update(action)
             env.step_count += 1
             obs = env.obs()

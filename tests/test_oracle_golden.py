@@ -11,6 +11,7 @@ import pytest
 import torch
 
 from oracle import tapes
+from _metrics import state_rel_err
 from oracle.f16_oracle import AeroNets, F16EnvOracle, body_accel, eas2tas, euler_step, load_factors, nlplant
 
 
@@ -72,10 +73,7 @@ def test_trajectory_vs_reference_fixture(task, fixture, max_steps, golden_dir):
         # aircraft whose episode history matches (same reset times) are compared; on the build container all do
         same = (env.step_count.numpy() == g[f"k{k}_step_count"])
         assert same.mean() > 0.9, (k, same.mean())
-        s_ref = g[f"k{k}_s"][same]
-        s = env.s.numpy()[same]
-        floor = 1e-3 * np.median(np.abs(s_ref), axis=0) + 1e-9
-        err = rel_err(s, s_ref, floor).max(axis=1)
+        err = state_rel_err(env.s.numpy()[same], g[f"k{k}_s"][same])
         tol = 2e-6 if k <= 10 else (1e-5 if k <= 100 else 1e-4)
         assert np.median(err) <= tol, (k, np.median(err))
         exact &= bool(np.array_equal(env.s.numpy(), g[f"k{k}_s"])) and bool(np.array_equal(obs.numpy(), g[f"k{k}_obs"]))

@@ -9,5 +9,5 @@ for b in 128 256 384 512; do
   NPLANE_LIB=$PWD/neuralplane_b200/_lib/libnplane_all.so NPLANE_BLOCK=$b timeout 300 python bench.py --steps 100 --warmup 10 --no-cpu --e2e-steps 3 > gpurun_out/bench_b$b.json 2> gpurun_out/bench_b$b.err
 done
 timeout 300 python bench.py --steps 100 --warmup 10 --no-cpu --e2e-steps 3 --no-cache > gpurun_out/bench_nocache.json 2> gpurun_out/bench_nocache.err
-tail -5 gpurun_out/smoke.log gpurun_out/pytest_gpu.log
+tail -n 5 gpurun_out/smoke.log; tail -n 15 gpurun_out/pytest_gpu.log
 cat gpurun_out/bench_*.json
