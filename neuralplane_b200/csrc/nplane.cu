@@ -56,7 +56,7 @@ struct np_env {
   np_buffers buf;
   bool bound = false;
   uint32_t step_index = 0;
-  int block = 256, grid = 0, smem = 0, num_sms = 0;
+  int block = 512, grid = 0, smem = 0, num_sms = 0;
 };
 
 struct StepParams {
@@ -735,7 +735,7 @@ int np_env_create(const np_env_cfg* cfg, const np_aero* aero, np_env** out) {
   int dev = 0;
   NP_CUDA(cudaGetDevice(&dev));
   NP_CUDA(cudaDeviceGetAttribute(&e->num_sms, cudaDevAttrMultiProcessorCount, dev));
-  e->block = 256;
+  e->block = 512;  // 16 warps/SM: measured 1.155 ms vs 1.49 ms (256) per 10^6-aircraft step (profiles/r01_block_sweep.txt)
   if (const char* b = getenv("NPLANE_BLOCK")) e->block = atoi(b);
   if (e->block != 128 && e->block != 256 && e->block != 384 && e->block != 512)
     return fail(NP_EINVAL, "NPLANE_BLOCK must be 128, 256, 384 or 512");
@@ -791,10 +791,10 @@ int np_env_step(np_env* env, const float* action_dev, const float* draws_dev, co
   switch (env->block) {
 #ifdef NPLANE_ALL_BLOCKS
     case 128: return launch_step<128, 2>(env, p, st);
-    case 384: return launch_step<384, 1>(env, p, st);
-    case 512: return launch_step<512, 1>(env, p, st);
-#endif
     case 256: return launch_step<256, 1>(env, p, st);
+    case 384: return launch_step<384, 1>(env, p, st);
+#endif
+    case 512: return launch_step<512, 1>(env, p, st);
     default: return fail(NP_EINVAL, "np_env_step: block size not compiled in (build with -DNPLANE_ALL_BLOCKS)");
   }
 }
