@@ -59,7 +59,7 @@ typedef struct np_env_cfg {
   int32_t n;            /* aircraft on this rank = num_envs * num_agents (env_base.py:25) */
   int32_t ld;           /* row pitch of the SoA arrays, >= n, multiple of 4 */
   int32_t task;         /* NP_TASK_* (control_env.py:28-35) */
-  int32_t use_coef_cache; /* 1: reuse the (alpha,beta)-only coefficients of the Overload evaluation in the next step */
+  int32_t use_coef_cache; /* 1: reuse the 16 (alpha,beta)-MLP outputs of the Overload evaluation in the next step */
   uint64_t seed;        /* Philox key for reset draws / observation noise when no tape is injected */
   uint64_t index_base;  /* global index of local aircraft 0 (rank sharding; RNG streams are per global index) */
   float dt, airspeed, noise_scale;
@@ -74,6 +74,7 @@ typedef struct np_env_cfg {
 /* Device buffers the env works on (replace the tensors of F16_model.py:19-22, heading_task.py:26-28,
  * env_base.py:30-33). */
 typedef struct np_buffers {
+  /* all SoA rows: 16-byte aligned base, ld even and >= n rounded up to even (the step kernel moves float2 pairs) */
   float* s_dev;            /* [12][ld] state rows: npos epos alt phi theta psi vt alpha beta P Q R */
   float* u_dev;            /* [5][ld]  controls: T el ail rud lef (row 4 stays 0 and is never read) */
   float* tgt_dev;          /* [3][ld]  task targets */
@@ -93,6 +94,11 @@ size_t np_last_error(char* buf, size_t cap);
 int np_aero_create(const float* blob, size_t n_floats, const np_net_desc* descs, const double* norm,
                    int n_nets, np_aero** out);
 int np_aero_destroy(np_aero* aero);
+/* Host-only: build the device image np_aero_create uploads (weights of the 22 multi-input MLPs + the exact
+ * piecewise-linear tables of the 21 one-input nets; layout in neuralplane_b200/csrc/f16_layout.h).  With
+ * out_words == NULL only *n_words is returned.  Used by the CPU tests of the table construction. */
+int np_aero_pack_host(const float* blob, size_t n_floats, const np_net_desc* descs, const double* norm, int n_nets,
+                      uint32_t* out_words, size_t cap_words, size_t* n_words);
 
 size_t np_env_workspace_bytes(const np_env_cfg* cfg);
 int np_env_create(const np_env_cfg* cfg, const np_aero* aero, np_env** out);

@@ -56,6 +56,8 @@ SYMBOLS = {
     "np_last_error": (C.c_size_t, [C.c_char_p, C.c_size_t]),
     "np_aero_create": (C.c_int, [_P, C.c_size_t, C.POINTER(NetDesc), _P, C.c_int, C.POINTER(_P)]),
     "np_aero_destroy": (C.c_int, [_P]),
+    "np_aero_pack_host": (C.c_int, [_P, C.c_size_t, C.POINTER(NetDesc), _P, C.c_int, _P, C.c_size_t,
+                                    C.POINTER(C.c_size_t)]),
     "np_env_workspace_bytes": (C.c_size_t, [C.POINTER(EnvCfg)]),
     "np_env_create": (C.c_int, [C.POINTER(EnvCfg), _P, C.POINTER(_P)]),
     "np_env_bind": (C.c_int, [_P, C.POINTER(Buffers)]),
@@ -74,7 +76,7 @@ _lib = None
 
 def build(force=False, verbose=False, extra_flags=()):
     """Compile csrc/nplane.cu for sm_100a into _lib/libnplane.so (nvcc cross-compiles without a GPU)."""
-    srcs = [os.path.join(CSRC, f) for f in ("nplane.cu", "f16_device.cuh")] + [HEADER]
+    srcs = [os.path.join(CSRC, f) for f in ("nplane.cu", "f16_device.cuh", "f16_layout.h", "aero_pack.h")] + [HEADER]
     if not force and os.path.exists(LIB_PATH) and all(os.path.getmtime(LIB_PATH) >= os.path.getmtime(s) for s in srcs):
         return LIB_PATH
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"

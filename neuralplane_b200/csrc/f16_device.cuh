@@ -1,9 +1,10 @@
-// Device-side building blocks of the F-16 step: the 43 MLP aero surrogates, the 6-DoF equations of
-// motion, atmosphere, observation helpers and the counter-based RNG.
+// Device-side building blocks of the F-16 step: the aero-coefficient surrogates (22 MLPs on packed FFMA2 for two
+// aircraft per thread, 21 one-input nets as exact piecewise-linear tables), the 6-DoF equations of motion,
+// atmosphere, observation helpers and the counter-based RNG.
 //
 // Numerics contract: this translation unit is compiled with -fmad=false, so every `a*b+c` written
 // below rounds twice exactly like the reference's eager PyTorch ops do; the MLP inner products use
-// explicit fmaf() (the reference's nn.Linear goes through an FMA-based sgemm with unspecified
+// explicit FMAs (the reference's nn.Linear goes through an FMA-based sgemm with unspecified
 // summation order, so no order is "the" reference order there).  Division and sqrt are IEEE
 // (nvcc defaults -prec-div/-prec-sqrt=true); sinf/cosf/tanf/powf are the accurate CUDA libm versions.
 //
@@ -14,91 +15,29 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "f16_layout.h"
+
 namespace npl {
 
 // ------------------------------------------------------------------------------------------------
-// Net table: canonical order of neuralplane_b200/data/f16_aero.npz (tools/pack_f16_aero.py).
+// Shared-memory access helpers.  Weights / tables are read with explicit ld.shared (warp-broadcast for the
+// weights).  Besides pinning the access width, the non-volatile asm keeps several thousand weight loads out of
+// the compiler's alias analysis; ordering against the one-time TMA staging is carried by the data dependence on
+// the base address, which callers obtain from aero_base_after_staging() after the staging barrier.
 // ------------------------------------------------------------------------------------------------
-struct NetArch {
-  int nin, h1, h2, h3;  // h3 == 0: two hidden layers
-};
-
-constexpr int kNumNets = 43;
-constexpr int kNumUsed = 42;  // net 42 (delta_Czq_lef) is never consumed (F16_dynamics.py:167-175)
-
-// coefficient slots == net indices
-enum Coef : int {
-  kCx = 0, kCz, kCm, kCn, kCl, kEtaEl,                                  // el-dependent (G1, G2)
-  kCy, kdCl_a20, kdCx_lef, kdCl_lef,                                     // (a,b) [20,10]       (G3, G4)
-  kdCz_lef, kdCm_lef, kdCy_lef, kdCn_lef,                                // (a,b) [20,10,5] lef (G5)
-  kdCy_r30, kdCn_r30, kdCl_r30, kdCn_a20,                                // (a,b) [20,10,5] r   (G6)
-  kdCy_a20,                                                              // (a,b) [20,10,10]    (G7)
-  kdCy_a20_lef, kdCn_a20_lef, kdCl_a20_lef,                              // (a,b) [20,20,10]    (G8)
-  kCxq, kCzq, kCmq, kCyp, kCyr, kCnr, kCnp, kClp, kClr,                  // (a) ALPHA1          (G9)
-  kdCnbeta, kdClbeta, kdCm,
-  kdCxq_lef, kdCyr_lef, kdClr_lef, kdClp_lef, kdCmq_lef, kdCnr_lef, kdCnp_lef,  // (a) lef   (G10)
-  kdCyp_lef,                                                             // (a) [20,10,5] lef   (G11)
-  kdCzq_lef                                                              // unused
-};
-constexpr int kFirstAB = kCy;               // nets [kFirstAB, kNumUsed) depend on (alpha, beta) only
-constexpr int kNumAB = kNumUsed - kFirstAB;  // 36
-
-constexpr NetArch arch_of(int k) {
-  return k <= kCl ? NetArch{3, 20, 10, 0}
-       : k == kEtaEl ? NetArch{1, 20, 10, 0}
-       : k <= kdCl_lef ? NetArch{2, 20, 10, 0}
-       : k <= kdCn_a20 ? NetArch{2, 20, 10, 5}
-       : k == kdCy_a20 ? NetArch{2, 20, 10, 10}
-       : k <= kdCl_a20_lef ? NetArch{2, 20, 20, 10}
-       : k <= kdCnp_lef ? NetArch{1, 20, 10, 0}
-       : k == kdCyp_lef ? NetArch{1, 20, 10, 5}
-       : NetArch{1, 20, 10, 0};
-}
-
-// Input normalisation groups (mean_std.csv): which (mean, std) pair z-scores each input of a net.
-enum ZId : int { kZaC = 0, kZbC, kZeC, kZeEta, kZaR, kZbR, kZaLef2, kZaA1, kZaLef1, kNumZ };
-// (kZbR is also the beta normalisation of the lef-2D nets.)
-struct ZSel { int a, b, e; };
-constexpr ZSel zsel_of(int k) {
-  return k <= kCl ? ZSel{kZaC, kZbC, kZeC}
-       : k == kEtaEl ? ZSel{-1, -1, kZeEta}
-       : (k == kCy || k == kdCl_a20 || (k >= kdCy_r30 && k <= kdCy_a20)) ? ZSel{kZaR, kZbR, -1}
-       : (k <= kdCl_a20_lef) ? ZSel{kZaLef2, kZbR, -1}
-       : (k <= kdCm) ? ZSel{kZaA1, -1, -1}
-       : ZSel{kZaLef1, -1, -1};
-}
-
-// Device blob layout (floats): [znorm: kNumZ x {mean, std}] [onorm: 43 x {mean, std}] [weights...]
-// per net, per layer: bias[out] then W^T[in][out] (input-major), the layer padded to a multiple of 4 floats
-// so every layer starts 16-byte aligned for LDS.128.
-constexpr int pad4(int x) { return (x + 3) & ~3; }
-constexpr int layer_floats(int in, int out) { return pad4(out + in * out); }
-constexpr int net_floats(NetArch a) {
-  return layer_floats(a.nin, a.h1) + layer_floats(a.h1, a.h2) +
-         (a.h3 ? layer_floats(a.h2, a.h3) + layer_floats(a.h3, 1) : layer_floats(a.h2, 1));
-}
-constexpr int kZnormOff = 0;
-constexpr int kOnormOff = pad4(2 * kNumZ);
-constexpr int kWeightOff = kOnormOff + pad4(2 * kNumNets);
-constexpr int net_offset(int k) {
-  int off = kWeightOff;
-  for (int i = 0; i < k; ++i) off += net_floats(arch_of(i));
-  return off;
-}
-constexpr int kBlobFloats = net_offset(kNumNets);
-constexpr int kBlobBytes = kBlobFloats * 4;
-static_assert(kBlobBytes % 16 == 0, "blob must be a whole number of 16-byte chunks for cp.async.bulk");
-
-// ------------------------------------------------------------------------------------------------
-// MLP evaluation: one aircraft per thread, weights broadcast from shared memory with LDS.128.
-// ------------------------------------------------------------------------------------------------
-// Weights are read with explicit ld.shared.v4 (LDS.128, warp-broadcast).  Besides pinning the access width,
-// the non-volatile asm keeps several thousand weight loads out of the compiler's alias analysis (which otherwise
-// dominates compile time); ordering against the one-time TMA staging is carried by the data dependence on
-// `wbase`, which callers obtain from aero_base_after_staging() after the staging barrier.
 __device__ __forceinline__ float4 lds128(uint32_t addr) {
   float4 q;
   asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(q.x), "=f"(q.y), "=f"(q.z), "=f"(q.w) : "r"(addr));
+  return q;
+}
+__device__ __forceinline__ float lds32f(uint32_t addr) {
+  float q;
+  asm("ld.shared.f32 %0, [%1];" : "=f"(q) : "r"(addr));
+  return q;
+}
+__device__ __forceinline__ uint32_t lds32u(uint32_t addr) {
+  uint32_t q;
+  asm("ld.shared.u32 %0, [%1];" : "=r"(q) : "r"(addr));
   return q;
 }
 // Re-materialise an address through a volatile mov: loads keyed on the result can be neither hoisted out of the
@@ -108,14 +47,19 @@ __device__ __forceinline__ uint32_t opaque_u32(uint32_t x) {
   asm volatile("mov.u32 %0, %1;" : "=r"(y) : "r"(x));
   return y;
 }
-__device__ __forceinline__ uint32_t aero_base_after_staging(const float* blob_smem) {
+__device__ __forceinline__ uint32_t aero_base_after_staging(const void* blob_smem) {
   uint32_t a;
   asm volatile("mov.u32 %0, %1;" : "=r"(a) : "r"((uint32_t)__cvta_generic_to_shared(blob_smem)) : "memory");
   return a;
 }
 
+// ------------------------------------------------------------------------------------------------
+// MLP evaluation: TWO aircraft per thread packed in the halves of a 64-bit register pair; every weight is one
+// warp-broadcast LDS.128 lane feeding an FFMA2 (fma.rn.f32x2 with a scalar-broadcast multiplicand), i.e. one
+// issue slot per two multiply-adds.
+// ------------------------------------------------------------------------------------------------
 template <int IN, int OUT, bool RELU>
-__device__ __forceinline__ void dense(uint32_t w, const float (&x)[IN], float (&y)[OUT]) {
+__device__ __forceinline__ void dense2(uint32_t w, const float2 (&x)[IN], float2 (&y)[OUT]) {
   constexpr int NF = OUT + IN * OUT;
   constexpr int NV = (NF + 3) / 4;
 #pragma unroll
@@ -126,117 +70,158 @@ __device__ __forceinline__ void dense(uint32_t w, const float (&x)[IN], float (&
     for (int k = 0; k < 4; ++k) {
       const int f = 4 * v + k;
       if (f < OUT) {
-        y[f] = e[k];
+        y[f] = make_float2(e[k], e[k]);
       } else if (f < NF) {
         const int g = f - OUT;
-        y[g % OUT] = fmaf(x[g / OUT], e[k], y[g % OUT]);
+        y[g % OUT] = __ffma2_rn(make_float2(e[k], e[k]), x[g / OUT], y[g % OUT]);
       }
     }
   }
   if (RELU) {
 #pragma unroll
-    for (int j = 0; j < OUT; ++j) y[j] = fmaxf(y[j], 0.0f);
+    for (int j = 0; j < OUT; ++j) y[j] = make_float2(fmaxf(y[j].x, 0.0f), fmaxf(y[j].y, 0.0f));
   }
 }
 
 template <int NIN, int H1, int H2, int H3>
-__device__ __forceinline__ float mlp(uint32_t w, float z0, float z1, float z2) {
-  float x[NIN];
+__device__ __forceinline__ float2 mlp2(uint32_t w, float2 z0, float2 z1, float2 z2) {
+  float2 x[NIN];
   x[0] = z0;
   if (NIN > 1) x[NIN > 1 ? 1 : 0] = z1;
   if (NIN > 2) x[NIN > 2 ? 2 : 0] = z2;
-  float a[H1];
-  dense<NIN, H1, true>(w, x, a);
+  float2 a[H1];
+  dense2<NIN, H1, true>(w, x, a);
   w += 4 * layer_floats(NIN, H1);
-  float b[H2];
-  dense<H1, H2, true>(w, a, b);
+  float2 b[H2];
+  dense2<H1, H2, true>(w, a, b);
   w += 4 * layer_floats(H1, H2);
-  float y[1];
+  float2 y[1];
   if constexpr (H3 > 0) {
-    float c[H3];
-    dense<H2, H3, true>(w, b, c);
+    float2 c[H3];
+    dense2<H2, H3, true>(w, b, c);
     w += 4 * layer_floats(H2, H3);
-    dense<H3, 1, false>(w, c, y);
+    dense2<H3, 1, false>(w, c, y);
   } else {
-    dense<H2, 1, false>(w, b, y);
+    dense2<H2, 1, false>(w, b, y);
   }
   return y[0];
 }
 
-// z-scores of (alpha_deg, beta_deg, el_deg) for every normalisation group: (x - mean) / std with a true
-// divide (hifi_F16_AeroData.py:32-33).
-struct ZIn {
-  float z[kNumZ];
+// z-scores of (alpha_deg, beta_deg, el_deg) for the normalisation groups of the MLP nets: (x - mean) / std with a
+// true divide (hifi_F16_AeroData.py:32-33).  Lanes .x / .y are the thread's two aircraft.
+struct ZIn2 {
+  float2 z[kNumZ];
 };
-__device__ __forceinline__ void zscores_ab(const float* __restrict__ blob, float alpha_deg, float beta_deg, ZIn& o) {
-  const float* zn = blob + kZnormOff;
-  o.z[kZaC] = (alpha_deg - zn[2 * kZaC]) / zn[2 * kZaC + 1];
-  o.z[kZbC] = (beta_deg - zn[2 * kZbC]) / zn[2 * kZbC + 1];
-  o.z[kZaR] = (alpha_deg - zn[2 * kZaR]) / zn[2 * kZaR + 1];
-  o.z[kZbR] = (beta_deg - zn[2 * kZbR]) / zn[2 * kZbR + 1];
-  o.z[kZaLef2] = (alpha_deg - zn[2 * kZaLef2]) / zn[2 * kZaLef2 + 1];
-  o.z[kZaA1] = (alpha_deg - zn[2 * kZaA1]) / zn[2 * kZaA1 + 1];
-  o.z[kZaLef1] = (alpha_deg - zn[2 * kZaLef1]) / zn[2 * kZaLef1 + 1];
+__device__ __forceinline__ float2 zscore2(const float* __restrict__ blob, int zid, float2 x) {
+  const float2 ms = reinterpret_cast<const float2*>(blob + kZnormOff)[zid];
+  return make_float2((x.x - ms.x) / ms.y, (x.y - ms.x) / ms.y);
 }
-__device__ __forceinline__ void zscores_el(const float* __restrict__ blob, float el_deg, ZIn& o) {
-  const float* zn = blob + kZnormOff;
-  o.z[kZeC] = (el_deg - zn[2 * kZeC]) / zn[2 * kZeC + 1];
-  o.z[kZeEta] = (el_deg - zn[2 * kZeEta]) / zn[2 * kZeEta + 1];
+__device__ __forceinline__ void zscores_ab2(const float* __restrict__ blob, float2 alpha_deg, float2 beta_deg, ZIn2& o) {
+  o.z[kZaC] = zscore2(blob, kZaC, alpha_deg);
+  o.z[kZbC] = zscore2(blob, kZbC, beta_deg);
+  o.z[kZaR] = zscore2(blob, kZaR, alpha_deg);
+  o.z[kZbR] = zscore2(blob, kZbR, beta_deg);
+  o.z[kZaLef2] = zscore2(blob, kZaLef2, alpha_deg);
+}
+__device__ __forceinline__ void zscores_el2(const float* __restrict__ blob, float2 el_deg, ZIn2& o) {
+  o.z[kZeC] = zscore2(blob, kZeC, el_deg);
 }
 
 // y * std + mean, two roundings (hifi_F16_AeroData.py:36-37).
-__device__ __forceinline__ float denorm(const float* __restrict__ blob, int k, float y) {
+__device__ __forceinline__ float2 denorm2(const float* __restrict__ blob, int k, float2 y) {
   const float2 ms = reinterpret_cast<const float2*>(blob + kOnormOff)[k];
-  return y * ms.y + ms.x;
+  return make_float2(y.x * ms.y + ms.x, y.y * ms.y + ms.x);
 }
 
-// Evaluate nets [K0, K1) of one architecture/normalisation group in a rolled loop; result k goes to
-// out[k * stride].  The loop keeps the code footprint at one body per group.
-template <int K0, int K1>
-__device__ __forceinline__ void eval_group(const float* __restrict__ blob, uint32_t wbase, const ZIn& zi,
-                                           float* __restrict__ out, int stride) {
+// Evaluate MLP nets [K0, K0 + count) of one architecture / normalisation group in a rolled loop; result k goes to
+// out[k * stride] (a float2: both aircraft of this thread).  The loop keeps the code footprint at one body per group.
+template <int K0>
+__device__ __forceinline__ void eval_group2(const float* __restrict__ blob, uint32_t wbase, const ZIn2& zi,
+                                            float2* __restrict__ out, int stride, int count) {
   constexpr NetArch A = arch_of(K0);
   constexpr ZSel Z = zsel_of(K0);
   constexpr int NF = net_floats(A);
-  float z0, z1 = 0.f, z2 = 0.f;
-  if constexpr (A.nin == 3) {
-    z0 = zi.z[Z.a]; z1 = zi.z[Z.b]; z2 = zi.z[Z.e];
-  } else if constexpr (A.nin == 2) {
-    z0 = zi.z[Z.a]; z1 = zi.z[Z.b];
-  } else {
-    z0 = Z.a >= 0 ? zi.z[Z.a >= 0 ? Z.a : 0] : zi.z[Z.e >= 0 ? Z.e : 0];
-  }
-  uint32_t w = wbase + 4 * net_offset(K0);
+  static_assert(A.nin >= 2, "one-input nets are table-driven");
+  const float2 z0 = zi.z[Z.a], z1 = zi.z[Z.b];
+  float2 z2 = make_float2(0.f, 0.f);
+  if constexpr (A.nin == 3) z2 = zi.z[Z.e >= 0 ? Z.e : 0];
+  uint32_t w = wbase + 4 * mlp_offset(K0);
 #pragma unroll 1
-  for (int k = K0; k < K1; ++k, w += 4 * NF) {
-    const float y = mlp<A.nin, A.h1, A.h2, A.h3>(w, z0, z1, z2);
-    out[k * stride] = denorm(blob, k, y);
+  for (int k = K0; k < K0 + count; ++k, w += 4 * NF) {
+    const float2 y = mlp2<A.nin, A.h1, A.h2, A.h3>(w, z0, z1, z2);
+    out[k * stride] = denorm2(blob, k, y);
   }
 }
 
-// The (alpha, beta)-only nets: slots [kFirstAB, kNumUsed).
-__device__ __forceinline__ void eval_ab_nets(const float* __restrict__ blob, uint32_t wbase, const ZIn& zi, float* __restrict__ out,
-                                             int stride) {
-  eval_group<kCy, kdCl_a20 + 1>(blob, wbase, zi, out, stride);
-  eval_group<kdCx_lef, kdCl_lef + 1>(blob, wbase, zi, out, stride);
-  eval_group<kdCz_lef, kdCn_lef + 1>(blob, wbase, zi, out, stride);
-  eval_group<kdCy_r30, kdCn_a20 + 1>(blob, wbase, zi, out, stride);
-  eval_group<kdCy_a20, kdCy_a20 + 1>(blob, wbase, zi, out, stride);
-  eval_group<kdCy_a20_lef, kdCl_a20_lef + 1>(blob, wbase, zi, out, stride);
-  eval_group<kCxq, kdCm + 1>(blob, wbase, zi, out, stride);
-  eval_group<kdCxq_lef, kdCnp_lef + 1>(blob, wbase, zi, out, stride);
-  eval_group<kdCyp_lef, kdCyp_lef + 1>(blob, wbase, zi, out, stride);
+// The 16 two-input (alpha, beta) nets: slots [kFirstAB2, kFirstA1).
+__device__ __forceinline__ void eval_ab2_nets(const float* __restrict__ blob, uint32_t wbase, const ZIn2& zi,
+                                              float2* __restrict__ out, int stride) {
+  eval_group2<kCy>(blob, wbase, zi, out, stride, 2);           // Cy, delta_Cl_a20
+  eval_group2<kdCx_lef>(blob, wbase, zi, out, stride, 2);      // delta_Cx_lef, delta_Cl_lef
+  eval_group2<kdCz_lef>(blob, wbase, zi, out, stride, 4);
+  eval_group2<kdCy_r30>(blob, wbase, zi, out, stride, 4);
+  eval_group2<kdCy_a20>(blob, wbase, zi, out, stride, 1);
+  eval_group2<kdCy_a20_lef>(blob, wbase, zi, out, stride, 3);
 }
-// The elevator-dependent nets: Cx Cz Cm Cn Cl (alpha, beta, el) and eta_el (el).
-__device__ __forceinline__ void eval_el_nets(const float* __restrict__ blob, uint32_t wbase, const ZIn& zi, float* __restrict__ out,
-                                             int stride) {
-  eval_group<kCx, kCl + 1>(blob, wbase, zi, out, stride);
-  eval_group<kEtaEl, kEtaEl + 1>(blob, wbase, zi, out, stride);
+// The three-input nets Cx Cz Cm Cn Cl (alpha, beta, el): `count` = 5 for a full nlplant, 2 (Cx, Cz) when only the
+// force equations are needed (the Overload check).
+__device__ __forceinline__ void eval_el3_nets(const float* __restrict__ blob, uint32_t wbase, const ZIn2& zi,
+                                              float2* __restrict__ out, int stride, int count) {
+  eval_group2<kCx>(blob, wbase, zi, out, stride, count);
 }
-// Only Cx and Cz: all the force equations (and so the Overload check) need from the el-dependent nets.
-__device__ __forceinline__ void eval_el_force_nets(const float* __restrict__ blob, uint32_t wbase, const ZIn& zi,
-                                                   float* __restrict__ out, int stride) {
-  eval_group<kCx, kCz + 1>(blob, wbase, zi, out, stride);
+
+// ------------------------------------------------------------------------------------------------
+// One-input nets as exact piecewise-linear tables (aero_pack.h): binary search of the merged breakpoint list,
+// one byte per net from the segment map, one LDS.128 (a0, y0, slope) + one FMA per net.
+// ------------------------------------------------------------------------------------------------
+struct AeroTabs {
+  uint32_t bp_a, segmap, ent_a, bp_e, ent_e;  // shared-memory byte addresses
+  int levels_a, levels_e;
+};
+__device__ __forceinline__ AeroTabs aero_tabs(const void* blob_smem, uint32_t base) {
+  const int32_t* h = reinterpret_cast<const int32_t*>(blob_smem);
+  AeroTabs t;
+  t.bp_a = base + 4u * (uint32_t)h[kHdrBpA];
+  t.segmap = base + 4u * (uint32_t)h[kHdrSegmap];
+  t.ent_a = base + 4u * (uint32_t)h[kHdrEntA];
+  t.bp_e = base + 4u * (uint32_t)h[kHdrBpE];
+  t.ent_e = base + 4u * (uint32_t)h[kHdrEntE];
+  t.levels_a = h[kHdrLevelsA];
+  t.levels_e = h[kHdrLevelsE];
+  return t;
+}
+// number of breakpoints <= x in a sorted, +inf padded list of 2^levels - 1 floats (NaN -> 0)
+__device__ __forceinline__ uint32_t pwl_search(uint32_t bp, int levels, float x) {
+  uint32_t pos = 0;
+#pragma unroll 1
+  for (uint32_t step = 1u << (levels - 1); step > 0; step >>= 1) {
+    const float b = lds32f(bp + 4u * (pos + step - 1u));
+    pos += (b <= x) ? step : 0u;
+  }
+  return pos;
+}
+__device__ __forceinline__ float pwl_entry(uint32_t ent, uint32_t idx, float x) {
+  const float4 e = lds128(ent + 16u * idx);
+  return fmaf(e.z, x - e.x, e.y);
+}
+__device__ __forceinline__ float eta_el_of(const AeroTabs& t, float el_deg) {
+  return pwl_entry(t.ent_e, pwl_search(t.bp_e, t.levels_e, el_deg), el_deg);
+}
+// The alpha-only coefficients: net k -> out[k - kFirstA1], k - kFirstA1 < COUNT.
+template <int COUNT>
+__device__ __forceinline__ void alpha_coefs(const void* blob_smem, const AeroTabs& t, float alpha_deg, float* __restrict__ out) {
+  const uint32_t m = pwl_search(t.bp_a, t.levels_a, alpha_deg);
+  const uint32_t row = t.segmap + (uint32_t)kSegmapRowBytes * m;
+  const int32_t* taboff = reinterpret_cast<const int32_t*>(blob_smem) + kHdrTabOff;
+#pragma unroll
+  for (int w = 0; w < (COUNT + 3) / 4; ++w) {
+    const uint32_t word = lds32u(row + 4u * w);
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      const int k = 4 * w + b;
+      if (k < COUNT) out[k] = pwl_entry(t.ent_a, (uint32_t)taboff[k] + ((word >> (8 * b)) & 0xFFu), alpha_deg);
+    }
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -282,7 +267,8 @@ __device__ __forceinline__ float wrap_pi(float a) {
 }
 
 // Force (body-axis velocity derivative) part of nlplant: returns Vt_dot, alpha_dot, beta_dot
-// (F16_dynamics.py:197-207,215-220).  `c` indexes coefficient k at c[k * cs].
+// (F16_dynamics.py:197-207,215-220).  `c` indexes MLP coefficient k (< kNumSlots) at c[k * cs]; `a1` holds the
+// alpha-only (table-driven) coefficients, net k at a1[k - kFirstA1].
 struct ForceOut {
   float vt_dot, alpha_dot, beta_dot;
 };
@@ -290,19 +276,19 @@ struct AeroTotals {
   float Cx, Cy, Cz;
 };
 
-__device__ __forceinline__ AeroTotals force_totals(const float* __restrict__ c, int cs, float vt, float P, float Q,
+__device__ __forceinline__ AeroTotals force_totals(const float* __restrict__ c, int cs, const float* __restrict__ a1, float vt, float P, float Q,
                                                    float R, float dail, float drud, float dlef) {
   constexpr float cbar = 11.32f, B = 30.0f;
   const float k2 = cbar / (2.0f * vt);
   const float b2 = B / (2.0f * vt);
   AeroTotals t;
-  const float dXdQ = k2 * (c[kCxq * cs] + c[kdCxq_lef * cs] * dlef);
+  const float dXdQ = k2 * (a1[kCxq - kFirstA1] + a1[kdCxq_lef - kFirstA1] * dlef);
   t.Cx = c[kCx * cs] + c[kdCx_lef * cs] * dlef + dXdQ * Q;
-  const float dZdQ = k2 * (c[kCzq * cs] + c[kdCz_lef * cs] * dlef);  // sic (F16_dynamics.py:199)
+  const float dZdQ = k2 * (a1[kCzq - kFirstA1] + c[kdCz_lef * cs] * dlef);  // sic (F16_dynamics.py:199)
   t.Cz = c[kCz * cs] + c[kdCz_lef * cs] * dlef + dZdQ * Q;
   const float dYdail = c[kdCy_a20 * cs] + c[kdCy_a20_lef * cs] * dlef;
-  const float dYdR = b2 * (c[kCyr * cs] + c[kdCyr_lef * cs] * dlef);
-  const float dYdP = b2 * (c[kCyp * cs] + c[kdCyp_lef * cs] * dlef);
+  const float dYdR = b2 * (a1[kCyr - kFirstA1] + a1[kdCyr_lef - kFirstA1] * dlef);
+  const float dYdP = b2 * (a1[kCyp - kFirstA1] + a1[kdCyp_lef - kFirstA1] * dlef);
   t.Cy = c[kCy * cs] + c[kdCy_lef * cs] * dlef + dYdail * dail + c[kdCy_r30 * cs] * drud + dYdR * R + dYdP * P;
   return t;
 }
@@ -331,23 +317,21 @@ __device__ __forceinline__ ForceOut force_eqs(const AeroTotals& t, const BodyVel
   return o;
 }
 
-// Full nlplant: xdot[0..11] from s[0..11], controls (T, el, ail, rud, lef) and the 42 coefficients.
-// Coefficients must already be evaluated at (alpha_deg, beta_deg, el) of this (s, u).
-__device__ __forceinline__ void nlplant_from_coefs(const float* s, float T, float ail, float rud, float lef,
-                                                   const Trig& g, float tp, const float* __restrict__ c, int cs,
-                                                   float* xdot) {
+// The part of nlplant beyond the force equations: navigation + Euler-angle kinematics (xdot[0..5], :133-138) and the
+// moment equations (xdot[9..11], :208-214,221-227), given the force totals `t` of the same (s, u).
+__device__ __forceinline__ void nlplant_kin_moments(const float* s, float ail, float rud, float lef, const Trig& g,
+                                                    float qbar, float vt, const BodyVel& b, const AeroTotals& t,
+                                                    const float* __restrict__ c, int cs, const float* __restrict__ a1,
+                                                    float* xdot) {
   constexpr float B = 30.0f, S = 300.0f, cbar = 11.32f;
   constexpr float Jy = 55814.0f, Jxz = 982.0f, Jz = 63100.0f, Jx = 9496.0f;
   constexpr float xcg_arm = (float)(0.35 - 0.30);          // (xcgr - xcg) evaluated in double, then f32
   constexpr float cbar_over_B = (float)(11.32 / 30.0);
   const float P = s[9], Q = s[10], R = s[11];
   const float beta_deg = s[8] * kR2D;
-  const float vt = s[6] <= 0.01f ? 0.01f : s[6];           // :104
   const float dail = ail / 21.5f;
   const float drud = rud / 30.0f;
   const float dlef = 1.0f - lef / 25.0f;
-  const float qbar = qbar_of(tp, vt);
-  const BodyVel b = body_vel(vt, g);
 
   // navigation + Euler-angle kinematics (:133-138)
   xdot[0] = b.U * (g.ct * g.cpsi) + b.V * (g.sphi * g.cpsi * g.st - g.cphi * g.spsi) +
@@ -359,28 +343,22 @@ __device__ __forceinline__ void nlplant_from_coefs(const float* s, float T, floa
   xdot[4] = Q * g.cphi - R * g.sphi;
   xdot[5] = (Q * g.sphi + R * g.cphi) / g.ct;
 
-  // aero build-up (:197-214)
-  const AeroTotals t = force_totals(c, cs, vt, P, Q, R, dail, drud, dlef);
+  // aero build-up (:208-214)
   const float k2 = cbar / (2.0f * vt);
   const float b2 = B / (2.0f * vt);
-  const float dMdQ = k2 * (c[kCmq * cs] + c[kdCmq_lef * cs] * dlef);
+  const float dMdQ = k2 * (a1[kCmq - kFirstA1] + a1[kdCmq_lef - kFirstA1] * dlef);
   const float Cm_tot = c[kCm * cs] * c[kEtaEl * cs] + t.Cz * xcg_arm + c[kdCm_lef * cs] * dlef + dMdQ * Q +
-                       c[kdCm * cs];  // + delta_Cm_ds (== 0, hifi_F16_AeroData.py:811-818)
+                       a1[kdCm - kFirstA1];  // + delta_Cm_ds (== 0, hifi_F16_AeroData.py:811-818)
   const float dNdail = c[kdCn_a20 * cs] + c[kdCn_a20_lef * cs] * dlef;
-  const float dNdR = b2 * (c[kCnr * cs] + c[kdCnr_lef * cs] * dlef);
-  const float dNdP = b2 * (c[kCnp * cs] + c[kdCnp_lef * cs] * dlef);
+  const float dNdR = b2 * (a1[kCnr - kFirstA1] + a1[kdCnr_lef - kFirstA1] * dlef);
+  const float dNdP = b2 * (a1[kCnp - kFirstA1] + a1[kdCnp_lef - kFirstA1] * dlef);
   const float Cn_tot = c[kCn * cs] + c[kdCn_lef * cs] * dlef - t.Cy * xcg_arm * cbar_over_B + dNdail * dail +
-                       c[kdCn_r30 * cs] * drud + dNdR * R + dNdP * P + c[kdCnbeta * cs] * beta_deg;
+                       c[kdCn_r30 * cs] * drud + dNdR * R + dNdP * P + a1[kdCnbeta - kFirstA1] * beta_deg;
   const float dLdail = c[kdCl_a20 * cs] + c[kdCl_a20_lef * cs] * dlef;
-  const float dLdR = b2 * (c[kClr * cs] + c[kdClr_lef * cs] * dlef);
-  const float dLdP = b2 * (c[kClp * cs] + c[kdClp_lef * cs] * dlef);
+  const float dLdR = b2 * (a1[kClr - kFirstA1] + a1[kdClr_lef - kFirstA1] * dlef);
+  const float dLdP = b2 * (a1[kClp - kFirstA1] + a1[kdClp_lef - kFirstA1] * dlef);
   const float Cl_tot = c[kCl * cs] + c[kdCl_lef * cs] * dlef + dLdail * dail + c[kdCl_r30 * cs] * drud + dLdR * R +
-                       dLdP * P + c[kdClbeta * cs] * beta_deg;
-
-  const ForceOut f = force_eqs(t, b, g, vt, P, Q, R, qbar, T);
-  xdot[6] = f.vt_dot;
-  xdot[7] = f.alpha_dot;
-  xdot[8] = f.beta_dot;
+                       dLdP * P + a1[kdClbeta - kFirstA1] * beta_deg;
 
   // moments (:221-227); the Heng (= 0) terms add exact zeros and are omitted.
   const float L_tot = Cl_tot * qbar * S * B;
@@ -394,6 +372,38 @@ __device__ __forceinline__ void nlplant_from_coefs(const float* s, float T, floa
   xdot[9] = (Jz * L_tot + Jxz * N_tot - kQR * Q * R + kPQ * P * Q) / denom;
   xdot[10] = (M_tot + kJzJx * P * R - Jxz * (P * P - R * R)) / Jy;
   xdot[11] = (Jx * N_tot + Jxz * L_tot + kPQ2 * P * Q - kPQ * Q * R) / denom;
+}
+
+// The force part shared by the Euler derivative and the Overload check: clamps vt (:104), builds the force
+// totals and solves the force equations.  Outputs the pieces nlplant_kin_moments needs.
+struct ForcePart {
+  float vt, qbar;
+  BodyVel b;
+  AeroTotals t;
+  ForceOut f;
+};
+__device__ __forceinline__ ForcePart force_part(const float* s, float T, float ail, float rud, float lef, const Trig& g,
+                                                float tp, const float* __restrict__ c, int cs,
+                                                const float* __restrict__ a1) {
+  ForcePart o;
+  o.vt = s[6] <= 0.01f ? 0.01f : s[6];           // :104
+  o.qbar = qbar_of(tp, o.vt);
+  o.b = body_vel(o.vt, g);
+  o.t = force_totals(c, cs, a1, o.vt, s[9], s[10], s[11], ail / 21.5f, rud / 30.0f, 1.0f - lef / 25.0f);
+  o.f = force_eqs(o.t, o.b, g, o.vt, s[9], s[10], s[11], o.qbar, T);
+  return o;
+}
+
+// Full nlplant: xdot[0..11] from s[0..11], controls (T, el, ail, rud, lef) and the coefficients, which must already
+// be evaluated at (alpha_deg, beta_deg, el) of this (s, u).
+__device__ __forceinline__ void nlplant_from_coefs(const float* s, float T, float ail, float rud, float lef,
+                                                   const Trig& g, float tp, const float* __restrict__ c, int cs,
+                                                   const float* __restrict__ a1, float* xdot) {
+  const ForcePart fp = force_part(s, T, ail, rud, lef, g, tp, c, cs, a1);
+  nlplant_kin_moments(s, ail, rud, lef, g, fp.qbar, fp.vt, fp.b, fp.t, c, cs, a1, xdot);
+  xdot[6] = fp.f.vt_dot;
+  xdot[7] = fp.f.alpha_dot;
+  xdot[8] = fp.f.beta_dot;
 }
 
 // Body-axis accelerations of F16Model.get_acceleration (F16_model.py:132-148) from Vt_dot/alpha_dot/beta_dot.

@@ -2,10 +2,11 @@
 //
 // One persistent kernel launch per BaseEnv.step() (reference: envs/env_base.py:99-109):
 //   masked episodic reset -> control low-pass -> nlplant(s,u') -> explicit Euler -> step_count -> 22-D obs
-//   -> nlplant(s',u') for the Overload check -> six termination predicates -> reward -> stores.
-// Layout: SoA state rows [F][ld] (coalesced 128 B per warp per field), AoS obs rows staged in shared memory and
-// written with one cp.async.bulk (TMA 1-D bulk store) per warp, the 43-net weight blob TMA-bulk-loaded into
-// shared memory once per persistent CTA and read as warp-broadcast LDS.128.
+//   -> nlplant(s',u') force part for the Overload check -> six termination predicates -> reward -> stores.
+// Layout: SoA state rows [F][ld]; every thread owns TWO adjacent aircraft, so each field access is one coalesced
+// 8-byte-per-lane (256 B per warp) transaction and the MLP arithmetic runs on packed FFMA2 (two aircraft per issue
+// slot).  The aero image (22 MLP weight sets + the piecewise-linear tables of the 21 one-input nets, aero_pack.h)
+// is TMA-bulk-loaded into shared memory once per persistent CTA; weights are read as warp-broadcast LDS.128.
 //
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -fmad=false (see f16_device.cuh for why).
 #include <cuda_runtime.h>
@@ -17,6 +18,7 @@
 #include <vector>
 
 #include "../../include/nplane.h"
+#include "aero_pack.h"
 #include "f16_device.cuh"
 
 using namespace npl;
@@ -39,14 +41,11 @@ static int fail(int code, const std::string& msg) {
 // ------------------------------------------------------------------------------------------------
 // handles
 // ------------------------------------------------------------------------------------------------
-constexpr int kC0Off = kBlobFloats;                 // 36 (alpha,beta)-net outputs at alpha = beta = 0
-constexpr int kAeroFloats = kBlobFloats + pad4(kNumAB);
-constexpr int kAeroBytes = kAeroFloats * 4;
-constexpr int kCacheRows = kNumAB + 2;              // + alpha key, beta key
-static_assert(kAeroBytes % 16 == 0, "bulk copy granularity");
+constexpr int kCacheRows = kNumAB2 + 2;  // 16 (alpha,beta)-MLP outputs + alpha key + beta key
 
 struct np_aero {
-  float* blob_dev = nullptr;  // kAeroFloats
+  uint32_t* image_dev = nullptr;
+  int bytes = 0;  // multiple of 16
   int device = 0;
 };
 
@@ -56,7 +55,7 @@ struct np_env {
   np_buffers buf;
   bool bound = false;
   uint32_t step_index = 0;
-  int block = 512, grid = 0, smem = 0, num_sms = 0;
+  int block = 256, grid = 0, smem = 0, num_sms = 0;
 };
 
 struct StepParams {
@@ -70,7 +69,8 @@ struct StepParams {
   float* reward;
   float* cache;                  // [kCacheRows][ld]
   unsigned long long* counters;  // [NP_NUM_COUNTERS]
-  const float* aero;             // kAeroFloats, global
+  const uint32_t* aero;          // device image, aero_bytes
+  int aero_bytes;
   const float* action;           // [n][4]
   const float* draws;            // [n][5] or null
   const float* noise;            // [n][22] or null
@@ -106,23 +106,16 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
                "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
 }
-__device__ __forceinline__ void bulk_s2g(void* dst_gmem, const void* src_smem, uint32_t bytes) {
-  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem), "r"(smem_u32(src_smem)),
-               "r"(bytes)
-               : "memory");
-  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-}
-__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 
-// Stage the aero blob into shared memory once per CTA: one elected thread issues TMA bulk copies that
+// Stage the aero image into shared memory once per CTA: one elected thread issues TMA bulk copies that
 // complete on an mbarrier; everyone waits on it.
-__device__ __forceinline__ void stage_aero(float* blob_s, const float* aero_g, uint64_t* bar) {
+__device__ __forceinline__ void stage_aero(void* blob_s, const void* aero_g, uint32_t bytes, uint64_t* bar) {
   if (threadIdx.x == 0) {
     mbar_init(bar, 1);
-    mbar_expect_tx(bar, kAeroBytes);
+    mbar_expect_tx(bar, bytes);
     constexpr uint32_t kChunk = 16384;
-    for (uint32_t off = 0; off < (uint32_t)kAeroBytes; off += kChunk) {
-      const uint32_t nb = min(kChunk, (uint32_t)kAeroBytes - off);
+    for (uint32_t off = 0; off < bytes; off += kChunk) {
+      const uint32_t nb = min(kChunk, bytes - off);
       bulk_g2s(reinterpret_cast<char*>(blob_s) + off, reinterpret_cast<const char*>(aero_g) + off, nb, bar);
     }
   }
@@ -131,7 +124,7 @@ __device__ __forceinline__ void stage_aero(float* blob_s, const float* aero_g, u
 }
 
 // ------------------------------------------------------------------------------------------------
-// shared pieces of reset / obs / task logic
+// shared pieces of reset / obs / task logic (one aircraft)
 // ------------------------------------------------------------------------------------------------
 struct Draws {
   float d[NP_NUM_DRAWS];
@@ -227,251 +220,271 @@ __device__ __forceinline__ void add_obs_noise(const StepParams& p, int i, float*
   }
 }
 
-// Write a block's obs rows: staged [BS][22] in smem -> one TMA bulk store per fully-populated warp.
-template <int BS>
-__device__ __forceinline__ void store_obs(float* __restrict__ obs_g, float* stage, const float* o, int i, int n,
-                                          bool active) {
-  const int lane = threadIdx.x & 31;
-  const int warp_first = i - lane;  // aircraft index of lane 0
-  float* wstage = stage + (threadIdx.x - lane) * NP_NUM_OBS;
-  if (warp_first + 32 <= n) {
-#pragma unroll
-    for (int j = 0; j < NP_NUM_OBS; ++j) wstage[lane * NP_NUM_OBS + j] = o[j];
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the TMA engine
-    __syncwarp();
-    if (lane == 0) bulk_s2g(obs_g + (size_t)warp_first * NP_NUM_OBS, wstage, 32 * NP_NUM_OBS * 4);
-  } else if (active) {
-#pragma unroll
-    for (int j = 0; j < NP_NUM_OBS; ++j) obs_g[(size_t)i * NP_NUM_OBS + j] = o[j];
-  }
+// one aircraft pair of an SoA row: a single 8-byte store, or only the first aircraft for the odd tail
+__device__ __forceinline__ void store_pair(float* row, int pr, float2 v, bool both) {
+  if (both) reinterpret_cast<float2*>(row)[pr] = v;
+  else row[2 * pr] = v.x;
 }
 
-__device__ __forceinline__ void count_cause(unsigned long long* counters, int which, bool pred) {
-  const unsigned m = __ballot_sync(0xffffffffu, pred);
-  if (m != 0 && (threadIdx.x & 31) == 0) atomicAdd(&counters[which], (unsigned long long)__popc(m));
+// one atomic per warp per cause: the thread's two aircraft contribute p0 and p1
+__device__ __forceinline__ void count_cause2(unsigned long long* counters, int which, bool p0, bool p1) {
+  const int k = __popc(__ballot_sync(0xffffffffu, p0)) + __popc(__ballot_sync(0xffffffffu, p1));
+  if (k != 0 && (threadIdx.x & 31) == 0) atomicAdd(&counters[which], (unsigned long long)k);
 }
 
 // ------------------------------------------------------------------------------------------------
 // K1: the fused step kernel
 // ------------------------------------------------------------------------------------------------
-template <int BS>
-constexpr int step_smem_bytes() {
-  return kAeroBytes + kNumUsed * BS * 4 + BS * NP_NUM_OBS * 4 + 16;
-}
+static int step_smem_bytes(int aero_bytes, int bs) { return aero_bytes + kNumSlots * bs * 8 + 16; }
 
-template <int BS, int MINB, bool CACHE>
+template <int BS, int MINB>
 __global__ void __launch_bounds__(BS, MINB) f16_step_kernel(const __grid_constant__ StepParams p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   float* blob = reinterpret_cast<float*>(smem_raw);
-  float* coef_all = blob + kAeroFloats;                 // [kNumUsed][BS]
-  float* ostage = coef_all + kNumUsed * BS;             // [BS][22]
-  uint64_t* bar = reinterpret_cast<uint64_t*>(ostage + BS * NP_NUM_OBS);
+  float2* coef_all = reinterpret_cast<float2*>(smem_raw + p.aero_bytes);     // [kNumSlots][BS] float2
+  uint64_t* bar = reinterpret_cast<uint64_t*>(coef_all + kNumSlots * BS);
 
-  stage_aero(blob, p.aero, bar);
+  stage_aero(blob, p.aero, (uint32_t)p.aero_bytes, bar);
   const uint32_t wb0 = aero_base_after_staging(blob);
+  const AeroTabs tabs = aero_tabs(blob, wb0);
+  const float* c0 = blob + reinterpret_cast<const int32_t*>(blob)[kHdrC0];
 
   const np_env_cfg& c = p.cfg;
   const int n = c.n, ld = c.ld;
-  float* coef = coef_all + threadIdx.x;                 // coefficient k of this thread: coef[k * BS]
-  bool obs_pending = false;
+  const int npairs = (n + 1) >> 1;
+  float2* coef2 = coef_all + threadIdx.x;                       // slot k of this thread's pair: coef2[k * BS]
+  float* cf = reinterpret_cast<float*>(coef2);                  // aircraft a, slot k: cf[a + k * 2 * BS]
+  constexpr int CS = 2 * BS;
+  const bool use_cache = c.use_coef_cache != 0;
 
-  for (int base = blockIdx.x * BS; base < n; base += gridDim.x * BS) {
-    const int i = base + threadIdx.x;
-    const bool active = i < n;
-    const int il = active ? i : n - 1;  // inactive lanes shadow the last aircraft and never store
-    uint32_t wb = opaque_u32(wb0);
+  for (int pbase = blockIdx.x * BS; pbase < npairs; pbase += gridDim.x * BS) {
+    const int pr = pbase + threadIdx.x;
+    const int prl = pr < npairs ? pr : npairs - 1;  // inactive lanes shadow the last pair and never store
+    const bool act[2] = {2 * pr < n, 2 * pr + 1 < n};
+    const int idx[2] = {min(2 * prl, n - 1), min(2 * prl + 1, n - 1)};  // row index into [n][*] arrays
 
     // ---- load ----------------------------------------------------------------------------------
-    float s[12], u[4], tgt[3], a[4];
+    float s[2][12], u[2][4], tgt[2][3], a[2][4];
+    int steps[2];
+    bool rst[2];
 #pragma unroll
-    for (int j = 0; j < 12; ++j) s[j] = p.s[(size_t)j * ld + il];
+    for (int j = 0; j < 12; ++j) {
+      const float2 v = reinterpret_cast<const float2*>(p.s + (size_t)j * ld)[prl];
+      s[0][j] = v.x; s[1][j] = v.y;
+    }
 #pragma unroll
-    for (int j = 0; j < 4; ++j) u[j] = p.u[(size_t)j * ld + il];
+    for (int j = 0; j < 4; ++j) {
+      const float2 v = reinterpret_cast<const float2*>(p.u + (size_t)j * ld)[prl];
+      u[0][j] = v.x; u[1][j] = v.y;
+    }
 #pragma unroll
-    for (int j = 0; j < 3; ++j) tgt[j] = p.tgt[(size_t)j * ld + il];
-    int steps = p.step_count[il];
-    const bool rst = (p.flags[il] | p.flags[ld + il] | p.flags[2 * ld + il]) != 0;
+    for (int j = 0; j < 3; ++j) {
+      const float2 v = reinterpret_cast<const float2*>(p.tgt + (size_t)j * ld)[prl];
+      tgt[0][j] = v.x; tgt[1][j] = v.y;
+    }
     {
-      const float4 av = reinterpret_cast<const float4*>(p.action)[il];
-      a[0] = av.x; a[1] = av.y; a[2] = av.z; a[3] = av.w;
+      const int2 v = reinterpret_cast<const int2*>(p.step_count)[prl];
+      steps[0] = v.x; steps[1] = v.y;
+      const uchar2 f0 = reinterpret_cast<const uchar2*>(p.flags)[prl];
+      const uchar2 f1 = reinterpret_cast<const uchar2*>(p.flags + ld)[prl];
+      const uchar2 f2 = reinterpret_cast<const uchar2*>(p.flags + 2 * (size_t)ld)[prl];
+      rst[0] = (f0.x | f1.x | f2.x) != 0;
+      rst[1] = (f0.y | f1.y | f2.y) != 0;
+    }
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      const float4 av = reinterpret_cast<const float4*>(p.action)[idx[q]];
+      a[q][0] = av.x; a[q][1] = av.y; a[q][2] = av.z; a[q][3] = av.w;
     }
 
-    // ---- episodic reset of terminated aircraft (env_base.py:83-97) --------------------------------
-    if (rst) {
-      const Draws r = reset_draws(p, il);
-      reset_aircraft(c, r, s, u, tgt);
-      steps = 0;
-    }
-    count_cause(p.counters, 7, rst && active);
-
-    // ---- control low-pass (F16_model.py:52-57) ---------------------------------------------------
+    // ---- episodic reset of terminated aircraft (env_base.py:83-97) + control low-pass (F16_model.py:52-57) ----
 #pragma unroll
-    for (int j = 0; j < 4; ++j) a[j] = fminf(fmaxf(a[j], -1.0f), 1.0f);
-    u[0] = 0.9f * u[0] + 0.1f * a[0] * 0.225f * 76300.0f / 0.3048f;
-    u[1] = 0.9f * u[1] + 0.1f * a[1] * 45.0f;
-    u[2] = 0.9f * u[2] + 0.1f * a[2] * 45.0f;
-    u[3] = 0.9f * u[3] + 0.1f * a[3] * 45.0f;
+    for (int q = 0; q < 2; ++q) {
+      if (rst[q]) {
+        const Draws r = reset_draws(p, idx[q]);
+        reset_aircraft(c, r, s[q], u[q], tgt[q]);
+        steps[q] = 0;
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) a[q][j] = fminf(fmaxf(a[q][j], -1.0f), 1.0f);
+      u[q][0] = 0.9f * u[q][0] + 0.1f * a[q][0] * 0.225f * 76300.0f / 0.3048f;
+      u[q][1] = 0.9f * u[q][1] + 0.1f * a[q][1] * 45.0f;
+      u[q][2] = 0.9f * u[q][2] + 0.1f * a[q][2] * 45.0f;
+      u[q][3] = 0.9f * u[q][3] + 0.1f * a[q][3] * 45.0f;
+    }
+    count_cause2(p.counters, 7, rst[0] && act[0], rst[1] && act[1]);
 
-    // ---- coefficients at (s, u') -------------------------------------------------------------------
-    ZIn zi;
-    zscores_el(blob, u[1], zi);
+    // ---- (alpha,beta)-MLP outputs at (s): cache hit (the Overload evaluation of the previous step was at exactly
+    //      this alpha, beta), a reset lane (constants for alpha = beta = 0), or a miss -> the warp evaluates ----
+    bool miss;
     {
-      bool need_eval = true;
-      if (CACHE) {
-        if (rst) {  // alpha = beta = 0 after a reset: constants precomputed at np_aero_create
+      bool hit[2] = {rst[0], rst[1]};
+      if (use_cache) {
+        const float2 ka = reinterpret_cast<const float2*>(p.cache + (size_t)kNumAB2 * ld)[prl];
+        const float2 kb = reinterpret_cast<const float2*>(p.cache + (size_t)(kNumAB2 + 1) * ld)[prl];
+        hit[0] |= __float_as_uint(ka.x) == __float_as_uint(s[0][7]) && __float_as_uint(kb.x) == __float_as_uint(s[0][8]);
+        hit[1] |= __float_as_uint(ka.y) == __float_as_uint(s[1][7]) && __float_as_uint(kb.y) == __float_as_uint(s[1][8]);
+      }
+      miss = __any_sync(0xffffffffu, !(hit[0] && hit[1]));
+      if (!miss) {
 #pragma unroll 4
-          for (int k = 0; k < kNumAB; ++k) coef[(kFirstAB + k) * BS] = blob[kC0Off + k];
-          need_eval = false;
-        } else {
-          const float ka = p.cache[(size_t)kNumAB * ld + il], kb = p.cache[(size_t)(kNumAB + 1) * ld + il];
-          if (__float_as_uint(ka) == __float_as_uint(s[7]) && __float_as_uint(kb) == __float_as_uint(s[8])) {
-#pragma unroll 4
-            for (int k = 0; k < kNumAB; ++k) coef[(kFirstAB + k) * BS] = p.cache[(size_t)k * ld + il];
-            need_eval = false;
+        for (int k = 0; k < kNumAB2; ++k) {
+          float2 v = make_float2(c0[k], c0[k]);
+          if (use_cache) {
+            const float2 cv = reinterpret_cast<const float2*>(p.cache + (size_t)k * ld)[prl];
+            if (!rst[0]) v.x = cv.x;
+            if (!rst[1]) v.y = cv.y;
           }
+          coef2[(kFirstAB2 + k) * BS] = v;
         }
       }
-      if (need_eval) {  // first step after external state writes, or CACHE == false
-        zscores_ab(blob, s[7] * kR2D, s[8] * kR2D, zi);
-        eval_ab_nets(blob, wb, zi, coef, BS);
-      } else {
-        const float* zn = blob + kZnormOff;
-        zi.z[kZaC] = (s[7] * kR2D - zn[2 * kZaC]) / zn[2 * kZaC + 1];
-        zi.z[kZbC] = (s[8] * kR2D - zn[2 * kZbC]) / zn[2 * kZbC + 1];
-      }
-    }
-    eval_el_nets(blob, wb, zi, coef, BS);
-
-    // ---- Euler step (F16_model.py:64-67; torchdiffeq fixed-grid euler on t=[0,dt]) -----------------
-    {
-      const Trig g = make_trig(s);
-      const float tp = tfac_pow(s[2]);
-      float xdot[12];
-      nlplant_from_coefs(s, u[0], u[2], u[3], 0.0f, g, tp, coef, BS, xdot);
-      const float h = c.dt - 0.0f;
-#pragma unroll
-      for (int j = 0; j < 12; ++j) s[j] = s[j] + h * xdot[j];
-    }
-    steps += 1;  // env_base.py:102
-
-    // ---- observation of the new state (env_base.py:103) -------------------------------------------
-    const Trig g2 = make_trig(s);
-    const float tp2 = tfac_pow(s[2]);
-    {
-      float o[NP_NUM_OBS];
-      make_obs(c, s, u, tgt, g2, eas2tas_of(tp2), o);
-      add_obs_noise(p, il, o);
-      if (obs_pending) {  // the previous slab's bulk store must have finished reading the staging rows
-        if ((threadIdx.x & 31) == 0) bulk_wait_read();
-        __syncwarp();
-      }
-      store_obs<BS>(p.obs, ostage, o, i, n, active);
-      obs_pending = true;
     }
 
-    // ---- coefficients at (s', u'): Overload check now, Euler derivative of the next step later ---------
-    wb = opaque_u32(wb0);
-    zscores_ab(blob, s[7] * kR2D, s[8] * kR2D, zi);
-    eval_ab_nets(blob, wb, zi, coef, BS);
-    if (CACHE && active) {
+    // ---- two passes over the same code: pass 0 = Euler derivative at (s, u'), then obs of the new state;
+    //      pass 1 = force equations at (s', u') for the Overload check, terminations, reward ------------------
+    bool bad[2], done[2];
+    float rew[2];
+    int causes[2] = {0, 0};
+#pragma unroll 1
+    for (int pass = 0; pass < 2; ++pass) {
+      const uint32_t wb = opaque_u32(wb0);
+      const float2 adeg = make_float2(s[0][7] * kR2D, s[1][7] * kR2D);
+      const float2 bdeg = make_float2(s[0][8] * kR2D, s[1][8] * kR2D);
+      ZIn2 zi;
+      zscores_ab2(blob, adeg, bdeg, zi);
+      zscores_el2(blob, make_float2(u[0][1], u[1][1]), zi);
+      if (pass == 1 || miss) eval_ab2_nets(blob, wb, zi, coef2, BS);
+      eval_el3_nets(blob, wb, zi, coef2, BS, pass == 0 ? 5 : 2);
+      if (pass == 1 && use_cache && act[0]) {  // the next step's Euler derivative needs exactly these
 #pragma unroll 4
-      for (int k = 0; k < kNumAB; ++k) p.cache[(size_t)k * ld + i] = coef[(kFirstAB + k) * BS];
-      p.cache[(size_t)kNumAB * ld + i] = s[7];
-      p.cache[(size_t)(kNumAB + 1) * ld + i] = s[8];
-    }
-    eval_el_force_nets(blob, wb, zi, coef, BS);
-
-    // ---- terminations (task_base.py:75-96) --------------------------------------------------------
-    bool bad, done;
-    {
-      const float vt_c = s[6] <= 0.01f ? 0.01f : s[6];
-      const AeroTotals t = force_totals(coef, BS, vt_c, s[9], s[10], s[11], u[2] / 21.5f, u[3] / 30.0f, 1.0f);
-      const ForceOut f = force_eqs(t, body_vel(vt_c, g2), g2, vt_c, s[9], s[10], s[11], qbar_of(tp2, vt_c), u[0]);
-      float ax, ay, az;
-      body_accel(s, g2, f, ax, ay, az);
-      const float acc = sqrtf(ax * ax + ay * ay + az * az);
-      const bool overload = (acc - c.acceleration_limit) > 0.0f;            // overload.py:37-42
-      const bool low_alt = (s[2] - c.altitude_limit) < 0.0f;                // low_altitude.py:29-30
-      const float vel = (s[6] + c.airspeed * 1.0f) * 0.3048f / 340.0f;
-      const bool hi = (vel - c.max_velocity) >= 0.0f;                       // high_speed.py:29-30
-      const bool lo = (vel - c.min_velocity) <= 0.0f;                       // low_speed.py:29-30
-      const float a_deg = s[7] * 180.0f / kPi, b_deg = s[8] * 180.0f / kPi; // extreme_state.py:32-36
-      const bool ext = (a_deg < c.min_alpha) | (a_deg > c.max_alpha) | (b_deg < c.min_beta) | (b_deg > c.max_beta);
-      const bool late = steps >= c.max_check_interval;
-      bool off;
-      if (c.task == NP_TASK_HEADING) {                                      // unreach_heading.py:38-53
-        off = (fabsf(wrap_pi(s[5] - tgt[1])) >= (float)(3.141592653589793 / 36.0)) | (fabsf(s[2] - tgt[0]) >= 100.0f) |
-              (fabsf(s[6] - tgt[2]) >= 20.0f);
-        done = !off && !late && (steps >= c.min_check_interval);
-      } else if (c.task == NP_TASK_CONTROL) {                               // unreach_posture.py:37-55
-        off = (fabsf(wrap_pi(s[5] - tgt[1])) >= (float)(3.141592653589793 / 36.0)) |
-              (fabsf(s[4] - tgt[0]) >= (float)(3.141592653589793 / 36.0)) | (fabsf(s[6] - tgt[2]) >= 20.0f);
-        done = !off && !late;
-      } else {                                                              // unreach_target.py:35-47
-        off = (fabsf(s[0] - tgt[0]) >= 100.0f) | (fabsf(s[1] - tgt[1]) >= 100.0f) | (fabsf(s[2] - tgt[2]) >= 100.0f);
-        done = !off && !late;
+        for (int k = 0; k < kNumAB2; ++k) store_pair(p.cache + (size_t)k * ld, pr, coef2[(kFirstAB2 + k) * BS], act[1]);
+        store_pair(p.cache + (size_t)kNumAB2 * ld, pr, make_float2(s[0][7], s[1][7]), act[1]);
+        store_pair(p.cache + (size_t)(kNumAB2 + 1) * ld, pr, make_float2(s[0][8], s[1][8]), act[1]);
       }
-      const bool unreach = late && off;
-      bad = overload | low_alt | hi | lo | ext | unreach;
-      count_cause(p.counters, 0, overload && active);
-      count_cause(p.counters, 1, low_alt && active);
-      count_cause(p.counters, 2, hi && active);
-      count_cause(p.counters, 3, lo && active);
-      count_cause(p.counters, 4, ext && active);
-      count_cause(p.counters, 5, unreach && active);
-      count_cause(p.counters, 6, done && active);
+
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        float* sq = s[q];
+        const float* uq = u[q];
+        const float* tq = tgt[q];
+        const float* cq = cf + q;
+        const Trig g = make_trig(sq);
+        const float tp = tfac_pow(sq[2]);
+        float a1[kNumA1];
+        alpha_coefs<kNumUsed - kFirstA1>(blob, tabs, q == 0 ? adeg.x : adeg.y, a1);
+        const ForcePart fp = force_part(sq, uq[0], uq[2], uq[3], 0.0f, g, tp, cq, CS, a1);
+
+        if (pass == 0) {
+          // ---- Euler step (F16_model.py:64-67; torchdiffeq fixed-grid euler on t=[0,dt]) ---------------
+          cf[q + kEtaEl * CS] = eta_el_of(tabs, uq[1]);
+          float xdot[12];
+          nlplant_kin_moments(sq, uq[2], uq[3], 0.0f, g, fp.qbar, fp.vt, fp.b, fp.t, cq, CS, a1, xdot);
+          xdot[6] = fp.f.vt_dot; xdot[7] = fp.f.alpha_dot; xdot[8] = fp.f.beta_dot;
+          const float h = c.dt - 0.0f;
+#pragma unroll
+          for (int j = 0; j < 12; ++j) sq[j] = sq[j] + h * xdot[j];
+          steps[q] += 1;  // env_base.py:102
+
+          // ---- observation of the new state (env_base.py:103) ----------------------------------------
+          const Trig g2 = make_trig(sq);
+          float o[NP_NUM_OBS];
+          make_obs(c, sq, uq, tq, g2, eas2tas_of(tfac_pow(sq[2])), o);
+          add_obs_noise(p, idx[q], o);
+          if (act[q]) {
+            float2* orow = reinterpret_cast<float2*>(p.obs + (size_t)(2 * pr + q) * NP_NUM_OBS);  // 88-B rows: 8-B aligned
+#pragma unroll
+            for (int j = 0; j < NP_NUM_OBS / 2; ++j) orow[j] = make_float2(o[2 * j], o[2 * j + 1]);
+          }
+        } else {
+          // ---- terminations (task_base.py:75-96) on the new state --------------------------------------
+          float ax, ay, az;
+          body_accel(sq, g, fp.f, ax, ay, az);
+          const float acc = sqrtf(ax * ax + ay * ay + az * az);
+          const bool overload = (acc - c.acceleration_limit) > 0.0f;            // overload.py:37-42
+          const bool low_alt = (sq[2] - c.altitude_limit) < 0.0f;               // low_altitude.py:29-30
+          const float vel = (sq[6] + c.airspeed * 1.0f) * 0.3048f / 340.0f;
+          const bool hi = (vel - c.max_velocity) >= 0.0f;                       // high_speed.py:29-30
+          const bool lo = (vel - c.min_velocity) <= 0.0f;                       // low_speed.py:29-30
+          const float a_deg = sq[7] * 180.0f / kPi, b_deg = sq[8] * 180.0f / kPi;  // extreme_state.py:32-36
+          const bool ext = (a_deg < c.min_alpha) | (a_deg > c.max_alpha) | (b_deg < c.min_beta) | (b_deg > c.max_beta);
+          const bool late = steps[q] >= c.max_check_interval;
+          bool off, dn;
+          float d0, d1, d2, rw;
+          if (c.task == NP_TASK_HEADING) {                                      // unreach_heading.py:38-53
+            const float dpsi = wrap_pi(sq[5] - tq[1]);
+            off = (fabsf(dpsi) >= (float)(3.141592653589793 / 36.0)) | (fabsf(sq[2] - tq[0]) >= 100.0f) |
+                  (fabsf(sq[6] - tq[2]) >= 20.0f);
+            dn = !off && !late && (steps[q] >= c.min_check_interval);
+            d0 = (sq[2] - tq[0]) * 0.3048f / 1000.0f;                           // heading_reward.py:26-35
+            d1 = dpsi / kPi;
+            d2 = (sq[6] - tq[2]) * 0.3048f / 340.0f;
+            rw = -(d0 * d0) + -(d1 * d1) + -(d2 * d2);
+          } else if (c.task == NP_TASK_CONTROL) {                               // unreach_posture.py:37-55
+            const float dpsi = wrap_pi(sq[5] - tq[1]);
+            off = (fabsf(dpsi) >= (float)(3.141592653589793 / 36.0)) |
+                  (fabsf(sq[4] - tq[0]) >= (float)(3.141592653589793 / 36.0)) | (fabsf(sq[6] - tq[2]) >= 20.0f);
+            dn = !off && !late;
+            d0 = wrap_pi(sq[4] - tq[0]) / kPi;                                  // posture_reward.py:26-34
+            d1 = dpsi / kPi;
+            d2 = (sq[6] - tq[2]) * 0.3048f / 340.0f;
+            rw = -(d0 * d0) + -(d1 * d1) + -(d2 * d2);
+          } else {                                                              // unreach_target.py:35-47
+            off = (fabsf(sq[0] - tq[0]) >= 100.0f) | (fabsf(sq[1] - tq[1]) >= 100.0f) | (fabsf(sq[2] - tq[2]) >= 100.0f);
+            dn = !off && !late;
+            d0 = (sq[0] - tq[0]) * 0.3048f / 1000.0f;                           // position_reward.py:26-34
+            d1 = (sq[1] - tq[1]) * 0.3048f / 1000.0f;
+            d2 = (sq[2] - tq[2]) * 0.3048f / 1000.0f;
+            rw = 0.1f * (-(d0 * d0) + -(d1 * d1) + -(d2 * d2));
+          }
+          const bool unreach = late && off;
+          bad[q] = overload | low_alt | hi | lo | ext | unreach;
+          done[q] = dn;
+          rew[q] = rw + (float)(-200 * (int)bad[q] + 200 * (int)dn);           // event_driven_reward.py:28
+          causes[q] = act[q] ? ((int)overload | ((int)low_alt << 1) | ((int)hi << 2) | ((int)lo << 3) | ((int)ext << 4) |
+                                ((int)unreach << 5) | ((int)dn << 6))
+                             : 0;
+        }
+      }
     }
 
-    // ---- reward (task_base.py:60-73) --------------------------------------------------------------
-    float rew;
-    {
-      float d0, d1, d2;
-      if (c.task == NP_TASK_HEADING) {                                      // heading_reward.py:26-35
-        d0 = (s[2] - tgt[0]) * 0.3048f / 1000.0f;
-        d1 = wrap_pi(s[5] - tgt[1]) / kPi;
-        d2 = (s[6] - tgt[2]) * 0.3048f / 340.0f;
-        rew = -(d0 * d0) + -(d1 * d1) + -(d2 * d2);
-      } else if (c.task == NP_TASK_CONTROL) {                               // posture_reward.py:26-34
-        d0 = wrap_pi(s[4] - tgt[0]) / kPi;
-        d1 = wrap_pi(s[5] - tgt[1]) / kPi;
-        d2 = (s[6] - tgt[2]) * 0.3048f / 340.0f;
-        rew = -(d0 * d0) + -(d1 * d1) + -(d2 * d2);
-      } else {                                                              // position_reward.py:26-34
-        d0 = (s[0] - tgt[0]) * 0.3048f / 1000.0f;
-        d1 = (s[1] - tgt[1]) * 0.3048f / 1000.0f;
-        d2 = (s[2] - tgt[2]) * 0.3048f / 1000.0f;
-        rew = 0.1f * (-(d0 * d0) + -(d1 * d1) + -(d2 * d2));
-      }
-      rew = rew + (float)(-200 * (int)bad + 200 * (int)done);               // event_driven_reward.py:28
-    }
+    // ---- termination-cause counters (replace the reference's per-condition print(torch.sum(...)) syncs) --------
+#pragma unroll
+    for (int w = 0; w < 7; ++w) count_cause2(p.counters, w, (causes[0] >> w) & 1, (causes[1] >> w) & 1);
 
     // ---- store ----------------------------------------------------------------------------------
-    if (active) {
+    if (act[0]) {  // a half-active tail pair (odd n) stores its first aircraft only
 #pragma unroll
-      for (int j = 0; j < 12; ++j) p.s[(size_t)j * ld + i] = s[j];
+      for (int j = 0; j < 12; ++j) store_pair(p.s + (size_t)j * ld, pr, make_float2(s[0][j], s[1][j]), act[1]);
 #pragma unroll
-      for (int j = 0; j < 4; ++j) p.u[(size_t)j * ld + i] = u[j];
+      for (int j = 0; j < 4; ++j) store_pair(p.u + (size_t)j * ld, pr, make_float2(u[0][j], u[1][j]), act[1]);
 #pragma unroll
-      for (int j = 0; j < 3; ++j) p.tgt[(size_t)j * ld + i] = tgt[j];
-      p.step_count[i] = steps;
-      p.flags[i] = done ? 1 : 0;
-      p.flags[ld + i] = bad ? 1 : 0;
-      p.flags[2 * ld + i] = 0;  // Timeout is commented out of the control tasks (heading_task.py:45)
-      p.reward[i] = rew;
+      for (int j = 0; j < 3; ++j) store_pair(p.tgt + (size_t)j * ld, pr, make_float2(tgt[0][j], tgt[1][j]), act[1]);
+      store_pair(p.reward, pr, make_float2(rew[0], rew[1]), act[1]);
+      if (act[1]) {
+        reinterpret_cast<int2*>(p.step_count)[pr] = make_int2(steps[0], steps[1]);
+        reinterpret_cast<uchar2*>(p.flags)[pr] = make_uchar2(done[0] ? 1 : 0, done[1] ? 1 : 0);
+        reinterpret_cast<uchar2*>(p.flags + ld)[pr] = make_uchar2(bad[0] ? 1 : 0, bad[1] ? 1 : 0);
+        reinterpret_cast<uchar2*>(p.flags + 2 * (size_t)ld)[pr] = make_uchar2(0, 0);  // Timeout is commented out (heading_task.py:45)
+      } else {
+        p.step_count[2 * pr] = steps[0];
+        p.flags[2 * pr] = done[0] ? 1 : 0;
+        p.flags[ld + 2 * pr] = bad[0] ? 1 : 0;
+        p.flags[2 * (size_t)ld + 2 * pr] = 0;
+      }
     }
   }
-  if (obs_pending && (threadIdx.x & 31) == 0) bulk_wait_read();
 }
 
 // ------------------------------------------------------------------------------------------------
-// K3: standalone reset (BaseEnv.reset, env_base.py:83-97)
+// K3: standalone reset (BaseEnv.reset, env_base.py:83-97) -- HBM-bound, one aircraft per thread
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) f16_reset_kernel(const __grid_constant__ StepParams p) {
   const np_env_cfg& c = p.cfg;
   const int n = c.n, ld = c.ld;
+  const float* c0 = reinterpret_cast<const float*>(p.aero) + reinterpret_cast<const int32_t*>(p.aero)[kHdrC0];
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     float s[12], u[4], tgt[3];
-    const bool rst = (p.flags[i] | p.flags[ld + i] | p.flags[2 * ld + i]) != 0;
+    const bool rst = (p.flags[i] | p.flags[ld + i] | p.flags[2 * (size_t)ld + i]) != 0;
     if (rst) {
       const Draws r = reset_draws(p, i);
       reset_aircraft(c, r, s, u, tgt);
@@ -483,9 +496,9 @@ __global__ void __launch_bounds__(256) f16_reset_kernel(const __grid_constant__ 
 #pragma unroll
       for (int j = 0; j < 3; ++j) p.tgt[(size_t)j * ld + i] = tgt[j];
       p.step_count[i] = 0;
-      for (int k = 0; k < kNumAB; ++k) p.cache[(size_t)k * ld + i] = p.aero[kC0Off + k];
-      p.cache[(size_t)kNumAB * ld + i] = 0.0f;
-      p.cache[(size_t)(kNumAB + 1) * ld + i] = 0.0f;
+      for (int k = 0; k < kNumAB2; ++k) p.cache[(size_t)k * ld + i] = c0[k];
+      p.cache[(size_t)kNumAB2 * ld + i] = 0.0f;
+      p.cache[(size_t)(kNumAB2 + 1) * ld + i] = 0.0f;
       atomicAdd(&p.counters[7], 1ull);
     } else {
 #pragma unroll
@@ -495,7 +508,7 @@ __global__ void __launch_bounds__(256) f16_reset_kernel(const __grid_constant__ 
 #pragma unroll
       for (int j = 0; j < 3; ++j) tgt[j] = p.tgt[(size_t)j * ld + i];
     }
-    p.flags[i] = 0; p.flags[ld + i] = 0; p.flags[2 * ld + i] = 0;
+    p.flags[i] = 0; p.flags[ld + i] = 0; p.flags[2 * (size_t)ld + i] = 0;
     const Trig g = make_trig(s);
     float o[NP_NUM_OBS];
     make_obs(c, s, u, tgt, g, eas2tas_of(tfac_pow(s[2])), o);
@@ -506,84 +519,121 @@ __global__ void __launch_bounds__(256) f16_reset_kernel(const __grid_constant__ 
 }
 
 // ------------------------------------------------------------------------------------------------
-// stand-alone nlplant / coefficient kernels (model plug-in getters, parity tests)
+// stand-alone nlplant / coefficient kernels (model plug-in getters, parity tests): same device code as K1,
+// two points per thread
 // ------------------------------------------------------------------------------------------------
 constexpr int kAuxBS = 128;
-constexpr int kAuxSmem = kAeroBytes + kNumNets * kAuxBS * 4 + 16;
+static int aux_smem_bytes(int aero_bytes) { return aero_bytes + kNumSlots * kAuxBS * 8 + 16; }
 
-__global__ void __launch_bounds__(kAuxBS) f16_nlplant_kernel(const float* __restrict__ aero, const float* __restrict__ S,
-                                                             const float* __restrict__ U, float* __restrict__ X, int n,
-                                                             int ld) {
+__global__ void __launch_bounds__(kAuxBS) f16_nlplant_kernel(const uint32_t* __restrict__ aero, int aero_bytes,
+                                                             const float* __restrict__ S, const float* __restrict__ U,
+                                                             float* __restrict__ X, int n, int ld) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   float* blob = reinterpret_cast<float*>(smem_raw);
-  float* coef_all = blob + kAeroFloats;
-  uint64_t* bar = reinterpret_cast<uint64_t*>(coef_all + kNumNets * kAuxBS);
-  stage_aero(blob, aero, bar);
+  float2* coef_all = reinterpret_cast<float2*>(smem_raw + aero_bytes);
+  uint64_t* bar = reinterpret_cast<uint64_t*>(coef_all + kNumSlots * kAuxBS);
+  stage_aero(blob, aero, (uint32_t)aero_bytes, bar);
   const uint32_t wb0 = aero_base_after_staging(blob);
-  float* coef = coef_all + threadIdx.x;
-  for (int base = blockIdx.x * kAuxBS; base < n; base += gridDim.x * kAuxBS) {
-    const int i = base + threadIdx.x;
-    const int il = i < n ? i : n - 1;
+  const AeroTabs tabs = aero_tabs(blob, wb0);
+  float2* coef2 = coef_all + threadIdx.x;
+  float* cf = reinterpret_cast<float*>(coef2);
+  constexpr int CS = 2 * kAuxBS;
+  const int npairs = (n + 1) >> 1;
+  for (int pbase = blockIdx.x * kAuxBS; pbase < npairs; pbase += gridDim.x * kAuxBS) {
+    const int pr = pbase + threadIdx.x;
+    const int prl = pr < npairs ? pr : npairs - 1;
     const uint32_t wb = opaque_u32(wb0);
-    float s[12], u[5];
+    float s[2][12], u[2][5];
 #pragma unroll
-    for (int j = 0; j < 12; ++j) s[j] = S[(size_t)j * ld + il];
+    for (int j = 0; j < 12; ++j) {
+      const float2 v = reinterpret_cast<const float2*>(S + (size_t)j * ld)[prl];
+      s[0][j] = v.x; s[1][j] = v.y;
+    }
 #pragma unroll
-    for (int j = 0; j < 5; ++j) u[j] = U[(size_t)j * ld + il];
-    ZIn zi;
-    zscores_ab(blob, s[7] * kR2D, s[8] * kR2D, zi);
-    zscores_el(blob, u[1], zi);
-    eval_el_nets(blob, wb, zi, coef, kAuxBS);
-    eval_ab_nets(blob, wb, zi, coef, kAuxBS);
-    const Trig g = make_trig(s);
-    float xdot[12];
-    nlplant_from_coefs(s, u[0], u[2], u[3], u[4], g, tfac_pow(s[2]), coef, kAuxBS, xdot);
-    if (i < n) {
+    for (int j = 0; j < 5; ++j) {
+      const float2 v = reinterpret_cast<const float2*>(U + (size_t)j * ld)[prl];
+      u[0][j] = v.x; u[1][j] = v.y;
+    }
+    const float2 adeg = make_float2(s[0][7] * kR2D, s[1][7] * kR2D);
+    const float2 bdeg = make_float2(s[0][8] * kR2D, s[1][8] * kR2D);
+    ZIn2 zi;
+    zscores_ab2(blob, adeg, bdeg, zi);
+    zscores_el2(blob, make_float2(u[0][1], u[1][1]), zi);
+    eval_ab2_nets(blob, wb, zi, coef2, kAuxBS);
+    eval_el3_nets(blob, wb, zi, coef2, kAuxBS, 5);
+    float xdot[2][12];
 #pragma unroll
-      for (int j = 0; j < 12; ++j) X[(size_t)j * ld + i] = xdot[j];
+    for (int q = 0; q < 2; ++q) {
+      cf[q + kEtaEl * CS] = eta_el_of(tabs, u[q][1]);
+      float a1[kNumA1];
+      alpha_coefs<kNumUsed - kFirstA1>(blob, tabs, q == 0 ? adeg.x : adeg.y, a1);
+      const Trig g = make_trig(s[q]);
+      nlplant_from_coefs(s[q], u[q][0], u[q][2], u[q][3], u[q][4], g, tfac_pow(s[q][2]), cf + q, CS, a1, xdot[q]);
+    }
+    if (pr < npairs) {  // rows are ld >= n + (n & 1) floats long
+#pragma unroll
+      for (int j = 0; j < 12; ++j)
+        reinterpret_cast<float2*>(X + (size_t)j * ld)[pr] = make_float2(xdot[0][j], xdot[1][j]);
     }
   }
 }
 
-__global__ void __launch_bounds__(kAuxBS) f16_coeffs_kernel(const float* __restrict__ aero, const float* __restrict__ A,
-                                                            const float* __restrict__ Bd, const float* __restrict__ E,
-                                                            float* __restrict__ out, int n, int ld) {
+__global__ void __launch_bounds__(kAuxBS) f16_coeffs_kernel(const uint32_t* __restrict__ aero, int aero_bytes,
+                                                            const float* __restrict__ A, const float* __restrict__ Bd,
+                                                            const float* __restrict__ E, float* __restrict__ out, int n,
+                                                            int ld) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   float* blob = reinterpret_cast<float*>(smem_raw);
-  float* coef_all = blob + kAeroFloats;
-  uint64_t* bar = reinterpret_cast<uint64_t*>(coef_all + kNumNets * kAuxBS);
-  stage_aero(blob, aero, bar);
+  float2* coef_all = reinterpret_cast<float2*>(smem_raw + aero_bytes);
+  uint64_t* bar = reinterpret_cast<uint64_t*>(coef_all + kNumSlots * kAuxBS);
+  stage_aero(blob, aero, (uint32_t)aero_bytes, bar);
   const uint32_t wb0 = aero_base_after_staging(blob);
-  float* coef = coef_all + threadIdx.x;
-  for (int base = blockIdx.x * kAuxBS; base < n; base += gridDim.x * kAuxBS) {
-    const int i = base + threadIdx.x;
-    const int il = i < n ? i : n - 1;
+  const AeroTabs tabs = aero_tabs(blob, wb0);
+  float2* coef2 = coef_all + threadIdx.x;
+  float* cf = reinterpret_cast<float*>(coef2);
+  constexpr int CS = 2 * kAuxBS;
+  const int npairs = (n + 1) >> 1;
+  for (int pbase = blockIdx.x * kAuxBS; pbase < npairs; pbase += gridDim.x * kAuxBS) {
+    const int pr = pbase + threadIdx.x;
+    const int prl = pr < npairs ? pr : npairs - 1;
+    const int i0 = min(2 * prl, n - 1), i1 = min(2 * prl + 1, n - 1);
     const uint32_t wb = opaque_u32(wb0);
-    ZIn zi;
-    zscores_ab(blob, A[il], Bd[il], zi);
-    zscores_el(blob, E[il], zi);
-    eval_el_nets(blob, wb, zi, coef, kAuxBS);
-    eval_ab_nets(blob, wb, zi, coef, kAuxBS);
-    eval_group<kdCzq_lef, kdCzq_lef + 1>(blob, wb, zi, coef, kAuxBS);
-    if (i < n) {
-      for (int k = 0; k < kNumNets; ++k) out[(size_t)k * ld + i] = coef[k * kAuxBS];
+    const float2 adeg = make_float2(A[i0], A[i1]), bdeg = make_float2(Bd[i0], Bd[i1]), edeg = make_float2(E[i0], E[i1]);
+    ZIn2 zi;
+    zscores_ab2(blob, adeg, bdeg, zi);
+    zscores_el2(blob, edeg, zi);
+    eval_ab2_nets(blob, wb, zi, coef2, kAuxBS);
+    eval_el3_nets(blob, wb, zi, coef2, kAuxBS, 5);
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      const int i = 2 * pr + q;
+      float a1[kNumA1];
+      alpha_coefs<kNumA1>(blob, tabs, q == 0 ? adeg.x : adeg.y, a1);
+      const float eta = eta_el_of(tabs, q == 0 ? edeg.x : edeg.y);
+      if (i < n) {
+        for (int k = 0; k < kNumSlots; ++k) out[(size_t)k * ld + i] = k == kEtaEl ? eta : cf[q + k * CS];
+#pragma unroll
+        for (int k = 0; k < kNumA1; ++k) out[(size_t)(kFirstA1 + k) * ld + i] = a1[k];
+      }
     }
   }
 }
 
-// (alpha,beta)-net outputs at alpha = beta = 0, appended to the device blob at np_aero_create.
-__global__ void __launch_bounds__(128) f16_c0_kernel(float* aero) {
+// (alpha,beta)-MLP outputs at alpha = beta = 0, written into the image at np_aero_create (same device code as K1,
+// so a reset lane sees bit-identical values whether it takes the constants or an evaluation).
+__global__ void __launch_bounds__(32) f16_c0_kernel(uint32_t* aero, int aero_bytes) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   float* blob = reinterpret_cast<float*>(smem_raw);
-  float* coef = blob + kAeroFloats;
-  uint64_t* bar = reinterpret_cast<uint64_t*>(coef + pad4(kNumNets));  // 8-byte aligned
-  stage_aero(blob, aero, bar);
+  float2* coef2 = reinterpret_cast<float2*>(smem_raw + aero_bytes);
+  uint64_t* bar = reinterpret_cast<uint64_t*>(coef2 + kNumSlots);
+  stage_aero(blob, aero, (uint32_t)aero_bytes, bar);
   const uint32_t wb = aero_base_after_staging(blob);
   if (threadIdx.x == 0) {
-    ZIn zi;
-    zscores_ab(blob, 0.0f * kR2D, 0.0f * kR2D, zi);
-    eval_ab_nets(blob, wb, zi, coef, 1);
-    for (int k = 0; k < kNumAB; ++k) aero[kC0Off + k] = coef[kFirstAB + k];
+    ZIn2 zi;
+    zscores_ab2(blob, make_float2(0.0f * kR2D, 0.0f * kR2D), make_float2(0.0f * kR2D, 0.0f * kR2D), zi);
+    eval_ab2_nets(blob, wb, zi, coef2, 1);
+    float* c0 = reinterpret_cast<float*>(aero) + reinterpret_cast<const int32_t*>(blob)[kHdrC0];
+    for (int k = 0; k < kNumAB2; ++k) c0[k] = coef2[kFirstAB2 + k].x;
   }
 }
 
@@ -603,65 +653,34 @@ size_t np_last_error(char* buf, size_t cap) {
   return g_err.size();
 }
 
+int np_aero_pack_host(const float* blob, size_t n_floats, const np_net_desc* descs, const double* norm, int n_nets,
+                      uint32_t* out_words, size_t cap_words, size_t* n_words) {
+  if (!blob || !descs || !norm || !n_words) return fail(NP_EINVAL, "np_aero_pack_host: null argument");
+  std::vector<uint32_t> image;
+  const std::string err = pack_aero_image(blob, n_floats, descs, norm, n_nets, &image);
+  if (!err.empty()) return fail(NP_EINVAL, "np_aero_pack_host: " + err);
+  *n_words = image.size();
+  if (out_words) {
+    if (cap_words < image.size()) return fail(NP_EINVAL, "np_aero_pack_host: output buffer too small");
+    memcpy(out_words, image.data(), image.size() * 4);
+  }
+  return NP_OK;
+}
+
 int np_aero_create(const float* blob, size_t n_floats, const np_net_desc* descs, const double* norm, int n_nets,
                    np_aero** out) {
   if (!blob || !descs || !norm || !out) return fail(NP_EINVAL, "np_aero_create: null argument");
-  if (n_nets != kNumNets) return fail(NP_EINVAL, "np_aero_create: expected 43 nets");
-  std::vector<float> host(kAeroFloats, 0.0f);
-  bool zset[kNumZ] = {};
-  auto set_z = [&](int zid, double mean, double sd, std::string* err) {
-    const float m = (float)mean, s = (float)sd;
-    if (zset[zid] && (host[kZnormOff + 2 * zid] != m || host[kZnormOff + 2 * zid + 1] != s))
-      *err = "np_aero_create: nets of one normalisation group disagree on (mean, std)";
-    host[kZnormOff + 2 * zid] = m;
-    host[kZnormOff + 2 * zid + 1] = s;
-    zset[zid] = true;
-  };
-  for (int k = 0; k < kNumNets; ++k) {
-    const np_net_desc& d = descs[k];
-    const NetArch a = arch_of(k);
-    const ZSel z = zsel_of(k);
-    const int nl = a.h3 ? 4 : 3;
-    const int dims[5] = {a.nin, a.h1, a.h2, a.h3 ? a.h3 : 1, a.h3 ? 1 : 0};
-    if (d.n_in != a.nin || d.n_layers != nl) return fail(NP_EINVAL, "np_aero_create: net architecture mismatch (depth)");
-    for (int l = 0; l <= nl; ++l)
-      if (d.dims[l] != dims[l]) return fail(NP_EINVAL, "np_aero_create: net architecture mismatch (width)");
-    const int want_sel[3] = {z.a >= 0 ? 0 : 2, a.nin >= 2 ? 1 : -1, a.nin == 3 ? 2 : -1};
-    for (int j = 0; j < a.nin; ++j)
-      if (d.sel[j] != want_sel[j]) return fail(NP_EINVAL, "np_aero_create: net input selection mismatch");
-    std::string err;
-    const double* nm = norm + 8 * k;
-    for (int j = 0; j < a.nin; ++j) {
-      const int zid = d.sel[j] == 0 ? z.a : (d.sel[j] == 1 ? z.b : z.e);
-      set_z(zid, nm[j], nm[3 + j], &err);
-    }
-    if (!err.empty()) return fail(NP_EINVAL, err);
-    host[kOnormOff + 2 * k] = (float)nm[6];
-    host[kOnormOff + 2 * k + 1] = (float)nm[7];
-    // weights: source per layer W[out][in] then b[out]; device per layer b[out] then W^T[in][out], padded to 4
-    size_t src = (size_t)d.w_off;
-    int dst = net_offset(k);
-    for (int l = 0; l < nl; ++l) {
-      const int in = dims[l], o = dims[l + 1];
-      if (src + (size_t)in * o + o > n_floats) return fail(NP_EINVAL, "np_aero_create: blob too short");
-      const float* W = blob + src;
-      const float* b = W + (size_t)in * o;
-      for (int j = 0; j < o; ++j) host[dst + j] = b[j];
-      for (int i = 0; i < in; ++i)
-        for (int j = 0; j < o; ++j) host[dst + o + i * o + j] = W[(size_t)j * in + i];
-      src += (size_t)in * o + o;
-      dst += layer_floats(in, o);
-    }
-  }
-  for (int zid = 0; zid < kNumZ; ++zid)
-    if (!zset[zid]) return fail(NP_EINVAL, "np_aero_create: normalisation group without nets");
+  std::vector<uint32_t> image;
+  const std::string err = pack_aero_image(blob, n_floats, descs, norm, n_nets, &image);
+  if (!err.empty()) return fail(NP_EINVAL, "np_aero_create: " + err);
   np_aero* a = new np_aero();
+  a->bytes = (int)image.size() * 4;
   cudaGetDevice(&a->device);
-  NP_CUDA(cudaMalloc(&a->blob_dev, kAeroBytes));
-  NP_CUDA(cudaMemcpy(a->blob_dev, host.data(), kAeroBytes, cudaMemcpyHostToDevice));
-  constexpr int c0_smem = kAeroBytes + pad4(kNumNets) * 4 + 16;
+  NP_CUDA(cudaMalloc(&a->image_dev, a->bytes));
+  NP_CUDA(cudaMemcpy(a->image_dev, image.data(), a->bytes, cudaMemcpyHostToDevice));
+  const int c0_smem = a->bytes + kNumSlots * 8 + 16;
   NP_CUDA(cudaFuncSetAttribute(f16_c0_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, c0_smem));
-  f16_c0_kernel<<<1, 128, c0_smem>>>(a->blob_dev);
+  f16_c0_kernel<<<1, 32, c0_smem>>>(a->image_dev, a->bytes);
   NP_CUDA(cudaGetLastError());
   NP_CUDA(cudaDeviceSynchronize());
   *out = a;
@@ -670,29 +689,31 @@ int np_aero_create(const float* blob, size_t n_floats, const np_net_desc* descs,
 
 int np_aero_destroy(np_aero* aero) {
   if (!aero) return NP_OK;
-  cudaFree(aero->blob_dev);
+  cudaFree(aero->image_dev);
   delete aero;
   return NP_OK;
 }
 
 size_t np_env_workspace_bytes(const np_env_cfg* cfg) {
   if (!cfg) return 0;
-  return (size_t)kCacheRows * (size_t)cfg->ld * sizeof(float) + 256 /* counters, 128-B aligned tail */;
+  return (((size_t)kCacheRows * (size_t)cfg->ld * sizeof(float) + 127) / 128) * 128 + 256 /* counters */;
 }
 
 }  // extern "C"
 
 template <int BS, int MINB>
 static int launch_step(np_env* env, const StepParams& p, cudaStream_t st) {
-  constexpr int smem = step_smem_bytes<BS>();
-  static bool configured[2] = {false, false};
-  const bool cache = env->cfg.use_coef_cache != 0;
-  auto kern = cache ? f16_step_kernel<BS, MINB, true> : f16_step_kernel<BS, MINB, false>;
-  if (!configured[cache]) {
+  const int smem = step_smem_bytes(p.aero_bytes, BS);
+  static int configured[64] = {};  // per device: the attribute lives in the device's context
+  auto kern = f16_step_kernel<BS, MINB>;
+  int dev = 0;
+  NP_CUDA(cudaGetDevice(&dev));
+  if (configured[dev & 63] < smem) {
     NP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    configured[cache] = true;
+    configured[dev & 63] = smem;
   }
-  const int want = (env->cfg.n + BS - 1) / BS;
+  const int npairs = (env->cfg.n + 1) / 2;
+  const int want = (npairs + BS - 1) / BS;
   const int grid = want < env->num_sms * MINB ? want : env->num_sms * MINB;
   env->grid = grid;
   env->smem = smem;
@@ -714,7 +735,8 @@ static StepParams make_params(np_env* env, const float* action, const float* dra
   p.cache = reinterpret_cast<float*>(env->buf.workspace_dev);
   p.counters = reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(env->buf.workspace_dev) +
                                                      (((size_t)kCacheRows * env->cfg.ld * 4 + 127) / 128) * 128);
-  p.aero = env->aero->blob_dev;
+  p.aero = env->aero->image_dev;
+  p.aero_bytes = env->aero->bytes;
   p.action = action;
   p.draws = draws;
   p.noise = noise;
@@ -726,7 +748,8 @@ extern "C" {
 
 int np_env_create(const np_env_cfg* cfg, const np_aero* aero, np_env** out) {
   if (!cfg || !aero || !out) return fail(NP_EINVAL, "np_env_create: null argument");
-  if (cfg->n <= 0 || cfg->ld < cfg->n || cfg->ld % 4) return fail(NP_EINVAL, "np_env_create: need n > 0, ld >= n, ld % 4 == 0");
+  if (cfg->n <= 0 || cfg->ld < cfg->n + (cfg->n & 1) || cfg->ld % 4)
+    return fail(NP_EINVAL, "np_env_create: need n > 0, ld >= n rounded up to even, ld % 4 == 0");
   if (cfg->task < NP_TASK_HEADING || cfg->task > NP_TASK_TRACKING) return fail(NP_EINVAL, "np_env_create: unknown task");
   np_env* e = new np_env();
   e->cfg = *cfg;
@@ -735,7 +758,7 @@ int np_env_create(const np_env_cfg* cfg, const np_aero* aero, np_env** out) {
   int dev = 0;
   NP_CUDA(cudaGetDevice(&dev));
   NP_CUDA(cudaDeviceGetAttribute(&e->num_sms, cudaDevAttrMultiProcessorCount, dev));
-  e->block = 512;  // 16 warps/SM: measured 1.155 ms vs 1.49 ms (256) per 10^6-aircraft step (profiles/r01_block_sweep.txt)
+  e->block = 256;
   if (const char* b = getenv("NPLANE_BLOCK")) e->block = atoi(b);
   if (e->block != 128 && e->block != 256 && e->block != 384 && e->block != 512)
     return fail(NP_EINVAL, "NPLANE_BLOCK must be 128, 256, 384 or 512");
@@ -748,12 +771,14 @@ int np_env_bind(np_env* env, const np_buffers* b) {
   if (!b->s_dev || !b->u_dev || !b->tgt_dev || !b->step_count_dev || !b->flags_dev || !b->obs_dev || !b->reward_dev ||
       !b->workspace_dev)
     return fail(NP_EINVAL, "np_env_bind: null buffer");
-  if (((uintptr_t)b->obs_dev & 15) || ((uintptr_t)b->workspace_dev & 127))
-    return fail(NP_EINVAL, "np_env_bind: obs must be 16-byte and workspace 128-byte aligned");
+  if (((uintptr_t)b->obs_dev & 15) || ((uintptr_t)b->workspace_dev & 127) || ((uintptr_t)b->s_dev & 15) ||
+      ((uintptr_t)b->u_dev & 15) || ((uintptr_t)b->tgt_dev & 15) || ((uintptr_t)b->reward_dev & 7) ||
+      ((uintptr_t)b->step_count_dev & 7) || ((uintptr_t)b->flags_dev & 1))
+    return fail(NP_EINVAL, "np_env_bind: buffers must be 16-byte (workspace 128-byte) aligned");
   env->buf = *b;
   env->bound = true;
   // invalidate the coefficient-cache keys: 0xFFFFFFFF is a NaN pattern no stored alpha/beta can equal bitwise
-  NP_CUDA(cudaMemset(reinterpret_cast<float*>(b->workspace_dev) + (size_t)kNumAB * env->cfg.ld, 0xFF,
+  NP_CUDA(cudaMemset(reinterpret_cast<float*>(b->workspace_dev) + (size_t)kNumAB2 * env->cfg.ld, 0xFF,
                      2 * (size_t)env->cfg.ld * sizeof(float)));
   return NP_OK;
 }
@@ -790,11 +815,11 @@ int np_env_step(np_env* env, const float* action_dev, const float* draws_dev, co
   cudaStream_t st = (cudaStream_t)stream;
   switch (env->block) {
 #ifdef NPLANE_ALL_BLOCKS
-    case 128: return launch_step<128, 2>(env, p, st);
-    case 256: return launch_step<256, 1>(env, p, st);
+    case 128: return launch_step<128, 4>(env, p, st);
     case 384: return launch_step<384, 1>(env, p, st);
-#endif
     case 512: return launch_step<512, 1>(env, p, st);
+#endif
+    case 256: return launch_step<256, 2>(env, p, st);
     default: return fail(NP_EINVAL, "np_env_step: block size not compiled in (build with -DNPLANE_ALL_BLOCKS)");
   }
 }
@@ -817,14 +842,20 @@ int np_env_launch_info(const np_env* env, int* grid, int* block, int* smem_bytes
 }
 
 int np_f16_nlplant(const np_aero* aero, const float* s_dev, const float* u_dev, float* xdot_dev, int n, int ld, void* stream) {
-  if (!aero || !s_dev || !u_dev || !xdot_dev || n <= 0 || ld < n) return fail(NP_EINVAL, "np_f16_nlplant: bad argument");
-  static bool configured = false;
-  if (!configured) {
-    NP_CUDA(cudaFuncSetAttribute(f16_nlplant_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAuxSmem));
-    configured = true;
+  if (!aero || !s_dev || !u_dev || !xdot_dev || n <= 0 || ld < n + (n & 1) || (ld & 1))
+    return fail(NP_EINVAL, "np_f16_nlplant: bad argument (need even ld >= n rounded up to even)");
+  if (((uintptr_t)s_dev | (uintptr_t)u_dev | (uintptr_t)xdot_dev) & 7) return fail(NP_EINVAL, "np_f16_nlplant: 8-byte alignment");
+  const int smem = aux_smem_bytes(aero->bytes);
+  static int configured[64] = {};
+  int dev = 0;
+  NP_CUDA(cudaGetDevice(&dev));
+  if (configured[dev & 63] < smem) {
+    NP_CUDA(cudaFuncSetAttribute(f16_nlplant_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured[dev & 63] = smem;
   }
-  const int want = (n + kAuxBS - 1) / kAuxBS;
-  f16_nlplant_kernel<<<want < 296 ? want : 296, kAuxBS, kAuxSmem, (cudaStream_t)stream>>>(aero->blob_dev, s_dev, u_dev, xdot_dev, n, ld);
+  const int want = ((n + 1) / 2 + kAuxBS - 1) / kAuxBS;
+  f16_nlplant_kernel<<<want < 296 ? want : 296, kAuxBS, smem, (cudaStream_t)stream>>>(aero->image_dev, aero->bytes, s_dev, u_dev,
+                                                                                   xdot_dev, n, ld);
   NP_CUDA(cudaGetLastError());
   return NP_OK;
 }
@@ -833,14 +864,17 @@ int np_f16_coeffs(const np_aero* aero, const float* alpha_deg_dev, const float* 
                   float* out_dev, int n, int ld, void* stream) {
   if (!aero || !alpha_deg_dev || !beta_deg_dev || !el_deg_dev || !out_dev || n <= 0 || ld < n)
     return fail(NP_EINVAL, "np_f16_coeffs: bad argument");
-  static bool configured = false;
-  if (!configured) {
-    NP_CUDA(cudaFuncSetAttribute(f16_coeffs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAuxSmem));
-    configured = true;
+  const int smem = aux_smem_bytes(aero->bytes);
+  static int configured[64] = {};
+  int dev = 0;
+  NP_CUDA(cudaGetDevice(&dev));
+  if (configured[dev & 63] < smem) {
+    NP_CUDA(cudaFuncSetAttribute(f16_coeffs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured[dev & 63] = smem;
   }
-  const int want = (n + kAuxBS - 1) / kAuxBS;
-  f16_coeffs_kernel<<<want < 296 ? want : 296, kAuxBS, kAuxSmem, (cudaStream_t)stream>>>(aero->blob_dev, alpha_deg_dev, beta_deg_dev,
-                                                                                      el_deg_dev, out_dev, n, ld);
+  const int want = ((n + 1) / 2 + kAuxBS - 1) / kAuxBS;
+  f16_coeffs_kernel<<<want < 296 ? want : 296, kAuxBS, smem, (cudaStream_t)stream>>>(aero->image_dev, aero->bytes, alpha_deg_dev,
+                                                                                  beta_deg_dev, el_deg_dev, out_dev, n, ld);
   NP_CUDA(cudaGetLastError());
   return NP_OK;
 }
