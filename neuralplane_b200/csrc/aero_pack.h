@@ -212,7 +212,9 @@ inline std::string pack_aero_image(const float* blob, size_t n_floats, const np_
   std::vector<float> bp_a;
   for (double v : merged)
     if (bp_a.empty() || (float)v != bp_a.back()) bp_a.push_back((float)v);
-  const int La = levels_for(bp_a.size()), Le = levels_for(tabs[kEtaEl].bp.size());
+  if (levels_for(bp_a.size()) > kLevelsA || levels_for(tabs[kEtaEl].bp.size()) > kLevelsE)
+    return "too many breakpoints for the fixed-depth table search";
+  const int La = kLevelsA, Le = kLevelsE;
   const size_t Ma = bp_a.size();
 
   std::vector<uint32_t>& im = *image;

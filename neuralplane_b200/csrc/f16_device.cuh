@@ -58,6 +58,13 @@ __device__ __forceinline__ uint32_t aero_base_after_staging(const void* blob_sme
 // warp-broadcast LDS.128 lane feeding an FFMA2 (fma.rn.f32x2 with a scalar-broadcast multiplicand), i.e. one
 // issue slot per two multiply-adds.
 // ------------------------------------------------------------------------------------------------
+// NPL_SYNC: CTA-wide barriers that keep the warps of a CTA in the same code region, so the (large, mostly
+// straight-line) instruction stream is fetched once per CTA instead of once per warp.  0 none, 1 per net group,
+// 2 per net.  All callers evaluate the nets in CTA-uniform control flow.
+#ifndef NPL_SYNC
+#define NPL_SYNC 0
+#endif
+
 template <int IN, int OUT, bool RELU>
 __device__ __forceinline__ void dense2(uint32_t w, const float2 (&x)[IN], float2 (&y)[OUT]) {
   constexpr int NF = OUT + IN * OUT;
@@ -146,8 +153,10 @@ __device__ __forceinline__ void eval_group2(const float* __restrict__ blob, uint
   float2 z2 = make_float2(0.f, 0.f);
   if constexpr (A.nin == 3) z2 = zi.z[Z.e >= 0 ? Z.e : 0];
   uint32_t w = wbase + 4 * mlp_offset(K0);
+  if (NPL_SYNC == 1) __syncthreads();
 #pragma unroll 1
   for (int k = K0; k < K0 + count; ++k, w += 4 * NF) {
+    if (NPL_SYNC == 2) __syncthreads();
     const float2 y = mlp2<A.nin, A.h1, A.h2, A.h3>(w, z0, z1, z2);
     out[k * stride] = denorm2(blob, k, y);
   }
@@ -176,7 +185,6 @@ __device__ __forceinline__ void eval_el3_nets(const float* __restrict__ blob, ui
 // ------------------------------------------------------------------------------------------------
 struct AeroTabs {
   uint32_t bp_a, segmap, ent_a, bp_e, ent_e;  // shared-memory byte addresses
-  int levels_a, levels_e;
 };
 __device__ __forceinline__ AeroTabs aero_tabs(const void* blob_smem, uint32_t base) {
   const int32_t* h = reinterpret_cast<const int32_t*>(blob_smem);
@@ -186,31 +194,49 @@ __device__ __forceinline__ AeroTabs aero_tabs(const void* blob_smem, uint32_t ba
   t.ent_a = base + 4u * (uint32_t)h[kHdrEntA];
   t.bp_e = base + 4u * (uint32_t)h[kHdrBpE];
   t.ent_e = base + 4u * (uint32_t)h[kHdrEntE];
-  t.levels_a = h[kHdrLevelsA];
-  t.levels_e = h[kHdrLevelsE];
   return t;
 }
-// number of breakpoints <= x in a sorted, +inf padded list of 2^levels - 1 floats (NaN -> 0)
-__device__ __forceinline__ uint32_t pwl_search(uint32_t bp, int levels, float x) {
-  uint32_t pos = 0;
-#pragma unroll 1
-  for (uint32_t step = 1u << (levels - 1); step > 0; step >>= 1) {
-    const float b = lds32f(bp + 4u * (pos + step - 1u));
-    pos += (b <= x) ? step : 0u;
+// Number of breakpoints <= x in a sorted, +inf padded list of 2^LEVELS - 1 floats (NaN -> 0), for the thread's two
+// aircraft at once: two independent dependent-load chains in flight instead of one.
+#ifndef NPL_JOINT_SEARCH
+#define NPL_JOINT_SEARCH 0  // fully unrolled search measured 7 % slower end to end (profiles/r01_variants.txt)
+#endif
+template <int LEVELS>
+__device__ __forceinline__ void pwl_search2(uint32_t bp, float x0, float x1, uint32_t& p0, uint32_t& p1) {
+  p0 = 0; p1 = 0;
+#if NPL_JOINT_SEARCH
+#pragma unroll
+  for (int l = LEVELS - 1; l >= 0; --l) {
+    const uint32_t step = 1u << l;
+    const float b0 = lds32f(bp + 4u * (p0 + step - 1u));
+    const float b1 = lds32f(bp + 4u * (p1 + step - 1u));
+    p0 += (b0 <= x0) ? step : 0u;
+    p1 += (b1 <= x1) ? step : 0u;
   }
-  return pos;
+#else
+#pragma unroll 1
+  for (uint32_t step = 1u << (LEVELS - 1); step > 0; step >>= 1) {
+    const float b0 = lds32f(bp + 4u * (p0 + step - 1u));
+    const float b1 = lds32f(bp + 4u * (p1 + step - 1u));
+    p0 += (b0 <= x0) ? step : 0u;
+    p1 += (b1 <= x1) ? step : 0u;
+  }
+#endif
 }
 __device__ __forceinline__ float pwl_entry(uint32_t ent, uint32_t idx, float x) {
   const float4 e = lds128(ent + 16u * idx);
   return fmaf(e.z, x - e.x, e.y);
 }
-__device__ __forceinline__ float eta_el_of(const AeroTabs& t, float el_deg) {
-  return pwl_entry(t.ent_e, pwl_search(t.bp_e, t.levels_e, el_deg), el_deg);
+__device__ __forceinline__ float2 eta_el2(const AeroTabs& t, float2 el_deg) {
+  uint32_t p0, p1;
+  pwl_search2<kLevelsE>(t.bp_e, el_deg.x, el_deg.y, p0, p1);
+  return make_float2(pwl_entry(t.ent_e, p0, el_deg.x), pwl_entry(t.ent_e, p1, el_deg.y));
 }
-// The alpha-only coefficients: net k -> out[k - kFirstA1], k - kFirstA1 < COUNT.
+// The alpha-only coefficients of one aircraft from its merged-segment index m: net k -> out[k - kFirstA1],
+// k - kFirstA1 < COUNT.
 template <int COUNT>
-__device__ __forceinline__ void alpha_coefs(const void* blob_smem, const AeroTabs& t, float alpha_deg, float* __restrict__ out) {
-  const uint32_t m = pwl_search(t.bp_a, t.levels_a, alpha_deg);
+__device__ __forceinline__ void alpha_coefs(const void* blob_smem, const AeroTabs& t, uint32_t m, float alpha_deg,
+                                            float* __restrict__ out) {
   const uint32_t row = t.segmap + (uint32_t)kSegmapRowBytes * m;
   const int32_t* taboff = reinterpret_cast<const int32_t*>(blob_smem) + kHdrTabOff;
 #pragma unroll
@@ -442,6 +468,18 @@ __device__ __forceinline__ void box_muller(uint32_t a, uint32_t b, float& n0, fl
   const float r = sqrtf(-2.0f * __logf(u1));
   float sn, cs;
   __sincosf(kTwoPi * u01(b), &sn, &cs);
+  n0 = r * cs;
+  n1 = r * sn;
+}
+// Two standard normals from ONE 32-bit word (observation noise only): 16-bit radius and angle uniforms taken at
+// bin midpoints, fast-math log / sqrt / sincos.  |n| <= 4.8; mean 0, variance 1 to < 1e-4.
+__device__ __forceinline__ void box_muller16(uint32_t w, float& n0, float& n1) {
+  const float u1 = ((float)(w >> 16) + 0.5f) * 1.52587890625e-5f;     // (0,1)
+  const float th = ((float)(w & 0xFFFFu) + 0.5f) * (kTwoPi * 1.52587890625e-5f);
+  float r;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(-2.0f * __logf(u1)));
+  float sn, cs;
+  __sincosf(th, &sn, &cs);
   n0 = r * cs;
   n1 = r * sn;
 }

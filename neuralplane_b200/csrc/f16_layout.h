@@ -82,6 +82,8 @@ constexpr int mlp_offset(int k) {      // word offset of MLP net k's weights (k 
   return off;
 }
 constexpr int kWeightFloats = mlp_offset(kFirstA1) - kWeightOff;
+constexpr int kLevelsA = 10;           // merged alpha breakpoint list: 2^10 - 1 slots (+inf padded)
+constexpr int kLevelsE = 6;            // eta_el breakpoint list: 2^6 - 1 slots
 constexpr int kSegmapRowBytes = 24;    // 21 alpha nets, padded to 6 words
 constexpr int kMaxAeroBytes = 72 * 1024;
 static_assert(kWeightOff % 4 == 0 && kWeightFloats % 4 == 0, "16-byte alignment of the weight block");

@@ -23,6 +23,10 @@
 
 using namespace npl;
 
+#ifndef NPL_NOISE16
+#define NPL_NOISE16 1
+#endif
+
 // ------------------------------------------------------------------------------------------------
 // error plumbing
 // ------------------------------------------------------------------------------------------------
@@ -206,6 +210,23 @@ __device__ __forceinline__ void add_obs_noise(const StepParams& p, int i, float*
   } else if (sc != 0.0f) {
     const uint64_t gi = p.cfg.index_base + (uint64_t)i;
     const uint2 key = make_uint2((uint32_t)p.cfg.seed, (uint32_t)(p.cfg.seed >> 32));
+#if NPL_NOISE16
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {  // 3 x 4 words -> 12 pairs of normals, 22 used
+      const uint4 r = philox4x32_10(make_uint4((uint32_t)gi, (uint32_t)(gi >> 32), p.step_index, 0x0B5E0000u + q), key);
+      const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int j = 8 * q + 2 * k;
+        if (j < NP_NUM_OBS) {
+          float n0, n1;
+          box_muller16(w[k], n0, n1);
+          o[j] = o[j] + n0 * sc;
+          o[j + 1] = o[j + 1] + n1 * sc;
+        }
+      }
+    }
+#else
 #pragma unroll
     for (int q = 0; q < 6; ++q) {
       const uint4 r = philox4x32_10(make_uint4((uint32_t)gi, (uint32_t)(gi >> 32), p.step_index, 0x0B5E0000u + q), key);
@@ -217,6 +238,7 @@ __device__ __forceinline__ void add_obs_noise(const StepParams& p, int i, float*
       if (4 * q + 2 < NP_NUM_OBS) o[4 * q + 2] = o[4 * q + 2] + n2 * sc;
       if (4 * q + 3 < NP_NUM_OBS) o[4 * q + 3] = o[4 * q + 3] + n3 * sc;
     }
+#endif
   }
 }
 
@@ -325,7 +347,7 @@ __global__ void __launch_bounds__(BS, MINB) f16_step_kernel(const __grid_constan
         hit[0] |= __float_as_uint(ka.x) == __float_as_uint(s[0][7]) && __float_as_uint(kb.x) == __float_as_uint(s[0][8]);
         hit[1] |= __float_as_uint(ka.y) == __float_as_uint(s[1][7]) && __float_as_uint(kb.y) == __float_as_uint(s[1][8]);
       }
-      miss = __any_sync(0xffffffffu, !(hit[0] && hit[1]));
+      miss = NPL_SYNC ? (__syncthreads_or(!(hit[0] && hit[1])) != 0) : (__any_sync(0xffffffffu, !(hit[0] && hit[1])) != 0);
       if (!miss) {
 #pragma unroll 4
         for (int k = 0; k < kNumAB2; ++k) {
@@ -361,6 +383,9 @@ __global__ void __launch_bounds__(BS, MINB) f16_step_kernel(const __grid_constan
         store_pair(p.cache + (size_t)kNumAB2 * ld, pr, make_float2(s[0][7], s[1][7]), act[1]);
         store_pair(p.cache + (size_t)(kNumAB2 + 1) * ld, pr, make_float2(s[0][8], s[1][8]), act[1]);
       }
+      uint32_t seg[2];
+      pwl_search2<kLevelsA>(tabs.bp_a, adeg.x, adeg.y, seg[0], seg[1]);
+      if (pass == 0) coef2[kEtaEl * BS] = eta_el2(tabs, make_float2(u[0][1], u[1][1]));
 
 #pragma unroll
       for (int q = 0; q < 2; ++q) {
@@ -371,12 +396,11 @@ __global__ void __launch_bounds__(BS, MINB) f16_step_kernel(const __grid_constan
         const Trig g = make_trig(sq);
         const float tp = tfac_pow(sq[2]);
         float a1[kNumA1];
-        alpha_coefs<kNumUsed - kFirstA1>(blob, tabs, q == 0 ? adeg.x : adeg.y, a1);
+        alpha_coefs<kNumUsed - kFirstA1>(blob, tabs, seg[q], q == 0 ? adeg.x : adeg.y, a1);
         const ForcePart fp = force_part(sq, uq[0], uq[2], uq[3], 0.0f, g, tp, cq, CS, a1);
 
         if (pass == 0) {
           // ---- Euler step (F16_model.py:64-67; torchdiffeq fixed-grid euler on t=[0,dt]) ---------------
-          cf[q + kEtaEl * CS] = eta_el_of(tabs, uq[1]);
           float xdot[12];
           nlplant_kin_moments(sq, uq[2], uq[3], 0.0f, g, fp.qbar, fp.vt, fp.b, fp.t, cq, CS, a1, xdot);
           xdot[6] = fp.f.vt_dot; xdot[7] = fp.f.alpha_dot; xdot[8] = fp.f.beta_dot;
@@ -386,9 +410,12 @@ __global__ void __launch_bounds__(BS, MINB) f16_step_kernel(const __grid_constan
           steps[q] += 1;  // env_base.py:102
 
           // ---- observation of the new state (env_base.py:103) ----------------------------------------
+          // (recomputing the trig / atmosphere terms of the new state in pass 1 measured faster than carrying them
+          //  through registers or shared memory across the second MLP evaluation: profiles/r01_variants.txt)
           const Trig g2 = make_trig(sq);
+          const float tp2 = tfac_pow(sq[2]);
           float o[NP_NUM_OBS];
-          make_obs(c, sq, uq, tq, g2, eas2tas_of(tfac_pow(sq[2])), o);
+          make_obs(c, sq, uq, tq, g2, eas2tas_of(tp2), o);
           add_obs_noise(p, idx[q], o);
           if (act[q]) {
             float2* orow = reinterpret_cast<float2*>(p.obs + (size_t)(2 * pr + q) * NP_NUM_OBS);  // 88-B rows: 8-B aligned
@@ -562,11 +589,13 @@ __global__ void __launch_bounds__(kAuxBS) f16_nlplant_kernel(const uint32_t* __r
     eval_ab2_nets(blob, wb, zi, coef2, kAuxBS);
     eval_el3_nets(blob, wb, zi, coef2, kAuxBS, 5);
     float xdot[2][12];
+    uint32_t seg[2];
+    pwl_search2<kLevelsA>(tabs.bp_a, adeg.x, adeg.y, seg[0], seg[1]);
+    coef2[kEtaEl * kAuxBS] = eta_el2(tabs, make_float2(u[0][1], u[1][1]));
 #pragma unroll
     for (int q = 0; q < 2; ++q) {
-      cf[q + kEtaEl * CS] = eta_el_of(tabs, u[q][1]);
       float a1[kNumA1];
-      alpha_coefs<kNumUsed - kFirstA1>(blob, tabs, q == 0 ? adeg.x : adeg.y, a1);
+      alpha_coefs<kNumUsed - kFirstA1>(blob, tabs, seg[q], q == 0 ? adeg.x : adeg.y, a1);
       const Trig g = make_trig(s[q]);
       nlplant_from_coefs(s[q], u[q][0], u[q][2], u[q][3], u[q][4], g, tfac_pow(s[q][2]), cf + q, CS, a1, xdot[q]);
     }
@@ -604,12 +633,15 @@ __global__ void __launch_bounds__(kAuxBS) f16_coeffs_kernel(const uint32_t* __re
     zscores_el2(blob, edeg, zi);
     eval_ab2_nets(blob, wb, zi, coef2, kAuxBS);
     eval_el3_nets(blob, wb, zi, coef2, kAuxBS, 5);
+    uint32_t seg[2];
+    pwl_search2<kLevelsA>(tabs.bp_a, adeg.x, adeg.y, seg[0], seg[1]);
+    const float2 eta2 = eta_el2(tabs, edeg);
 #pragma unroll
     for (int q = 0; q < 2; ++q) {
       const int i = 2 * pr + q;
       float a1[kNumA1];
-      alpha_coefs<kNumA1>(blob, tabs, q == 0 ? adeg.x : adeg.y, a1);
-      const float eta = eta_el_of(tabs, q == 0 ? edeg.x : edeg.y);
+      alpha_coefs<kNumA1>(blob, tabs, seg[q], q == 0 ? adeg.x : adeg.y, a1);
+      const float eta = q == 0 ? eta2.x : eta2.y;
       if (i < n) {
         for (int k = 0; k < kNumSlots; ++k) out[(size_t)k * ld + i] = k == kEtaEl ? eta : cf[q + k * CS];
 #pragma unroll
@@ -625,15 +657,15 @@ __global__ void __launch_bounds__(32) f16_c0_kernel(uint32_t* aero, int aero_byt
   extern __shared__ __align__(128) unsigned char smem_raw[];
   float* blob = reinterpret_cast<float*>(smem_raw);
   float2* coef2 = reinterpret_cast<float2*>(smem_raw + aero_bytes);
-  uint64_t* bar = reinterpret_cast<uint64_t*>(coef2 + kNumSlots);
+  uint64_t* bar = reinterpret_cast<uint64_t*>(coef2 + kNumSlots * 32);
   stage_aero(blob, aero, (uint32_t)aero_bytes, bar);
   const uint32_t wb = aero_base_after_staging(blob);
+  ZIn2 zi;  // every lane evaluates the same point into its own slots (uniform control flow); lane 0 publishes
+  zscores_ab2(blob, make_float2(0.0f * kR2D, 0.0f * kR2D), make_float2(0.0f * kR2D, 0.0f * kR2D), zi);
+  eval_ab2_nets(blob, wb, zi, coef2 + threadIdx.x, 32);
   if (threadIdx.x == 0) {
-    ZIn2 zi;
-    zscores_ab2(blob, make_float2(0.0f * kR2D, 0.0f * kR2D), make_float2(0.0f * kR2D, 0.0f * kR2D), zi);
-    eval_ab2_nets(blob, wb, zi, coef2, 1);
     float* c0 = reinterpret_cast<float*>(aero) + reinterpret_cast<const int32_t*>(blob)[kHdrC0];
-    for (int k = 0; k < kNumAB2; ++k) c0[k] = coef2[kFirstAB2 + k].x;
+    for (int k = 0; k < kNumAB2; ++k) c0[k] = coef2[(kFirstAB2 + k) * 32].x;
   }
 }
 
@@ -678,7 +710,7 @@ int np_aero_create(const float* blob, size_t n_floats, const np_net_desc* descs,
   cudaGetDevice(&a->device);
   NP_CUDA(cudaMalloc(&a->image_dev, a->bytes));
   NP_CUDA(cudaMemcpy(a->image_dev, image.data(), a->bytes, cudaMemcpyHostToDevice));
-  const int c0_smem = a->bytes + kNumSlots * 8 + 16;
+  const int c0_smem = a->bytes + kNumSlots * 32 * 8 + 16;
   NP_CUDA(cudaFuncSetAttribute(f16_c0_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, c0_smem));
   f16_c0_kernel<<<1, 32, c0_smem>>>(a->image_dev, a->bytes);
   NP_CUDA(cudaGetLastError());
