@@ -26,6 +26,17 @@ UNIT = "aircraft-steps/s"
 WORKLOAD = "F16 Heading task, ControlEnv, num_agents=10^6 per GPU, random-policy rollout (BASELINE configs[1])"
 
 
+def measured_traffic(kernel="f16_step_kernel"):
+    """DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture (profiles/traffic.json:
+    dram__bytes_read.sum + dram__bytes_write.sum at n = 10^6), or None."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    try:
+        d = json.load(open(p))[kernel]
+        return float(d["dram_bytes_per_launch"]), d
+    except Exception:
+        return None, None
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -97,7 +108,7 @@ def cpu_port_throughput(n, budget_s, threads=None):
         env.step(acts[steps % 3], draws, noise)
         steps += 1
         el = time.perf_counter() - t0
-        if (el >= budget_s and steps >= 3) or steps >= 50:
+        if (el >= budget_s and steps >= 3) or steps >= 2000:
             break
     return n * steps / el, steps, el, torch.get_num_threads()
 
@@ -167,6 +178,7 @@ def main():
     import torch
     import torch.distributed as dist
     from neuralplane_b200 import ControlEnv, GPUVecEnv
+    from neuralplane_b200.sharding import max_over_ranks, reduce_counters
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
@@ -199,10 +211,7 @@ def main():
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
-    t = torch.tensor([ms], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_max = float(t.item())
+    ms_max = max_over_ranks(ms)
     clocks = sampler.stop() if sampler else None
 
     # end to end through the numpy boundary the runners call (GPUVecEnv.step): pinned host buffers, H2D + D2H inside
@@ -216,18 +225,18 @@ def main():
     for k in range(Ke):
         venv.step(host_actions[k % 2])
     torch.cuda.synchronize()
-    te = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_value = world * n * Ke / float(te.item())
+    e2e_value = world * n * Ke / max_over_ranks(time.perf_counter() - t0)
 
-    counters = env.termination_counters()
+    counters = reduce_counters(env.termination_counters())
     if rank == 0:
         hbm_peak, peak_src = peaks()
         value = world * n * K / (ms_max * 1e-3)
         per_launch_s = ms * 1e-3 / K
         achieved = ALGO_BYTES_PER_STEP * n / per_launch_s / 1e9
         info = env.launch_info()
+        traffic, traffic_src = measured_traffic()
+        if traffic is not None and n != int(traffic_src.get("n", n)):
+            traffic = traffic * n / float(traffic_src["n"])      # per-aircraft traffic is size independent
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -241,9 +250,15 @@ def main():
             "gpu_launches": K,
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                         "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
+                         "frac": achieved / hbm_peak, "traffic": traffic,
+                         "traffic_unit": "bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum)",
+                         "traffic_source": (traffic_src or {}).get("source"),
+                         "algorithmic_bytes_per_launch": ALGO_BYTES_PER_STEP * n, "peak_source": peak_src,
                          "kernel": "f16_step_kernel", "algorithmic_bytes_per_aircraft_step": ALGO_BYTES_PER_STEP,
-                         "fp32_note": "the step is fp32-issue bound (about 190 FLOP/B); see DESIGN.md",
+                         "fp32_note": "the step is fp32-pipe bound, not HBM bound (DESIGN.md section 3): FFMA2 is half rate, so the "
+                                      "7 550 MACs/aircraft-step that remain after the exact table conversion cap K1 at "
+                                      "about 4.9e9 aircraft-steps/s (148 SM x 128 MAC/clk x 1.965 GHz)",
+                         "fma_pipe_frac": (7550.0 * n / per_launch_s) / (148 * 128 * 1.965e9),
                          "reference_equivalent_gflops": ALGO_FLOP_PER_STEP * n / per_launch_s / 1e9},
             "termination_counters": counters,
         }

@@ -25,11 +25,14 @@
 extern "C" {
 #endif
 
-#define NP_ABI_VERSION 1
+#define NP_ABI_VERSION 2
 
 enum { NP_OK = 0, NP_EINVAL = 1, NP_ECUDA = 2, NP_ESTATE = 3 };
 
 enum { NP_TASK_HEADING = 0, NP_TASK_CONTROL = 1, NP_TASK_TRACKING = 2 };
+
+/* aircraft plug-in (control_env.py:22-27): F16 = envs/models/F16_model.py, UAV = envs/models/UAV_model.py */
+enum { NP_MODEL_F16 = 0, NP_MODEL_UAV = 1 };
 
 #define NP_NUM_NETS 43       /* hifi_F16_AeroData.py:44-129 */
 #define NP_NUM_STATE 12      /* F16_model.py:19 */
@@ -69,6 +72,8 @@ typedef struct np_env_cfg {
   float max_distance, min_distance;
   int32_t max_check_interval, min_check_interval;
   float init_T, max_altitude, min_altitude, max_vt, min_vt;
+  int32_t model;        /* NP_MODEL_* ; the UAV plug-in needs no np_aero (pass NULL to np_env_create) */
+  int32_t reserved_;
 } np_env_cfg;
 
 /* Device buffers the env works on (replace the tensors of F16_model.py:19-22, heading_task.py:26-28,
@@ -129,6 +134,11 @@ int np_env_counters(np_env* env, uint64_t* out, void* stream);
  * Backs F16Model.get_extended_state and the getters built on it (F16_model.py:47-49,75-91,132-182). */
 int np_f16_nlplant(const np_aero* aero, const float* s_dev, const float* u_dev, float* xdot_dev, int n, int ld,
                    void* stream);
+
+/* UAVDynamics.nlplant (envs/models/UAV/UAV_dynamics.py:15-84) on SoA rows: xdot_dev [12][ld] from s_dev [12][ld] and
+ * the three body forces u_dev [3+][ld].  Backs UAVModel.get_extended_state and the getters built on it
+ * (UAV_model.py:47-49,72-84,120-157). */
+int np_uav_nlplant(const float* s_dev, const float* u_dev, float* xdot_dev, int n, int ld, void* stream);
 
 /* The 43 coefficient nets (hifi_F16_AeroData.py:748-819): out_dev [43][ld] in f16_aero.npz order from
  * alpha_deg/beta_deg/el_deg [n]. */

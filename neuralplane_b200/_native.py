@@ -19,6 +19,7 @@ NVCC_FLAGS = ["-O3", "-std=c++17", "--expt-relaxed-constexpr", "-gencode", "arch
 
 NP_OK = 0
 TASK_IDS = {"heading": 0, "control": 1, "tracking": 2}
+MODEL_IDS = {"F16": 0, "UAV": 1}
 NUM_NETS, NUM_OBS, NUM_DRAWS, NUM_COUNTERS = 43, 22, 5, 8
 COUNTER_NAMES = ("overload", "low_altitude", "high_speed", "low_speed", "extreme_state", "unreach", "reached", "resets")
 
@@ -40,7 +41,7 @@ class EnvCfg(C.Structure):
                 ("max_distance", C.c_float), ("min_distance", C.c_float),
                 ("max_check_interval", C.c_int32), ("min_check_interval", C.c_int32),
                 ("init_T", C.c_float), ("max_altitude", C.c_float), ("min_altitude", C.c_float),
-                ("max_vt", C.c_float), ("min_vt", C.c_float)]
+                ("max_vt", C.c_float), ("min_vt", C.c_float), ("model", C.c_int32), ("reserved_", C.c_int32)]
 
 
 class Buffers(C.Structure):
@@ -68,6 +69,7 @@ SYMBOLS = {
     "np_env_counters": (C.c_int, [_P, C.POINTER(C.c_uint64), _P]),
     "np_env_launch_info": (C.c_int, [_P, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "np_f16_nlplant": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, _P]),
+    "np_uav_nlplant": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, _P]),
     "np_f16_coeffs": (C.c_int, [_P, _P, _P, _P, _P, C.c_int, C.c_int, _P]),
 }
 
@@ -76,7 +78,7 @@ _lib = None
 
 def build(force=False, verbose=False, extra_flags=()):
     """Compile csrc/nplane.cu for sm_100a into _lib/libnplane.so (nvcc cross-compiles without a GPU)."""
-    srcs = [os.path.join(CSRC, f) for f in ("nplane.cu", "f16_device.cuh", "f16_layout.h", "aero_pack.h")] + [HEADER]
+    srcs = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [HEADER]
     if not force and os.path.exists(LIB_PATH) and all(os.path.getmtime(LIB_PATH) >= os.path.getmtime(s) for s in srcs):
         return LIB_PATH
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"

@@ -20,6 +20,7 @@
 #include "../../include/nplane.h"
 #include "aero_pack.h"
 #include "f16_device.cuh"
+#include "uav_device.cuh"
 
 using namespace npl;
 
@@ -546,6 +547,193 @@ __global__ void __launch_bounds__(256) f16_reset_kernel(const __grid_constant__ 
 }
 
 // ------------------------------------------------------------------------------------------------
+// K2: the UAV plug-in (envs/models/UAV_model.py, UAV/UAV_dynamics.py) behind the same tasks.  Trivial arithmetic,
+// HBM-bound: one aircraft per thread, coalesced SoA rows, one launch per BaseEnv.step().
+// Algorithmic bytes per aircraft-step: 268 = read 96 (s 48, F 12, tgt 12, step 4, flags 4, action 16) +
+// write 172 (s 48, F 12, tgt 12, step 4, flags 4, obs 88, reward 4).
+// ------------------------------------------------------------------------------------------------
+// task.reset on the getter view (heading_task.py:49-69, control_task.py:49-68, tracking_task.py:48-71)
+__device__ __forceinline__ void uav_task_reset(const np_env_cfg& c, const UavView& v, const Draws& r, float* tgt) {
+  if (c.task == NP_TASK_HEADING) {
+    tgt[0] = v.alt + 1000.0f;
+    tgt[1] = wrap_pi(v.heading + (float)(2.0 * 3.141592653589793 / 3.0));
+    tgt[2] = v.vt + 0.0f;
+  } else if (c.task == NP_TASK_CONTROL) {
+    tgt[0] = wrap_pi(v.pitch + 2.0f * (r.d[2] - 0.5f) * c.max_pitch_increment);
+    tgt[1] = wrap_pi(v.heading + 2.0f * (r.d[3] - 0.5f) * c.max_heading_increment);
+    tgt[2] = v.vt + 2.0f * (r.d[4] - 0.5f) * c.max_velocities_u_increment;
+  } else {
+    const float dist = r.d[2] * (c.max_distance - c.min_distance) + c.min_distance;
+    const float th1 = r.d[3] * kPi / 3.0f - (float)(3.141592653589793 / 6.0);
+    const float th2 = r.d[4] * kPi / 3.0f - (float)(3.141592653589793 / 6.0);
+    tgt[0] = v.npos + dist * cosf(th1) * cosf(th2);
+    tgt[1] = v.epos + dist * cosf(th1) * sinf(th2);
+    tgt[2] = v.alt + dist * sinf(th1);
+  }
+}
+
+// UAVModel.reset (UAV_model.py:32-45): SI state, zero forces except u[0] = init_T
+__device__ __forceinline__ void uav_reset_aircraft(const np_env_cfg& c, const Draws& r, float* s, float* F) {
+#pragma unroll
+  for (int j = 0; j < 12; ++j) s[j] = 0.0f;
+  s[2] = (r.d[0] * (c.max_altitude - c.min_altitude) + c.min_altitude) * 0.3048f;
+  s[6] = (r.d[1] * (c.max_vt - c.min_vt) + c.min_vt) * 0.3048f;
+  F[0] = c.init_T; F[1] = 0.0f; F[2] = 0.0f;
+}
+
+// 22-D observation through the getters (heading_task.py:93-152): AOA = AOS = thrust = surfaces = 0 for this model
+__device__ __forceinline__ void uav_make_obs(const np_env_cfg& c, const float* s, const UavView& v, const float* tgt, float* o) {
+  if (c.task == NP_TASK_HEADING) {
+    o[0] = (v.alt - tgt[0]) * 0.3048f / 1000.0f;
+    o[1] = wrap_pi(v.heading - tgt[1]);
+    o[2] = (v.vt - tgt[2]) * 0.3048f / 340.0f;
+  } else if (c.task == NP_TASK_CONTROL) {
+    o[0] = wrap_pi(v.pitch - tgt[0]);
+    o[1] = wrap_pi(v.heading - tgt[1]);
+    o[2] = (v.vt - tgt[2]) * 0.3048f / 340.0f;
+  } else {
+    o[0] = (v.npos - tgt[0]) * 0.3048f / 1000.0f;
+    o[1] = (v.epos - tgt[1]) * 0.3048f / 1000.0f;
+    o[2] = (v.alt - tgt[2]) * 0.3048f / 1000.0f;
+  }
+  const float eas = (v.vt + c.airspeed * 1.0f) / v.e2t;  // UAV_model.py:94-102
+  o[3] = v.alt * 0.3048f / 5000.0f;
+  sincosf(v.roll, &o[4], &o[5]);
+  sincosf(v.pitch, &o[6], &o[7]);
+  o[8] = eas * 0.3048f / 340.0f;
+  o[9] = 0.0f; o[10] = 1.0f; o[11] = 0.0f; o[12] = 1.0f;  // sin / cos of get_AOA() = get_AOS() = 0
+  o[13] = s[9]; o[14] = s[10]; o[15] = s[11];
+  o[16] = 0.0f / 0.225f / 76300.0f * 0.3048f;             // get_thrust() = 0
+  o[17] = 0.0f / 45.0f; o[18] = 0.0f / 45.0f; o[19] = 0.0f / 45.0f; o[20] = 0.0f / 45.0f;
+  o[21] = v.e2t;
+}
+
+template <bool STEP>
+__global__ void __launch_bounds__(256) uav_env_kernel(const __grid_constant__ StepParams p) {
+  const np_env_cfg& c = p.cfg;
+  const int n = c.n, ld = c.ld;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    float s[12], F[3], tgt[3];
+#pragma unroll
+    for (int j = 0; j < 12; ++j) s[j] = p.s[(size_t)j * ld + i];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) F[j] = p.u[(size_t)j * ld + i];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) tgt[j] = p.tgt[(size_t)j * ld + i];
+    int steps = p.step_count[i];
+    const bool rst = (p.flags[i] | p.flags[ld + i] | p.flags[2 * (size_t)ld + i]) != 0;
+
+    // ---- BaseEnv.reset (env_base.py:83-97) ---------------------------------------------------------
+    if (rst) {
+      const Draws r = reset_draws(p, i);
+      uav_reset_aircraft(c, r, s, F);
+      uav_task_reset(c, uav_view(s), r, tgt);
+      steps = 0;
+      atomicAdd(&p.counters[7], 1ull);
+    }
+    bool bad = false, done = false;
+    float rew = 0.0f;
+    if (STEP) {
+      // ---- UAVModel.update (UAV_model.py:51-62): clamp, force low-pass, one explicit Euler step ------------
+      const float4 av = reinterpret_cast<const float4*>(p.action)[i];
+      const float a[3] = {fminf(fmaxf(av.x, -1.0f), 1.0f), fminf(fmaxf(av.y, -1.0f), 1.0f), fminf(fmaxf(av.z, -1.0f), 1.0f)};
+#pragma unroll
+      for (int j = 0; j < 3; ++j) F[j] = 0.9f * F[j] + 0.1f * a[j] * 27000.0f;
+      float xdot[12];
+      uav_nlplant(s, F, xdot);
+      const float h = c.dt - 0.0f;
+#pragma unroll
+      for (int j = 0; j < 12; ++j) s[j] = s[j] + h * xdot[j];
+      steps += 1;
+    }
+    // ---- obs (env_base.py:103) ----------------------------------------------------------------------
+    const UavView v = uav_view(s);
+    {
+      float o[NP_NUM_OBS];
+      uav_make_obs(c, s, v, tgt, o);
+      add_obs_noise(p, i, o);
+      float2* orow = reinterpret_cast<float2*>(p.obs + (size_t)i * NP_NUM_OBS);
+#pragma unroll
+      for (int j = 0; j < NP_NUM_OBS / 2; ++j) orow[j] = make_float2(o[2 * j], o[2 * j + 1]);
+    }
+    if (STEP) {
+      // ---- terminations (task_base.py:75-96) through the getters ------------------------------------------
+      float xdot[12];
+      uav_nlplant(s, F, xdot);                                              // get_acceleration (UAV_model.py:120-130)
+      const float vu = s[6] / 0.3048f, vv = s[7] / 0.3048f, vw = s[8] / 0.3048f;
+      const float ax = xdot[6] / 0.3048f + s[10] * vw - s[11] * vv;
+      const float ay = xdot[7] / 0.3048f + s[11] * vu - s[9] * vw;
+      const float az = xdot[8] / 0.3048f + s[9] * vv - s[10] * vu;
+      const float acc = sqrtf(ax * ax + ay * ay + az * az);
+      const bool overload = (acc - c.acceleration_limit) > 0.0f;
+      const bool low_alt = (v.alt - c.altitude_limit) < 0.0f;
+      const float vel = (v.vt + c.airspeed * 1.0f) * 0.3048f / 340.0f;
+      const bool hi = (vel - c.max_velocity) >= 0.0f;
+      const bool lo = (vel - c.min_velocity) <= 0.0f;
+      const float a_deg = 0.0f * 180.0f / kPi;                              // get_AOA() = get_AOS() = 0
+      const bool ext = (a_deg < c.min_alpha) | (a_deg > c.max_alpha) | (a_deg < c.min_beta) | (a_deg > c.max_beta);
+      const bool late = steps >= c.max_check_interval;
+      bool off;
+      float d0, d1, d2;
+      if (c.task == NP_TASK_HEADING) {
+        const float dpsi = wrap_pi(v.heading - tgt[1]);
+        off = (fabsf(dpsi) >= (float)(3.141592653589793 / 36.0)) | (fabsf(v.alt - tgt[0]) >= 100.0f) |
+              (fabsf(v.vt - tgt[2]) >= 20.0f);
+        done = !off && !late && (steps >= c.min_check_interval);
+        d0 = (v.alt - tgt[0]) * 0.3048f / 1000.0f; d1 = dpsi / kPi; d2 = (v.vt - tgt[2]) * 0.3048f / 340.0f;
+        rew = -(d0 * d0) + -(d1 * d1) + -(d2 * d2);
+      } else if (c.task == NP_TASK_CONTROL) {
+        const float dpsi = wrap_pi(v.heading - tgt[1]);
+        off = (fabsf(dpsi) >= (float)(3.141592653589793 / 36.0)) | (fabsf(v.pitch - tgt[0]) >= (float)(3.141592653589793 / 36.0)) |
+              (fabsf(v.vt - tgt[2]) >= 20.0f);
+        done = !off && !late;
+        d0 = wrap_pi(v.pitch - tgt[0]) / kPi; d1 = dpsi / kPi; d2 = (v.vt - tgt[2]) * 0.3048f / 340.0f;
+        rew = -(d0 * d0) + -(d1 * d1) + -(d2 * d2);
+      } else {
+        off = (fabsf(v.npos - tgt[0]) >= 100.0f) | (fabsf(v.epos - tgt[1]) >= 100.0f) | (fabsf(v.alt - tgt[2]) >= 100.0f);
+        done = !off && !late;
+        d0 = (v.npos - tgt[0]) * 0.3048f / 1000.0f; d1 = (v.epos - tgt[1]) * 0.3048f / 1000.0f;
+        d2 = (v.alt - tgt[2]) * 0.3048f / 1000.0f;
+        rew = 0.1f * (-(d0 * d0) + -(d1 * d1) + -(d2 * d2));
+      }
+      const bool unreach = late && off;
+      bad = overload | low_alt | hi | lo | ext | unreach;
+      rew = rew + (float)(-200 * (int)bad + 200 * (int)done);
+      const bool cause[7] = {overload, low_alt, hi, lo, ext, unreach, done};
+#pragma unroll
+      for (int w = 0; w < 7; ++w)
+        if (cause[w]) atomicAdd(&p.counters[w], 1ull);   // ptxas aggregates warp-uniform-address atomics (REDUX + one ATOM)
+      p.reward[i] = rew;
+    }
+    // ---- store -------------------------------------------------------------------------------------
+#pragma unroll
+    for (int j = 0; j < 12; ++j) p.s[(size_t)j * ld + i] = s[j];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) p.u[(size_t)j * ld + i] = F[j];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) p.tgt[(size_t)j * ld + i] = tgt[j];
+    p.step_count[i] = steps;
+    p.flags[i] = done ? 1 : 0;
+    p.flags[ld + i] = bad ? 1 : 0;
+    p.flags[2 * (size_t)ld + i] = 0;
+  }
+}
+
+__global__ void __launch_bounds__(256) uav_nlplant_kernel(const float* __restrict__ S, const float* __restrict__ U,
+                                                          float* __restrict__ X, int n, int ld) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    float s[12], F[3], xdot[12];
+#pragma unroll
+    for (int j = 0; j < 12; ++j) s[j] = S[(size_t)j * ld + i];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) F[j] = U[(size_t)j * ld + i];
+    uav_nlplant(s, F, xdot);
+#pragma unroll
+    for (int j = 0; j < 12; ++j) X[(size_t)j * ld + i] = xdot[j];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // stand-alone nlplant / coefficient kernels (model plug-in getters, parity tests): same device code as K1,
 // two points per thread
 // ------------------------------------------------------------------------------------------------
@@ -767,8 +955,8 @@ static StepParams make_params(np_env* env, const float* action, const float* dra
   p.cache = reinterpret_cast<float*>(env->buf.workspace_dev);
   p.counters = reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(env->buf.workspace_dev) +
                                                      (((size_t)kCacheRows * env->cfg.ld * 4 + 127) / 128) * 128);
-  p.aero = env->aero->image_dev;
-  p.aero_bytes = env->aero->bytes;
+  p.aero = env->aero ? env->aero->image_dev : nullptr;
+  p.aero_bytes = env->aero ? env->aero->bytes : 0;
   p.action = action;
   p.draws = draws;
   p.noise = noise;
@@ -779,7 +967,9 @@ static StepParams make_params(np_env* env, const float* action, const float* dra
 extern "C" {
 
 int np_env_create(const np_env_cfg* cfg, const np_aero* aero, np_env** out) {
-  if (!cfg || !aero || !out) return fail(NP_EINVAL, "np_env_create: null argument");
+  if (!cfg || !out) return fail(NP_EINVAL, "np_env_create: null argument");
+  if (cfg->model != NP_MODEL_F16 && cfg->model != NP_MODEL_UAV) return fail(NP_EINVAL, "np_env_create: unknown aircraft model");
+  if (cfg->model == NP_MODEL_F16 && !aero) return fail(NP_EINVAL, "np_env_create: the F16 plug-in needs an np_aero");
   if (cfg->n <= 0 || cfg->ld < cfg->n + (cfg->n & 1) || cfg->ld % 4)
     return fail(NP_EINVAL, "np_env_create: need n > 0, ld >= n rounded up to even, ld % 4 == 0");
   if (cfg->task < NP_TASK_HEADING || cfg->task > NP_TASK_TRACKING) return fail(NP_EINVAL, "np_env_create: unknown task");
@@ -817,8 +1007,8 @@ int np_env_bind(np_env* env, const np_buffers* b) {
 
 int np_env_set_cfg(np_env* env, const np_env_cfg* cfg) {
   if (!env || !cfg) return fail(NP_EINVAL, "np_env_set_cfg: null argument");
-  if (cfg->n != env->cfg.n || cfg->ld != env->cfg.ld || cfg->task != env->cfg.task)
-    return fail(NP_EINVAL, "np_env_set_cfg: n, ld and task are fixed at creation");
+  if (cfg->n != env->cfg.n || cfg->ld != env->cfg.ld || cfg->task != env->cfg.task || cfg->model != env->cfg.model)
+    return fail(NP_EINVAL, "np_env_set_cfg: n, ld, task and model are fixed at creation");
   env->cfg = *cfg;
   return NP_OK;
 }
@@ -834,7 +1024,8 @@ int np_env_reset(np_env* env, const float* draws_dev, const float* noise_dev, vo
   env->step_index++;
   const int want = (env->cfg.n + 255) / 256;
   const int grid = want < env->num_sms * 8 ? want : env->num_sms * 8;
-  f16_reset_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(p);
+  if (env->cfg.model == NP_MODEL_UAV) uav_env_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(p);
+  else f16_reset_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(p);
   NP_CUDA(cudaGetLastError());
   return NP_OK;
 }
@@ -845,6 +1036,14 @@ int np_env_step(np_env* env, const float* action_dev, const float* draws_dev, co
   StepParams p = make_params(env, action_dev, draws_dev, noise_dev);
   env->step_index++;
   cudaStream_t st = (cudaStream_t)stream;
+  if (env->cfg.model == NP_MODEL_UAV) {
+    const int want = (env->cfg.n + 255) / 256;
+    env->grid = want < env->num_sms * 8 ? want : env->num_sms * 8;
+    env->smem = 0;
+    uav_env_kernel<true><<<env->grid, 256, 0, st>>>(p);
+    NP_CUDA(cudaGetLastError());
+    return NP_OK;
+  }
   switch (env->block) {
 #ifdef NPLANE_ALL_BLOCKS
     case 128: return launch_step<128, 4>(env, p, st);
@@ -888,6 +1087,14 @@ int np_f16_nlplant(const np_aero* aero, const float* s_dev, const float* u_dev, 
   const int want = ((n + 1) / 2 + kAuxBS - 1) / kAuxBS;
   f16_nlplant_kernel<<<want < 296 ? want : 296, kAuxBS, smem, (cudaStream_t)stream>>>(aero->image_dev, aero->bytes, s_dev, u_dev,
                                                                                    xdot_dev, n, ld);
+  NP_CUDA(cudaGetLastError());
+  return NP_OK;
+}
+
+int np_uav_nlplant(const float* s_dev, const float* u_dev, float* xdot_dev, int n, int ld, void* stream) {
+  if (!s_dev || !u_dev || !xdot_dev || n <= 0 || ld < n) return fail(NP_EINVAL, "np_uav_nlplant: bad argument");
+  const int want = (n + 255) / 256;
+  uav_nlplant_kernel<<<want < 1184 ? want : 1184, 256, 0, (cudaStream_t)stream>>>(s_dev, u_dev, xdot_dev, n, ld);
   NP_CUDA(cudaGetLastError());
   return NP_OK;
 }

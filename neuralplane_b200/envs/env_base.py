@@ -67,6 +67,7 @@ class BaseEnv:
     def _cfg_struct(self):
         c = nv.EnvCfg()
         c.n, c.ld, c.task = self.n, self.ld, self.task.task_id
+        c.model = self.model.model_id
         c.use_coef_cache = 1 if self.use_coef_cache else 0
         c.seed, c.index_base = self._seed & (2 ** 64 - 1), self.index_base
         for key, default in _CFG_KEYS:
@@ -82,7 +83,8 @@ class BaseEnv:
         L = nv.lib()
         self._cfg = self._cfg_struct()
         with torch.cuda.device(self.device):
-            nv.check(L.np_env_create(C.byref(self._cfg), self.model.aero.handle, C.byref(self._handle)), "np_env_create")
+            aero = self.model.aero.handle if self.model.aero is not None else None
+            nv.check(L.np_env_create(C.byref(self._cfg), aero, C.byref(self._handle)), "np_env_create")
             nbytes = L.np_env_workspace_bytes(C.byref(self._cfg))
             self._workspace = torch.zeros(nbytes, dtype=torch.uint8, device=self.device)
             b = nv.Buffers(self.model._s.data_ptr(), self.model._u.data_ptr(), self._tgt.data_ptr(),

@@ -12,6 +12,8 @@ from .model_base import BaseModel
 
 
 class F16Model(BaseModel):
+    model_id = nv.MODEL_IDS["F16"]
+
     def __init__(self, config, n, device, random_seed, aero=None, ld=None):
         super().__init__(config, n, device, random_seed)
         self.num_states = getattr(self.config, 'num_states', 12)

@@ -160,8 +160,34 @@ def recorded_trajectory(name, head=400):
     print(name, {k: v.shape for k, v in out.items()}["npos"])
 
 
+def uav_trajectory(task, n, steps, scale, seed, name):
+    """ControlEnv(model='UAV') from the unmodified reference with num_controls = 3 (the one fix it needs to survive
+    its second step): state / obs / reward / flags at every checkpoint."""
+    ref = RefEnv(n, task, "UAV", seed=0, noise_scale=0.0)
+    ref.env.model.num_controls = 3
+    ref.env.model.u = torch.zeros(n, 3)
+    obs0 = ref.reset(torch.from_numpy(tapes.reset_draw_tape(seed, 0, n)))
+    out = {"obs0": obs0.numpy().copy(), "meta": np.array([n, steps, seed], dtype=np.int64), "scale": np.float32(scale)}
+    n_bad = []
+    for k in range(1, steps + 1):
+        a = torch.from_numpy(tapes.action_tape(seed, k, n, scale))
+        d = torch.from_numpy(tapes.reset_draw_tape(seed, k, n))
+        obs, rew, done, bad, exc = ref.step(a, d)
+        n_bad.append(int(bad.sum()))
+        if k in CHECKPOINTS or k == steps:
+            for key, v in snap(ref, obs, rew, done, bad, exc).items():
+                out[f"k{k}_{key}"] = v
+    out["n_bad"] = np.array(n_bad, dtype=np.int32)
+    np.savez_compressed(os.path.join(HERE, name), **out)
+    print(name, "bad events", sum(n_bad))
+
+
 if __name__ == "__main__":
     torch.set_num_threads(8)
+    if len(sys.argv) > 1 and sys.argv[1] == "uav":          # regenerate only the UAV fixtures
+        uav_trajectory("control", 64, 400, 1.0, 15, "uav_control_traj.npz")
+        uav_trajectory("heading", 64, 400, 1.0, 16, "uav_heading_traj.npz")
+        sys.exit(0)
     recorded_trajectory("ref_recorded_trajectory.npz")
     nlplant_kat("f16_nlplant_kat.npz")
     done_branch("heading_done_branch.npz")
@@ -171,3 +197,5 @@ if __name__ == "__main__":
                                               ("tracking", 64, 300, 1.0, 14, "tracking_traj.npz")):
         trajectory(task, n, steps, scale, seed, name)
         add_truth(name, task)
+    uav_trajectory("control", 64, 400, 1.0, 15, "uav_control_traj.npz")
+    uav_trajectory("heading", 64, 400, 1.0, 16, "uav_heading_traj.npz")

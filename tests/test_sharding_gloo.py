@@ -1,0 +1,64 @@
+"""Host-side N>1 logic on CPU: world_size-2 gloo process group (the GPU path uses the same functions over nccl)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from neuralplane_b200.sharding import gather_rows, max_over_ranks, reduce_counters, shard_range
+
+
+@pytest.mark.parametrize("n,world", [(1_000_000, 1), (1_000_000, 2), (1_000_000, 8), (1_000_001, 8), (7, 4), (1, 2), (0, 3)])
+def test_shard_ranges_partition_the_population(n, world):
+    spans = [shard_range(n, r, world) for r in range(world)]
+    pos = 0
+    for r, (lo, cnt) in enumerate(spans):
+        assert lo == pos or cnt == 0
+        assert lo % 2 == 0                      # pairs are never split across ranks
+        pos = lo + cnt if cnt else pos
+    assert pos == n
+    sizes = [c for _, c in spans]
+    assert max(sizes) - min(sizes) <= 2
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, n_total, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        lo, cnt = shard_range(n_total, rank, world)
+        counters = {"overload": 10 * (rank + 1), "resets": cnt, "reached": rank}
+        red = reduce_counters(counters)
+        ms = max_over_ranks(1.0 + rank)
+        rows = torch.arange(lo, lo + cnt, dtype=torch.float32).reshape(-1, 1).repeat(1, 8)   # 8-float records
+        allrows = gather_rows(rows)
+        q.put((rank, lo, cnt, red, ms, allrows[:, 0].numpy().copy()))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_world_size_2_collectives_over_gloo():
+    world, n_total = 2, 4096
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, n_total, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted((q.get(timeout=120) for _ in procs), key=lambda x: x[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, lo, cnt, red, ms, col in res:
+        assert red == {"overload": 30, "resets": n_total, "reached": 1}
+        assert ms == 2.0
+        assert np.array_equal(col, np.arange(n_total, dtype=np.float32))      # rank-ordered gather = global order
+    assert res[0][1] == 0 and res[0][2] + res[1][2] == n_total
