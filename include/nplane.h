@@ -125,6 +125,22 @@ int np_env_reset(np_env* env, const float* draws_dev, const float* noise_dev, vo
 int np_env_step(np_env* env, const float* action_dev, const float* draws_dev, const float* noise_dev,
                 void* stream);
 
+/* PlanningEnv.step(action) (envs/planning_env.py:144-177) as ONE kernel launch: reset -> clamp -> pitch / heading /
+ * speed targets from the 3-D high-level action (:146-152) -> n_sub (reference: 50) x { low-level controller ->
+ * F16Model.update -> freeze aircraft already terminated in this env step (:162-166) -> step_count -> terminations,
+ * OR-accumulated } -> obs / reward of the last sub-step.  The low-level controller is the reference's PID stack
+ * (algorithms/pid/controller.py:43-74,114-148 etc., see csrc/ctrl_device.cuh) in place of the GRU PPO actor whose
+ * checkpoint the reference does not ship (planning_env.py:16).  action3_dev: [n][3] row-major.  The controller state
+ * ([12][ld] floats) lives in the workspace and persists across episodes, as the reference's Controller does. */
+int np_env_plan_step(np_env* env, const float* action3_dev, int n_sub, const float* draws_dev, const float* noise_dev,
+                     void* stream);
+
+/* Byte offset, inside the workspace, of the controller state block [12][ld] f32: rows {roll, pitch, yaw, speed} x
+ * {error, integrator, last_out} (pid.py:22-33, rollController.py:24,40).  Lets the host wrapper expose it. */
+size_t np_env_pid_offset_bytes(const np_env_cfg* cfg);
+/* started = 0 re-arms the first-call initialisation of the PIDs (PID.reset, pid.py:13,22-27). */
+int np_env_set_pid_started(np_env* env, int started);
+
 /* Termination-cause counters accumulated on device since creation (replaces the per-condition
  * print(torch.sum(bad_done)) host syncs, e.g. overload.py:32-34).  Synchronises `stream`.
  * out[0..7] = overload, low_altitude, high_speed, low_speed, extreme_state, unreach, reached(done), resets. */

@@ -11,5 +11,6 @@ buffers.  There is no CPU fallback.
 from .envs.control_env import ControlEnv  # noqa: F401
 from .envs.env_base import BaseEnv  # noqa: F401
 from .envs.env_wrappers import GPUVecEnv  # noqa: F401
+from .envs.planning_env import PlanningEnv  # noqa: F401
 
-__all__ = ["ControlEnv", "BaseEnv", "GPUVecEnv"]
+__all__ = ["ControlEnv", "PlanningEnv", "BaseEnv", "GPUVecEnv"]

@@ -21,6 +21,7 @@
 #include "aero_pack.h"
 #include "f16_device.cuh"
 #include "uav_device.cuh"
+#include "ctrl_device.cuh"
 
 using namespace npl;
 
@@ -60,6 +61,7 @@ struct np_env {
   np_buffers buf;
   bool bound = false;
   uint32_t step_index = 0;
+  bool pid_started = false;  // the fused PID controller has run at least once (PID.reset, pid.py:13)
   int block = 256, grid = 0, smem = 0, num_sms = 0;
 };
 
@@ -76,7 +78,10 @@ struct StepParams {
   unsigned long long* counters;  // [NP_NUM_COUNTERS]
   const uint32_t* aero;          // device image, aero_bytes
   int aero_bytes;
-  const float* action;           // [n][4]
+  const float* action;           // [n][4]; planning step: [n][3]
+  float* pid;                    // [kPidRows][ld] controller state (planning step)
+  int n_sub;                     // FDM sub-steps per env step (planning: 50, planning_env.py:153)
+  int pid_first;                 // 1: the controllers have never run (PID.reset, pid.py:13)
   const float* draws;            // [n][5] or null
   const float* noise;            // [n][22] or null
   uint32_t step_index;
@@ -260,7 +265,11 @@ __device__ __forceinline__ void count_cause2(unsigned long long* counters, int w
 // ------------------------------------------------------------------------------------------------
 static int step_smem_bytes(int aero_bytes, int bs) { return aero_bytes + kNumSlots * bs * 8 + 16; }
 
-template <int BS, int MINB>
+// PLAN = false: BaseEnv.step (one FDM step driven by the caller's 4-D action).
+// PLAN = true : PlanningEnv.step (planning_env.py:144-177): the caller's 3-D action sets pitch / heading / speed targets
+//               that the fused PID controller (ctrl_device.cuh) tracks for n_sub FDM sub-steps; aircraft that terminate
+//               inside the env step are frozen (s <- recent_s); state stays in registers across the sub-steps.
+template <int BS, int MINB, bool PLAN>
 __global__ void __launch_bounds__(BS, MINB) f16_step_kernel(const __grid_constant__ StepParams p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   float* blob = reinterpret_cast<float*>(smem_raw);
@@ -316,11 +325,16 @@ __global__ void __launch_bounds__(BS, MINB) f16_step_kernel(const __grid_constan
     }
 #pragma unroll
     for (int q = 0; q < 2; ++q) {
-      const float4 av = reinterpret_cast<const float4*>(p.action)[idx[q]];
-      a[q][0] = av.x; a[q][1] = av.y; a[q][2] = av.z; a[q][3] = av.w;
+      if (PLAN) {
+        a[q][0] = p.action[(size_t)idx[q] * 3 + 0]; a[q][1] = p.action[(size_t)idx[q] * 3 + 1];
+        a[q][2] = p.action[(size_t)idx[q] * 3 + 2]; a[q][3] = 0.0f;
+      } else {
+        const float4 av = reinterpret_cast<const float4*>(p.action)[idx[q]];
+        a[q][0] = av.x; a[q][1] = av.y; a[q][2] = av.z; a[q][3] = av.w;
+      }
     }
 
-    // ---- episodic reset of terminated aircraft (env_base.py:83-97) + control low-pass (F16_model.py:52-57) ----
+    // ---- episodic reset of terminated aircraft (env_base.py:83-97) --------------------------------------------
 #pragma unroll
     for (int q = 0; q < 2; ++q) {
       if (rst[q]) {
@@ -328,12 +342,23 @@ __global__ void __launch_bounds__(BS, MINB) f16_step_kernel(const __grid_constan
         reset_aircraft(c, r, s[q], u[q], tgt[q]);
         steps[q] = 0;
       }
+    }
+    // planning step: targets from the high-level action (planning_env.py:146-152) and the controller state
+    float plan_tgt[2][3], pid[2][kPidRows];
+    if (PLAN) {
 #pragma unroll
-      for (int j = 0; j < 4; ++j) a[q][j] = fminf(fmaxf(a[q][j], -1.0f), 1.0f);
-      u[q][0] = 0.9f * u[q][0] + 0.1f * a[q][0] * 0.225f * 76300.0f / 0.3048f;
-      u[q][1] = 0.9f * u[q][1] + 0.1f * a[q][1] * 45.0f;
-      u[q][2] = 0.9f * u[q][2] + 0.1f * a[q][2] * 45.0f;
-      u[q][3] = 0.9f * u[q][3] + 0.1f * a[q][3] * 45.0f;
+      for (int q = 0; q < 2; ++q) {
+#pragma unroll
+        for (int j = 0; j < 3; ++j) a[q][j] = fminf(fmaxf(a[q][j], -1.0f), 1.0f);
+        plan_tgt[q][0] = s[q][4] + a[q][0] * 0.3f;
+        plan_tgt[q][1] = s[q][5] + a[q][1] * 0.3f;
+        plan_tgt[q][2] = s[q][6] + a[q][2] * 30.0f;
+      }
+#pragma unroll
+      for (int j = 0; j < kPidRows; ++j) {
+        const float2 v = reinterpret_cast<const float2*>(p.pid + (size_t)j * ld)[prl];
+        pid[0][j] = v.x; pid[1][j] = v.y;
+      }
     }
     count_cause2(p.counters, 7, rst[0] && act[0], rst[1] && act[1]);
 
@@ -365,9 +390,24 @@ __global__ void __launch_bounds__(BS, MINB) f16_step_kernel(const __grid_constan
 
     // ---- two passes over the same code: pass 0 = Euler derivative at (s, u'), then obs of the new state;
     //      pass 1 = force equations at (s', u') for the Overload check, terminations, reward ------------------
-    bool bad[2], done[2];
+    bool bad[2] = {false, false}, done[2] = {false, false};   // flags were cleared by the reset above (env_base.py:93-95)
     float rew[2];
     int causes[2] = {0, 0};
+    const int nsub = PLAN ? p.n_sub : 1;
+#pragma unroll 1
+    for (int sub = 0; sub < nsub; ++sub) {
+    // ---- action of this FDM step + control low-pass (F16_model.py:52-57) ------------------------------------
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      if (PLAN) pid_controller(s[q], c.airspeed, c.dt, plan_tgt[q][0], plan_tgt[q][1], plan_tgt[q][2], pid[q],
+                               p.pid_first != 0 && sub == 0, a[q]);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) a[q][j] = fminf(fmaxf(a[q][j], -1.0f), 1.0f);
+      u[q][0] = 0.9f * u[q][0] + 0.1f * a[q][0] * 0.225f * 76300.0f / 0.3048f;
+      u[q][1] = 0.9f * u[q][1] + 0.1f * a[q][1] * 45.0f;
+      u[q][2] = 0.9f * u[q][2] + 0.1f * a[q][2] * 45.0f;
+      u[q][3] = 0.9f * u[q][3] + 0.1f * a[q][3] * 45.0f;
+    }
 #pragma unroll 1
     for (int pass = 0; pass < 2; ++pass) {
       const uint32_t wb = opaque_u32(wb0);
@@ -376,9 +416,10 @@ __global__ void __launch_bounds__(BS, MINB) f16_step_kernel(const __grid_constan
       ZIn2 zi;
       zscores_ab2(blob, adeg, bdeg, zi);
       zscores_el2(blob, make_float2(u[0][1], u[1][1]), zi);
-      if (pass == 1 || miss) eval_ab2_nets(blob, wb, zi, coef2, BS);
+      // after the first sub-step the slots already hold the outputs at the current (alpha, beta): pass 1 left them there
+      if (pass == 1 || (miss && sub == 0)) eval_ab2_nets(blob, wb, zi, coef2, BS);
       eval_el3_nets(blob, wb, zi, coef2, BS, pass == 0 ? 5 : 2);
-      if (pass == 1 && use_cache && act[0]) {  // the next step's Euler derivative needs exactly these
+      if (pass == 1 && use_cache && act[0] && sub == nsub - 1) {  // the next step's Euler derivative needs exactly these
 #pragma unroll 4
         for (int k = 0; k < kNumAB2; ++k) store_pair(p.cache + (size_t)k * ld, pr, coef2[(kFirstAB2 + k) * BS], act[1]);
         store_pair(p.cache + (size_t)kNumAB2 * ld, pr, make_float2(s[0][7], s[1][7]), act[1]);
@@ -406,9 +447,11 @@ __global__ void __launch_bounds__(BS, MINB) f16_step_kernel(const __grid_constan
           nlplant_kin_moments(sq, uq[2], uq[3], 0.0f, g, fp.qbar, fp.vt, fp.b, fp.t, cq, CS, a1, xdot);
           xdot[6] = fp.f.vt_dot; xdot[7] = fp.f.alpha_dot; xdot[8] = fp.f.beta_dot;
           const float h = c.dt - 0.0f;
+          const bool frozen = PLAN && (bad[q] || done[q]);  // planning_env.py:162-166: s <- recent_s (u keeps filtering)
 #pragma unroll
-          for (int j = 0; j < 12; ++j) sq[j] = sq[j] + h * xdot[j];
+          for (int j = 0; j < 12; ++j) sq[j] = frozen ? sq[j] : sq[j] + h * xdot[j];
           steps[q] += 1;  // env_base.py:102
+          if (PLAN && sub != nsub - 1) continue;  // only the last sub-step's observation is returned (:177)
 
           // ---- observation of the new state (env_base.py:103) ----------------------------------------
           // (recomputing the trig / atmosphere terms of the new state in pass 1 measured faster than carrying them
@@ -465,15 +508,17 @@ __global__ void __launch_bounds__(BS, MINB) f16_step_kernel(const __grid_constan
             rw = 0.1f * (-(d0 * d0) + -(d1 * d1) + -(d2 * d2));
           }
           const bool unreach = late && off;
-          bad[q] = overload | low_alt | hi | lo | ext | unreach;
-          done[q] = dn;
-          rew[q] = rw + (float)(-200 * (int)bad[q] + 200 * (int)dn);           // event_driven_reward.py:28
-          causes[q] = act[q] ? ((int)overload | ((int)low_alt << 1) | ((int)hi << 2) | ((int)lo << 3) | ((int)ext << 4) |
-                                ((int)unreach << 5) | ((int)dn << 6))
-                             : 0;
+          bad[q] |= overload | low_alt | hi | lo | ext | unreach;               // OR-accumulated (env_base.py:70-75)
+          done[q] |= dn;
+          rew[q] = rw + (float)(-200 * (int)bad[q] + 200 * (int)done[q]);       // event_driven_reward.py:28
+          causes[q] |= act[q] ? ((int)overload | ((int)low_alt << 1) | ((int)hi << 2) | ((int)lo << 3) | ((int)ext << 4) |
+                                 ((int)unreach << 5) | ((int)dn << 6))
+                              : 0;
         }
       }
     }
+
+    }  // sub-steps
 
     // ---- termination-cause counters (replace the reference's per-condition print(torch.sum(...)) syncs) --------
 #pragma unroll
@@ -488,6 +533,10 @@ __global__ void __launch_bounds__(BS, MINB) f16_step_kernel(const __grid_constan
 #pragma unroll
       for (int j = 0; j < 3; ++j) store_pair(p.tgt + (size_t)j * ld, pr, make_float2(tgt[0][j], tgt[1][j]), act[1]);
       store_pair(p.reward, pr, make_float2(rew[0], rew[1]), act[1]);
+      if (PLAN) {
+#pragma unroll
+        for (int j = 0; j < kPidRows; ++j) store_pair(p.pid + (size_t)j * ld, pr, make_float2(pid[0][j], pid[1][j]), act[1]);
+      }
       if (act[1]) {
         reinterpret_cast<int2*>(p.step_count)[pr] = make_int2(steps[0], steps[1]);
         reinterpret_cast<uchar2*>(p.flags)[pr] = make_uchar2(done[0] ? 1 : 0, done[1] ? 1 : 0);
@@ -916,16 +965,16 @@ int np_aero_destroy(np_aero* aero) {
 
 size_t np_env_workspace_bytes(const np_env_cfg* cfg) {
   if (!cfg) return 0;
-  return (((size_t)kCacheRows * (size_t)cfg->ld * sizeof(float) + 127) / 128) * 128 + 256 /* counters */;
+  return (((size_t)(kCacheRows + kPidRows) * (size_t)cfg->ld * sizeof(float) + 127) / 128) * 128 + 256 /* counters */;
 }
 
 }  // extern "C"
 
-template <int BS, int MINB>
+template <int BS, int MINB, bool PLAN>
 static int launch_step(np_env* env, const StepParams& p, cudaStream_t st) {
   const int smem = step_smem_bytes(p.aero_bytes, BS);
   static int configured[64] = {};  // per device: the attribute lives in the device's context
-  auto kern = f16_step_kernel<BS, MINB>;
+  auto kern = f16_step_kernel<BS, MINB, PLAN>;
   int dev = 0;
   NP_CUDA(cudaGetDevice(&dev));
   if (configured[dev & 63] < smem) {
@@ -953,8 +1002,11 @@ static StepParams make_params(np_env* env, const float* action, const float* dra
   p.obs = env->buf.obs_dev;
   p.reward = env->buf.reward_dev;
   p.cache = reinterpret_cast<float*>(env->buf.workspace_dev);
+  p.pid = p.cache + (size_t)kCacheRows * env->cfg.ld;
+  p.n_sub = 1;
+  p.pid_first = 0;
   p.counters = reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(env->buf.workspace_dev) +
-                                                     (((size_t)kCacheRows * env->cfg.ld * 4 + 127) / 128) * 128);
+                                                     (((size_t)(kCacheRows + kPidRows) * env->cfg.ld * 4 + 127) / 128) * 128);
   p.aero = env->aero ? env->aero->image_dev : nullptr;
   p.aero_bytes = env->aero ? env->aero->bytes : 0;
   p.action = action;
@@ -1046,13 +1098,36 @@ int np_env_step(np_env* env, const float* action_dev, const float* draws_dev, co
   }
   switch (env->block) {
 #ifdef NPLANE_ALL_BLOCKS
-    case 128: return launch_step<128, 4>(env, p, st);
-    case 384: return launch_step<384, 1>(env, p, st);
-    case 512: return launch_step<512, 1>(env, p, st);
+    case 128: return launch_step<128, 4, false>(env, p, st);
+    case 384: return launch_step<384, 1, false>(env, p, st);
+    case 512: return launch_step<512, 1, false>(env, p, st);
 #endif
-    case 256: return launch_step<256, 2>(env, p, st);
+    case 256: return launch_step<256, 2, false>(env, p, st);
     default: return fail(NP_EINVAL, "np_env_step: block size not compiled in (build with -DNPLANE_ALL_BLOCKS)");
   }
+}
+
+int np_env_plan_step(np_env* env, const float* action3_dev, int n_sub, const float* draws_dev, const float* noise_dev,
+                     void* stream) {
+  if (!env || !env->bound) return fail(NP_ESTATE, "np_env_plan_step: env not bound");
+  if (env->cfg.model != NP_MODEL_F16) return fail(NP_EINVAL, "np_env_plan_step: the fused PID controller flies the F16 plug-in");
+  if (!action3_dev || ((uintptr_t)action3_dev & 3) || n_sub < 1) return fail(NP_EINVAL, "np_env_plan_step: bad action pointer or n_sub");
+  StepParams p = make_params(env, action3_dev, draws_dev, noise_dev);
+  p.n_sub = n_sub;
+  p.pid_first = env->pid_started ? 0 : 1;
+  env->pid_started = true;
+  env->step_index++;
+  return launch_step<256, 2, true>(env, p, (cudaStream_t)stream);
+}
+
+size_t np_env_pid_offset_bytes(const np_env_cfg* cfg) {
+  return cfg ? (size_t)kCacheRows * (size_t)cfg->ld * sizeof(float) : 0;
+}
+
+int np_env_set_pid_started(np_env* env, int started) {
+  if (!env) return fail(NP_EINVAL, "np_env_set_pid_started: null env");
+  env->pid_started = started != 0;
+  return NP_OK;
 }
 
 int np_env_counters(np_env* env, uint64_t* out, void* stream) {

@@ -160,6 +160,90 @@ def recorded_trajectory(name, head=400):
     print(name, {k: v.shape for k, v in out.items()}["npos"])
 
 
+class RefPidPlanner:
+    """PlanningEnv.step (envs/planning_env.py:144-177) assembled from the reference's OWN parts, with the low-level
+    GRU PPO actor (whose checkpoint is not in the repository, planning_env.py:16) replaced by the reference's PID
+    stack: RollController / PitchController / YawController (`Controller.stabilize`, algorithms/pid/controller.py:
+    69-74), `L1Controller.update_heading_hold` + `nav_roll` for the heading target (controller.py:114-124), the
+    pitch target fed straight to the pitch loop, and a TAS loop built from the reference `PID` class with the gains
+    of algorithms/pid/config/speedcontroller.yaml (the reference's SpeedController class itself is not runnable:
+    it reads attributes it never defines, speedController.py:24-45).  Everything that is stepped -- F16Model,
+    TrackingTask, terminations, rewards, the controllers -- is unmodified reference code."""
+
+    N_SUB = 50
+
+    def __init__(self, n):
+        import_reference()
+        if REF_ROOT not in sys.path:
+            sys.path.insert(0, REF_ROOT)
+        from algorithms.pid.controller import Controller
+        import algorithms.pid.pid as pid
+        self.ref = RefEnv(n, "tracking", "F16", seed=0, noise_scale=0.0)
+        env = self.ref.env
+        with contextlib.redirect_stdout(io.StringIO()):
+            self.ctl = Controller(dt=env.model.dt, n=n, device="cpu")
+        self.speed_pid = pid.PID(Kp=5, Ki=25, Kd=0, Kff=80, Kimax=100, dt=env.model.dt, n=n, device="cpu")
+        self.speed_last_out = torch.zeros((n, 1))
+
+    def step(self, action, draws):
+        ref, env, ctl = self.ref, self.ref.env, self.ctl
+        with contextlib.redirect_stdout(io.StringIO()):
+            with ref._inject(draws):
+                env.reset()                                                     # :145
+            action = torch.clamp(action, -1, 1)
+            roll, pitch, yaw = env.model.get_posture()
+            vt = env.model.get_vt()
+            target_pitch = pitch + action[:, 0] * 0.3                           # :150-152
+            target_heading = yaw + action[:, 1] * 0.3
+            target_vt = vt + action[:, 2] * 30
+            for i in range(self.N_SUB):
+                ctl.pitch_dem = target_pitch.reshape(-1, 1)
+                ctl.update_heading_hold(target_heading.reshape(-1, 1), env)
+                TAS = env.model.get_TAS().reshape(-1, 1)
+                limit = torch.abs(self.speed_last_out) >= 100
+                self.speed_pid.update_all(target_vt.reshape(-1, 1) * 0.3048 / 340, TAS * 0.3048 / 340, limit)
+                out = self.speed_pid.get_ff() + self.speed_pid.get_p() + self.speed_pid.get_i() + self.speed_pid.get_d()
+                self.speed_last_out = out
+                ctl.throttle_dem = torch.clamp(out / 100, 0, 1)
+                ctl.stabilize(env)
+                ego_actions = ctl.get_action()
+                env.model.update(ego_actions)                                   # :160
+                reset = (env.is_done.bool() | env.bad_done.bool()) | env.exceed_time_limit.bool()
+                env.model.s[reset] = env.model.recent_s[reset]                  # :162-166
+                env.step_count += 1
+                obs = env.obs()
+                done, bad_done, exceed, _ = env.done({})
+                reward = env.reward()
+        self.targets = torch.stack((target_pitch, target_heading, target_vt), 1)
+        return obs, reward, done, bad_done, exceed
+
+    def pid_state(self):
+        c = self.ctl
+        rows = []
+        for p, last in ((c.roll_controller.rate_pid, c.roll_controller.last_out), (c.pitch_controller.rate_pid, c.pitch_controller.last_out),
+                        (c.yaw_controller.rate_pid, c.yaw_controller.last_out), (self.speed_pid, self.speed_last_out)):
+            rows += [p.error.reshape(-1), p.integrator.reshape(-1), last.reshape(-1)]
+        return torch.stack(rows, 1)
+
+
+def planning_trajectory(n, steps, scale, seed, name):
+    """RefPidPlanner trajectory: one record per planning step (= 50 reference sub-steps)."""
+    pl = RefPidPlanner(n)
+    ref = pl.ref
+    obs0 = ref.reset(torch.from_numpy(tapes.reset_draw_tape(seed, 0, n)))
+    out = {"obs0": obs0.numpy().copy(), "meta": np.array([n, steps, seed], dtype=np.int64), "scale": np.float32(scale)}
+    for k in range(1, steps + 1):
+        a = torch.from_numpy(tapes.action_tape(seed, k, n, scale, num_actions=3))
+        d = torch.from_numpy(tapes.reset_draw_tape(seed, k, n))
+        obs, rew, done, bad, exc = pl.step(a, d)
+        for key, v in snap(ref, obs, rew, done, bad, exc).items():
+            out[f"k{k}_{key}"] = v
+        out[f"k{k}_pid"] = pl.pid_state().numpy().copy()
+        out[f"k{k}_targets"] = pl.targets.numpy().copy()
+        print(name, "planning step", k, "bad", int(bad.sum()), "done", int(done.sum()), flush=True)
+    np.savez_compressed(os.path.join(HERE, name), **out)
+
+
 def uav_trajectory(task, n, steps, scale, seed, name):
     """ControlEnv(model='UAV') from the unmodified reference with num_controls = 3 (the one fix it needs to survive
     its second step): state / obs / reward / flags at every checkpoint."""
@@ -184,6 +268,9 @@ def uav_trajectory(task, n, steps, scale, seed, name):
 
 if __name__ == "__main__":
     torch.set_num_threads(8)
+    if len(sys.argv) > 1 and sys.argv[1] == "planning":     # regenerate only the planning fixture
+        planning_trajectory(48, 16, 1.0, 17, "planning_pid_traj.npz")
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "uav":          # regenerate only the UAV fixtures
         uav_trajectory("control", 64, 400, 1.0, 15, "uav_control_traj.npz")
         uav_trajectory("heading", 64, 400, 1.0, 16, "uav_heading_traj.npz")
@@ -199,3 +286,4 @@ if __name__ == "__main__":
         add_truth(name, task)
     uav_trajectory("control", 64, 400, 1.0, 15, "uav_control_traj.npz")
     uav_trajectory("heading", 64, 400, 1.0, 16, "uav_heading_traj.npz")
+    planning_trajectory(48, 16, 1.0, 17, "planning_pid_traj.npz")
