@@ -145,7 +145,7 @@ def run_reference(args, rank, world):
     el = time.perf_counter() - t0
     v = n * K / el
     sample = f"{K} steps x {n} aircraft of the same workload (oracle port, torch CPU ops, {thr} threads)"
-    print(json.dumps({
+    args.emit(({
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": K, "warmup": W,
         "ms_per_step": 1e3 * el / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic", "config": {"workload": WORKLOAD, "sample_aircraft": n},
@@ -172,6 +172,17 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    # stdout carries exactly ONE JSON line: libraries that print there (NCCL's version banner) go to stderr instead
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(obj):
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
+        print(json.dumps(obj), flush=True)
+
+    args.emit = emit
     if args.impl == "reference":
         return run_reference(args, rank, world)
 
@@ -267,7 +278,7 @@ def main():
             out["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": thr, "kind": "port",
                                    "sample": f"{steps} steps x {args.cpu_n} aircraft of the same workload in {el:.1f} s "
                                              f"(oracle port of the reference step, torch CPU ops)"}
-        print(json.dumps(out))
+        emit(out)
     if world > 1:
         dist.destroy_process_group()
 
