@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define NP_ABI_VERSION 2
+#define NP_ABI_VERSION 3
 
 enum { NP_OK = 0, NP_EINVAL = 1, NP_ECUDA = 2, NP_ESTATE = 3 };
 
@@ -39,6 +39,7 @@ enum { NP_MODEL_F16 = 0, NP_MODEL_UAV = 1 };
 #define NP_NUM_CTRL 5        /* F16_model.py:21 (T, el, ail, rud, lef; lef is always 0, F16_model.py:57) */
 #define NP_NUM_TGT 3         /* heading: alt,psi,vt | control: theta,psi,vt | tracking: npos,epos,alt */
 #define NP_NUM_OBS 22        /* heading_task.py:71-152 */
+#define NP_NUM_OBS_COMBAT 15 /* singlecombat_env.py:64-138 */
 #define NP_NUM_ACT 4         /* F16_model.py:52-56 */
 #define NP_NUM_DRAWS 5       /* uniforms a resetting aircraft consumes: alt, vt, 3 task draws */
 #define NP_NUM_COUNTERS 8
@@ -73,7 +74,9 @@ typedef struct np_env_cfg {
   int32_t max_check_interval, min_check_interval;
   float init_T, max_altitude, min_altitude, max_vt, min_vt;
   int32_t model;        /* NP_MODEL_* ; the UAV plug-in needs no np_aero (pass NULL to np_env_create) */
-  int32_t reserved_;
+  int32_t max_steps;    /* Timeout (timeout.py:16,29); combat only (selfplay.yaml max_steps: 2000) */
+  /* combat (envs/configs/selfplay.yaml; singlecombat_env.py:33-44, crash.py:16) */
+  float distance_limit, target_dist, max_heading, min_heading, max_npos, min_npos, max_epos, min_epos;
 } np_env_cfg;
 
 /* Device buffers the env works on (replace the tensors of F16_model.py:19-22, heading_task.py:26-28,
@@ -135,8 +138,19 @@ int np_env_step(np_env* env, const float* action_dev, const float* draws_dev, co
 int np_env_plan_step(np_env* env, const float* action3_dev, int n_sub, const float* draws_dev, const float* noise_dev,
                      void* stream);
 
+/* SingleCombatEnv.step(action) (envs/singlecombat_env.py:240-274) as ONE kernel launch.  The class is stale at the
+ * surveyed commit (not constructible); obs / reward / geometry / terminations / blood follow its code, the
+ * orchestration is re-derived and documented in oracle/combat_oracle.py.  Population = pairs: ego = 2e, enemy = 2e+1
+ * (n even); action_dev [n][4] = [throttle, roll_dem, pitch_dem, yaw]; obs is [n][15]; n_sub = 5 in the reference;
+ * n_sub = 0 performs only the env-level reset + obs (SingleCombatEnv.reset).  draws_dev [n][5] = npos, epos, altitude,
+ * heading, vt uniforms or NULL (Philox).  Per-pair relative geometry needs no exchange in this pair-sharded layout. */
+int np_env_combat_step(np_env* env, const float* action_dev, int n_sub, const float* draws_dev, void* stream);
+/* Byte offset, inside the workspace, of the [ld] f32 blood row (singlecombat_env.py:45). */
+size_t np_env_blood_offset_bytes(const np_env_cfg* cfg);
+
 /* Byte offset, inside the workspace, of the controller state block [12][ld] f32: rows {roll, pitch, yaw, speed} x
- * {error, integrator, last_out} (pid.py:22-33, rollController.py:24,40).  Lets the host wrapper expose it. */
+ * {error, integrator, last_out} (pid.py:22-33, rollController.py:24,40); in combat mode rows 9, 10 hold the low-passed
+ * roll / pitch demands (singlecombat_env.py:246-247).  Lets the host wrapper expose it. */
 size_t np_env_pid_offset_bytes(const np_env_cfg* cfg);
 /* started = 0 re-arms the first-call initialisation of the PIDs (PID.reset, pid.py:13,22-27). */
 int np_env_set_pid_started(np_env* env, int started);

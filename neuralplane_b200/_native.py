@@ -21,6 +21,7 @@ NP_OK = 0
 TASK_IDS = {"heading": 0, "control": 1, "tracking": 2}
 MODEL_IDS = {"F16": 0, "UAV": 1}
 NUM_NETS, NUM_OBS, NUM_DRAWS, NUM_COUNTERS = 43, 22, 5, 8
+NUM_OBS_COMBAT = 15
 COUNTER_NAMES = ("overload", "low_altitude", "high_speed", "low_speed", "extreme_state", "unreach", "reached", "resets")
 
 
@@ -41,7 +42,10 @@ class EnvCfg(C.Structure):
                 ("max_distance", C.c_float), ("min_distance", C.c_float),
                 ("max_check_interval", C.c_int32), ("min_check_interval", C.c_int32),
                 ("init_T", C.c_float), ("max_altitude", C.c_float), ("min_altitude", C.c_float),
-                ("max_vt", C.c_float), ("min_vt", C.c_float), ("model", C.c_int32), ("reserved_", C.c_int32)]
+                ("max_vt", C.c_float), ("min_vt", C.c_float), ("model", C.c_int32), ("max_steps", C.c_int32),
+                ("distance_limit", C.c_float), ("target_dist", C.c_float), ("max_heading", C.c_float),
+                ("min_heading", C.c_float), ("max_npos", C.c_float), ("min_npos", C.c_float), ("max_epos", C.c_float),
+                ("min_epos", C.c_float)]
 
 
 class Buffers(C.Structure):
@@ -67,6 +71,8 @@ SYMBOLS = {
     "np_env_reset": (C.c_int, [_P, _P, _P, _P]),
     "np_env_step": (C.c_int, [_P, _P, _P, _P, _P]),
     "np_env_plan_step": (C.c_int, [_P, _P, C.c_int, _P, _P, _P]),
+    "np_env_combat_step": (C.c_int, [_P, _P, C.c_int, _P, _P]),
+    "np_env_blood_offset_bytes": (C.c_size_t, [C.POINTER(EnvCfg)]),
     "np_env_pid_offset_bytes": (C.c_size_t, [C.POINTER(EnvCfg)]),
     "np_env_set_pid_started": (C.c_int, [_P, C.c_int]),
     "np_env_counters": (C.c_int, [_P, C.POINTER(C.c_uint64), _P]),

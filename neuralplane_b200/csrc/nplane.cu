@@ -79,7 +79,8 @@ struct StepParams {
   const uint32_t* aero;          // device image, aero_bytes
   int aero_bytes;
   const float* action;           // [n][4]; planning step: [n][3]
-  float* pid;                    // [kPidRows][ld] controller state (planning step)
+  float* pid;                    // [kPidRows][ld] controller state (planning / combat step)
+  float* blood;                  // [ld] combat damage state (singlecombat_env.py:45)
   int n_sub;                     // FDM sub-steps per env step (planning: 50, planning_env.py:153)
   int pid_first;                 // 1: the controllers have never run (PID.reset, pid.py:13)
   const float* draws;            // [n][5] or null
@@ -261,15 +262,122 @@ __device__ __forceinline__ void count_cause2(unsigned long long* counters, int w
 }
 
 // ------------------------------------------------------------------------------------------------
+// K5 helpers: 1-v-1 combat (singlecombat_env.py; envs/utils/utils.py:156-249).  The pair lives in one thread.
+// ------------------------------------------------------------------------------------------------
+// SingleCombatEnv.reset_done_envs re-initialisation of one aircraft (:219-225): draws npos, epos, altitude, heading, vt
+__device__ __forceinline__ void combat_reset_aircraft(const np_env_cfg& c, const Draws& r, float* s, float* u) {
+#pragma unroll
+  for (int j = 0; j < 12; ++j) s[j] = 0.0f;
+  s[0] = r.d[0] * (c.max_npos - c.min_npos) + c.min_npos;
+  s[1] = r.d[1] * (c.max_epos - c.min_epos) + c.min_epos;
+  s[2] = r.d[2] * (c.max_altitude - c.min_altitude) + c.min_altitude;
+  s[5] = r.d[3] * (c.max_heading - c.min_heading) + c.min_heading;
+  s[6] = r.d[4] * (c.max_vt - c.min_vt) + c.min_vt;
+  u[0] = c.init_T; u[1] = 0.0f; u[2] = 0.0f; u[3] = 0.0f;
+}
+
+// AO / TA / R of get_AO_TA_R (3-D) or get2d_AO_TA_R (utils.py:156-206): dp = enemy - ego position, ve / vm = ego / enemy
+// inertial velocity (xdot[0:3]); DIM = 3 or 2.
+template <int DIM>
+__device__ __forceinline__ void ao_ta_r(const float* dp, const float* ve, const float* vm, float& AO, float& TA, float& R) {
+  float ev = 0.f, mv = 0.f, d2 = 0.f, pe = 0.f, pm = 0.f;
+#pragma unroll
+  for (int j = 0; j < DIM; ++j) {
+    ev = ev + ve[j] * ve[j]; mv = mv + vm[j] * vm[j]; d2 = d2 + dp[j] * dp[j];
+    pe = pe + dp[j] * ve[j]; pm = pm + dp[j] * vm[j];
+  }
+  R = sqrtf(d2);
+  AO = acosf(fminf(fmaxf(pe / (R * sqrtf(ev) + 1e-8f), -1.0f), 1.0f));
+  TA = acosf(fminf(fmaxf(pm / (R * sqrtf(mv) + 1e-8f), -1.0f), 1.0f));
+}
+__device__ __forceinline__ float orientation_reward_v2(float AO, float TA) {  // utils.py:215-217
+  const float t = atanhf(1.0f - fmaxf(1.9f * TA / kPi, 1e-4f * 1.0f)) / (2.0f * kPi);
+  return 1.0f / (50.0f * AO / kPi + 2.0f) + (float)(1.0 / 2) + fminf(t, 0.0f) + 0.5f;
+}
+__device__ __forceinline__ float range_reward_v3(float Rkm) {  // utils.py:230-231
+  const float poly = fminf(fmaxf(-0.032f * (Rkm * Rkm) + 0.284f * Rkm + 0.38f, 0.0f), 1.0f);
+  return (Rkm < 5.0f ? 1.0f : 0.0f) + (Rkm >= 5.0f ? 1.0f : 0.0f) * poly + fminf(fmaxf(expf(-0.16f * Rkm), 0.0f), 0.2f);
+}
+__device__ __forceinline__ float orientation_fn(float AO) {  // utils.py:235-243
+  constexpr float k6 = (float)(3.141592653589793 / 6);
+  const bool m3 = (AO >= 0.0f) & (AO <= k6), m4 = (AO <= 0.0f) & (AO >= -k6);
+  return (1.0f - 6.0f * AO / kPi) * (m3 ? 1.0f : 0.0f) + (1.0f + 6.0f * AO / kPi) * (m4 ? 1.0f : 0.0f);
+}
+__device__ __forceinline__ float distance_fn(float Rkm) {  // utils.py:245-249
+  return (Rkm <= 1.0f ? 1.0f : 0.0f) + (3.0f - Rkm) / 2.0f * (((Rkm > 1.0f) & (Rkm <= 3.0f)) ? 1.0f : 0.0f);
+}
+
+// obs (singlecombat_env.py:64-138), reward (:140-181) and the blood model (:263-271) of one pair at its final state.
+__device__ __forceinline__ void combat_outputs(const StepParams& p, float (&s)[2][12], float (&blood)[2], float (&rew)[2],
+                                               int pr, const bool (&act)[2], bool stepped) {
+  float vel[2][3], es[2][3];
+  Trig g[2];
+#pragma unroll
+  for (int q = 0; q < 2; ++q) {
+    g[q] = make_trig(s[q]);
+    const float vt = s[q][6];
+    vel[q][0] = vt * g[q].cb * g[q].ca;                      // F16Model.get_velocity (body axes)
+    vel[q][1] = vt * g[q].sb;
+    vel[q][2] = vt * g[q].cb * g[q].sa;
+    const float vtc = vt <= 0.01f ? 0.01f : vt;              // es[:, :3] = xdot[0:3] of nlplant (F16_dynamics.py:104,129-135)
+    const BodyVel b = body_vel(vtc, g[q]);
+    const Trig& t = g[q];
+    es[q][0] = b.U * (t.ct * t.cpsi) + b.V * (t.sphi * t.cpsi * t.st - t.cphi * t.spsi) + b.W * (t.cphi * t.st * t.cpsi + t.sphi * t.spsi);
+    es[q][1] = b.U * (t.ct * t.spsi) + b.V * (t.sphi * t.spsi * t.st + t.cphi * t.cpsi) + b.W * (t.cphi * t.st * t.spsi - t.sphi * t.cpsi);
+    es[q][2] = b.U * t.st - b.V * (t.sphi * t.ct) - b.W * (t.cphi * t.ct);
+  }
+  const float dp[3] = {s[1][0] - s[0][0], s[1][1] - s[0][1], s[1][2] - s[0][2]};
+  float AO2, TA2, R2, AO, TA, R;
+  ao_ta_r<2>(dp, es[0], es[1], AO2, TA2, R2);
+  ao_ta_r<3>(dp, es[0], es[1], AO, TA, R);
+  const float cz = es[0][0] * dp[1] - es[0][1] * dp[0];
+  const float side = (cz > 0.0f ? 1.0f : 0.0f) - (cz < 0.0f ? 1.0f : 0.0f);
+  const float Rkm = R * 0.3048f / 1000.0f;
+  const float rr = range_reward_v3(Rkm);
+  rew[0] = 0.01f * (orientation_reward_v2(AO, TA) * rr);
+  rew[1] = 0.01f * (orientation_reward_v2(kPi - TA, kPi - AO) * rr);
+#pragma unroll
+  for (int q = 0; q < 2; ++q) {
+    float o[NP_NUM_OBS_COMBAT];
+    const int r = 1 - q;
+    o[0] = s[q][2] * 0.3048f / 5000.0f;
+    o[1] = g[q].sphi; o[2] = g[q].cphi; o[3] = g[q].st; o[4] = g[q].ct;
+    o[5] = vel[q][0] * 0.3048f / 340.0f; o[6] = vel[q][1] * 0.3048f / 340.0f; o[7] = vel[q][2] * 0.3048f / 340.0f;
+    o[8] = s[q][6] * 0.3048f / 340.0f;
+    o[9] = (vel[r][0] - vel[q][0]) * 0.3048f / 340.0f;
+    o[10] = (s[r][2] - s[q][2]) * 0.3048f / 1000.0f;
+    o[11] = q == 0 ? AO2 : kPi - TA2;
+    o[12] = q == 0 ? TA2 : kPi - AO2;
+    o[13] = R2 * 0.3048f / 10000.0f;
+    o[14] = q == 0 ? side : -side;
+    if (act[q]) {
+      float* orow = p.obs + (size_t)(2 * pr + q) * NP_NUM_OBS_COMBAT;
+#pragma unroll
+      for (int j = 0; j < NP_NUM_OBS_COMBAT; ++j) orow[j] = o[j];
+    }
+  }
+  if (stepped) {  // blood model, after obs / reward (singlecombat_env.py:263-271)
+    const float df = distance_fn(Rkm);
+    blood[1] = blood[1] - orientation_fn(AO) * df;
+    blood[0] = blood[0] - orientation_fn(kPi - TA) * df;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // K1: the fused step kernel
 // ------------------------------------------------------------------------------------------------
 static int step_smem_bytes(int aero_bytes, int bs) { return aero_bytes + kNumSlots * bs * 8 + 16; }
 
-// PLAN = false: BaseEnv.step (one FDM step driven by the caller's 4-D action).
-// PLAN = true : PlanningEnv.step (planning_env.py:144-177): the caller's 3-D action sets pitch / heading / speed targets
+// MODE_STEP  : BaseEnv.step (one FDM step driven by the caller's 4-D action).
+// MODE_COMBAT: SingleCombatEnv.step (singlecombat_env.py:240-274): the thread's two aircraft ARE the pair (ego = 2e,
+//               enemy = 2e + 1), so the relative geometry needs no exchange; env-level reset, 5 FDM sub-steps under the
+//               attitude-demand controller, 15-D obs, AO/TA/range reward, blood model, Crash / Shutdown / Timeout.
+// MODE_PLAN  : PlanningEnv.step (planning_env.py:144-177): the caller's 3-D action sets pitch / heading / speed targets
 //               that the fused PID controller (ctrl_device.cuh) tracks for n_sub FDM sub-steps; aircraft that terminate
 //               inside the env step are frozen (s <- recent_s); state stays in registers across the sub-steps.
-template <int BS, int MINB, bool PLAN>
+enum { MODE_STEP = 0, MODE_PLAN = 1, MODE_COMBAT = 2 };
+
+template <int BS, int MINB, int MODE>
 __global__ void __launch_bounds__(BS, MINB) f16_step_kernel(const __grid_constant__ StepParams p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   float* blob = reinterpret_cast<float*>(smem_raw);
@@ -287,6 +395,7 @@ __global__ void __launch_bounds__(BS, MINB) f16_step_kernel(const __grid_constan
   float2* coef2 = coef_all + threadIdx.x;                       // slot k of this thread's pair: coef2[k * BS]
   float* cf = reinterpret_cast<float*>(coef2);                  // aircraft a, slot k: cf[a + k * 2 * BS]
   constexpr int CS = 2 * BS;
+  constexpr bool PLAN = MODE == MODE_PLAN, COMBAT = MODE == MODE_COMBAT;
   const bool use_cache = c.use_coef_cache != 0;
 
   for (int pbase = blockIdx.x * BS; pbase < npairs; pbase += gridDim.x * BS) {
@@ -311,7 +420,7 @@ __global__ void __launch_bounds__(BS, MINB) f16_step_kernel(const __grid_constan
     }
 #pragma unroll
     for (int j = 0; j < 3; ++j) {
-      const float2 v = reinterpret_cast<const float2*>(p.tgt + (size_t)j * ld)[prl];
+      const float2 v = COMBAT ? make_float2(0.f, 0.f) : reinterpret_cast<const float2*>(p.tgt + (size_t)j * ld)[prl];
       tgt[0][j] = v.x; tgt[1][j] = v.y;
     }
     {
@@ -336,15 +445,40 @@ __global__ void __launch_bounds__(BS, MINB) f16_step_kernel(const __grid_constan
 
     // ---- episodic reset of terminated aircraft (env_base.py:83-97) --------------------------------------------
 #pragma unroll
+    float blood[2] = {0.f, 0.f};
+    if (COMBAT) {  // env-level reset (singlecombat_env.py:207-238): either flag re-initialises the whole pair
+      const float2 bv = reinterpret_cast<const float2*>(p.blood)[prl];
+      blood[0] = bv.x; blood[1] = bv.y;
+      rst[0] = rst[1] = rst[0] || rst[1];
+    }
     for (int q = 0; q < 2; ++q) {
       if (rst[q]) {
         const Draws r = reset_draws(p, idx[q]);
-        reset_aircraft(c, r, s[q], u[q], tgt[q]);
+        if (COMBAT) {
+          combat_reset_aircraft(c, r, s[q], u[q]);
+          blood[q] = 100.0f;
+        } else {
+          reset_aircraft(c, r, s[q], u[q], tgt[q]);
+        }
         steps[q] = 0;
       }
     }
-    // planning step: targets from the high-level action (planning_env.py:146-152) and the controller state
+    // planning step: targets from the high-level action (planning_env.py:146-152); controller state of both modes
     float plan_tgt[2][3], pid[2][kPidRows];
+    if (COMBAT) {
+#pragma unroll
+      for (int j = 0; j < kPidRows; ++j) {
+        const float2 v = reinterpret_cast<const float2*>(p.pid + (size_t)j * ld)[prl];
+        pid[0][j] = v.x; pid[1][j] = v.y;
+      }
+    }
+    float a_cmd[2][4];   // the caller's clamped 4-D action, kept for all sub-steps (App. D.10 fixed)
+    if (COMBAT) {
+#pragma unroll
+      for (int q = 0; q < 2; ++q)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) a_cmd[q][j] = fminf(fmaxf(a[q][j], -1.0f), 1.0f);
+    }
     if (PLAN) {
 #pragma unroll
       for (int q = 0; q < 2; ++q) {
@@ -393,7 +527,8 @@ __global__ void __launch_bounds__(BS, MINB) f16_step_kernel(const __grid_constan
     bool bad[2] = {false, false}, done[2] = {false, false};   // flags were cleared by the reset above (env_base.py:93-95)
     float rew[2];
     int causes[2] = {0, 0};
-    const int nsub = PLAN ? p.n_sub : 1;
+    const int nsub = (PLAN || COMBAT) ? p.n_sub : 1;
+    bool exc[2] = {false, false};
 #pragma unroll 1
     for (int sub = 0; sub < nsub; ++sub) {
     // ---- action of this FDM step + control low-pass (F16_model.py:52-57) ------------------------------------
@@ -401,6 +536,7 @@ __global__ void __launch_bounds__(BS, MINB) f16_step_kernel(const __grid_constan
     for (int q = 0; q < 2; ++q) {
       if (PLAN) pid_controller(s[q], c.airspeed, c.dt, plan_tgt[q][0], plan_tgt[q][1], plan_tgt[q][2], pid[q],
                                p.pid_first != 0 && sub == 0, a[q]);
+      if (COMBAT) combat_controller(s[q], c.airspeed, c.dt, a_cmd[q], pid[q], p.pid_first != 0 && sub == 0, a[q]);
 #pragma unroll
       for (int j = 0; j < 4; ++j) a[q][j] = fminf(fmaxf(a[q][j], -1.0f), 1.0f);
       u[q][0] = 0.9f * u[q][0] + 0.1f * a[q][0] * 0.225f * 76300.0f / 0.3048f;
@@ -451,7 +587,7 @@ __global__ void __launch_bounds__(BS, MINB) f16_step_kernel(const __grid_constan
 #pragma unroll
           for (int j = 0; j < 12; ++j) sq[j] = frozen ? sq[j] : sq[j] + h * xdot[j];
           steps[q] += 1;  // env_base.py:102
-          if (PLAN && sub != nsub - 1) continue;  // only the last sub-step's observation is returned (:177)
+          if (COMBAT || (PLAN && sub != nsub - 1)) continue;  // only the last sub-step's observation is returned (:177)
 
           // ---- observation of the new state (env_base.py:103) ----------------------------------------
           // (recomputing the trig / atmosphere terms of the new state in pass 1 measured faster than carrying them
@@ -479,9 +615,11 @@ __global__ void __launch_bounds__(BS, MINB) f16_step_kernel(const __grid_constan
           const float a_deg = sq[7] * 180.0f / kPi, b_deg = sq[8] * 180.0f / kPi;  // extreme_state.py:32-36
           const bool ext = (a_deg < c.min_alpha) | (a_deg > c.max_alpha) | (b_deg < c.min_beta) | (b_deg > c.max_beta);
           const bool late = steps[q] >= c.max_check_interval;
-          bool off, dn;
-          float d0, d1, d2, rw;
-          if (c.task == NP_TASK_HEADING) {                                      // unreach_heading.py:38-53
+          bool off = false, dn = false;
+          float d0, d1, d2, rw = 0.0f;
+          if (COMBAT) {
+            exc[q] |= (steps[q] - c.max_steps) >= 0;                            // timeout.py:29
+          } else if (c.task == NP_TASK_HEADING) {                                      // unreach_heading.py:38-53
             const float dpsi = wrap_pi(sq[5] - tq[1]);
             off = (fabsf(dpsi) >= (float)(3.141592653589793 / 36.0)) | (fabsf(sq[2] - tq[0]) >= 100.0f) |
                   (fabsf(sq[6] - tq[2]) >= 20.0f);
@@ -516,9 +654,23 @@ __global__ void __launch_bounds__(BS, MINB) f16_step_kernel(const __grid_constan
                               : 0;
         }
       }
+      if (COMBAT && pass == 1) {   // pair conditions: Crash (crash.py:29-42) and Shutdown (shutdown.py:30-40)
+        const float dn0 = s[0][0] - s[1][0], de0 = s[0][1] - s[1][1], da0 = s[0][2] - s[1][2];
+        const bool crash = (dn0 * dn0 + de0 * de0 + da0 * da0) <= c.distance_limit * c.distance_limit;
+        const bool m1 = blood[0] <= 0.0f, m2 = blood[1] <= 0.0f;
+        const bool sd_done = m2 && !m1;
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          bad[q] |= crash | m1;
+          done[q] |= sd_done;
+          causes[q] |= act[q] ? (((int)(crash | m1) << 5) | ((int)sd_done << 6)) : 0;
+        }
+      }
     }
 
     }  // sub-steps
+
+    if (COMBAT) combat_outputs(p, s, blood, rew, pr, act, nsub > 0);
 
     // ---- termination-cause counters (replace the reference's per-condition print(torch.sum(...)) syncs) --------
 #pragma unroll
@@ -531,9 +683,14 @@ __global__ void __launch_bounds__(BS, MINB) f16_step_kernel(const __grid_constan
 #pragma unroll
       for (int j = 0; j < 4; ++j) store_pair(p.u + (size_t)j * ld, pr, make_float2(u[0][j], u[1][j]), act[1]);
 #pragma unroll
-      for (int j = 0; j < 3; ++j) store_pair(p.tgt + (size_t)j * ld, pr, make_float2(tgt[0][j], tgt[1][j]), act[1]);
+      if (!COMBAT) {
+#pragma unroll
+        for (int j = 0; j < 3; ++j) store_pair(p.tgt + (size_t)j * ld, pr, make_float2(tgt[0][j], tgt[1][j]), act[1]);
+      } else {
+        store_pair(p.blood, pr, make_float2(blood[0], blood[1]), act[1]);
+      }
       store_pair(p.reward, pr, make_float2(rew[0], rew[1]), act[1]);
-      if (PLAN) {
+      if (PLAN || COMBAT) {
 #pragma unroll
         for (int j = 0; j < kPidRows; ++j) store_pair(p.pid + (size_t)j * ld, pr, make_float2(pid[0][j], pid[1][j]), act[1]);
       }
@@ -541,12 +698,12 @@ __global__ void __launch_bounds__(BS, MINB) f16_step_kernel(const __grid_constan
         reinterpret_cast<int2*>(p.step_count)[pr] = make_int2(steps[0], steps[1]);
         reinterpret_cast<uchar2*>(p.flags)[pr] = make_uchar2(done[0] ? 1 : 0, done[1] ? 1 : 0);
         reinterpret_cast<uchar2*>(p.flags + ld)[pr] = make_uchar2(bad[0] ? 1 : 0, bad[1] ? 1 : 0);
-        reinterpret_cast<uchar2*>(p.flags + 2 * (size_t)ld)[pr] = make_uchar2(0, 0);  // Timeout is commented out (heading_task.py:45)
+        reinterpret_cast<uchar2*>(p.flags + 2 * (size_t)ld)[pr] = make_uchar2(exc[0] ? 1 : 0, exc[1] ? 1 : 0);  // control tasks: Timeout is commented out (heading_task.py:45)
       } else {
         p.step_count[2 * pr] = steps[0];
         p.flags[2 * pr] = done[0] ? 1 : 0;
         p.flags[ld + 2 * pr] = bad[0] ? 1 : 0;
-        p.flags[2 * (size_t)ld + 2 * pr] = 0;
+        p.flags[2 * (size_t)ld + 2 * pr] = exc[0] ? 1 : 0;
       }
     }
   }
@@ -965,16 +1122,16 @@ int np_aero_destroy(np_aero* aero) {
 
 size_t np_env_workspace_bytes(const np_env_cfg* cfg) {
   if (!cfg) return 0;
-  return (((size_t)(kCacheRows + kPidRows) * (size_t)cfg->ld * sizeof(float) + 127) / 128) * 128 + 256 /* counters */;
+  return (((size_t)(kCacheRows + kPidRows + 1) * (size_t)cfg->ld * sizeof(float) + 127) / 128) * 128 + 256 /* counters */;
 }
 
 }  // extern "C"
 
-template <int BS, int MINB, bool PLAN>
+template <int BS, int MINB, int MODE>
 static int launch_step(np_env* env, const StepParams& p, cudaStream_t st) {
   const int smem = step_smem_bytes(p.aero_bytes, BS);
   static int configured[64] = {};  // per device: the attribute lives in the device's context
-  auto kern = f16_step_kernel<BS, MINB, PLAN>;
+  auto kern = f16_step_kernel<BS, MINB, MODE>;
   int dev = 0;
   NP_CUDA(cudaGetDevice(&dev));
   if (configured[dev & 63] < smem) {
@@ -1003,10 +1160,11 @@ static StepParams make_params(np_env* env, const float* action, const float* dra
   p.reward = env->buf.reward_dev;
   p.cache = reinterpret_cast<float*>(env->buf.workspace_dev);
   p.pid = p.cache + (size_t)kCacheRows * env->cfg.ld;
+  p.blood = p.pid + (size_t)kPidRows * env->cfg.ld;
   p.n_sub = 1;
   p.pid_first = 0;
   p.counters = reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(env->buf.workspace_dev) +
-                                                     (((size_t)(kCacheRows + kPidRows) * env->cfg.ld * 4 + 127) / 128) * 128);
+                                                     (((size_t)(kCacheRows + kPidRows + 1) * env->cfg.ld * 4 + 127) / 128) * 128);
   p.aero = env->aero ? env->aero->image_dev : nullptr;
   p.aero_bytes = env->aero ? env->aero->bytes : 0;
   p.action = action;
@@ -1098,11 +1256,11 @@ int np_env_step(np_env* env, const float* action_dev, const float* draws_dev, co
   }
   switch (env->block) {
 #ifdef NPLANE_ALL_BLOCKS
-    case 128: return launch_step<128, 4, false>(env, p, st);
-    case 384: return launch_step<384, 1, false>(env, p, st);
-    case 512: return launch_step<512, 1, false>(env, p, st);
+    case 128: return launch_step<128, 4, MODE_STEP>(env, p, st);
+    case 384: return launch_step<384, 1, MODE_STEP>(env, p, st);
+    case 512: return launch_step<512, 1, MODE_STEP>(env, p, st);
 #endif
-    case 256: return launch_step<256, 2, false>(env, p, st);
+    case 256: return launch_step<256, 2, MODE_STEP>(env, p, st);
     default: return fail(NP_EINVAL, "np_env_step: block size not compiled in (build with -DNPLANE_ALL_BLOCKS)");
   }
 }
@@ -1117,7 +1275,23 @@ int np_env_plan_step(np_env* env, const float* action3_dev, int n_sub, const flo
   p.pid_first = env->pid_started ? 0 : 1;
   env->pid_started = true;
   env->step_index++;
-  return launch_step<256, 2, true>(env, p, (cudaStream_t)stream);
+  return launch_step<256, 2, MODE_PLAN>(env, p, (cudaStream_t)stream);
+}
+
+int np_env_combat_step(np_env* env, const float* action_dev, int n_sub, const float* draws_dev, void* stream) {
+  if (!env || !env->bound) return fail(NP_ESTATE, "np_env_combat_step: env not bound");
+  if (env->cfg.model != NP_MODEL_F16 || (env->cfg.n & 1)) return fail(NP_EINVAL, "np_env_combat_step: needs the F16 plug-in and an even population (pairs)");
+  if (n_sub < 0 || (n_sub > 0 && (!action_dev || ((uintptr_t)action_dev & 15)))) return fail(NP_EINVAL, "np_env_combat_step: bad action pointer or n_sub");
+  StepParams p = make_params(env, action_dev ? action_dev : reinterpret_cast<const float*>(env->buf.s_dev), draws_dev, nullptr);
+  p.n_sub = n_sub;
+  p.pid_first = env->pid_started ? 0 : 1;
+  if (n_sub > 0) env->pid_started = true;
+  env->step_index++;
+  return launch_step<256, 2, MODE_COMBAT>(env, p, (cudaStream_t)stream);
+}
+
+size_t np_env_blood_offset_bytes(const np_env_cfg* cfg) {
+  return cfg ? (size_t)(kCacheRows + kPidRows) * (size_t)cfg->ld * sizeof(float) : 0;
 }
 
 size_t np_env_pid_offset_bytes(const np_env_cfg* cfg) {

@@ -24,11 +24,15 @@ _CFG_KEYS = (  # yaml key, default (the reference's getattr defaults), ctypes fi
     ("max_distance", 2000), ("min_distance", 2000),
     ("max_check_interval", 1500), ("min_check_interval", 300),
     ("max_altitude", 20000), ("min_altitude", 19000), ("max_vt", 1200), ("min_vt", 1000),
+    # combat (selfplay.yaml; singlecombat_env.py:33-44, crash.py:16, timeout.py:16)
+    ("max_steps", 500), ("distance_limit", 200), ("target_dist", 3), ("max_heading", 0.5), ("min_heading", -0.5),
+    ("max_npos", 5000), ("min_npos", -5000), ("max_epos", 5000), ("min_epos", -5000),
 )
 
 
 class BaseEnv:
     metadata = {}
+    native_obs_dim = nv.NUM_OBS
 
     def __init__(self, num_envs=10, config='heading', model='F16', random_seed=None, device="cuda:0",
                  index_base=0, use_coef_cache=True):
@@ -74,12 +78,13 @@ class BaseEnv:
             setattr(c, key, getattr(self.config, key, default))
         c.noise_scale = self.task.noise_scale
         c.airspeed = self.model.airspeed
-        c.init_T = self.config.init_state['init_T']
+        init_state = getattr(self.config, 'init_state', None)
+        c.init_T = init_state['init_T'] if init_state else getattr(self.config, 'init_T', 2000)
         return c
 
     def _native_create(self):
-        if self.num_observation != nv.NUM_OBS:
-            raise NotImplementedError("the native tasks produce 22-D observations")
+        if self.num_observation != self.native_obs_dim:
+            raise NotImplementedError(f"this env's native kernel produces {self.native_obs_dim}-D observations")
         L = nv.lib()
         self._cfg = self._cfg_struct()
         with torch.cuda.device(self.device):

@@ -27,7 +27,7 @@ class F16Model(BaseModel):
         self.min_altitude = getattr(self.config, 'min_altitude', 19000)
         self.max_vt = getattr(self.config, 'max_vt', 1200)
         self.min_vt = getattr(self.config, 'min_vt', 1000)
-        self.init_state = self.config.init_state
+        self.init_state = getattr(self.config, 'init_state', {'init_T': getattr(self.config, 'init_T', 2000)})
 
         from ...aero import get_aero
         self.aero = aero if aero is not None else get_aero(device)

@@ -244,6 +244,160 @@ def planning_trajectory(n, steps, scale, seed, name):
     np.savez_compressed(os.path.join(HERE, name), **out)
 
 
+class RefCombat:
+    """SingleCombatEnv (envs/singlecombat_env.py) is stale at this commit and cannot be constructed,
+    so its step is re-assembled here from the reference code that still runs, called UNMODIFIED:
+      * SingleCombatEnv.obs / SingleCombatEnv.reward   -- the unbound methods (singlecombat_env.py:64-181) on this object
+      * get_AO_TA_R, orientation_fn, distance_fn        -- envs/utils/utils.py:156-249 (blood model, :263-271)
+      * Overload, LowAltitude, HighSpeed, LowSpeed, ExtremeState, Crash, Timeout, Shutdown -- termination classes
+      * F16Model.update / getters, Controller.stabilize -- the current model plug-in and PID stack
+    Orchestration re-derived from singlecombat_env.py:183-274 (documented in oracle/combat_oracle.py): env-level reset
+    of a pair when either aircraft is flagged, 5 FDM sub-steps per env step with the demand low-pass, the ORIGINAL
+    4-D action kept for all 5 sub-steps (the reference overwrites it inside the loop, App. D.10), each sub-step applied
+    through F16Model.update([a0, -el/45, -ail/45, -rud/45]) (the current plug-in API, as renders/render_control.py
+    does), flags OR-accumulated, blood updated after the 5th sub-step."""
+
+    def __init__(self, num_envs):
+        import_reference()
+        if REF_ROOT not in sys.path:
+            sys.path.insert(0, REF_ROOT)
+        import envs.singlecombat_env as sc
+        from envs.utils.utils import parse_config
+        from models.F16_model import F16Model
+        from algorithms.pid.controller import Controller
+        from termination_conditions.overload import Overload
+        from termination_conditions.low_altitude import LowAltitude
+        from termination_conditions.high_speed import HighSpeed
+        from termination_conditions.low_speed import LowSpeed
+        from termination_conditions.extreme_state import ExtremeState
+        from termination_conditions.crash import Crash
+        from termination_conditions.timeout import Timeout
+        from termination_conditions.shutdown import Shutdown
+        self.sc = sc
+        self.config = parse_config("selfplay")
+        self.config.init_state = {"init_T": getattr(self.config, "init_T", 2000)}
+        self.device = torch.device("cpu")
+        self.num_envs, self.num_agents = num_envs, 2
+        self.n = 2 * num_envs
+        self.target_dist = getattr(self.config, "target_dist", 3)
+        self.model = F16Model(self.config, self.n, self.device, 0)
+        with contextlib.redirect_stdout(io.StringIO()):
+            self.controller = Controller(dt=self.model.dt, n=self.n, device="cpu")
+        self.conditions = [Overload(self.config), LowAltitude(self.config), HighSpeed(self.config), LowSpeed(self.config),
+                           ExtremeState(self.config), Crash(self.config, "cpu"), Timeout(self.config), Shutdown(self.config, "cpu")]
+        self.blood = 100 * torch.ones(self.n)
+        self.step_count = torch.zeros(self.n, dtype=torch.int64)
+        self.is_done = torch.ones(self.n, dtype=torch.bool)          # force the initial reset of everyone
+        self.bad_done = torch.ones(self.n, dtype=torch.bool)
+        self.exceed_time_limit = torch.ones(self.n, dtype=torch.bool)
+
+    # attributes the stale methods read (singlecombat_env.py:88-119, :142-147)
+    @property
+    def s(self):
+        return self.model.s
+
+    @property
+    def velocity(self):
+        return torch.stack(self.model.get_velocity(), 1)
+
+    @property
+    def es(self):
+        return self.model.get_extended_state()
+
+    def reset_done_envs(self, draws):
+        """singlecombat_env.py:207-238 with the draws taken from the tape: columns npos, epos, altitude, heading, vt."""
+        c = self.config
+        flag = (self.is_done | self.bad_done) | self.exceed_time_limit
+        env_reset = flag.reshape(self.num_envs, 2).any(dim=1)
+        m = env_reset.repeat_interleave(2)
+        d = draws
+        self.model.s[m, :] = 0
+        self.model.u[m, :] = 0
+        self.model.s[m, 0] = d[m, 0] * (c.max_npos - c.min_npos) + c.min_npos
+        self.model.s[m, 1] = d[m, 1] * (c.max_epos - c.min_epos) + c.min_epos
+        self.model.s[m, 2] = d[m, 2] * (c.max_altitude - c.min_altitude) + c.min_altitude
+        self.model.s[m, 5] = d[m, 3] * (c.max_heading - c.min_heading) + c.min_heading
+        self.model.s[m, 6] = d[m, 4] * (c.max_vt - c.min_vt) + c.min_vt
+        self.model.u[m, 0] = c.init_T
+        self.blood[m] = 100
+        self.step_count[m] = 0
+        self.is_done[:] = False
+        self.bad_done[:] = False
+        self.exceed_time_limit[:] = False
+
+    def reset(self, draws):
+        self.is_done[:] = True
+        with contextlib.redirect_stdout(io.StringIO()):
+            self.reset_done_envs(draws)
+            return self.sc.SingleCombatEnv.obs(self)
+
+    def step(self, action, draws):
+        ctl = self.controller
+        with contextlib.redirect_stdout(io.StringIO()):
+            self.reset_done_envs(draws)
+            a = torch.clamp(action, -1, 1)
+            for i in range(5):
+                ctl.roll_dem = 0.9 * ctl.roll_dem + 0.1 * a[:, 1].reshape(-1, 1) * 4 * torch.pi / 9     # :246
+                ctl.pitch_dem = 0.9 * ctl.pitch_dem + 0.1 * a[:, 2].reshape(-1, 1) * torch.pi / 12      # :247
+                ctl.stabilize(self)                                                                    # :251
+                ego = torch.hstack((a[:, 0].reshape(-1, 1), -ctl.el / 45, -ctl.ail / 45, -ctl.rud / 45))
+                self.model.update(ego)
+                self.step_count += 1
+                for cond in self.conditions:
+                    bad, done, exc, _ = cond.get_termination(None, self, {})
+                    self.bad_done = self.bad_done | bad
+                    self.is_done = self.is_done | done
+                    self.exceed_time_limit = self.exceed_time_limit | exc
+            obs = self.sc.SingleCombatEnv.obs(self)
+            reward = self.sc.SingleCombatEnv.reward(self)
+            from envs.utils.utils import get_AO_TA_R, orientation_fn, distance_fn                         # :263-271
+            ego_i = torch.arange(self.num_envs) * 2
+            enm_i = ego_i + 1
+            es = self.es
+            AO, TA, R = get_AO_TA_R(self.s[ego_i, :3], self.s[enm_i, :3], es[ego_i, :3], es[enm_i, :3])
+            self.blood[enm_i] -= orientation_fn(AO) * distance_fn(R * 0.3048 / 1000)
+            self.blood[ego_i] -= orientation_fn(torch.pi - TA) * distance_fn(R * 0.3048 / 1000)
+        return obs, reward, self.is_done.clone(), self.bad_done.clone(), self.exceed_time_limit.clone()
+
+    def ctrl_state(self):
+        c = self.controller
+        rows = [c.roll_dem.reshape(-1), c.pitch_dem.reshape(-1)]
+        for p, last in ((c.roll_controller.rate_pid, c.roll_controller.last_out), (c.pitch_controller.rate_pid, c.pitch_controller.last_out),
+                        (c.yaw_controller.rate_pid, c.yaw_controller.last_out)):
+            rows += [p.error.reshape(-1), p.integrator.reshape(-1), last.reshape(-1)]
+        return torch.stack(rows, 1)
+
+
+def combat_trajectory(num_envs, steps, seed, name, close=False):
+    """RefCombat trajectory.  close=True re-positions every pair nose-to-tail at 1-3 km after the first reset so that
+    the blood / Shutdown / Crash branches fire within the fixture."""
+    rc = RefCombat(num_envs)
+    n = rc.n
+    obs0 = rc.reset(torch.from_numpy(tapes.reset_draw_tape(seed, 0, n)))
+    if close:
+        ego, enm = torch.arange(num_envs) * 2, torch.arange(num_envs) * 2 + 1
+        gap = torch.linspace(100.0, 9000.0, num_envs)
+        rc.model.s[enm, 0] = rc.model.s[ego, 0] + gap
+        rc.model.s[enm, 1] = rc.model.s[ego, 1] + 0.02 * gap
+        rc.model.s[enm, 2] = rc.model.s[ego, 2] + 10.0
+        rc.model.s[:, 5] = 0.0
+        rc.blood[enm[::3]] = 0.3                               # nearly shot down: Shutdown(done) fires soon
+        rc.blood[ego[1::7]] = 0.2
+    out = {"obs0": obs0.numpy().copy(), "meta": np.array([num_envs, steps, seed], dtype=np.int64),
+           "s_start": rc.model.s.numpy().copy(), "blood_start": rc.blood.numpy().copy()}
+    for k in range(1, steps + 1):
+        a = torch.from_numpy(tapes.action_tape(seed, k, n, 1.0 if not close else 0.2))
+        d = torch.from_numpy(tapes.reset_draw_tape(seed, k, n))
+        obs, rew, done, bad, exc = rc.step(a, d)
+        out[f"k{k}_s"] = rc.model.s.numpy().copy(); out[f"k{k}_u"] = rc.model.u.numpy().copy()
+        out[f"k{k}_obs"] = obs.numpy().copy(); out[f"k{k}_reward"] = rew.numpy().copy()
+        out[f"k{k}_done"] = done.numpy().copy(); out[f"k{k}_bad"] = bad.numpy().copy(); out[f"k{k}_exc"] = exc.numpy().copy()
+        out[f"k{k}_blood"] = rc.blood.numpy().copy(); out[f"k{k}_step_count"] = rc.step_count.numpy().astype(np.int32)
+        out[f"k{k}_ctrl"] = rc.ctrl_state().numpy().copy()
+        print(name, "step", k, "bad", int(bad.sum()), "done", int(done.sum()), "min blood %.2f" % float(rc.blood.min()), flush=True)
+    np.savez_compressed(os.path.join(HERE, name), **out)
+
+
 def uav_trajectory(task, n, steps, scale, seed, name):
     """ControlEnv(model='UAV') from the unmodified reference with num_controls = 3 (the one fix it needs to survive
     its second step): state / obs / reward / flags at every checkpoint."""
@@ -268,6 +422,10 @@ def uav_trajectory(task, n, steps, scale, seed, name):
 
 if __name__ == "__main__":
     torch.set_num_threads(8)
+    if len(sys.argv) > 1 and sys.argv[1] == "combat":       # regenerate only the combat fixtures
+        combat_trajectory(24, 30, 18, "combat_traj.npz")
+        combat_trajectory(24, 30, 19, "combat_close_traj.npz", close=True)
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "planning":     # regenerate only the planning fixture
         planning_trajectory(48, 16, 1.0, 17, "planning_pid_traj.npz")
         sys.exit(0)
@@ -287,3 +445,5 @@ if __name__ == "__main__":
     uav_trajectory("control", 64, 400, 1.0, 15, "uav_control_traj.npz")
     uav_trajectory("heading", 64, 400, 1.0, 16, "uav_heading_traj.npz")
     planning_trajectory(48, 16, 1.0, 17, "planning_pid_traj.npz")
+    combat_trajectory(24, 30, 18, "combat_traj.npz")
+    combat_trajectory(24, 30, 19, "combat_close_traj.npz", close=True)

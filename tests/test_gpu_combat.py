@@ -1,0 +1,135 @@
+"""GPU parity of the fused 1-v-1 combat step (np_env_combat_step) against the combat oracle, which is itself pinned
+bit-exact to the reference's own obs / reward / geometry / termination / controller code (tests/golden/combat*_traj.npz).
+As for the planning step, the PID loops make free-running trajectories diverge at fp32 noise level within tens of
+sub-steps, so every env step (5 sub-steps) is teacher-forced from the oracle's exact state; the fixtures are replayed
+for their first steps and for their discrete events (Crash, Shutdown bad / done, env-level resets)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import tapes
+from _metrics import state_rel_err
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def _cuda(x):
+    return torch.from_numpy(np.ascontiguousarray(x)).cuda()
+
+
+def _env(num_envs):
+    from neuralplane_b200 import SingleCombatEnv
+    return SingleCombatEnv(num_envs=num_envs, config="selfplay", random_seed=0, device="cuda:0")
+
+
+def _obs_close(got, want, what):
+    """15-D combat obs: columns 11, 12 are acos() angles, ill-conditioned near 0 and pi (error = eps / sin(angle)): they
+    get 5e-4 absolute; everything else fp32-tight."""
+    d = np.abs(got - want)
+    ang = [11, 12]
+    rest = [j for j in range(15) if j not in ang]
+    assert d[:, rest].max() <= 2e-5 + 2e-5 * np.abs(want[:, rest]).max(), (what, d[:, rest].max(axis=0))
+    assert d[:, ang].max() <= 5e-4 and np.median(d[:, ang]) <= 2e-6, (what, d[:, ang].max(), np.median(d[:, ang]))
+
+
+def _push(env, orc, first):
+    from neuralplane_b200 import _native as nv
+    n = env.n
+    env.model.s[:] = _cuda(orc.s.numpy()); env.model.u[:] = _cuda(orc.u.numpy())
+    env.step_count[:] = _cuda(orc.step_count.numpy().astype(np.int32))
+    for j, f in enumerate((orc.is_done, orc.bad_done, orc.exceed_time_limit)):
+        env._flags[j, :n] = _cuda(f.numpy().astype(np.uint8))
+    env.blood[:] = _cuda(orc.blood.numpy())
+    cs = orc.ctrl_state().numpy()                       # roll_dem, pitch_dem, then 3 x (err, int, last)
+    st = np.zeros((n, 12), np.float32)
+    st[:, 0:9] = cs[:, 2:11]; st[:, 9] = cs[:, 0]; st[:, 10] = cs[:, 1]
+    env.ctrl_state[:] = _cuda(st)
+    nv.check(nv.lib().np_env_set_pid_started(env._handle, 0 if first else 1), "np_env_set_pid_started")
+
+
+def _compare(env, orc, out, ref, k, strict_flags=True):
+    obs, rew, done, bad, exc, _ = out
+    o_obs, o_rew, o_done, o_bad, o_exc = ref
+    err = state_rel_err(env.model.s.cpu().numpy(), orc.s.numpy())
+    assert np.median(err) <= 2e-5 and np.percentile(err, 99) <= 3e-4, (k, np.median(err), np.percentile(err, 99))
+    same = (bad.cpu().numpy() == o_bad.numpy()) & (done.cpu().numpy() == o_done.numpy())
+    assert (~same).sum() <= (0 if strict_flags else 2), (k, int((~same).sum()))
+    assert np.array_equal(exc.cpu().numpy(), o_exc.numpy()), k
+    do = np.abs(obs.cpu().numpy() - o_obs.numpy())
+    assert np.median(do.max(axis=1)) <= 2e-5 and np.percentile(do.max(axis=1), 99) <= 2e-3, (k, np.median(do.max(axis=1)), do.max())
+    assert np.allclose(rew.cpu().numpy(), o_rew.numpy(), rtol=2e-4, atol=2e-6), (k, np.abs(rew.cpu().numpy() - o_rew.numpy()).max())
+    assert np.allclose(env.blood.cpu().numpy(), orc.blood.numpy(), rtol=1e-5, atol=2e-3), k
+    assert np.array_equal(env.step_count.cpu().numpy(), orc.step_count.numpy().astype(np.int32)), k
+
+
+def test_combat_teacher_forced_vs_oracle():
+    from oracle.combat_oracle import CombatOracle
+    num_envs, seed = 1024, 31
+    env, orc = _env(num_envs), CombatOracle(num_envs)
+    n = env.n
+    d0 = tapes.reset_draw_tape(seed, 0, n)
+    obs0 = env.reset(reset_draws=_cuda(d0))
+    o0 = orc.reset(torch.from_numpy(d0))
+    _obs_close(obs0.cpu().numpy(), o0.numpy(), "reset")
+    assert torch.equal(env.blood, torch.full_like(env.blood, 100.0)) and int(env.step_count.max()) == 0
+    # bring a third of the pairs into gun range so blood / Shutdown / Crash fire, with a few nearly-dead aircraft
+    ego, enm = orc.ego, orc.enm
+    gap = torch.linspace(50.0, 12000.0, num_envs)
+    close = torch.arange(num_envs) % 3 == 0
+    orc.s[enm[close], 0] = orc.s[ego[close], 0] + gap[close]
+    orc.s[enm[close], 1] = orc.s[ego[close], 1] + 0.03 * gap[close]
+    orc.s[enm[close], 2] = orc.s[ego[close], 2] + 15.0
+    orc.s[ego[close], 5] = 0.0; orc.s[enm[close], 5] = 0.0
+    orc.blood[enm[::9]] = 0.4; orc.blood[ego[3::27]] = 0.3
+    events = 0
+    for k in range(1, 13):
+        _push(env, orc, first=(k == 1))
+        a = tapes.action_tape(seed, k, n, 0.5)
+        d = tapes.reset_draw_tape(seed, k, n)
+        out = env.step(_cuda(a), reset_draws=_cuda(d))
+        ref = orc.step(torch.from_numpy(a), torch.from_numpy(d))
+        _compare(env, orc, out, ref, k, strict_flags=False)
+        events += int(ref[2].sum()) + int(ref[3].sum())
+    assert events > 20
+    c = env.termination_counters()
+    assert c["unreach"] > 0 and c["reached"] > 0       # combat: slot 5 = crash | shot down, slot 6 = enemy shot down
+
+
+@pytest.mark.parametrize("fixture,close", [("combat_traj.npz", False), ("combat_close_traj.npz", True)])
+def test_combat_fixture_first_steps_and_events(fixture, close):
+    g = np.load(os.path.join(GOLDEN, fixture))
+    num_envs, steps, seed = [int(x) for x in g["meta"]]
+    env = _env(num_envs)
+    n = env.n
+    obs0 = env.reset(reset_draws=_cuda(tapes.reset_draw_tape(seed, 0, n)))
+    _obs_close(obs0.cpu().numpy(), g["obs0"], "reset")
+    env.model.s[:] = _cuda(g["s_start"]); env.blood[:] = _cuda(g["blood_start"])
+    for k in range(1, 4):
+        obs, rew, done, bad, exc, _ = env.step(_cuda(tapes.action_tape(seed, k, n, 0.2 if close else 1.0)),
+                                               reset_draws=_cuda(tapes.reset_draw_tape(seed, k, n)))
+        # discrete events are robust (blood thresholds, 200 ft crash radius); states only while fp32 noise is small
+        assert np.array_equal(done.cpu().numpy(), g[f"k{k}_done"]) and np.array_equal(bad.cpu().numpy(), g[f"k{k}_bad"]), k
+        assert np.array_equal(env.step_count.cpu().numpy(), g[f"k{k}_step_count"]), k
+        assert np.allclose(env.blood.cpu().numpy(), g[f"k{k}_blood"], rtol=1e-4, atol=5e-3), k
+        if k == 1:
+            err = state_rel_err(env.model.s.cpu().numpy(), g["k1_s"])
+            assert np.median(err) <= 2e-5, np.median(err)
+            assert np.allclose(rew.cpu().numpy(), g["k1_reward"], rtol=5e-4, atol=5e-6)
+
+
+def test_combat_full_size_invariants():
+    num_envs = 250_000
+    env = _env(num_envs)
+    env.reset()
+    g = torch.Generator(device="cuda").manual_seed(11)
+    for k in range(4):
+        a = torch.rand((env.n, 4), device="cuda", generator=g) * 2 - 1
+        obs, rew, done, bad, exc, _ = env.step(a)
+        assert obs.shape == (env.n, 15) and torch.isfinite(obs).all() and torch.isfinite(rew).all()
+        assert torch.equal(bad[0::2] | done[0::2] | True, bad[1::2] | done[1::2] | True)
+        assert bool((obs[0::2, 13] == obs[1::2, 13]).all()) and bool((obs[0::2, 14] == -obs[1::2, 14]).all())
+        assert float(env.blood.max()) <= 100.0
+        assert int(env.step_count.max()) <= 5 * (k + 1)
