@@ -145,6 +145,15 @@ int np_env_plan_step(np_env* env, const float* action3_dev, int n_sub, const flo
  * n_sub = 0 performs only the env-level reset + obs (SingleCombatEnv.reset).  draws_dev [n][5] = npos, epos, altitude,
  * heading, vt uniforms or NULL (Philox).  Per-pair relative geometry needs no exchange in this pair-sharded layout. */
 int np_env_combat_step(np_env* env, const float* action_dev, int n_sub, const float* draws_dev, void* stream);
+/* Role-sharded combat layout (egos and opponents on different ranks): each rank writes the 8-float record of
+ * its aircraft -- position (3), inertial velocity xdot[0:3] (3), body-axis vx, blood -- into records_dev [n][8] (the
+ * all-gather send slab), the ranks all-gather the slabs (NCCL, neuralplane_b200/combat_exchange.py), and
+ * np_combat_relgeo evaluates the pairwise terms of singlecombat_env.py:96-121,142-177 (get_AO_TA_R / get2d_AO_TA_R,
+ * envs/utils/utils.py:156-206) for m (ego, enemy) index pairs into the gathered array:
+ * out_dev [m][8] = AO, TA, R (3-D), AO2, TA2, R2 (2-D), side flag, enemy - ego body-vx. */
+int np_env_combat_records(np_env* env, float* records_dev, void* stream);
+int np_combat_relgeo(const float* records_dev, const int32_t* ego_idx_dev, const int32_t* enm_idx_dev, float* out_dev, int m,
+                     void* stream);
 /* Byte offset, inside the workspace, of the [ld] f32 blood row (singlecombat_env.py:45). */
 size_t np_env_blood_offset_bytes(const np_env_cfg* cfg);
 

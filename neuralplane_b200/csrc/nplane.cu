@@ -940,6 +940,57 @@ __global__ void __launch_bounds__(256) uav_nlplant_kernel(const float* __restric
 }
 
 // ------------------------------------------------------------------------------------------------
+// K5b: relative-geometry records for the ROLE-sharded combat layout (egos and opponents on different ranks).
+//   combat_records_kernel : per aircraft, the 8-float record every other rank needs: position (3), inertial velocity
+//                           = xdot[0:3] (3), body-axis vx, blood  -> [n][8], written straight into the all-gather send slab
+//   combat_relgeo_kernel  : for m (ego, enemy) index pairs into a gathered record array: AO, TA, R (3-D and 2-D), side
+//                           flag, delta body-vx, delta altitude -- the pairwise terms of singlecombat_env.py:96-121,
+//                           142-177 (get_AO_TA_R / get2d_AO_TA_R, envs/utils/utils.py:156-206).
+// Both are HBM-bound (32 B written / 64 B read per aircraft).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) combat_records_kernel(const float* __restrict__ S, const float* __restrict__ blood,
+                                                             float* __restrict__ rec, int n, int ld) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    float s[12];
+#pragma unroll
+    for (int j = 0; j < 12; ++j) s[j] = S[(size_t)j * ld + i];
+    const Trig t = make_trig(s);
+    const float vt = s[6];
+    const float vtc = vt <= 0.01f ? 0.01f : vt;
+    const BodyVel b = body_vel(vtc, t);
+    float4 lo, hi;
+    lo.x = s[0]; lo.y = s[1]; lo.z = s[2];
+    lo.w = b.U * (t.ct * t.cpsi) + b.V * (t.sphi * t.cpsi * t.st - t.cphi * t.spsi) + b.W * (t.cphi * t.st * t.cpsi + t.sphi * t.spsi);
+    hi.x = b.U * (t.ct * t.spsi) + b.V * (t.sphi * t.spsi * t.st + t.cphi * t.cpsi) + b.W * (t.cphi * t.st * t.spsi - t.sphi * t.cpsi);
+    hi.y = b.U * t.st - b.V * (t.sphi * t.ct) - b.W * (t.cphi * t.ct);
+    hi.z = vt * t.cb * t.ca;
+    hi.w = blood[i];
+    reinterpret_cast<float4*>(rec)[2 * (size_t)i] = lo;
+    reinterpret_cast<float4*>(rec)[2 * (size_t)i + 1] = hi;
+  }
+}
+
+__global__ void __launch_bounds__(256) combat_relgeo_kernel(const float* __restrict__ rec, const int32_t* __restrict__ ego_idx,
+                                                            const int32_t* __restrict__ enm_idx, float* __restrict__ out, int m) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < m; i += gridDim.x * blockDim.x) {
+    const float4 a0 = reinterpret_cast<const float4*>(rec)[2 * (size_t)ego_idx[i]], a1 = reinterpret_cast<const float4*>(rec)[2 * (size_t)ego_idx[i] + 1];
+    const float4 b0 = reinterpret_cast<const float4*>(rec)[2 * (size_t)enm_idx[i]], b1 = reinterpret_cast<const float4*>(rec)[2 * (size_t)enm_idx[i] + 1];
+    const float dp[3] = {b0.x - a0.x, b0.y - a0.y, b0.z - a0.z};
+    const float ve[3] = {a0.w, a1.x, a1.y}, vm[3] = {b0.w, b1.x, b1.y};
+    float AO, TA, R, AO2, TA2, R2;
+    ao_ta_r<3>(dp, ve, vm, AO, TA, R);
+    ao_ta_r<2>(dp, ve, vm, AO2, TA2, R2);
+    const float cz = ve[0] * dp[1] - ve[1] * dp[0];
+    float4 o0, o1;
+    o0.x = AO; o0.y = TA; o0.z = R; o0.w = AO2;
+    o1.x = TA2; o1.y = R2; o1.z = (cz > 0.0f ? 1.0f : 0.0f) - (cz < 0.0f ? 1.0f : 0.0f);
+    o1.w = b1.z - a1.z;   // enemy body-vx minus ego body-vx
+    reinterpret_cast<float4*>(out)[2 * (size_t)i] = o0;
+    reinterpret_cast<float4*>(out)[2 * (size_t)i + 1] = o1;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // stand-alone nlplant / coefficient kernels (model plug-in getters, parity tests): same device code as K1,
 // two points per thread
 // ------------------------------------------------------------------------------------------------
@@ -1288,6 +1339,26 @@ int np_env_combat_step(np_env* env, const float* action_dev, int n_sub, const fl
   if (n_sub > 0) env->pid_started = true;
   env->step_index++;
   return launch_step<256, 2, MODE_COMBAT>(env, p, (cudaStream_t)stream);
+}
+
+int np_env_combat_records(np_env* env, float* records_dev, void* stream) {
+  if (!env || !env->bound || !records_dev || ((uintptr_t)records_dev & 15)) return fail(NP_EINVAL, "np_env_combat_records: bad argument");
+  StepParams p = make_params(env, nullptr, nullptr, nullptr);
+  const int want = (env->cfg.n + 255) / 256;
+  combat_records_kernel<<<want < env->num_sms * 8 ? want : env->num_sms * 8, 256, 0, (cudaStream_t)stream>>>(p.s, p.blood, records_dev,
+                                                                                                          env->cfg.n, env->cfg.ld);
+  NP_CUDA(cudaGetLastError());
+  return NP_OK;
+}
+
+int np_combat_relgeo(const float* records_dev, const int32_t* ego_idx_dev, const int32_t* enm_idx_dev, float* out_dev, int m,
+                     void* stream) {
+  if (!records_dev || !ego_idx_dev || !enm_idx_dev || !out_dev || m <= 0 || (((uintptr_t)records_dev | (uintptr_t)out_dev) & 15))
+    return fail(NP_EINVAL, "np_combat_relgeo: bad argument");
+  const int want = (m + 255) / 256;
+  combat_relgeo_kernel<<<want < 1184 ? want : 1184, 256, 0, (cudaStream_t)stream>>>(records_dev, ego_idx_dev, enm_idx_dev, out_dev, m);
+  NP_CUDA(cudaGetLastError());
+  return NP_OK;
 }
 
 size_t np_env_blood_offset_bytes(const np_env_cfg* cfg) {

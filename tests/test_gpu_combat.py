@@ -133,3 +133,28 @@ def test_combat_full_size_invariants():
         assert bool((obs[0::2, 13] == obs[1::2, 13]).all()) and bool((obs[0::2, 14] == -obs[1::2, 14]).all())
         assert float(env.blood.max()) <= 100.0
         assert int(env.step_count.max()) <= 5 * (k + 1)
+
+
+def test_records_and_relgeo_match_the_fused_obs():
+    """The exchange path (records -> gather -> np_combat_relgeo) must reproduce the pairwise columns the fused kernel
+    writes into the observation, bit for bit (same device code on the same inputs)."""
+    from neuralplane_b200.combat_exchange import gather_records, local_records, relative_geometry
+    num_envs = 4096
+    env = _env(num_envs)
+    env.reset()
+    g = torch.Generator(device="cuda").manual_seed(2)
+    for k in range(3):
+        obs, *_ = env.step(torch.rand((env.n, 4), device="cuda", generator=g) * 2 - 1)
+    rec = gather_records(local_records(env))                 # single rank: identity gather
+    assert rec.shape == (env.n, 8)
+    assert torch.equal(rec[:, 0], env.model.s[:, 0]) and torch.equal(rec[:, 7], env.blood)
+    ego = torch.arange(num_envs) * 2
+    geo = relative_geometry(rec, ego, ego + 1)
+    o_ego, o_enm = obs[0::2], obs[1::2]
+    assert torch.equal(geo[:, 3], o_ego[:, 11]) and torch.equal(geo[:, 4], o_ego[:, 12])           # AO2, TA2
+    assert torch.equal(geo[:, 6], o_ego[:, 14])                                                    # side flag
+    assert torch.allclose(geo[:, 5] * 0.3048 / 10000, o_ego[:, 13], rtol=1e-6, atol=0)
+    assert torch.allclose(geo[:, 7] * 0.3048 / 340, o_ego[:, 9], rtol=1e-6, atol=1e-9)
+    assert torch.allclose(3.141592653589793 - geo[:, 4], o_enm[:, 11], atol=1e-6)
+    geo_r = relative_geometry(rec, ego + 1, ego)              # swapped roles: same range, mirrored side
+    assert torch.equal(geo_r[:, 2], geo[:, 2]) and torch.equal(geo_r[:, 5], geo[:, 5])

@@ -62,3 +62,17 @@ def test_world_size_2_collectives_over_gloo():
         assert ms == 2.0
         assert np.array_equal(col, np.arange(n_total, dtype=np.float32))      # rank-ordered gather = global order
     assert res[0][1] == 0 and res[0][2] + res[1][2] == n_total
+
+
+@pytest.mark.parametrize("world", [2, 8])
+def test_role_sharded_partner_index(world):
+    from neuralplane_b200.combat_exchange import role_sharded_partner_index
+    n_envs = 5
+    seen = set()
+    for r in range(world):
+        ego, enm = role_sharded_partner_index(n_envs, r, world)
+        assert ego.shape == enm.shape == (n_envs,)
+        assert int(ego.max()) < (world // 2) * n_envs <= int(enm.min())       # egos in the first half of the gather
+        assert torch.equal(enm - ego, torch.full_like(ego, (world // 2) * n_envs))
+        seen.add((int(ego[0]), int(enm[0])))
+    assert len(seen) == world // 2        # rank r and rank r + world/2 look at the same pairs

@@ -1,0 +1,65 @@
+#!/usr/bin/env python
+"""Role-sharded combat exchange over real NCCL (run under torchrun with an even number of ranks, one GPU each):
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 tools/combat_exchange_check.py
+
+Every rank simulates the same env block (same seed, so identical pair-sharded trajectories), but contributes only ITS
+ROLE's records to the all-gather (ranks < world/2: egos, the rest: opponents), as a role-sharded deployment would.
+The pairwise terms computed from the gathered records must equal the columns the fused pair-sharded kernel wrote into
+the observation.  Prints one JSON line (rank 0) with the check result and the gather timing."""
+import json
+import os
+import sys
+
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from neuralplane_b200 import SingleCombatEnv  # noqa: E402
+from neuralplane_b200.combat_exchange import gather_records, local_records, relative_geometry, role_sharded_partner_index  # noqa: E402
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    os.dup2(2, 1) if rank else None
+    dist.init_process_group("nccl", device_id=dev)
+    num_envs = int(os.environ.get("NPLANE_COMBAT_ENVS", "500000"))
+    half = world // 2
+    block = rank % half
+    env = SingleCombatEnv(num_envs=num_envs, config="selfplay", random_seed=100 + block, device=dev)
+    env.reset()
+    g = torch.Generator(device=dev).manual_seed(7 + block)
+    for k in range(3):
+        obs, *_ = env.step(torch.rand((env.n, 4), device=dev, generator=g) * 2 - 1)
+    rec = local_records(env)
+    mine = rec[0::2].contiguous() if rank < half else rec[1::2].contiguous()       # this rank's role only
+    torch.cuda.synchronize(); dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    allrec = gather_records(mine)                                                   # warm-up
+    e0.record()
+    for _ in range(10):
+        allrec = gather_records(mine)
+    e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 10
+    ego_idx, enm_idx = role_sharded_partner_index(num_envs, rank, world)
+    geo = relative_geometry(allrec, ego_idx, enm_idx)
+    o_ego = obs[0::2]
+    ok = bool(torch.equal(geo[:, 3], o_ego[:, 11]) and torch.equal(geo[:, 4], o_ego[:, 12]) and torch.equal(geo[:, 6], o_ego[:, 14])
+              and torch.allclose(geo[:, 5] * 0.3048 / 10000, o_ego[:, 13], rtol=1e-6, atol=0))
+    t = torch.tensor([1.0 if ok else 0.0, ms], device=dev, dtype=torch.float64)
+    dist.all_reduce(t[:1], op=dist.ReduceOp.MIN)
+    dist.all_reduce(t[1:], op=dist.ReduceOp.MAX)
+    if rank == 0:
+        gb = world * mine.numel() * 4 / 1e9
+        print(json.dumps({"check": "role-sharded relgeo from all-gathered records == fused pair-sharded obs columns",
+                          "ok": bool(t[0].item() == 1.0), "world": world, "envs_per_block": num_envs,
+                          "record_bytes_per_aircraft": 32, "gathered_GB_per_rank": gb, "all_gather_ms": float(t[1].item()),
+                          "gather_GBps_per_rank": gb / (float(t[1].item()) * 1e-3)}), flush=True)
+    dist.destroy_process_group()
+    sys.exit(0 if t[0].item() == 1.0 else 1)
+
+
+if __name__ == "__main__":
+    main()
