@@ -10,7 +10,11 @@ import torch
 
 
 class GPUVecEnv:
-    def __init__(self, env_fns):
+    def __init__(self, env_fns, device_tensors=False):
+        """device_tensors=True (SURVEY f-2): step()/reset() take and return torch CUDA tensors in the same
+        (num_envs, agents, .) shapes, with no host round trip and no synchronisation -- for policies that live on
+        the same GPU.  The default reproduces the reference's numpy boundary."""
+        self.device_tensors = bool(device_tensors)
         assert len(env_fns) == 1, "Number of create env funcitions must be 1!"
         self.gpu_vec_env = env_fns[0]()
         assert hasattr(self.gpu_vec_env, "num_envs"), "Parameter of env must contain num_envs!"
@@ -21,14 +25,17 @@ class GPUVecEnv:
         self.agents = e.num_agents
         self.closed = False
         n, D = e.n, e.num_observation
-        self._act_h = torch.empty((n, 4), dtype=torch.float32).pin_memory()
-        self._act_d = torch.empty((n, 4), dtype=torch.float32, device=e.device)
+        self._A = A = getattr(e, "action_width", 4)     # PlanningEnv takes 3-D actions
+        self._flip = 0
+        self.h2d_bytes_per_step = 0 if self.device_tensors else n * A * 4
+        self.d2h_bytes_per_step = 0 if self.device_tensors else n * D * 4 + n * 4 + 3 * n
+        if self.device_tensors:
+            return
+        self._act_h = torch.empty((n, A), dtype=torch.float32).pin_memory()
+        self._act_d = torch.empty((n, A), dtype=torch.float32, device=e.device)
         self._out = [dict(obs=torch.empty((n, D), dtype=torch.float32).pin_memory(),
                           rew=torch.empty(n, dtype=torch.float32).pin_memory(),
                           flags=torch.empty((3, n), dtype=torch.uint8).pin_memory()) for _ in range(2)]
-        self._flip = 0
-        self.h2d_bytes_per_step = self._act_h.numel() * 4
-        self.d2h_bytes_per_step = n * D * 4 + n * 4 + 3 * n
 
     def _download(self, with_rest=True):
         e = self.gpu_vec_env
@@ -41,10 +48,21 @@ class GPUVecEnv:
         torch.cuda.current_stream(e.device).synchronize()
         return o
 
+    def _step_device(self, actions):
+        e = self.gpu_vec_env
+        import torch as _t
+        a = _t.as_tensor(actions, device=e.device, dtype=_t.float32).reshape(self.num_envs * self.agents, -1)
+        obs, rew, done, bad, exc, info = e.step(a)
+        shp = (self.num_envs, self.agents, 1)
+        return (obs.view(self.num_envs, self.agents, e.num_observation), rew.view(shp), done.view(shp), bad.view(shp),
+                exc.view(shp), info)
+
     def step(self, actions):
+        if self.device_tensors:
+            return self._step_device(actions)
         e = self.gpu_vec_env
         a = np.asarray(actions, dtype=np.float32).reshape(self.num_envs * self.agents, -1)
-        self._act_h.copy_(torch.from_numpy(a[:, :4]))
+        self._act_h.copy_(torch.from_numpy(a[:, :self._A]))
         self._act_d.copy_(self._act_h, non_blocking=True)
         e.step(self._act_d)
         o = self._download()
@@ -56,6 +74,8 @@ class GPUVecEnv:
 
     def reset(self):
         e = self.gpu_vec_env
+        if self.device_tensors:
+            return e.reset().view(self.num_envs, self.agents, e.num_observation)
         e.reset()
         o = self._download(with_rest=False)
         return o["obs"].numpy().reshape(self.num_envs, self.agents, e.num_observation)

@@ -17,6 +17,8 @@ from .utils.utils import wrap_PI
 
 
 class PlanningEnv(BaseEnv):
+    action_width = 3
+
     def __init__(self, num_envs=1, config='tracking', model='F16', random_seed=None, device="cuda:0", n_substeps=50, **kw):
         self.n_substeps = int(n_substeps)
         super().__init__(num_envs, config, model, random_seed, device, **kw)

@@ -382,3 +382,26 @@ def test_gpuvecenv_numpy_boundary(dev):
     assert obs.shape == (ne, 1, 22) and rew.shape == (ne, 1, 1) and done.shape == (ne, 1, 1)
     assert rew.dtype == np.float32 and done.dtype == np.bool_ and bad.dtype == np.bool_ and info == {}
     assert np.isfinite(obs).all()
+
+
+def test_gpuvecenv_device_tensor_mode(dev):
+    """SURVEY f-2: the same wrapper without the host round trip -- torch CUDA tensors in, (num_envs, agents, .) views out."""
+    from neuralplane_b200 import ControlEnv, GPUVecEnv, PlanningEnv, SingleCombatEnv
+    ne = 256
+    mk = lambda: ControlEnv(num_envs=ne, config="heading", model="F16", random_seed=4, device="cuda:0")
+    v_dev, v_np = GPUVecEnv([mk], device_tensors=True), GPUVecEnv([mk])
+    o_dev, o_np = v_dev.reset(), v_np.reset()
+    assert o_dev.is_cuda and o_dev.shape == (ne, 1, 22) and np.array_equal(o_dev.cpu().numpy(), o_np)
+    a = tapes.action_tape(4, 1, ne, 1.0).reshape(ne, 1, 4)
+    r_dev, r_np = v_dev.step(_cuda(a)), v_np.step(a)
+    for x, y in zip(r_dev[:5], r_np[:5]):
+        assert x.is_cuda and tuple(x.shape) == y.shape and np.array_equal(x.cpu().numpy(), y)
+    assert v_dev.h2d_bytes_per_step == 0 and v_np.d2h_bytes_per_step == ne * (22 * 4 + 4 + 3)
+    # the wrapper also fronts the 3-D planning and the 2-agent combat envs
+    vp = GPUVecEnv([lambda: PlanningEnv(num_envs=64, config="tracking", random_seed=1, device="cuda:0", n_substeps=3)])
+    obs, rew, *_ = vp.step(np.zeros((64, 1, 3), np.float32))
+    assert obs.shape == (64, 1, 22) and rew.shape == (64, 1, 1)
+    vc = GPUVecEnv([lambda: SingleCombatEnv(num_envs=32, config="selfplay", random_seed=1, device="cuda:0")])
+    assert vc.reset().shape == (32, 2, 15)
+    obs, rew, done, *_ = vc.step(np.zeros((32, 2, 4), np.float32))
+    assert obs.shape == (32, 2, 15) and rew.shape == (32, 2, 1) and done.shape == (32, 2, 1)
