@@ -432,6 +432,15 @@ __global__ void __launch_bounds__(BS, MINB) f16_step_kernel(const __grid_constan
       rst[0] = (f0.x | f1.x | f2.x) != 0;
       rst[1] = (f0.y | f1.y | f2.y) != 0;
     }
+    // cached (alpha,beta)-MLP outputs and their key: requested with the state rows (one memory round trip, not three)
+    // and parked straight in this thread's coefficient slots; reset lanes / misses overwrite them below
+    float2 ka = make_float2(0.f, 0.f), kb = ka;
+    if (use_cache) {
+      ka = reinterpret_cast<const float2*>(p.cache + (size_t)kNumAB2 * ld)[prl];
+      kb = reinterpret_cast<const float2*>(p.cache + (size_t)(kNumAB2 + 1) * ld)[prl];
+#pragma unroll
+      for (int k = 0; k < kNumAB2; ++k) coef2[(kFirstAB2 + k) * BS] = reinterpret_cast<const float2*>(p.cache + (size_t)k * ld)[prl];
+    }
 #pragma unroll
     for (int q = 0; q < 2; ++q) {
       if (PLAN) {
@@ -444,13 +453,13 @@ __global__ void __launch_bounds__(BS, MINB) f16_step_kernel(const __grid_constan
     }
 
     // ---- episodic reset of terminated aircraft (env_base.py:83-97) --------------------------------------------
-#pragma unroll
     float blood[2] = {0.f, 0.f};
     if (COMBAT) {  // env-level reset (singlecombat_env.py:207-238): either flag re-initialises the whole pair
       const float2 bv = reinterpret_cast<const float2*>(p.blood)[prl];
       blood[0] = bv.x; blood[1] = bv.y;
       rst[0] = rst[1] = rst[0] || rst[1];
     }
+#pragma unroll
     for (int q = 0; q < 2; ++q) {
       if (rst[q]) {
         const Draws r = reset_draws(p, idx[q]);
@@ -502,21 +511,16 @@ __global__ void __launch_bounds__(BS, MINB) f16_step_kernel(const __grid_constan
     {
       bool hit[2] = {rst[0], rst[1]};
       if (use_cache) {
-        const float2 ka = reinterpret_cast<const float2*>(p.cache + (size_t)kNumAB2 * ld)[prl];
-        const float2 kb = reinterpret_cast<const float2*>(p.cache + (size_t)(kNumAB2 + 1) * ld)[prl];
         hit[0] |= __float_as_uint(ka.x) == __float_as_uint(s[0][7]) && __float_as_uint(kb.x) == __float_as_uint(s[0][8]);
         hit[1] |= __float_as_uint(ka.y) == __float_as_uint(s[1][7]) && __float_as_uint(kb.y) == __float_as_uint(s[1][8]);
       }
       miss = NPL_SYNC ? (__syncthreads_or(!(hit[0] && hit[1])) != 0) : (__any_sync(0xffffffffu, !(hit[0] && hit[1])) != 0);
-      if (!miss) {
+      if (!miss && (rst[0] || rst[1])) {  // a reset lane sits at alpha = beta = 0: constants from the aero image
 #pragma unroll 4
         for (int k = 0; k < kNumAB2; ++k) {
-          float2 v = make_float2(c0[k], c0[k]);
-          if (use_cache) {
-            const float2 cv = reinterpret_cast<const float2*>(p.cache + (size_t)k * ld)[prl];
-            if (!rst[0]) v.x = cv.x;
-            if (!rst[1]) v.y = cv.y;
-          }
+          float2 v = coef2[(kFirstAB2 + k) * BS];
+          if (rst[0]) v.x = c0[k];
+          if (rst[1]) v.y = c0[k];
           coef2[(kFirstAB2 + k) * BS] = v;
         }
       }
@@ -587,22 +591,20 @@ __global__ void __launch_bounds__(BS, MINB) f16_step_kernel(const __grid_constan
 #pragma unroll
           for (int j = 0; j < 12; ++j) sq[j] = frozen ? sq[j] : sq[j] + h * xdot[j];
           steps[q] += 1;  // env_base.py:102
-          if (COMBAT || (PLAN && sub != nsub - 1)) continue;  // only the last sub-step's observation is returned (:177)
-
-          // ---- observation of the new state (env_base.py:103) ----------------------------------------
-          // (recomputing the trig / atmosphere terms of the new state in pass 1 measured faster than carrying them
-          //  through registers or shared memory across the second MLP evaluation: profiles/r01_variants.txt)
-          const Trig g2 = make_trig(sq);
-          const float tp2 = tfac_pow(sq[2]);
-          float o[NP_NUM_OBS];
-          make_obs(c, sq, uq, tq, g2, eas2tas_of(tp2), o);
-          add_obs_noise(p, idx[q], o);
-          if (act[q]) {
-            float2* orow = reinterpret_cast<float2*>(p.obs + (size_t)(2 * pr + q) * NP_NUM_OBS);  // 88-B rows: 8-B aligned
-#pragma unroll
-            for (int j = 0; j < NP_NUM_OBS / 2; ++j) orow[j] = make_float2(o[2 * j], o[2 * j + 1]);
-          }
         } else {
+          // ---- observation of the new state (env_base.py:103): pass 1's trig / atmosphere terms are exactly the ones
+          //      it needs, so it is produced here rather than with a third evaluation at the end of pass 0;
+          //      planning / combat return only the last sub-step's observation (planning_env.py:177) -------------
+          if (!COMBAT && (!PLAN || sub == nsub - 1)) {
+            float o[NP_NUM_OBS];
+            make_obs(c, sq, uq, tq, g, eas2tas_of(tp), o);
+            add_obs_noise(p, idx[q], o);
+            if (act[q]) {
+              float2* orow = reinterpret_cast<float2*>(p.obs + (size_t)(2 * pr + q) * NP_NUM_OBS);  // 88-B rows: 8-B aligned
+#pragma unroll
+              for (int j = 0; j < NP_NUM_OBS / 2; ++j) orow[j] = make_float2(o[2 * j], o[2 * j + 1]);
+            }
+          }
           // ---- terminations (task_base.py:75-96) on the new state --------------------------------------
           float ax, ay, az;
           body_accel(sq, g, fp.f, ax, ay, az);
@@ -682,7 +684,6 @@ __global__ void __launch_bounds__(BS, MINB) f16_step_kernel(const __grid_constan
       for (int j = 0; j < 12; ++j) store_pair(p.s + (size_t)j * ld, pr, make_float2(s[0][j], s[1][j]), act[1]);
 #pragma unroll
       for (int j = 0; j < 4; ++j) store_pair(p.u + (size_t)j * ld, pr, make_float2(u[0][j], u[1][j]), act[1]);
-#pragma unroll
       if (!COMBAT) {
 #pragma unroll
         for (int j = 0; j < 3; ++j) store_pair(p.tgt + (size_t)j * ld, pr, make_float2(tgt[0][j], tgt[1][j]), act[1]);
@@ -788,7 +789,8 @@ __device__ __forceinline__ void uav_reset_aircraft(const np_env_cfg& c, const Dr
 }
 
 // 22-D observation through the getters (heading_task.py:93-152): AOA = AOS = thrust = surfaces = 0 for this model
-__device__ __forceinline__ void uav_make_obs(const np_env_cfg& c, const float* s, const UavView& v, const float* tgt, float* o) {
+__device__ __forceinline__ void uav_make_obs(const np_env_cfg& c, const float* s, const UavView& v, const UavTrig& t, const float* tgt,
+                                             float* o) {
   if (c.task == NP_TASK_HEADING) {
     o[0] = (v.alt - tgt[0]) * 0.3048f / 1000.0f;
     o[1] = wrap_pi(v.heading - tgt[1]);
@@ -804,8 +806,7 @@ __device__ __forceinline__ void uav_make_obs(const np_env_cfg& c, const float* s
   }
   const float eas = (v.vt + c.airspeed * 1.0f) / v.e2t;  // UAV_model.py:94-102
   o[3] = v.alt * 0.3048f / 5000.0f;
-  sincosf(v.roll, &o[4], &o[5]);
-  sincosf(v.pitch, &o[6], &o[7]);
+  o[4] = t.sphi; o[5] = t.cphi; o[6] = t.st; o[7] = t.ct;
   o[8] = eas * 0.3048f / 340.0f;
   o[9] = 0.0f; o[10] = 1.0f; o[11] = 0.0f; o[12] = 1.0f;  // sin / cos of get_AOA() = get_AOS() = 0
   o[13] = s[9]; o[14] = s[10]; o[15] = s[11];
@@ -854,9 +855,10 @@ __global__ void __launch_bounds__(256) uav_env_kernel(const __grid_constant__ St
     }
     // ---- obs (env_base.py:103) ----------------------------------------------------------------------
     const UavView v = uav_view(s);
+    const UavTrig trig = uav_trig(s);   // of the state the observation, the Overload check and the reward all see
     {
       float o[NP_NUM_OBS];
-      uav_make_obs(c, s, v, tgt, o);
+      uav_make_obs(c, s, v, trig, tgt, o);
       add_obs_noise(p, i, o);
       float2* orow = reinterpret_cast<float2*>(p.obs + (size_t)i * NP_NUM_OBS);
 #pragma unroll
@@ -865,7 +867,7 @@ __global__ void __launch_bounds__(256) uav_env_kernel(const __grid_constant__ St
     if (STEP) {
       // ---- terminations (task_base.py:75-96) through the getters ------------------------------------------
       float xdot[12];
-      uav_nlplant(s, F, xdot);                                              // get_acceleration (UAV_model.py:120-130)
+      uav_nlplant(s, F, trig, xdot);                                        // get_acceleration (UAV_model.py:120-130)
       const float vu = s[6] / 0.3048f, vv = s[7] / 0.3048f, vw = s[8] / 0.3048f;
       const float ax = xdot[6] / 0.3048f + s[10] * vw - s[11] * vv;
       const float ay = xdot[7] / 0.3048f + s[11] * vu - s[9] * vw;

@@ -12,16 +12,25 @@
 
 namespace npl {
 
+// sin / cos / tan of the Euler angles, shared by nlplant and the observation of the same state
+struct UavTrig {
+  float st, ct, tt, sphi, cphi, spsi, cpsi;
+};
+__device__ __forceinline__ UavTrig uav_trig(const float* s) {
+  UavTrig t;
+  sincosf(s[4], &t.st, &t.ct);
+  t.tt = t.st / t.ct;  // tan(theta) from the two values already needed (<= 3 ulp; tanf itself is a 4-ulp function)
+  sincosf(s[3], &t.sphi, &t.cphi);
+  sincosf(s[5], &t.spsi, &t.cpsi);
+  return t;
+}
+
 // UAVDynamics.nlplant (UAV_dynamics.py:15-84) for one aircraft: xdot[0..11] from s[0..11], forces F[0..2].
-__device__ __forceinline__ void uav_nlplant(const float* s, const float* F, float* xdot) {
+__device__ __forceinline__ void uav_nlplant(const float* s, const float* F, const UavTrig& t, float* xdot) {
   constexpr float UAV_M = 300.0f, g = 9.81f;
   constexpr float M = 1.0f, N = 1.0f, L_bar = 1.0f, I_x = 1.0f, I_y = 1.0f, I_z = 1.0f, I_xz = 0.0f;
   const float U = s[6], V = s[7], W = s[8], P = s[9], Q = s[10], R = s[11];
-  float st, ct, sphi, cphi, spsi, cpsi;
-  sincosf(s[4], &st, &ct);
-  const float tt = tanf(s[4]);
-  sincosf(s[3], &sphi, &cphi);
-  sincosf(s[5], &spsi, &cpsi);
+  const float st = t.st, ct = t.ct, tt = t.tt, sphi = t.sphi, cphi = t.cphi, spsi = t.spsi, cpsi = t.cpsi;
   xdot[0] = U * (ct * cpsi) + V * (sphi * st * cpsi - cphi * spsi) + W * (sphi * spsi + cphi * st * cpsi);
   xdot[1] = U * (ct * spsi) + V * (sphi * st * spsi + cphi * cpsi) + W * (-sphi * cpsi + cphi * st * spsi);
   xdot[2] = U * st - V * (sphi * ct) - W * (cphi * ct);
@@ -38,6 +47,7 @@ __device__ __forceinline__ void uav_nlplant(const float* s, const float* F, floa
   xdot[10] = b2 / I_y;
   xdot[11] = (b0 * I_xz + b1 * I_x) / (I_z * I_x - I_xz * I_xz);
 }
+__device__ __forceinline__ void uav_nlplant(const float* s, const float* F, float* xdot) { uav_nlplant(s, F, uav_trig(s), xdot); }
 
 // What the task layer reads through the model getters (UAV_model.py:69-134), in the reference's units (feet).
 struct UavView {
