@@ -405,3 +405,34 @@ def test_gpuvecenv_device_tensor_mode(dev):
     assert vc.reset().shape == (32, 2, 15)
     obs, rew, done, *_ = vc.step(np.zeros((32, 2, 4), np.float32))
     assert obs.shape == (32, 2, 15) and rew.shape == (32, 2, 1) and done.shape == (32, 2, 1)
+
+
+def test_step_is_cuda_graph_capturable_and_stream_ordered(dev):
+    """include/nplane.h: step only ENQUEUES on the caller's stream and is CUDA-graph capturable.  A captured graph of 4
+    steps replayed 5 times must equal 20 eager steps bit for bit (noise off; resets from the in-kernel Philox stream are
+    keyed by the step index the host passes at capture time, so the comparison uses a tape of injected draws)."""
+    n = 4096
+    e_graph, e_eager = _env(n), _env(n)
+    d0 = _cuda(tapes.reset_draw_tape(8, 0, n))
+    e_graph.reset(reset_draws=d0); e_eager.reset(reset_draws=d0)
+    acts = [_cuda(tapes.action_tape(8, k, n, 1.0)) for k in range(4)]
+    draws = _cuda(tapes.reset_draw_tape(8, 1, n))
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        e_graph.step(acts[0], reset_draws=draws)          # warm-up on the side stream (lazy module loading)
+    torch.cuda.current_stream().wait_stream(side)
+    e_eager.step(acts[0], reset_draws=draws)
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        for k in range(4):
+            e_graph.step(acts[k], reset_draws=draws)
+    for _ in range(5):
+        g.replay()
+    for _ in range(5):
+        for k in range(4):
+            e_eager.step(acts[k], reset_draws=draws)
+    torch.cuda.synchronize()
+    assert torch.equal(e_graph.model.s, e_eager.model.s) and torch.equal(e_graph.last_obs, e_eager.last_obs)
+    assert torch.equal(e_graph.step_count, e_eager.step_count) and torch.equal(e_graph.last_reward, e_eager.last_reward)
+    assert e_graph.termination_counters() == e_eager.termination_counters()
