@@ -46,6 +46,7 @@ enum { NP_MODEL_F16 = 0, NP_MODEL_UAV = 1 };
 
 typedef struct np_aero np_aero; /* the 43 MLP surrogates, device-resident */
 typedef struct np_env np_env;   /* one ControlEnv(model='F16') population */
+typedef struct np_tables np_tables; /* the NASA F-16 aerodynamic tables (example/data/*.dat), device-resident */
 
 /* One row of the packed net table (neuralplane_b200/data/f16_aero.npz `desc`). */
 typedef struct np_net_desc {
@@ -173,6 +174,18 @@ int np_env_counters(np_env* env, uint64_t* out, void* stream);
  * Backs F16Model.get_extended_state and the getters built on it (F16_model.py:47-49,75-91,132-182). */
 int np_f16_nlplant(const np_aero* aero, const float* s_dev, const float* u_dev, float* xdot_dev, int n, int ld,
                    void* stream);
+
+/* Table aero back-end (SURVEY f-3): the NASA tables the MLP surrogates were fitted to, evaluated by multilinear
+ * interpolation as example/train_model/mexndinterp.py:84-110 and combined as example/train_model/hifi_F16_AeroData.py:
+ * 406-483.  breakpoints = ALPHA1(20) ALPHA2(14) BETA1(19) DH1(5) DH2(3) concatenated; values / offsets = the 43
+ * tables in the order of neuralplane_b200/data/f16_tables.npz (Fortran order, alpha fastest).  All HOST pointers.
+ * np_f16_table_coeffs: out_dev [44][ld] in the row order of the reference's golden file envs/models/F16/model/coefs.csv
+ * (rows 3..46) from alpha_deg / beta_deg / el_deg [n] (clamped to the grids). */
+int np_tables_create(const float* breakpoints, const int32_t* bp_sizes, const float* values, const int32_t* offsets, int n_tables,
+                     size_t n_values, np_tables** out);
+int np_tables_destroy(np_tables* tables);
+int np_f16_table_coeffs(const np_tables* tables, const float* alpha_deg_dev, const float* beta_deg_dev, const float* el_deg_dev,
+                        float* out_dev, int n, int ld, void* stream);
 
 /* UAVDynamics.nlplant (envs/models/UAV/UAV_dynamics.py:15-84) on SoA rows: xdot_dev [12][ld] from s_dev [12][ld] and
  * the three body forces u_dev [3+][ld].  Backs UAVModel.get_extended_state and the getters built on it

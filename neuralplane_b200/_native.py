@@ -80,6 +80,9 @@ SYMBOLS = {
     "np_env_counters": (C.c_int, [_P, C.POINTER(C.c_uint64), _P]),
     "np_env_launch_info": (C.c_int, [_P, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "np_f16_nlplant": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, _P]),
+    "np_tables_create": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_size_t, C.POINTER(_P)]),
+    "np_tables_destroy": (C.c_int, [_P]),
+    "np_f16_table_coeffs": (C.c_int, [_P, _P, _P, _P, _P, C.c_int, C.c_int, _P]),
     "np_uav_nlplant": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, _P]),
     "np_f16_coeffs": (C.c_int, [_P, _P, _P, _P, _P, C.c_int, C.c_int, _P]),
 }

@@ -22,6 +22,7 @@
 #include "f16_device.cuh"
 #include "uav_device.cuh"
 #include "ctrl_device.cuh"
+#include "tables_device.cuh"
 
 using namespace npl;
 
@@ -993,6 +994,24 @@ __global__ void __launch_bounds__(256) combat_relgeo_kernel(const float* __restr
 }
 
 // ------------------------------------------------------------------------------------------------
+// K6: table aero back-end (tables_device.cuh): 44 coefficients per (alpha, beta, el) point from the NASA tables
+// ------------------------------------------------------------------------------------------------
+struct np_tables {
+  float* image_dev = nullptr;  // kTablesFloats
+};
+
+__global__ void __launch_bounds__(256) f16_table_coeffs_kernel(const float* __restrict__ image, const float* __restrict__ A,
+                                                               const float* __restrict__ Bd, const float* __restrict__ E,
+                                                               float* __restrict__ out, int n, int ld) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  float* T = reinterpret_cast<float*>(smem_raw);
+  uint64_t* bar = reinterpret_cast<uint64_t*>(T + kTablesFloats);
+  stage_aero(T, image, (uint32_t)(kTablesFloats * 4), bar);
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    table_coefficients(T, A[i], Bd[i], E[i], out + i, ld);
+}
+
+// ------------------------------------------------------------------------------------------------
 // stand-alone nlplant / coefficient kernels (model plug-in getters, parity tests): same device code as K1,
 // two points per thread
 // ------------------------------------------------------------------------------------------------
@@ -1409,6 +1428,54 @@ int np_f16_nlplant(const np_aero* aero, const float* s_dev, const float* u_dev, 
   const int want = ((n + 1) / 2 + kAuxBS - 1) / kAuxBS;
   f16_nlplant_kernel<<<want < 296 ? want : 296, kAuxBS, smem, (cudaStream_t)stream>>>(aero->image_dev, aero->bytes, s_dev, u_dev,
                                                                                    xdot_dev, n, ld);
+  NP_CUDA(cudaGetLastError());
+  return NP_OK;
+}
+
+int np_tables_create(const float* breakpoints, const int32_t* bp_sizes, const float* values, const int32_t* offsets, int n_tables,
+                     size_t n_values, np_tables** out) {
+  if (!breakpoints || !bp_sizes || !values || !offsets || !out) return fail(NP_EINVAL, "np_tables_create: null argument");
+  const int want_sizes[5] = {kNA1, kNA2, kNB1, kND1, kND2};
+  for (int j = 0; j < 5; ++j)
+    if (bp_sizes[j] != want_sizes[j]) return fail(NP_EINVAL, "np_tables_create: breakpoint grid sizes must be 20, 14, 19, 5, 3");
+  if (n_tables != kNumTables || n_values != (size_t)kTableValues) return fail(NP_EINVAL, "np_tables_create: expected 43 tables / 13405 values");
+  for (int t = 0; t < kNumTables; ++t)
+    if (offsets[t] != table_offset(t) - kBpFloats) return fail(NP_EINVAL, "np_tables_create: table offsets do not match the fixed table order");
+  for (int j = 0, o = 0; j < 5; o += want_sizes[j], ++j)
+    for (int i = 1; i < want_sizes[j]; ++i)
+      if (!(breakpoints[o + i] > breakpoints[o + i - 1])) return fail(NP_EINVAL, "np_tables_create: breakpoints must increase");
+  std::vector<float> host(kTablesFloats, 0.0f);
+  memcpy(host.data(), breakpoints, 61 * sizeof(float));
+  memcpy(host.data() + kBpFloats, values, (size_t)kTableValues * sizeof(float));
+  np_tables* t = new np_tables();
+  NP_CUDA(cudaMalloc(&t->image_dev, kTablesFloats * sizeof(float)));
+  NP_CUDA(cudaMemcpy(t->image_dev, host.data(), kTablesFloats * sizeof(float), cudaMemcpyHostToDevice));
+  *out = t;
+  return NP_OK;
+}
+
+int np_tables_destroy(np_tables* t) {
+  if (!t) return NP_OK;
+  cudaFree(t->image_dev);
+  delete t;
+  return NP_OK;
+}
+
+int np_f16_table_coeffs(const np_tables* tables, const float* alpha_deg_dev, const float* beta_deg_dev, const float* el_deg_dev,
+                        float* out_dev, int n, int ld, void* stream) {
+  if (!tables || !alpha_deg_dev || !beta_deg_dev || !el_deg_dev || !out_dev || n <= 0 || ld < n)
+    return fail(NP_EINVAL, "np_f16_table_coeffs: bad argument");
+  const int smem = kTablesFloats * 4 + 16;
+  static int configured[64] = {};
+  int dev = 0;
+  NP_CUDA(cudaGetDevice(&dev));
+  if (!configured[dev & 63]) {
+    NP_CUDA(cudaFuncSetAttribute(f16_table_coeffs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured[dev & 63] = 1;
+  }
+  const int want = (n + 255) / 256;
+  f16_table_coeffs_kernel<<<want < 444 ? want : 444, 256, smem, (cudaStream_t)stream>>>(tables->image_dev, alpha_deg_dev, beta_deg_dev,
+                                                                                    el_deg_dev, out_dev, n, ld);
   NP_CUDA(cudaGetLastError());
   return NP_OK;
 }
