@@ -213,5 +213,15 @@ class BaseEnv:
         nv.check(nv.lib().np_env_launch_info(self._handle, C.byref(g), C.byref(b), C.byref(s), C.byref(m)), "np_env_launch_info")
         return {"grid": g.value, "block": b.value, "smem_bytes": s.value, "num_sms": m.value}
 
-    def render(self, count, filename='./tracks/F16SimRecording-'):
-        raise NotImplementedError("Tacview .acmi rendering (env_base.py:111-151) is host file I/O outside the hot path")
+    def render(self, count, filename='./tracks/F16SimRecording-', max_aircraft=16):
+        """Tacview track of the first `max_aircraft` aircraft (env_base.py:111-151); host file I/O, outside the hot path."""
+        from .acmi import AcmiWriter
+        w = getattr(self, "_acmi", None)
+        if w is None or w.prefix != filename or w.max_aircraft != max_aircraft:
+            w = self._acmi = AcmiWriter(filename, max_aircraft)
+        m = min(max_aircraft, self.n)
+        npos, epos, alt = (x[:m].cpu().numpy() for x in self.model.get_position())
+        roll, pitch, yaw = (x[:m].cpu().numpy() for x in self.model.get_posture())
+        flags = self._flags[:, :self.n]
+        ended = bool(flags.any())
+        return w.write(count, float(self.step_count[0]) * self.model.dt, npos, epos, alt, roll, pitch, yaw, ended)

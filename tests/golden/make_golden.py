@@ -244,6 +244,17 @@ def planning_trajectory(n, steps, scale, seed, name):
     np.savez_compressed(os.path.join(HERE, name), **out)
 
 
+def geodetic_golden(name):
+    """Values of the reference's enu_to_geodetic (envs/utils/utils.py:140-142) on 200 random ENU points."""
+    import_reference()
+    from utils.utils import enu_to_geodetic as ref_e2g
+    rng = np.random.RandomState(0)
+    pts = np.concatenate([rng.uniform(-3e5, 3e5, (200, 2)), rng.uniform(0, 2e4, (200, 1))], 1)
+    out = np.array([ref_e2g(float(e), float(n), float(u), 0, 0, 0) for e, n, u in pts])
+    np.savez_compressed(os.path.join(HERE, name), enu=pts, llh=out)
+    print(name, out.shape)
+
+
 class RefCombat:
     """SingleCombatEnv (envs/singlecombat_env.py) is stale at this commit and cannot be constructed,
     so its step is re-assembled here from the reference code that still runs, called UNMODIFIED:
@@ -425,6 +436,7 @@ if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "combat":       # regenerate only the combat fixtures
         combat_trajectory(24, 30, 18, "combat_traj.npz")
         combat_trajectory(24, 30, 19, "combat_close_traj.npz", close=True)
+    geodetic_golden("geodetic_golden.npz")
         sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "planning":     # regenerate only the planning fixture
         planning_trajectory(48, 16, 1.0, 17, "planning_pid_traj.npz")
