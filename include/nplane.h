@@ -129,6 +129,14 @@ int np_env_reset(np_env* env, const float* draws_dev, const float* noise_dev, vo
 int np_env_step(np_env* env, const float* action_dev, const float* draws_dev, const float* noise_dev,
                 void* stream);
 
+/* The same step restricted to aircraft [first_aircraft, first_aircraft + count) (first even; count even unless it ends
+ * the population).  Aircraft are independent, so a step may be issued as several ranges on different streams: the
+ * numpy boundary (GPUVecEnv, env_wrappers.py:93-103) pipelines H2D(actions) -> kernel -> D2H(obs) chunk by chunk.
+ * action_dev is still the base of the full [n][4] array.  advance_step_index = 1 on the first range of a logical
+ * step, 0 on the others (all ranges then share one RNG counter). */
+int np_env_step_range(np_env* env, const float* action_dev, const float* draws_dev, const float* noise_dev, int first_aircraft,
+                      int count, int advance_step_index, void* stream);
+
 /* PlanningEnv.step(action) (envs/planning_env.py:144-177) as ONE kernel launch: reset -> clamp -> pitch / heading /
  * speed targets from the 3-D high-level action (:146-152) -> n_sub (reference: 50) x { low-level controller ->
  * F16Model.update -> freeze aircraft already terminated in this env step (:162-166) -> step_count -> terminations,

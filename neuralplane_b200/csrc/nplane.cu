@@ -84,6 +84,7 @@ struct StepParams {
   float* blood;                  // [ld] combat damage state (singlecombat_env.py:45)
   int n_sub;                     // FDM sub-steps per env step (planning: 50, planning_env.py:153)
   int pid_first;                 // 1: the controllers have never run (PID.reset, pid.py:13)
+  int pair_begin, pair_end;      // aircraft pairs [pair_begin, pair_end) this launch works on (whole population by default)
   const float* draws;            // [n][5] or null
   const float* noise;            // [n][22] or null
   uint32_t step_index;
@@ -399,10 +400,11 @@ __global__ void __launch_bounds__(BS, MINB) f16_step_kernel(const __grid_constan
   constexpr bool PLAN = MODE == MODE_PLAN, COMBAT = MODE == MODE_COMBAT;
   const bool use_cache = c.use_coef_cache != 0;
 
-  for (int pbase = blockIdx.x * BS; pbase < npairs; pbase += gridDim.x * BS) {
+  const int pend = p.pair_end < npairs ? p.pair_end : npairs;
+  for (int pbase = p.pair_begin + blockIdx.x * BS; pbase < pend; pbase += gridDim.x * BS) {
     const int pr = pbase + threadIdx.x;
-    const int prl = pr < npairs ? pr : npairs - 1;  // inactive lanes shadow the last pair and never store
-    const bool act[2] = {2 * pr < n, 2 * pr + 1 < n};
+    const int prl = pr < pend ? pr : pend - 1;  // inactive lanes shadow the last pair and never store
+    const bool act[2] = {pr < pend && 2 * pr < n, pr < pend && 2 * pr + 1 < n};
     const int idx[2] = {min(2 * prl, n - 1), min(2 * prl + 1, n - 1)};  // row index into [n][*] arrays
 
     // ---- load ----------------------------------------------------------------------------------
@@ -820,7 +822,8 @@ template <bool STEP>
 __global__ void __launch_bounds__(256) uav_env_kernel(const __grid_constant__ StepParams p) {
   const np_env_cfg& c = p.cfg;
   const int n = c.n, ld = c.ld;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+  const int i_end = min(n, 2 * p.pair_end);
+  for (int i = 2 * p.pair_begin + blockIdx.x * blockDim.x + threadIdx.x; i < i_end; i += gridDim.x * blockDim.x) {
     float s[12], F[3], tgt[3];
 #pragma unroll
     for (int j = 0; j < 12; ++j) s[j] = p.s[(size_t)j * ld + i];
@@ -1210,7 +1213,8 @@ static int launch_step(np_env* env, const StepParams& p, cudaStream_t st) {
     NP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured[dev & 63] = smem;
   }
-  const int npairs = (env->cfg.n + 1) / 2;
+  const int npairs = p.pair_end - p.pair_begin;
+  if (npairs <= 0) return NP_OK;
   const int want = (npairs + BS - 1) / BS;
   const int grid = want < env->num_sms * MINB ? want : env->num_sms * MINB;
   env->grid = grid;
@@ -1235,6 +1239,8 @@ static StepParams make_params(np_env* env, const float* action, const float* dra
   p.blood = p.pid + (size_t)kPidRows * env->cfg.ld;
   p.n_sub = 1;
   p.pid_first = 0;
+  p.pair_begin = 0;
+  p.pair_end = (env->cfg.n + 1) / 2;
   p.counters = reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(env->buf.workspace_dev) +
                                                      (((size_t)(kCacheRows + kPidRows + 1) * env->cfg.ld * 4 + 127) / 128) * 128);
   p.aero = env->aero ? env->aero->image_dev : nullptr;
@@ -1312,14 +1318,35 @@ int np_env_reset(np_env* env, const float* draws_dev, const float* noise_dev, vo
   return NP_OK;
 }
 
+static int step_range_impl(np_env* env, const float* action_dev, const float* draws_dev, const float* noise_dev, int first,
+                           int count, bool advance, void* stream);
+
 int np_env_step(np_env* env, const float* action_dev, const float* draws_dev, const float* noise_dev, void* stream) {
   if (!env || !env->bound) return fail(NP_ESTATE, "np_env_step: env not bound");
+  return step_range_impl(env, action_dev, draws_dev, noise_dev, 0, env->cfg.n, true, stream);
+}
+
+int np_env_step_range(np_env* env, const float* action_dev, const float* draws_dev, const float* noise_dev, int first_aircraft,
+                      int count, int advance_step_index, void* stream) {
+  if (!env || !env->bound) return fail(NP_ESTATE, "np_env_step_range: env not bound");
+  if (first_aircraft < 0 || count < 0 || first_aircraft + count > env->cfg.n || (first_aircraft & 1) ||
+      ((count & 1) && first_aircraft + count != env->cfg.n))
+    return fail(NP_EINVAL, "np_env_step_range: the range must start on an even aircraft and cover whole pairs (except the tail)");
+  return step_range_impl(env, action_dev, draws_dev, noise_dev, first_aircraft, count, advance_step_index != 0, stream);
+}
+
+static int step_range_impl(np_env* env, const float* action_dev, const float* draws_dev, const float* noise_dev, int first,
+                           int count, bool advance, void* stream) {
   if (!action_dev || ((uintptr_t)action_dev & 15)) return fail(NP_EINVAL, "np_env_step: action must be a 16-byte aligned device pointer");
+  if (advance) env->step_index++;           // every range of one logical step sees the same RNG counter
   StepParams p = make_params(env, action_dev, draws_dev, noise_dev);
-  env->step_index++;
+  p.step_index = env->step_index - 1;
+  p.pair_begin = first / 2;
+  p.pair_end = (first + count + 1) / 2;
   cudaStream_t st = (cudaStream_t)stream;
   if (env->cfg.model == NP_MODEL_UAV) {
-    const int want = (env->cfg.n + 255) / 256;
+    if (count == 0) return NP_OK;
+    const int want = (count + 255) / 256;
     env->grid = want < env->num_sms * 8 ? want : env->num_sms * 8;
     env->smem = 0;
     uav_env_kernel<true><<<env->grid, 256, 0, st>>>(p);

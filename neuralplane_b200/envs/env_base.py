@@ -208,6 +208,16 @@ class BaseEnv:
             self.render(count=count)
         return self._obs, self._reward, self.is_done, self.bad_done, self.exceed_time_limit, {}
 
+    def step_range(self, action, first, count, advance=True, reset_draws=None, noise=None):
+        """One logical step may be issued as several aircraft ranges (on different streams): `action` is the full
+        [n, 4] device tensor, the range is [first, first + count); advance=True on the first range only."""
+        self._sync_cfg()
+        st = nv.lib().np_env_step_range(self._handle, action.data_ptr(),
+                                        self._ptr(reset_draws, (self.n, nv.NUM_DRAWS), "reset_draws"),
+                                        self._ptr(noise, (self.n, nv.NUM_OBS), "noise"), int(first), int(count),
+                                        1 if advance else 0, self._stream())
+        nv.check(st, "np_env_step_range")
+
     def launch_info(self):
         g, b, s, m = C.c_int(), C.c_int(), C.c_int(), C.c_int()
         nv.check(nv.lib().np_env_launch_info(self._handle, C.byref(g), C.byref(b), C.byref(s), C.byref(m)), "np_env_launch_info")

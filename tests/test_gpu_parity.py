@@ -436,3 +436,22 @@ def test_step_is_cuda_graph_capturable_and_stream_ordered(dev):
     assert torch.equal(e_graph.model.s, e_eager.model.s) and torch.equal(e_graph.last_obs, e_eager.last_obs)
     assert torch.equal(e_graph.step_count, e_eager.step_count) and torch.equal(e_graph.last_reward, e_eager.last_reward)
     assert e_graph.termination_counters() == e_eager.termination_counters()
+
+
+@pytest.mark.parametrize("model,task", [("F16", "heading"), ("UAV", "control")])
+def test_pipelined_numpy_boundary_equals_single_launch(dev, model, task):
+    """GPUVecEnv pipelines large populations in aircraft chunks on side streams (np_env_step_range); results must be
+    bit-identical to the single-launch path, odd population and in-kernel Philox resets / noise included."""
+    from neuralplane_b200 import ControlEnv, GPUVecEnv
+    ne = 20_001
+    mk = lambda: ControlEnv(num_envs=ne, config=task, model=model, random_seed=9, device="cuda:0")
+    v1, v4 = GPUVecEnv([mk], pipeline_chunks=1), GPUVecEnv([mk], pipeline_chunks=4)
+    assert v1._chunks is None and [c[1] - c[0] for c in v4._chunks] == [5000, 5000, 5000, 5001]
+    assert np.array_equal(v1.reset(), v4.reset())
+    for k in range(1, 60):
+        a = tapes.action_tape(9, k, ne, 1.0).reshape(ne, 1, 4)
+        r1, r4 = v1.step(a), v4.step(a)
+        for x, y in zip(r1[:5], r4[:5]):
+            assert np.array_equal(x, y), k
+    assert v1.gpu_vec_env.termination_counters() == v4.gpu_vec_env.termination_counters()
+    assert v1.gpu_vec_env.termination_counters()["resets"] > ne
