@@ -58,13 +58,6 @@ __device__ __forceinline__ uint32_t aero_base_after_staging(const void* blob_sme
 // warp-broadcast LDS.128 lane feeding an FFMA2 (fma.rn.f32x2 with a scalar-broadcast multiplicand), i.e. one
 // issue slot per two multiply-adds.
 // ------------------------------------------------------------------------------------------------
-// NPL_SYNC: CTA-wide barriers that keep the warps of a CTA in the same code region, so the (large, mostly
-// straight-line) instruction stream is fetched once per CTA instead of once per warp.  0 none, 1 per net group,
-// 2 per net.  All callers evaluate the nets in CTA-uniform control flow.
-#ifndef NPL_SYNC
-#define NPL_SYNC 0
-#endif
-
 template <int IN, int OUT, bool RELU>
 __device__ __forceinline__ void dense2(uint32_t w, const float2 (&x)[IN], float2 (&y)[OUT]) {
   constexpr int NF = OUT + IN * OUT;
@@ -153,10 +146,8 @@ __device__ __forceinline__ void eval_group2(const float* __restrict__ blob, uint
   float2 z2 = make_float2(0.f, 0.f);
   if constexpr (A.nin == 3) z2 = zi.z[Z.e >= 0 ? Z.e : 0];
   uint32_t w = wbase + 4 * mlp_offset(K0);
-  if (NPL_SYNC == 1) __syncthreads();
 #pragma unroll 1
   for (int k = K0; k < K0 + count; ++k, w += 4 * NF) {
-    if (NPL_SYNC == 2) __syncthreads();
     const float2 y = mlp2<A.nin, A.h1, A.h2, A.h3>(w, z0, z1, z2);
     out[k * stride] = denorm2(blob, k, y);
   }
@@ -198,30 +189,16 @@ __device__ __forceinline__ AeroTabs aero_tabs(const void* blob_smem, uint32_t ba
 }
 // Number of breakpoints <= x in a sorted, +inf padded list of 2^LEVELS - 1 floats (NaN -> 0), for the thread's two
 // aircraft at once: two independent dependent-load chains in flight instead of one.
-#ifndef NPL_JOINT_SEARCH
-#define NPL_JOINT_SEARCH 0  // fully unrolled search measured 7 % slower end to end (profiles/r01_variants.txt)
-#endif
 template <int LEVELS>
 __device__ __forceinline__ void pwl_search2(uint32_t bp, float x0, float x1, uint32_t& p0, uint32_t& p1) {
   p0 = 0; p1 = 0;
-#if NPL_JOINT_SEARCH
-#pragma unroll
-  for (int l = LEVELS - 1; l >= 0; --l) {
-    const uint32_t step = 1u << l;
-    const float b0 = lds32f(bp + 4u * (p0 + step - 1u));
-    const float b1 = lds32f(bp + 4u * (p1 + step - 1u));
-    p0 += (b0 <= x0) ? step : 0u;
-    p1 += (b1 <= x1) ? step : 0u;
-  }
-#else
-#pragma unroll 1
+#pragma unroll 1   // (a fully unrolled search measured 7 % slower end to end: profiles/r01_variants.txt)
   for (uint32_t step = 1u << (LEVELS - 1); step > 0; step >>= 1) {
     const float b0 = lds32f(bp + 4u * (p0 + step - 1u));
     const float b1 = lds32f(bp + 4u * (p1 + step - 1u));
     p0 += (b0 <= x0) ? step : 0u;
     p1 += (b1 <= x1) ? step : 0u;
   }
-#endif
 }
 __device__ __forceinline__ float pwl_entry(uint32_t ent, uint32_t idx, float x) {
   const float4 e = lds128(ent + 16u * idx);
@@ -463,14 +440,6 @@ __device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
   return ctr;
 }
 __device__ __forceinline__ float u01(uint32_t x) { return (float)(x >> 8) * 5.9604644775390625e-8f; }  // [0,1)
-__device__ __forceinline__ void box_muller(uint32_t a, uint32_t b, float& n0, float& n1) {
-  const float u1 = ((float)(a >> 8) + 1.0f) * 5.9604644775390625e-8f;  // (0,1]
-  const float r = sqrtf(-2.0f * __logf(u1));
-  float sn, cs;
-  __sincosf(kTwoPi * u01(b), &sn, &cs);
-  n0 = r * cs;
-  n1 = r * sn;
-}
 // Two standard normals from ONE 32-bit word (observation noise only): 16-bit radius and angle uniforms taken at
 // bin midpoints, fast-math log / sqrt / sincos.  |n| <= 4.8; mean 0, variance 1 to < 1e-4.
 __device__ __forceinline__ void box_muller16(uint32_t w, float& n0, float& n1) {

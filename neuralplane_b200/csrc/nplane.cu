@@ -26,10 +26,6 @@
 
 using namespace npl;
 
-#ifndef NPL_NOISE16
-#define NPL_NOISE16 1
-#endif
-
 // ------------------------------------------------------------------------------------------------
 // error plumbing
 // ------------------------------------------------------------------------------------------------
@@ -63,7 +59,7 @@ struct np_env {
   bool bound = false;
   uint32_t step_index = 0;
   bool pid_started = false;  // the fused PID controller has run at least once (PID.reset, pid.py:13)
-  int block = 256, grid = 0, smem = 0, num_sms = 0;
+  int block = 384, grid = 0, smem = 0, num_sms = 0;
 };
 
 struct StepParams {
@@ -219,7 +215,6 @@ __device__ __forceinline__ void add_obs_noise(const StepParams& p, int i, float*
   } else if (sc != 0.0f) {
     const uint64_t gi = p.cfg.index_base + (uint64_t)i;
     const uint2 key = make_uint2((uint32_t)p.cfg.seed, (uint32_t)(p.cfg.seed >> 32));
-#if NPL_NOISE16
 #pragma unroll
     for (int q = 0; q < 3; ++q) {  // 3 x 4 words -> 12 pairs of normals, 22 used
       const uint4 r = philox4x32_10(make_uint4((uint32_t)gi, (uint32_t)(gi >> 32), p.step_index, 0x0B5E0000u + q), key);
@@ -235,19 +230,6 @@ __device__ __forceinline__ void add_obs_noise(const StepParams& p, int i, float*
         }
       }
     }
-#else
-#pragma unroll
-    for (int q = 0; q < 6; ++q) {
-      const uint4 r = philox4x32_10(make_uint4((uint32_t)gi, (uint32_t)(gi >> 32), p.step_index, 0x0B5E0000u + q), key);
-      float n0, n1, n2, n3;
-      box_muller(r.x, r.y, n0, n1);
-      box_muller(r.z, r.w, n2, n3);
-      o[4 * q + 0] = o[4 * q + 0] + n0 * sc;
-      o[4 * q + 1] = o[4 * q + 1] + n1 * sc;
-      if (4 * q + 2 < NP_NUM_OBS) o[4 * q + 2] = o[4 * q + 2] + n2 * sc;
-      if (4 * q + 3 < NP_NUM_OBS) o[4 * q + 3] = o[4 * q + 3] + n3 * sc;
-    }
-#endif
   }
 }
 
@@ -517,7 +499,7 @@ __global__ void __launch_bounds__(BS, MINB) f16_step_kernel(const __grid_constan
         hit[0] |= __float_as_uint(ka.x) == __float_as_uint(s[0][7]) && __float_as_uint(kb.x) == __float_as_uint(s[0][8]);
         hit[1] |= __float_as_uint(ka.y) == __float_as_uint(s[1][7]) && __float_as_uint(kb.y) == __float_as_uint(s[1][8]);
       }
-      miss = NPL_SYNC ? (__syncthreads_or(!(hit[0] && hit[1])) != 0) : (__any_sync(0xffffffffu, !(hit[0] && hit[1])) != 0);
+      miss = __any_sync(0xffffffffu, !(hit[0] && hit[1])) != 0;
       if (!miss && (rst[0] || rst[1])) {  // a reset lane sits at alpha = beta = 0: constants from the aero image
 #pragma unroll 4
         for (int k = 0; k < kNumAB2; ++k) {
@@ -1268,10 +1250,13 @@ int np_env_create(const np_env_cfg* cfg, const np_aero* aero, np_env** out) {
   int dev = 0;
   NP_CUDA(cudaGetDevice(&dev));
   NP_CUDA(cudaDeviceGetAttribute(&e->num_sms, cudaDevAttrMultiProcessorCount, dev));
-  e->block = 256;
+  // 384 threads x 1 CTA/SM: 12 warps = 3 per scheduler (block sizes whose warp count is not a multiple of 4 load the
+  // four schedulers unevenly and measured 17 % slower), 168 registers -> no spills, and 131 KB of shared memory leaves
+  // the L1 large enough for what little is spilled; 256 x 2 CTA/SM (128 regs, 217 KB smem) measured 1.65e9 vs 2.05e9
+  // aircraft-steps/s (profiles/r01_variants.txt)
+  e->block = 384;
   if (const char* b = getenv("NPLANE_BLOCK")) e->block = atoi(b);
-  if (e->block != 128 && e->block != 256 && e->block != 384 && e->block != 512)
-    return fail(NP_EINVAL, "NPLANE_BLOCK must be 128, 256, 384 or 512");
+  if (e->block % 32 || e->block < 128 || e->block > 512) return fail(NP_EINVAL, "NPLANE_BLOCK must be a multiple of 32 in [128, 512]");
   *out = e;
   return NP_OK;
 }
@@ -1356,10 +1341,13 @@ static int step_range_impl(np_env* env, const float* action_dev, const float* dr
   switch (env->block) {
 #ifdef NPLANE_ALL_BLOCKS
     case 128: return launch_step<128, 4, MODE_STEP>(env, p, st);
-    case 384: return launch_step<384, 1, MODE_STEP>(env, p, st);
+    case 256: return launch_step<256, 2, MODE_STEP>(env, p, st);
+    case 320: return launch_step<320, 1, MODE_STEP>(env, p, st);
+    case 352: return launch_step<352, 1, MODE_STEP>(env, p, st);
+    case 448: return launch_step<448, 1, MODE_STEP>(env, p, st);
     case 512: return launch_step<512, 1, MODE_STEP>(env, p, st);
 #endif
-    case 256: return launch_step<256, 2, MODE_STEP>(env, p, st);
+    case 384: return launch_step<384, 1, MODE_STEP>(env, p, st);
     default: return fail(NP_EINVAL, "np_env_step: block size not compiled in (build with -DNPLANE_ALL_BLOCKS)");
   }
 }
@@ -1374,7 +1362,7 @@ int np_env_plan_step(np_env* env, const float* action3_dev, int n_sub, const flo
   p.pid_first = env->pid_started ? 0 : 1;
   env->pid_started = true;
   env->step_index++;
-  return launch_step<256, 2, MODE_PLAN>(env, p, (cudaStream_t)stream);
+  return launch_step<384, 1, MODE_PLAN>(env, p, (cudaStream_t)stream);
 }
 
 int np_env_combat_step(np_env* env, const float* action_dev, int n_sub, const float* draws_dev, void* stream) {
@@ -1386,7 +1374,7 @@ int np_env_combat_step(np_env* env, const float* action_dev, int n_sub, const fl
   p.pid_first = env->pid_started ? 0 : 1;
   if (n_sub > 0) env->pid_started = true;
   env->step_index++;
-  return launch_step<256, 2, MODE_COMBAT>(env, p, (cudaStream_t)stream);
+  return launch_step<384, 1, MODE_COMBAT>(env, p, (cudaStream_t)stream);
 }
 
 int np_env_combat_records(np_env* env, float* records_dev, void* stream) {
