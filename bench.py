@@ -211,10 +211,10 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local_rank) if rank == 0 else None   # started before the warm-up: nvidia-smi takes ~0.1 s to start
     for k in range(W):
         env.step(actions[k % 8])
     barrier()
-    sampler = ClockSampler(local_rank) if rank == 0 else None
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for k in range(K):
