@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define NP_ABI_VERSION 3
+#define NP_ABI_VERSION 4
 
 enum { NP_OK = 0, NP_EINVAL = 1, NP_ECUDA = 2, NP_ESTATE = 3 };
 
@@ -194,6 +194,13 @@ int np_tables_create(const float* breakpoints, const int32_t* bp_sizes, const fl
 int np_tables_destroy(np_tables* tables);
 int np_f16_table_coeffs(const np_tables* tables, const float* alpha_deg_dev, const float* beta_deg_dev, const float* el_deg_dev,
                         float* out_dev, int n, int ld, void* stream);
+/* An F16 env whose aero coefficients come from the tables instead of the MLP surrogates: the same BaseEnv.step/reset
+ * (np_env_reset / np_env_step / np_env_step_range) with hifi_F16's 42 consumed coefficients (F16_dynamics.py:167-175)
+ * interpolated in the step kernel.  `tables` must outlive the env.  The planning / combat steps are MLP-only.
+ * np_f16_table_nlplant = np_f16_nlplant for such an env's getters. */
+int np_env_create_tables(const np_env_cfg* cfg, const np_tables* tables, np_env** out);
+int np_f16_table_nlplant(const np_tables* tables, const float* s_dev, const float* u_dev, float* xdot_dev, int n, int ld,
+                         void* stream);
 
 /* UAVDynamics.nlplant (envs/models/UAV/UAV_dynamics.py:15-84) on SoA rows: xdot_dev [12][ld] from s_dev [12][ld] and
  * the three body forces u_dev [3+][ld].  Backs UAVModel.get_extended_state and the getters built on it

@@ -84,6 +84,8 @@ SYMBOLS = {
     "np_tables_create": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_size_t, C.POINTER(_P)]),
     "np_tables_destroy": (C.c_int, [_P]),
     "np_f16_table_coeffs": (C.c_int, [_P, _P, _P, _P, _P, C.c_int, C.c_int, _P]),
+    "np_env_create_tables": (C.c_int, [_P, _P, _P]),
+    "np_f16_table_nlplant": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, _P]),
     "np_uav_nlplant": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, _P]),
     "np_f16_coeffs": (C.c_int, [_P, _P, _P, _P, _P, C.c_int, C.c_int, _P]),
 }

@@ -49,3 +49,17 @@ class F16AeroTables:
                                           torch.cuda.current_stream(self.device).cuda_stream)
         nv.check(st, "np_f16_table_coeffs")
         return out.t()
+
+
+_cache = {}
+
+
+def get_tables(device):
+    """The per-device table image (shared by every table-backed env on that device)."""
+    device = torch.device(device)
+    if device.type != "cuda":
+        raise RuntimeError(f"neuralplane_b200 runs on CUDA devices only (got device={device}); there is no CPU fallback")
+    key = device.index if device.index is not None else torch.cuda.current_device()
+    if key not in _cache:
+        _cache[key] = F16AeroTables(torch.device("cuda", key))
+    return _cache[key]

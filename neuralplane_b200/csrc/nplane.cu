@@ -52,14 +52,19 @@ struct np_aero {
   int device = 0;
 };
 
+struct np_tables {
+  float* image_dev = nullptr;  // kTablesFloats (tables_device.cuh)
+};
+
 struct np_env {
   np_env_cfg cfg;
   const np_aero* aero = nullptr;
+  const np_tables* tables = nullptr;  // set instead of aero: the TABLE aero back-end
   np_buffers buf;
   bool bound = false;
   uint32_t step_index = 0;
   bool pid_started = false;  // the fused PID controller has run at least once (PID.reset, pid.py:13)
-  int block = 384, grid = 0, smem = 0, num_sms = 0;
+  int block = 384, tab_block = 384, grid = 0, smem = 0, num_sms = 0;
 };
 
 struct StepParams {
@@ -75,6 +80,7 @@ struct StepParams {
   unsigned long long* counters;  // [NP_NUM_COUNTERS]
   const uint32_t* aero;          // device image, aero_bytes
   int aero_bytes;
+  int tab;                       // 1: `aero` is the table image (tables_device.cuh), not the MLP image
   const float* action;           // [n][4]; planning step: [n][3]
   float* pid;                    // [kPidRows][ld] controller state (planning / combat step)
   float* blood;                  // [ld] combat damage state (singlecombat_env.py:45)
@@ -350,7 +356,7 @@ __device__ __forceinline__ void combat_outputs(const StepParams& p, float (&s)[2
 // ------------------------------------------------------------------------------------------------
 // K1: the fused step kernel
 // ------------------------------------------------------------------------------------------------
-static int step_smem_bytes(int aero_bytes, int bs) { return aero_bytes + kNumSlots * bs * 8 + 16; }
+static int step_smem_bytes(int aero_bytes, int bs, bool tab = false) { return aero_bytes + (tab ? 0 : kNumSlots * bs * 8) + 16; }
 
 // MODE_STEP  : BaseEnv.step (one FDM step driven by the caller's 4-D action).
 // MODE_COMBAT: SingleCombatEnv.step (singlecombat_env.py:240-274): the thread's two aircraft ARE the pair (ego = 2e,
@@ -360,27 +366,38 @@ static int step_smem_bytes(int aero_bytes, int bs) { return aero_bytes + kNumSlo
 //               that the fused PID controller (ctrl_device.cuh) tracks for n_sub FDM sub-steps; aircraft that terminate
 //               inside the env step are frozen (s <- recent_s); state stays in registers across the sub-steps.
 enum { MODE_STEP = 0, MODE_PLAN = 1, MODE_COMBAT = 2 };
+// TAB = true: the TABLE aero back-end (SURVEY f-3, tables_device.cuh).  The staged image is the 54 KB of NASA tables
+// instead of the MLP image; every coefficient is a multilinear interpolation into registers, so the shared coefficient
+// slots and the (alpha, beta) cache do not exist.  Everything around the coefficients is the same code.
 
-template <int BS, int MINB, int MODE>
+template <int BS, int MINB, int MODE, bool TAB = false>
 __global__ void __launch_bounds__(BS, MINB) f16_step_kernel(const __grid_constant__ StepParams p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   float* blob = reinterpret_cast<float*>(smem_raw);
-  float2* coef_all = reinterpret_cast<float2*>(smem_raw + p.aero_bytes);     // [kNumSlots][BS] float2
-  uint64_t* bar = reinterpret_cast<uint64_t*>(coef_all + kNumSlots * BS);
+  float2* coef_all = reinterpret_cast<float2*>(smem_raw + p.aero_bytes);     // [kNumSlots][BS] float2 (MLP back-end)
+  uint64_t* bar = reinterpret_cast<uint64_t*>(coef_all + (TAB ? 0 : kNumSlots * BS));
 
   stage_aero(blob, p.aero, (uint32_t)p.aero_bytes, bar);
-  const uint32_t wb0 = aero_base_after_staging(blob);
-  const AeroTabs tabs = aero_tabs(blob, wb0);
-  const float* c0 = blob + reinterpret_cast<const int32_t*>(blob)[kHdrC0];
+  uint32_t wb0 = 0;
+  AeroTabs tabs{};
+  const float* c0 = blob;
+  ZeroCells zc{};
+  if constexpr (TAB) {
+    zc = zero_cells(blob);
+  } else {
+    wb0 = aero_base_after_staging(blob);
+    tabs = aero_tabs(blob, wb0);
+    c0 = blob + reinterpret_cast<const int32_t*>(blob)[kHdrC0];
+  }
 
   const np_env_cfg& c = p.cfg;
   const int n = c.n, ld = c.ld;
   const int npairs = (n + 1) >> 1;
   float2* coef2 = coef_all + threadIdx.x;                       // slot k of this thread's pair: coef2[k * BS]
   float* cf = reinterpret_cast<float*>(coef2);                  // aircraft a, slot k: cf[a + k * 2 * BS]
-  constexpr int CS = 2 * BS;
+  constexpr int CS = TAB ? 1 : 2 * BS;
   constexpr bool PLAN = MODE == MODE_PLAN, COMBAT = MODE == MODE_COMBAT;
-  const bool use_cache = c.use_coef_cache != 0;
+  const bool use_cache = !TAB && c.use_coef_cache != 0;
 
   const int pend = p.pair_end < npairs ? p.pair_end : npairs;
   for (int pbase = p.pair_begin + blockIdx.x * BS; pbase < pend; pbase += gridDim.x * BS) {
@@ -492,8 +509,8 @@ __global__ void __launch_bounds__(BS, MINB) f16_step_kernel(const __grid_constan
 
     // ---- (alpha,beta)-MLP outputs at (s): cache hit (the Overload evaluation of the previous step was at exactly
     //      this alpha, beta), a reset lane (constants for alpha = beta = 0), or a miss -> the warp evaluates ----
-    bool miss;
-    {
+    bool miss = false;
+    if constexpr (!TAB) {
       bool hit[2] = {rst[0], rst[1]};
       if (use_cache) {
         hit[0] |= __float_as_uint(ka.x) == __float_as_uint(s[0][7]) && __float_as_uint(kb.x) == __float_as_uint(s[0][8]);
@@ -535,9 +552,11 @@ __global__ void __launch_bounds__(BS, MINB) f16_step_kernel(const __grid_constan
     }
 #pragma unroll 1
     for (int pass = 0; pass < 2; ++pass) {
-      const uint32_t wb = opaque_u32(wb0);
       const float2 adeg = make_float2(s[0][7] * kR2D, s[1][7] * kR2D);
       const float2 bdeg = make_float2(s[0][8] * kR2D, s[1][8] * kR2D);
+      uint32_t seg[2] = {0u, 0u};
+      if constexpr (!TAB) {
+      const uint32_t wb = opaque_u32(wb0);
       ZIn2 zi;
       zscores_ab2(blob, adeg, bdeg, zi);
       zscores_el2(blob, make_float2(u[0][1], u[1][1]), zi);
@@ -550,9 +569,9 @@ __global__ void __launch_bounds__(BS, MINB) f16_step_kernel(const __grid_constan
         store_pair(p.cache + (size_t)kNumAB2 * ld, pr, make_float2(s[0][7], s[1][7]), act[1]);
         store_pair(p.cache + (size_t)(kNumAB2 + 1) * ld, pr, make_float2(s[0][8], s[1][8]), act[1]);
       }
-      uint32_t seg[2];
       pwl_search2<kLevelsA>(tabs.bp_a, adeg.x, adeg.y, seg[0], seg[1]);
       if (pass == 0) coef2[kEtaEl * BS] = eta_el2(tabs, make_float2(u[0][1], u[1][1]));
+      }
 
 #pragma unroll
       for (int q = 0; q < 2; ++q) {
@@ -563,7 +582,13 @@ __global__ void __launch_bounds__(BS, MINB) f16_step_kernel(const __grid_constan
         const Trig g = make_trig(sq);
         const float tp = tfac_pow(sq[2]);
         float a1[kNumA1];
-        alpha_coefs<kNumUsed - kFirstA1>(blob, tabs, seg[q], q == 0 ? adeg.x : adeg.y, a1);
+        float ctab[TAB ? kNumSlots : 1];
+        if constexpr (TAB) {
+          table_env_coefs(blob, zc, q == 0 ? adeg.x : adeg.y, q == 0 ? bdeg.x : bdeg.y, uq[1], pass == 0, ctab, a1);
+          cq = ctab;
+        } else {
+          alpha_coefs<kNumUsed - kFirstA1>(blob, tabs, seg[q], q == 0 ? adeg.x : adeg.y, a1);
+        }
         const ForcePart fp = force_part(sq, uq[0], uq[2], uq[3], 0.0f, g, tp, cq, CS, a1);
 
         if (pass == 0) {
@@ -701,7 +726,7 @@ __global__ void __launch_bounds__(BS, MINB) f16_step_kernel(const __grid_constan
 __global__ void __launch_bounds__(256) f16_reset_kernel(const __grid_constant__ StepParams p) {
   const np_env_cfg& c = p.cfg;
   const int n = c.n, ld = c.ld;
-  const float* c0 = reinterpret_cast<const float*>(p.aero) + reinterpret_cast<const int32_t*>(p.aero)[kHdrC0];
+  const float* c0 = p.tab ? nullptr : reinterpret_cast<const float*>(p.aero) + reinterpret_cast<const int32_t*>(p.aero)[kHdrC0];
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     float s[12], u[4], tgt[3];
     const bool rst = (p.flags[i] | p.flags[ld + i] | p.flags[2 * (size_t)ld + i]) != 0;
@@ -716,9 +741,11 @@ __global__ void __launch_bounds__(256) f16_reset_kernel(const __grid_constant__ 
 #pragma unroll
       for (int j = 0; j < 3; ++j) p.tgt[(size_t)j * ld + i] = tgt[j];
       p.step_count[i] = 0;
-      for (int k = 0; k < kNumAB2; ++k) p.cache[(size_t)k * ld + i] = c0[k];
-      p.cache[(size_t)kNumAB2 * ld + i] = 0.0f;
-      p.cache[(size_t)(kNumAB2 + 1) * ld + i] = 0.0f;
+      if (c0) {  // the (alpha, beta)-MLP outputs at alpha = beta = 0 (the table back-end keeps no cache)
+        for (int k = 0; k < kNumAB2; ++k) p.cache[(size_t)k * ld + i] = c0[k];
+        p.cache[(size_t)kNumAB2 * ld + i] = 0.0f;
+        p.cache[(size_t)(kNumAB2 + 1) * ld + i] = 0.0f;
+      }
       atomicAdd(&p.counters[7], 1ull);
     } else {
 #pragma unroll
@@ -981,10 +1008,6 @@ __global__ void __launch_bounds__(256) combat_relgeo_kernel(const float* __restr
 // ------------------------------------------------------------------------------------------------
 // K6: table aero back-end (tables_device.cuh): 44 coefficients per (alpha, beta, el) point from the NASA tables
 // ------------------------------------------------------------------------------------------------
-struct np_tables {
-  float* image_dev = nullptr;  // kTablesFloats
-};
-
 __global__ void __launch_bounds__(256) f16_table_coeffs_kernel(const float* __restrict__ image, const float* __restrict__ A,
                                                                const float* __restrict__ Bd, const float* __restrict__ E,
                                                                float* __restrict__ out, int n, int ld) {
@@ -994,6 +1017,28 @@ __global__ void __launch_bounds__(256) f16_table_coeffs_kernel(const float* __re
   stage_aero(T, image, (uint32_t)(kTablesFloats * 4), bar);
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
     table_coefficients(T, A[i], Bd[i], E[i], out + i, ld);
+}
+
+// nlplant with the table back-end (the getters of a table-backed F16 plug-in): one aircraft per thread
+__global__ void __launch_bounds__(256) f16_table_nlplant_kernel(const float* __restrict__ image, const float* __restrict__ S,
+                                                                const float* __restrict__ U, float* __restrict__ X, int n, int ld) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  float* T = reinterpret_cast<float*>(smem_raw);
+  uint64_t* bar = reinterpret_cast<uint64_t*>(T + kTablesFloats);
+  stage_aero(T, image, (uint32_t)(kTablesFloats * 4), bar);
+  const ZeroCells zc = zero_cells(T);
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    float s[12], u[5], c[kNumSlots], a1[kNumA1], xdot[12];
+#pragma unroll
+    for (int j = 0; j < 12; ++j) s[j] = S[(size_t)j * ld + i];
+#pragma unroll
+    for (int j = 0; j < 5; ++j) u[j] = U[(size_t)j * ld + i];
+    table_env_coefs(T, zc, s[7] * kR2D, s[8] * kR2D, u[1], true, c, a1);
+    const Trig g = make_trig(s);
+    nlplant_from_coefs(s, u[0], u[2], u[3], u[4], g, tfac_pow(s[2]), c, 1, a1, xdot);
+#pragma unroll
+    for (int j = 0; j < 12; ++j) X[(size_t)j * ld + i] = xdot[j];
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1184,11 +1229,11 @@ size_t np_env_workspace_bytes(const np_env_cfg* cfg) {
 
 }  // extern "C"
 
-template <int BS, int MINB, int MODE>
+template <int BS, int MINB, int MODE, bool TAB = false>
 static int launch_step(np_env* env, const StepParams& p, cudaStream_t st) {
-  const int smem = step_smem_bytes(p.aero_bytes, BS);
+  const int smem = step_smem_bytes(p.aero_bytes, BS, TAB);
   static int configured[64] = {};  // per device: the attribute lives in the device's context
-  auto kern = f16_step_kernel<BS, MINB, MODE>;
+  auto kern = f16_step_kernel<BS, MINB, MODE, TAB>;
   int dev = 0;
   NP_CUDA(cudaGetDevice(&dev));
   if (configured[dev & 63] < smem) {
@@ -1227,6 +1272,12 @@ static StepParams make_params(np_env* env, const float* action, const float* dra
                                                      (((size_t)(kCacheRows + kPidRows + 1) * env->cfg.ld * 4 + 127) / 128) * 128);
   p.aero = env->aero ? env->aero->image_dev : nullptr;
   p.aero_bytes = env->aero ? env->aero->bytes : 0;
+  p.tab = 0;
+  if (env->tables) {
+    p.aero = reinterpret_cast<const uint32_t*>(env->tables->image_dev);
+    p.aero_bytes = kTablesFloats * 4;
+    p.tab = 1;
+  }
   p.action = action;
   p.draws = draws;
   p.noise = noise;
@@ -1236,16 +1287,29 @@ static StepParams make_params(np_env* env, const float* action, const float* dra
 
 extern "C" {
 
+static int env_create_impl(const np_env_cfg* cfg, const np_aero* aero, const np_tables* tables, np_env** out);
+
 int np_env_create(const np_env_cfg* cfg, const np_aero* aero, np_env** out) {
+  if (cfg && cfg->model == NP_MODEL_F16 && !aero) return fail(NP_EINVAL, "np_env_create: the F16 plug-in needs an np_aero");
+  return env_create_impl(cfg, aero, nullptr, out);
+}
+
+int np_env_create_tables(const np_env_cfg* cfg, const np_tables* tables, np_env** out) {
+  if (!tables) return fail(NP_EINVAL, "np_env_create_tables: null np_tables");
+  if (cfg && cfg->model != NP_MODEL_F16) return fail(NP_EINVAL, "np_env_create_tables: the tables are the F16 plug-in's aero data");
+  return env_create_impl(cfg, nullptr, tables, out);
+}
+
+static int env_create_impl(const np_env_cfg* cfg, const np_aero* aero, const np_tables* tables, np_env** out) {
   if (!cfg || !out) return fail(NP_EINVAL, "np_env_create: null argument");
   if (cfg->model != NP_MODEL_F16 && cfg->model != NP_MODEL_UAV) return fail(NP_EINVAL, "np_env_create: unknown aircraft model");
-  if (cfg->model == NP_MODEL_F16 && !aero) return fail(NP_EINVAL, "np_env_create: the F16 plug-in needs an np_aero");
   if (cfg->n <= 0 || cfg->ld < cfg->n + (cfg->n & 1) || cfg->ld % 4)
     return fail(NP_EINVAL, "np_env_create: need n > 0, ld >= n rounded up to even, ld % 4 == 0");
   if (cfg->task < NP_TASK_HEADING || cfg->task > NP_TASK_TRACKING) return fail(NP_EINVAL, "np_env_create: unknown task");
   np_env* e = new np_env();
   e->cfg = *cfg;
   e->aero = aero;
+  e->tables = tables;
   memset(&e->buf, 0, sizeof(e->buf));
   int dev = 0;
   NP_CUDA(cudaGetDevice(&dev));
@@ -1257,6 +1321,7 @@ int np_env_create(const np_env_cfg* cfg, const np_aero* aero, np_env** out) {
   e->block = 384;
   if (const char* b = getenv("NPLANE_BLOCK")) e->block = atoi(b);
   if (e->block % 32 || e->block < 128 || e->block > 512) return fail(NP_EINVAL, "NPLANE_BLOCK must be a multiple of 32 in [128, 512]");
+  if (const char* b = getenv("NPLANE_TAB_BLOCK")) e->tab_block = atoi(b);
   *out = e;
   return NP_OK;
 }
@@ -1338,6 +1403,17 @@ static int step_range_impl(np_env* env, const float* action_dev, const float* dr
     NP_CUDA(cudaGetLastError());
     return NP_OK;
   }
+  if (env->tables) {
+    switch (env->tab_block) {
+#if defined(NPLANE_ALL_BLOCKS) || defined(NPLANE_TAB_BLOCKS)
+      case 128: return launch_step<128, 4, MODE_STEP, true>(env, p, st);
+      case 256: return launch_step<256, 2, MODE_STEP, true>(env, p, st);
+      case 512: return launch_step<512, 1, MODE_STEP, true>(env, p, st);
+#endif
+      case 384: return launch_step<384, 1, MODE_STEP, true>(env, p, st);  // 4.36e9 vs 4.16e9 (256 x 2) / 4.20e9 (512) / 4.10e9 (128 x 4) at n = 10^6
+      default: return fail(NP_EINVAL, "np_env_step: table back-end block size not compiled in (build with -DNPLANE_ALL_BLOCKS)");
+    }
+  }
   switch (env->block) {
 #ifdef NPLANE_ALL_BLOCKS
     case 128: return launch_step<128, 4, MODE_STEP>(env, p, st);
@@ -1356,6 +1432,7 @@ int np_env_plan_step(np_env* env, const float* action3_dev, int n_sub, const flo
                      void* stream) {
   if (!env || !env->bound) return fail(NP_ESTATE, "np_env_plan_step: env not bound");
   if (env->cfg.model != NP_MODEL_F16) return fail(NP_EINVAL, "np_env_plan_step: the fused PID controller flies the F16 plug-in");
+  if (env->tables) return fail(NP_EINVAL, "np_env_plan_step: not built for the table aero back-end");
   if (!action3_dev || ((uintptr_t)action3_dev & 3) || n_sub < 1) return fail(NP_EINVAL, "np_env_plan_step: bad action pointer or n_sub");
   StepParams p = make_params(env, action3_dev, draws_dev, noise_dev);
   p.n_sub = n_sub;
@@ -1369,6 +1446,7 @@ int np_env_combat_step(np_env* env, const float* action_dev, int n_sub, const fl
   if (!env || !env->bound) return fail(NP_ESTATE, "np_env_combat_step: env not bound");
   if (env->cfg.model != NP_MODEL_F16 || (env->cfg.n & 1)) return fail(NP_EINVAL, "np_env_combat_step: needs the F16 plug-in and an even population (pairs)");
   if (n_sub < 0 || (n_sub > 0 && (!action_dev || ((uintptr_t)action_dev & 15)))) return fail(NP_EINVAL, "np_env_combat_step: bad action pointer or n_sub");
+  if (env->tables) return fail(NP_EINVAL, "np_env_combat_step: not built for the table aero back-end");
   StepParams p = make_params(env, action_dev ? action_dev : reinterpret_cast<const float*>(env->buf.s_dev), draws_dev, nullptr);
   p.n_sub = n_sub;
   p.pid_first = env->pid_started ? 0 : 1;
@@ -1422,7 +1500,7 @@ int np_env_counters(np_env* env, uint64_t* out, void* stream) {
 int np_env_launch_info(const np_env* env, int* grid, int* block, int* smem_bytes, int* num_sms) {
   if (!env) return fail(NP_EINVAL, "np_env_launch_info: null env");
   if (grid) *grid = env->grid;
-  if (block) *block = env->block;
+  if (block) *block = env->tables ? env->tab_block : env->block;
   if (smem_bytes) *smem_bytes = env->smem;
   if (num_sms) *num_sms = env->num_sms;
   return NP_OK;
@@ -1491,6 +1569,23 @@ int np_f16_table_coeffs(const np_tables* tables, const float* alpha_deg_dev, con
   const int want = (n + 255) / 256;
   f16_table_coeffs_kernel<<<want < 444 ? want : 444, 256, smem, (cudaStream_t)stream>>>(tables->image_dev, alpha_deg_dev, beta_deg_dev,
                                                                                     el_deg_dev, out_dev, n, ld);
+  NP_CUDA(cudaGetLastError());
+  return NP_OK;
+}
+
+int np_f16_table_nlplant(const np_tables* tables, const float* s_dev, const float* u_dev, float* xdot_dev, int n, int ld,
+                         void* stream) {
+  if (!tables || !s_dev || !u_dev || !xdot_dev || n <= 0 || ld < n) return fail(NP_EINVAL, "np_f16_table_nlplant: bad argument");
+  const int smem = kTablesFloats * 4 + 16;
+  static int configured[64] = {};
+  int dev = 0;
+  NP_CUDA(cudaGetDevice(&dev));
+  if (!configured[dev & 63]) {
+    NP_CUDA(cudaFuncSetAttribute(f16_table_nlplant_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured[dev & 63] = 1;
+  }
+  const int want = (n + 255) / 256;
+  f16_table_nlplant_kernel<<<want < 444 ? want : 444, 256, smem, (cudaStream_t)stream>>>(tables->image_dev, s_dev, u_dev, xdot_dev, n, ld);
   NP_CUDA(cudaGetLastError());
   return NP_OK;
 }

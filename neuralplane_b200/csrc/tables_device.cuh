@@ -8,6 +8,8 @@
 #pragma once
 #include <stdint.h>
 
+#include "f16_layout.h"
+
 namespace npl {
 
 constexpr int kNA1 = 20, kNA2 = 14, kNB1 = 19, kND1 = 5, kND2 = 3;
@@ -55,6 +57,22 @@ __device__ __forceinline__ Cell find_cell(const float* bp, int n, float x) {
   c.lam = (x - bp[i]) / (bp[i + 1] - bp[i]);
   return c;
 }
+// the same scan with the grid size known at compile time: every breakpoint load is independent of the others (warp-
+// broadcast LDS), so the scan costs its instruction count, not N shared-memory latencies (the step kernel's version)
+template <int N>
+__device__ __forceinline__ Cell find_cell_u(const float* bp, float x) {
+  float g[N];
+#pragma unroll
+  for (int j = 0; j < N; ++j) g[j] = bp[j];
+  x = fminf(fmaxf(x, g[0]), g[N - 1]);
+  int i = 0;
+#pragma unroll
+  for (int j = 1; j < N - 1; ++j) i += (g[j] <= x) ? 1 : 0;
+  Cell c;
+  c.i = i;
+  c.lam = (x - bp[i]) / (bp[i + 1] - bp[i]);
+  return c;
+}
 // successive linear interpolation, alpha first (mexndinterp.py:50-81): lambda * f2 + (1 - lambda) * f1
 __device__ __forceinline__ float lerp(float f1, float f2, float lam) { return lam * f2 + (1.0f - lam) * f1; }
 __device__ __forceinline__ float tab1(const float* t, Cell a) { return lerp(t[a.i], t[a.i + 1], a.lam); }
@@ -95,6 +113,63 @@ __device__ __forceinline__ void table_coefficients(const float* T, float alpha, 
   PUT(T2L(tCy_a20_lef) - Cy_lef - dCy_a20); PUT(T2L(tCn_a20_lef) - Cn_lef - dCn_a20); PUT(T2L(tCl_a20_lef) - Cl_lef - dCl_a20);
   PUT(T1(tdCNbeta)); PUT(T1(tdCLbeta)); PUT(T1(tdCm)); PUT(tab1(T + table_offset(tEta), d1)); PUT(0.0f);             // hifi_other_coeffs
 #undef PUT
+#undef T3
+#undef T2
+#undef T2L
+#undef T1
+#undef T1L
+}
+
+// The coefficients the env's nlplant consumes (F16_dynamics.py:167-175), written to the step kernel's slots: c[k] for
+// the Coef slots k < kNumSlots (f16_layout.h) and a1[k - kFirstA1] for the alpha-only ones -- the same expressions as
+// table_coefficients() above, minus the two rows nlplant never reads (delta_Czq_lef, delta_Cm_ds).  z1 / z2 are the
+// el = 0 cells of the two elevator grids (hifi_C_lef etc. subtract the el = 0 value), computed once per thread.
+struct ZeroCells {
+  Cell z1, z2;
+};
+__device__ __forceinline__ ZeroCells zero_cells(const float* T) {
+  ZeroCells z;
+  z.z1 = find_cell(T + kBpD1, kND1, 0.0f);
+  z.z2 = find_cell(T + kBpD2, kND2, 0.0f);
+  return z;
+}
+// full = false: only what the force equations read (Cx_tot, Cy_tot, Cz_tot: the Overload evaluation, F16_model.py:132-148).
+__device__ __forceinline__ void table_env_coefs(const float* T, const ZeroCells& z, float alpha, float beta, float el, bool full,
+                                                float* __restrict__ c, float* __restrict__ a1) {
+  const Cell ca = find_cell_u<kNA1>(T + kBpA1, alpha), cl = find_cell_u<kNA2>(T + kBpA2, alpha), cb = find_cell_u<kNB1>(T + kBpB1, beta);
+  const Cell d1 = find_cell_u<kND1>(T + kBpD1, el);
+#define T3(t, d) tab3(T + table_offset(t), kNA1, kNB1, ca, cb, d)
+#define T2(t) tab2(T + table_offset(t), kNA1, ca, cb)
+#define T2L(t) tab2(T + table_offset(t), kNA2, cl, cb)
+#define T1(t) tab1(T + table_offset(t), ca)
+#define T1L(t) tab1(T + table_offset(t), cl)
+#define A1(k) a1[(k) - kFirstA1]
+  // ---- force coefficients (force_totals, F16_dynamics.py:197-207) ----
+  const float Cy = T2(tCy);
+  const float Cx0 = T3(tCx, z.z1), Cz0 = T3(tCz, z.z1);
+  const float Cy_lef = T2L(tCy_lef);
+  const float dCy_a20 = T2(tCy_a20) - Cy;
+  c[kCx] = T3(tCx, d1); c[kCz] = T3(tCz, d1);
+  c[kCy] = Cy; c[kdCx_lef] = T2L(tCx_lef) - Cx0; c[kdCz_lef] = T2L(tCz_lef) - Cz0; c[kdCy_lef] = Cy_lef - Cy;
+  c[kdCy_r30] = T2(tCy_r30) - Cy; c[kdCy_a20] = dCy_a20; c[kdCy_a20_lef] = T2L(tCy_a20_lef) - Cy_lef - dCy_a20;
+  A1(kCxq) = T1(tCXq); A1(kCzq) = T1(tCZq); A1(kCyp) = T1(tCYp); A1(kCyr) = T1(tCYr);
+  A1(kdCxq_lef) = T1L(tdCXq_lef); A1(kdCyr_lef) = T1L(tdCYr_lef); A1(kdCyp_lef) = T1L(tdCYp_lef);
+  if (!full) return;
+  // ---- moment coefficients (nlplant_kin_moments, F16_dynamics.py:208-214) ----
+  const Cell d2 = find_cell_u<kND2>(T + kBpD2, el);
+  const float Cm0 = T3(tCm, z.z1), Cn0 = T3(tCn, z.z2), Cl0 = T3(tCl, z.z2);
+  const float Cn_lef = T2L(tCn_lef), Cl_lef = T2L(tCl_lef);
+  const float dCn_a20 = T2(tCn_a20) - Cn0, dCl_a20 = T2(tCl_a20) - Cl0;
+  c[kCm] = T3(tCm, d1); c[kCn] = T3(tCn, d2); c[kCl] = T3(tCl, d2);
+  c[kEtaEl] = tab1(T + table_offset(tEta), d1);
+  c[kdCl_a20] = dCl_a20; c[kdCl_lef] = Cl_lef - Cl0; c[kdCm_lef] = T2L(tCm_lef) - Cm0; c[kdCn_lef] = Cn_lef - Cn0;
+  c[kdCn_r30] = T2(tCn_r30) - Cn0; c[kdCl_r30] = T2(tCl_r30) - Cl0; c[kdCn_a20] = dCn_a20;
+  c[kdCn_a20_lef] = T2L(tCn_a20_lef) - Cn_lef - dCn_a20; c[kdCl_a20_lef] = T2L(tCl_a20_lef) - Cl_lef - dCl_a20;
+  A1(kCmq) = T1(tCMq); A1(kCnr) = T1(tCNr); A1(kCnp) = T1(tCNp); A1(kClp) = T1(tCLp); A1(kClr) = T1(tCLr);
+  A1(kdCnbeta) = T1(tdCNbeta); A1(kdClbeta) = T1(tdCLbeta); A1(kdCm) = T1(tdCm);
+  A1(kdClr_lef) = T1L(tdCLr_lef); A1(kdClp_lef) = T1L(tdCLp_lef);
+  A1(kdCmq_lef) = T1L(tdCMq_lef); A1(kdCnr_lef) = T1L(tdCNr_lef); A1(kdCnp_lef) = T1L(tdCNp_lef);
+#undef A1
 #undef T3
 #undef T2
 #undef T2L

@@ -89,7 +89,10 @@ class BaseEnv:
         self._cfg = self._cfg_struct()
         with torch.cuda.device(self.device):
             aero = self.model.aero.handle if self.model.aero is not None else None
-            nv.check(L.np_env_create(C.byref(self._cfg), aero, C.byref(self._handle)), "np_env_create")
+            if getattr(self.model, "aero_backend", "mlp") == "tables":
+                nv.check(L.np_env_create_tables(C.byref(self._cfg), aero, C.byref(self._handle)), "np_env_create_tables")
+            else:
+                nv.check(L.np_env_create(C.byref(self._cfg), aero, C.byref(self._handle)), "np_env_create")
             nbytes = L.np_env_workspace_bytes(C.byref(self._cfg))
             self._workspace = torch.zeros(nbytes, dtype=torch.uint8, device=self.device)
             b = nv.Buffers(self.model._s.data_ptr(), self.model._u.data_ptr(), self._tgt.data_ptr(),

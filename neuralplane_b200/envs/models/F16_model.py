@@ -29,8 +29,7 @@ class F16Model(BaseModel):
         self.min_vt = getattr(self.config, 'min_vt', 1000)
         self.init_state = getattr(self.config, 'init_state', {'init_T': getattr(self.config, 'init_T', 2000)})
 
-        from ...aero import get_aero
-        self.aero = aero if aero is not None else get_aero(device)
+        self.aero = aero if aero is not None else self._load_aero(device)
         self.ld = ld if ld is not None else _soa.pitch(n)
         self._s = torch.zeros((12, self.ld), device=device)     # field-major state rows
         self._u = torch.zeros((5, self.ld), device=device)      # T el ail rud lef
@@ -41,6 +40,10 @@ class F16Model(BaseModel):
         # nothing on the control-task path reads them, so they are not materialised per step here.
         self.recent_s = self.s
         self.recent_u = self.u
+
+    def _load_aero(self, device):
+        from ...aero import get_aero
+        return get_aero(device)
 
     # -- dynamics (native) ---------------------------------------------------------------------------------
     def reset(self, env):
@@ -153,3 +156,20 @@ class F16Model(BaseModel):
         ps = 1715.0 * rho * temp
         ps = torch.where(ps == 0, torch.full_like(ps, 1715.0), ps)
         return mach, qbar, ps
+
+
+class F16TablesModel(F16Model):
+    """The same F-16 plug-in with the TABLE aero back-end (SURVEY f-3): every aero coefficient is a multilinear
+    interpolation of the NASA tables (example/data/*.dat, example/train_model/hifi_F16_AeroData.py:406-483) instead of
+    the MLP surrogate fitted to them.  Selected with ControlEnv(model='F16_tables')."""
+    aero_backend = "tables"
+
+    def _load_aero(self, device):
+        from ...aero_tables import get_tables
+        return get_tables(device)
+
+    def get_extended_state(self):
+        st = nv.lib().np_f16_table_nlplant(self.aero.handle, self._s.data_ptr(), self._u.data_ptr(), self._xdot.data_ptr(),
+                                           self.n, self.ld, torch.cuda.current_stream(self.device).cuda_stream)
+        nv.check(st, "np_f16_table_nlplant")
+        return self._xdot.t()[:self.n]

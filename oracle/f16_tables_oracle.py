@@ -96,3 +96,24 @@ class F16Tables:
                 t("Cl_a20_lef", alpha, beta) - Cl_lef - dCl_a20,
                 t("delta_CNbeta", alpha), t("delta_CLbeta", alpha), t("delta_Cm", alpha), t("eta_el", el), z]
         return np.stack(rows, 0)
+
+
+class TableAero:
+    """Drop-in for f16_oracle.AeroNets: `coeffs(alpha_deg, beta_deg, el_deg)` -> {name: tensor} from the tables, so that
+    F16EnvOracle(aero=TableAero(...)) is the oracle of a table-backed env (ControlEnv(model='F16_tables')).  Both halves
+    are pinned on their own: the env logic bit-exactly to the reference env (tests/test_oracle_golden.py), the
+    coefficients to coefs.csv at 1e-12 (tests/test_tables_oracle_golden.py).  The reference itself never flies the
+    tables through its env (its hifi_F16 holds the MLP surrogates), so there is no end-to-end reference run to pin the
+    composition to.  Interpolation runs in float64; the result is cast to `dtype`."""
+
+    def __init__(self, dtype=None, path=TABLES_NPZ):
+        import torch
+        self.torch = torch
+        self.dtype = dtype or torch.float32
+        self.tables = F16Tables(path)
+
+    def coeffs(self, alpha_deg, beta_deg, el_deg):
+        t = self.torch
+        a, b, e = (x.detach().to(t.float64).numpy() for x in (alpha_deg, beta_deg, el_deg))
+        rows = self.tables.coefficients(a, b, e)
+        return {name: t.from_numpy(np.ascontiguousarray(rows[k])).to(self.dtype) for k, name in enumerate(COEF_NAMES)}

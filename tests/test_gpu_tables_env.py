@@ -1,0 +1,177 @@
+"""GPU parity of the TABLE-backed F-16 env (ControlEnv(model='F16_tables'), SURVEY f-3) against the CPU oracle
+F16EnvOracle(aero=TableAero()) -- the reference env logic (pinned bit-exactly to the reference env) with the reference
+table interpolation (pinned to coefs.csv at 1e-12) as its coefficient source.
+
+The reference never flies its tables through its env, so there is no reference-fp32 run to compare noise levels with;
+the bars are stated against the float64 evaluation of the same formulas ("truth") in absolute terms and, where the
+oracle's own fp32 evaluation exists, relative to its distance from truth.  The oracle interpolates in float64 and casts
+the coefficients to fp32, i.e. it is slightly *more* accurate than any pure-fp32 evaluation, so the ratio bars carry a
+small absolute allowance.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import tapes
+from _metrics import state_rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+def _cuda(x):
+    return torch.from_numpy(np.ascontiguousarray(x)).cuda()
+
+
+def _env(n, task="heading"):
+    from neuralplane_b200 import ControlEnv
+    env = ControlEnv(num_envs=n, config=task, model="F16_tables", random_seed=0, device="cuda:0")
+    env.task.noise_scale = 0.0
+    return env
+
+
+def _oracle(n, task, dtype):
+    from oracle.f16_oracle import F16EnvOracle
+    from oracle.f16_tables_oracle import TableAero
+    return F16EnvOracle(n, task, aero=TableAero(dtype=dtype), dtype=dtype)
+
+
+def test_table_nlplant_vs_oracle():
+    """np_f16_table_nlplant (the getters' back-end) vs the oracle nlplant fed by the oracle tables, 4096 states."""
+    from oracle.f16_oracle import nlplant as o_nlplant
+    from oracle.f16_tables_oracle import TableAero
+    n = 4096
+    s, u = tapes.random_envelope_states(11, n)
+    env = _env(n)
+    env.model.s[:] = _cuda(s)
+    env.model.u[:] = _cuda(u)
+    xdot = env.model.get_extended_state().cpu().numpy()
+    assert xdot.shape == (n, 17) and not xdot[:, 12:].any()
+    truth = o_nlplant(TableAero(dtype=torch.float64), torch.from_numpy(s).double(), torch.from_numpy(u).double()).numpy()
+    ref32 = o_nlplant(TableAero(dtype=torch.float32), torch.from_numpy(s), torch.from_numpy(u)).numpy()
+    floor = 1e-3 * np.median(np.abs(truth), axis=0) + 1e-12
+    e_ours = np.abs(xdot[:, :12] - truth) / (np.abs(truth) + floor)
+    e_ref = np.abs(ref32 - truth) / (np.abs(truth) + floor)
+    print("\ntable nlplant vs fp64: ours p50 %.2e p99 %.2e max %.2e | oracle-fp32 p50 %.2e p99 %.2e max %.2e" % (
+        np.median(e_ours), np.percentile(e_ours, 99), e_ours.max(), np.median(e_ref), np.percentile(e_ref, 99), e_ref.max()))
+    assert np.median(e_ours) <= 2 * np.median(e_ref) + 2e-8
+    assert np.percentile(e_ours, 99) <= 3 * np.percentile(e_ref, 99) + 1e-6
+    assert e_ours.max() <= 1e-3
+
+
+@pytest.mark.parametrize("task", ["heading", "control", "tracking"])
+def test_table_env_single_step(task):
+    """One env step from 20000 random in-envelope states: state vs float64 truth, obs / reward / flags vs the oracle."""
+    n = 20000
+    s, u = tapes.random_envelope_states(177, n)
+    r = tapes.uniform01(178, 1, (n, 4))
+    if task == "heading":
+        tgt = np.stack([s[:, 2] + (r[:, 0] - 0.5) * 400, s[:, 5] + (r[:, 1] - 0.5) * 0.3, s[:, 6] + (r[:, 2] - 0.5) * 60], 1)
+    elif task == "control":
+        tgt = np.stack([s[:, 4] + (r[:, 0] - 0.5) * 0.3, s[:, 5] + (r[:, 1] - 0.5) * 0.3, s[:, 6] + (r[:, 2] - 0.5) * 60], 1)
+    else:
+        tgt = np.stack([s[:, 0] + (r[:, 0] - 0.5) * 400, s[:, 1] + (r[:, 1] - 0.5) * 400, s[:, 2] + (r[:, 2] - 0.5) * 400], 1)
+    tgt = tgt.astype(np.float32)
+    steps = (r[:, 3] * 2600).astype(np.int64)
+    env = _env(n, task)
+    env.model.s[:] = _cuda(s); env.model.u[:] = _cuda(u)
+    env._tgt[:, :n] = _cuda(tgt.T.copy())
+    env.step_count[:] = _cuda(steps.astype(np.int32))
+    env._flags.zero_()
+    a, d = tapes.action_tape(179, 1, n, 1.0), tapes.reset_draw_tape(179, 1, n)
+    obs, rew, done, bad, exc, _ = env.step(_cuda(a), reset_draws=_cuda(d))
+    out = {}
+    for name, dt in (("f32", torch.float32), ("f64", torch.float64)):
+        o = _oracle(n, task, dt)
+        o.s = torch.from_numpy(s).to(dt); o.u = torch.from_numpy(u).to(dt); o.tgt = torch.from_numpy(tgt).to(dt)
+        o.step_count = torch.from_numpy(steps.copy())
+        o.is_done[:] = False; o.bad_done[:] = False; o.exceed_time_limit[:] = False
+        out[name] = (o, o.step(torch.from_numpy(a).to(dt), torch.from_numpy(d).to(dt)))
+    o32, (o_obs, o_rew, o_done, o_bad, o_exc) = out["f32"]
+    truth = out["f64"][0].s.numpy()
+    s_new = env.model.s.cpu().numpy()
+    e_ours, e_ref = state_rel_err(s_new, truth), state_rel_err(o32.s.numpy(), truth)
+    print("\n%s table env one step vs fp64: ours p50 %.2e p99 %.2e p99.9 %.2e max %.2e | oracle-fp32 p50 %.2e p99 %.2e p99.9 %.2e max %.2e" % (
+        task, np.median(e_ours), np.percentile(e_ours, 99), np.percentile(e_ours, 99.9), e_ours.max(),
+        np.median(e_ref), np.percentile(e_ref, 99), np.percentile(e_ref, 99.9), e_ref.max()))
+    assert np.median(e_ours) <= 2 * np.median(e_ref) + 1e-8
+    assert np.percentile(e_ours, 99) <= 2 * np.percentile(e_ref, 99) + 2e-7
+    # the tail: a handful of samples whose roll / yaw moment sums cancel to ~0, so that fp32 rounding of the interpolated
+    # coefficients (the oracle interpolates in float64) shows up relative to a near-zero component
+    assert np.percentile(e_ours, 99.9) <= 5e-5 and e_ours.max() <= 1e-3
+    assert np.allclose(env.model.u.cpu().numpy(), o32.u.numpy(), rtol=1e-6, atol=1e-6)
+    assert np.allclose(obs.cpu().numpy(), o_obs.numpy(), rtol=1e-5, atol=2e-6)
+    near = np.abs(o32.last_accel.numpy() - 300.0) / 300.0 < 1e-5
+    assert ((bad.cpu().numpy() != o_bad.numpy()) & ~near).sum() <= 2
+    assert (done.cpu().numpy() != o_done.numpy()).sum() <= 2
+    ok = bad.cpu().numpy() == o_bad.numpy()
+    assert np.allclose(rew.cpu().numpy()[ok], o_rew.numpy()[ok], rtol=1e-5, atol=1e-5)
+    assert 0 < int(o_bad.sum()) < n and int(o_done.sum()) > 0
+
+
+def test_table_env_trajectory_300_steps():
+    """n = 128 heading, 300 steps with resets (shared action / reset-draw tapes): the CUDA trajectory must sit as close
+    to the float64 truth as the oracle's fp32 one (x1.5 + 1e-7) over aircraft with the same reset history."""
+    n, steps, seed = 128, 300, 9
+    env, o32, o64 = _env(n), _oracle(n, "heading", torch.float32), _oracle(n, "heading", torch.float64)
+    d0 = tapes.reset_draw_tape(seed, 0, n)
+    obs0 = env.reset(reset_draws=_cuda(d0))
+    r0 = o32.reset(torch.from_numpy(d0)); o64.reset(torch.from_numpy(d0).double())
+    assert np.allclose(obs0.cpu().numpy(), r0.numpy(), rtol=1e-6, atol=1e-7)
+    report = []
+    for k in range(1, steps + 1):
+        a, d = tapes.action_tape(seed, k, n, 0.3), tapes.reset_draw_tape(seed, k, n)
+        obs, rew, done, bad, exc, _ = env.step(_cuda(a), reset_draws=_cuda(d))
+        r32 = o32.step(torch.from_numpy(a), torch.from_numpy(d))
+        o64.step(torch.from_numpy(a).double(), torch.from_numpy(d).double())
+        if k <= 20:
+            assert np.array_equal(bad.cpu().numpy(), r32[3].numpy()) and np.array_equal(done.cpu().numpy(), r32[2].numpy()), k
+            assert np.allclose(rew.cpu().numpy(), r32[1].numpy(), rtol=1e-5, atol=1e-5), k
+            assert np.allclose(obs.cpu().numpy(), r32[0].numpy(), rtol=1e-5, atol=5e-6), k
+        if k in (1, 10, 50, 100, 200, 300):
+            sc = env.step_count.cpu().numpy()
+            same = (sc == o64.step_count.numpy()) & (sc == o32.step_count.numpy())
+            e_ours = state_rel_err(env.model.s.cpu().numpy()[same], o64.s.numpy()[same])
+            e_ref = state_rel_err(o32.s.numpy()[same], o64.s.numpy()[same])
+            report.append((k, float(same.mean()), float(np.median(e_ours)), float(e_ours.max()), float(np.median(e_ref)), float(e_ref.max())))
+            assert same.mean() >= 0.8, report[-1]
+            assert np.median(e_ours) <= 1.5 * np.median(e_ref) + 1e-7, report[-1]
+    print("\ntable env trajectory: step | same-history | ours-vs-fp64 median, max | oracle32-vs-fp64 median, max")
+    for r in report:
+        print("   k=%4d same=%.3f  %.2e %.2e | %.2e %.2e" % r)
+
+
+def test_table_env_full_size_invariants():
+    """n = 10^6, 30 random steps: finite outputs, counters move, a sampled sub-population replays through the oracle."""
+    n, m = 1_000_000, 2048
+    dev = torch.device("cuda:0")
+    env = _env(n)
+    env.reset()
+    g = torch.Generator(device="cuda").manual_seed(3)
+    for _ in range(30):
+        env.step(torch.rand((n, 4), device=dev, generator=g) * 2 - 1)
+    idx = torch.from_numpy(np.sort(np.random.default_rng(1).choice(n, m, replace=False))).cuda()
+    orc = _oracle(m, "heading", torch.float32)
+    orc.s = env.model.s[idx].cpu(); orc.u = env.model.u[idx].cpu()
+    orc.tgt = env._tgt[:, idx].t().contiguous().cpu()
+    orc.step_count = env.step_count[idx].cpu().long()
+    orc.is_done = env.is_done[idx].cpu().clone(); orc.bad_done = env.bad_done[idx].cpu().clone()
+    orc.exceed_time_limit = env.exceed_time_limit[idx].cpu().clone()
+    a = torch.rand((n, 4), device=dev, generator=g) * 2 - 1
+    d = torch.rand((n, 5), device=dev, generator=g)
+    obs, rew, done, bad, exc, _ = env.step(a, reset_draws=d)
+    o_obs, o_rew, o_done, o_bad, o_exc = orc.step(a[idx].cpu(), d[idx].cpu())
+    assert np.allclose(obs[idx].cpu().numpy(), o_obs.numpy(), rtol=2e-5, atol=5e-6)
+    assert (bad[idx].cpu() != o_bad).sum() <= 1
+    assert torch.isfinite(env.model.s).all() and torch.isfinite(obs).all() and torch.isfinite(rew).all()
+    c = env.termination_counters()
+    assert c["resets"] >= n and c["overload"] > 0
+
+
+def test_table_env_rejects_planning_and_combat_steps():
+    import ctypes as C
+    from neuralplane_b200 import _native as nv
+    env = _env(64)
+    a = torch.zeros((64, 4), device="cuda")
+    st = torch.cuda.current_stream().cuda_stream
+    assert nv.lib().np_env_plan_step(env._handle, a.data_ptr(), 5, None, None, st) != 0
+    assert nv.lib().np_env_combat_step(env._handle, a.data_ptr(), 5, None, st) != 0

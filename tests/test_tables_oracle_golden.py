@@ -23,3 +23,28 @@ def test_table_coefficients_match_the_references_golden_vectors():
     for k, name in enumerate(COEF_NAMES):
         cols = in_alpha2 if k in ALPHA2_ROWS else slice(None)
         assert np.abs(out[k][cols] - g["coefs"][k][cols]).max() <= 1e-12, name
+
+
+def test_table_aero_adapter_feeds_the_env_oracle():
+    """TableAero plugs the tables into F16EnvOracle (the oracle of ControlEnv(model='F16_tables')): every coefficient
+    nlplant consumes is present, equals F16Tables.coefficients, and fp32 / fp64 env steps agree to fp32 rounding."""
+    import torch
+    from oracle import tapes
+    from oracle.f16_oracle import F16EnvOracle
+    from oracle.f16_tables_oracle import COEF_NAMES, F16Tables, TableAero
+    a, b, e = torch.tensor([5.0, 20.0, -5.0]), torch.tensor([0.0, 5.0, -10.0]), torch.tensor([-2.0, 5.0, 10.0])
+    c = TableAero(dtype=torch.float64).coeffs(a, b, e)
+    rows = F16Tables().coefficients(a.numpy().astype(np.float64), b.numpy().astype(np.float64), e.numpy().astype(np.float64))
+    assert set(c) == set(COEF_NAMES)
+    for k, name in enumerate(COEF_NAMES):
+        assert np.array_equal(c[name].numpy(), rows[k]), name
+    n = 64
+    o32 = F16EnvOracle(n, "heading", aero=TableAero(dtype=torch.float32))
+    o64 = F16EnvOracle(n, "heading", aero=TableAero(dtype=torch.float64), dtype=torch.float64)
+    d0 = tapes.reset_draw_tape(3, 0, n)
+    o32.reset(torch.from_numpy(d0)); o64.reset(torch.from_numpy(d0).double())
+    for k in range(1, 11):
+        act, d = tapes.action_tape(3, k, n, 0.3), tapes.reset_draw_tape(3, k, n)
+        o32.step(torch.from_numpy(act), torch.from_numpy(d)); o64.step(torch.from_numpy(act).double(), torch.from_numpy(d).double())
+    assert np.allclose(o32.s.numpy(), o64.s.numpy(), rtol=2e-5, atol=1e-5)
+    assert torch.isfinite(o64.s).all() and float(o64.s[:, 6].min()) > 500
