@@ -160,6 +160,23 @@ def recorded_trajectory(name, head=400):
     print(name, {k: v.shape for k, v in out.items()}["npos"])
 
 
+def eval_metrics_golden(name, head=400):
+    """The nine flight metrics of renders/evaluate_result.py:29-43, computed by executing THOSE reference lines on the
+    head of the reference's own recording (the float32 snapshot of ref_recorded_trajectory.npz, so the test input is
+    exactly the fixture)."""
+    src = open(os.path.join(REF_ROOT, "renders", "evaluate_result.py"), encoding="utf-8").read().splitlines()
+    lines = [ln for ln in src[28:43] if "=" in ln and not ln.lstrip().startswith("#")]
+    rec = np.load(os.path.join(HERE, "ref_recorded_trajectory.npz"))
+    ns = {"np": np}
+    for k in ("G", "vt", "pitch", "alpha", "beta", "altitude"):
+        ns[k + "_buf"] = rec[k][:head].astype(np.float64)
+    exec("\n".join(lines), ns)
+    names = ("G", "TAS", "RoC", "AOA", "ASM", "SSM", "OSM", "AOASM", "AOSSM")
+    np.savez_compressed(os.path.join(HERE, name), names=np.array(names), values=np.array([ns[k] for k in names], dtype=np.float64),
+                        head=np.array([head]))
+    print(name, {k: float(ns[k]) for k in names})
+
+
 class RefPidPlanner:
     """PlanningEnv.step (envs/planning_env.py:144-177) assembled from the reference's OWN parts, with the low-level
     GRU PPO actor (whose checkpoint is not in the repository, planning_env.py:16) replaced by the reference's PID
@@ -436,7 +453,12 @@ if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "combat":       # regenerate only the combat fixtures
         combat_trajectory(24, 30, 18, "combat_traj.npz")
         combat_trajectory(24, 30, 19, "combat_close_traj.npz", close=True)
-    geodetic_golden("geodetic_golden.npz")
+        sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "geodetic":     # regenerate only the geodetic (acmi) fixture
+        geodetic_golden("geodetic_golden.npz")
+        sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "metrics":      # regenerate only the flight-metrics fixture
+        eval_metrics_golden("eval_metrics.npz")
         sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "planning":     # regenerate only the planning fixture
         planning_trajectory(48, 16, 1.0, 17, "planning_pid_traj.npz")
@@ -446,6 +468,7 @@ if __name__ == "__main__":
         uav_trajectory("heading", 64, 400, 1.0, 16, "uav_heading_traj.npz")
         sys.exit(0)
     recorded_trajectory("ref_recorded_trajectory.npz")
+    eval_metrics_golden("eval_metrics.npz")
     nlplant_kat("f16_nlplant_kat.npz")
     done_branch("heading_done_branch.npz")
     for task, n, steps, scale, seed, name in (("heading", 128, 1000, 0.3, 11, "heading_traj_a03.npz"),
@@ -459,3 +482,4 @@ if __name__ == "__main__":
     planning_trajectory(48, 16, 1.0, 17, "planning_pid_traj.npz")
     combat_trajectory(24, 30, 18, "combat_traj.npz")
     combat_trajectory(24, 30, 19, "combat_close_traj.npz", close=True)
+    geodetic_golden("geodetic_golden.npz")
