@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define NP_ABI_VERSION 4
+#define NP_ABI_VERSION 5
 
 enum { NP_OK = 0, NP_EINVAL = 1, NP_ECUDA = 2, NP_ESTATE = 3 };
 
@@ -172,6 +172,22 @@ size_t np_env_blood_offset_bytes(const np_env_cfg* cfg);
 size_t np_env_pid_offset_bytes(const np_env_cfg* cfg);
 /* started = 0 re-arms the first-call initialisation of the PIDs (PID.reset, pid.py:13,22-27). */
 int np_env_set_pid_started(np_env* env, int started);
+
+/* Device-resident rollout buffer (SURVEY f-2; reference algorithms/utils/buffer.py, runner/F16sim_runner.py:141-157).
+ * np_env_rebind_outputs: point the env's obs [n][D] / reward [n] outputs at another device location (8-byte aligned), e.g.
+ *   slot t+1 of the rollout buffer's obs array, so the step kernel writes the rollout in place (no copy).  Unlike
+ *   np_env_bind it leaves the coefficient cache valid.
+ * np_rollout_masks: masks / bad_masks [num_envs][num_agents] f32 (0 where ANY agent of the env is done / bad_done) and
+ *   reset_env [num_envs] u8 (may be null) from the env's flag rows flags_dev [3][ld] (F16sim_runner.py:144-155).
+ * np_rollout_returns: ReplayBuffer.compute_returns (buffer.py:139-172), all four (use_gae, use_proper_time_limits)
+ *   variants, on [T][M] rewards / [T+1][M] value_preds, masks, bad_masks, returns (M = envs * agents); the caller has
+ *   written next_value into value_preds[T] (use_gae) or returns[T].  Arithmetic is numpy's fp32 order: bit-exact. */
+int np_env_rebind_outputs(np_env* env, float* obs_dev, float* reward_dev);
+int np_rollout_masks(const uint8_t* flags_dev, int ld, int num_envs, int num_agents, float* masks_dev, float* bad_masks_dev,
+                     uint8_t* reset_env_dev, void* stream);
+int np_rollout_returns(const float* rewards_dev, float* value_preds_dev, const float* masks_dev, const float* bad_masks_dev,
+                       float* returns_dev, int T, int M, double gamma, double gae_lambda, int use_gae, int use_proper_time_limits,
+                       void* stream);
 
 /* Termination-cause counters accumulated on device since creation (replaces the per-condition
  * print(torch.sum(bad_done)) host syncs, e.g. overload.py:32-34).  Synchronises `stream`.

@@ -85,6 +85,9 @@ SYMBOLS = {
     "np_tables_destroy": (C.c_int, [_P]),
     "np_f16_table_coeffs": (C.c_int, [_P, _P, _P, _P, _P, C.c_int, C.c_int, _P]),
     "np_env_create_tables": (C.c_int, [_P, _P, _P]),
+    "np_env_rebind_outputs": (C.c_int, [_P, _P, _P]),
+    "np_rollout_masks": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, _P, _P, _P, _P]),
+    "np_rollout_returns": (C.c_int, [_P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_double, C.c_double, C.c_int, C.c_int, _P]),
     "np_f16_table_nlplant": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, _P]),
     "np_uav_nlplant": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, _P]),
     "np_f16_coeffs": (C.c_int, [_P, _P, _P, _P, _P, C.c_int, C.c_int, _P]),

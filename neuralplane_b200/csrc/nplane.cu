@@ -1006,6 +1006,67 @@ __global__ void __launch_bounds__(256) combat_relgeo_kernel(const float* __restr
 }
 
 // ------------------------------------------------------------------------------------------------
+// K7: device-resident rollout buffer (SURVEY f-2).  ReplayBuffer.compute_returns (algorithms/utils/buffer.py:139-172) as a
+// backward scan, one thread per (env, agent) column -- rows are [T(+1)][M] so every load / store is coalesced; and the
+// mask derivation of F16SimRunner.insert (runner/F16sim_runner.py:141-157) straight from the env's flag rows.
+// Arithmetic order == numpy's fp32 evaluation of the reference expressions (built with -fmad=false): bit-exact.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) rollout_returns_kernel(const float* __restrict__ R, float* __restrict__ V,
+                                                              const float* __restrict__ Mk, const float* __restrict__ Bm,
+                                                              float* __restrict__ Ret, int T, int M, float gamma, float gl,
+                                                              int use_gae, int proper) {
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < M; j += gridDim.x * blockDim.x) {
+    if (use_gae) {
+      float gae = 0.0f, vnext = V[(size_t)T * M + j];   // value_preds[-1] = next_value was written by the caller
+#pragma unroll 4
+      for (int t = T - 1; t >= 0; --t) {
+        const size_t i = (size_t)t * M + j, i1 = i + M;
+        const float v = V[i], m = Mk[i1];
+        const float td = R[i] + gamma * vnext * m - v;                    // buffer.py:151 / :163
+        gae = td + gl * m * gae;                                          // :152 / :166  (gl = f32(gamma * gae_lambda))
+        if (proper) gae = gae * Bm[i1];                                   // :153
+        Ret[i] = gae + v;                                                 // :154 / :167
+        vnext = v;
+      }
+    } else {
+      float ret = Ret[(size_t)T * M + j];                // returns[-1] = next_value was written by the caller
+#pragma unroll 4
+      for (int t = T - 1; t >= 0; --t) {
+        const size_t i = (size_t)t * M + j, i1 = i + M;
+        const float m = Mk[i1];
+        if (proper) {                                                     // :158-159
+          const float bm = Bm[i1];
+          ret = (ret * gamma * m + R[i]) * bm + (1.0f - bm) * V[i];
+        } else {
+          ret = ret * gamma * m + R[i];                                   // :171
+        }
+        Ret[i] = ret;
+      }
+    }
+  }
+}
+
+// masks[e, a] = 0 where ANY agent of env e is done, bad_masks likewise for bad_done, reset_env[e] = any flag of any agent
+// (F16sim_runner.py:144-155); one thread per env.
+__global__ void __launch_bounds__(256) rollout_masks_kernel(const uint8_t* __restrict__ flags, int ld, int num_envs, int agents,
+                                                            float* __restrict__ masks, float* __restrict__ bad_masks,
+                                                            uint8_t* __restrict__ reset_env) {
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < num_envs; e += gridDim.x * blockDim.x) {
+    unsigned d = 0, b = 0, x = 0;
+    for (int a = 0; a < agents; ++a) {
+      const size_t i = (size_t)e * agents + a;
+      d |= flags[i]; b |= flags[ld + i]; x |= flags[2 * (size_t)ld + i];
+    }
+    const float mk = d ? 0.0f : 1.0f, bk = b ? 0.0f : 1.0f;
+    for (int a = 0; a < agents; ++a) {
+      masks[(size_t)e * agents + a] = mk;
+      bad_masks[(size_t)e * agents + a] = bk;
+    }
+    if (reset_env) reset_env[e] = (d | b | x) ? 1 : 0;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // K6: table aero back-end (tables_device.cuh): 44 coefficients per (alpha, beta, el) point from the NASA tables
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) f16_table_coeffs_kernel(const float* __restrict__ image, const float* __restrict__ A,
@@ -1340,6 +1401,39 @@ int np_env_bind(np_env* env, const np_buffers* b) {
   // invalidate the coefficient-cache keys: 0xFFFFFFFF is a NaN pattern no stored alpha/beta can equal bitwise
   NP_CUDA(cudaMemset(reinterpret_cast<float*>(b->workspace_dev) + (size_t)kNumAB2 * env->cfg.ld, 0xFF,
                      2 * (size_t)env->cfg.ld * sizeof(float)));
+  return NP_OK;
+}
+
+int np_env_rebind_outputs(np_env* env, float* obs_dev, float* reward_dev) {
+  if (!env || !env->bound) return fail(NP_ESTATE, "np_env_rebind_outputs: env not bound");
+  if (!obs_dev || !reward_dev || ((uintptr_t)obs_dev & 7) || ((uintptr_t)reward_dev & 7))
+    return fail(NP_EINVAL, "np_env_rebind_outputs: obs / reward must be 8-byte aligned device pointers");
+  env->buf.obs_dev = obs_dev;
+  env->buf.reward_dev = reward_dev;
+  return NP_OK;
+}
+
+int np_rollout_returns(const float* rewards_dev, float* value_preds_dev, const float* masks_dev, const float* bad_masks_dev,
+                       float* returns_dev, int T, int M, double gamma, double gae_lambda, int use_gae, int use_proper_time_limits,
+                       void* stream) {
+  if (!rewards_dev || !value_preds_dev || !masks_dev || !returns_dev || T <= 0 || M <= 0 || (use_proper_time_limits && !bad_masks_dev))
+    return fail(NP_EINVAL, "np_rollout_returns: bad argument");
+  const int want = (M + 255) / 256;
+  rollout_returns_kernel<<<want < 2368 ? want : 2368, 256, 0, (cudaStream_t)stream>>>(
+      rewards_dev, value_preds_dev, masks_dev, bad_masks_dev, returns_dev, T, M, (float)gamma, (float)(gamma * gae_lambda), use_gae,
+      use_proper_time_limits);
+  NP_CUDA(cudaGetLastError());
+  return NP_OK;
+}
+
+int np_rollout_masks(const uint8_t* flags_dev, int ld, int num_envs, int num_agents, float* masks_dev, float* bad_masks_dev,
+                     uint8_t* reset_env_dev, void* stream) {
+  if (!flags_dev || !masks_dev || !bad_masks_dev || num_envs <= 0 || num_agents <= 0 || (long long)num_envs * num_agents > ld)
+    return fail(NP_EINVAL, "np_rollout_masks: bad argument");
+  const int want = (num_envs + 255) / 256;
+  rollout_masks_kernel<<<want < 2368 ? want : 2368, 256, 0, (cudaStream_t)stream>>>(flags_dev, ld, num_envs, num_agents, masks_dev,
+                                                                                   bad_masks_dev, reset_env_dev);
+  NP_CUDA(cudaGetLastError());
   return NP_OK;
 }
 

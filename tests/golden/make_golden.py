@@ -177,6 +177,66 @@ def eval_metrics_golden(name, head=400):
     print(name, {k: float(ns[k]) for k in names})
 
 
+def rollout_golden(name, T=12, N=6, A=2, D=22, act=4, seed=23):
+    """The reference's OWN ReplayBuffer (algorithms/utils/buffer.py) driven through insert / compute_returns /
+    after_update for the four (use_gae, use_proper_time_limits) variants, with masks derived by the reference runner's
+    insert logic (runner/F16sim_runner.py:141-157, executed on a stand-in object carrying the attributes it reads)."""
+    import types
+    import_reference()
+    if REF_ROOT not in sys.path:
+        sys.path.insert(0, REF_ROOT)
+    import gym.spaces
+    from algorithms.utils.buffer import ReplayBuffer
+    rng = np.random.default_rng(seed)
+    obs_space = gym.spaces.Box(low=-10, high=10., shape=(D,))
+    act_space = gym.spaces.Box(low=-1, high=1., shape=(act,))
+    tape = {
+        "obs0": rng.standard_normal((N, A, D)).astype(np.float32),
+        "obs": rng.standard_normal((T, N, A, D)).astype(np.float32),
+        "actions": rng.uniform(-1, 1, (T, N, A, act)).astype(np.float32),
+        "rewards": rng.standard_normal((T, N, A, 1)).astype(np.float32),
+        "dones": rng.random((T, N, A, 1)) < 0.08,
+        "bad_dones": rng.random((T, N, A, 1)) < 0.10,
+        "exceed": rng.random((T, N, A, 1)) < 0.03,
+        "logp": rng.standard_normal((T, N, A, 1)).astype(np.float32),
+        "values": rng.standard_normal((T, N, A, 1)).astype(np.float32),
+        "rnn_a": rng.standard_normal((T, N, A, 1, 8)).astype(np.float32),
+        "rnn_c": rng.standard_normal((T, N, A, 1, 8)).astype(np.float32),
+        "next_value": rng.standard_normal((N, A, 1)).astype(np.float32),
+    }
+    out = {"meta": np.array([T, N, A, D, act, seed]), "gamma": np.array([0.99]), "gae_lambda": np.array([0.95])}
+    out.update({"tape_" + k: v for k, v in tape.items()})
+    # the reference runner's insert(), bound to a stand-in `self`
+    from runner.F16sim_runner import F16SimRunner
+    for use_gae in (True, False):
+        for proper in (True, False):
+            args = types.SimpleNamespace(buffer_size=T, n_rollout_threads=N, gamma=0.99, use_proper_time_limits=proper, use_gae=use_gae,
+                                         gae_lambda=0.95, recurrent_hidden_size=8, recurrent_hidden_layers=1)
+            buf = ReplayBuffer(args, A, obs_space, act_space)
+            buf.obs[0] = tape["obs0"].copy()
+            runner = types.SimpleNamespace(buffer=buf, n_rollout_threads=N, num_agents=A)
+            for t in range(T):
+                F16SimRunner.insert(runner, [tape["obs"][t], tape["actions"][t], tape["rewards"][t], tape["dones"][t], tape["bad_dones"][t],
+                                             tape["exceed"][t], tape["logp"][t], tape["values"][t], tape["rnn_a"][t].copy(), tape["rnn_c"][t].copy()])
+            buf.compute_returns(tape["next_value"])
+            key = f"gae{int(use_gae)}_proper{int(proper)}_"
+            out[key + "returns"] = buf.returns.copy()
+            out[key + "advantages"] = buf.advantages.copy()
+            if use_gae and proper:
+                for k in ("obs", "actions", "rewards", "masks", "bad_masks", "action_log_probs", "value_preds", "rnn_states_actor", "rnn_states_critic"):
+                    out["buf_" + k] = getattr(buf, k).copy()
+                out["buf_step_after"] = np.array([buf.step])
+                torch.manual_seed(5)                                    # recurrent_generator draws torch.randperm
+                for bi, batch in enumerate(ReplayBuffer.recurrent_generator(buf, 2, 4)):
+                    for name_, arr in zip(("obs", "actions", "masks", "logp", "adv", "returns", "values", "rnn_a", "rnn_c"), batch):
+                        out[f"gen{bi}_{name_}"] = np.asarray(arr).copy()
+                buf.after_update()
+                out["after_obs0"], out["after_masks0"], out["after_bad_masks0"] = buf.obs[0].copy(), buf.masks[0].copy(), buf.bad_masks[0].copy()
+                out["after_rnn_a0"] = buf.rnn_states_actor[0].copy()
+    np.savez_compressed(os.path.join(HERE, name), **out)
+    print(name, {k: v.shape for k, v in out.items() if k.endswith("returns")})
+
+
 class RefPidPlanner:
     """PlanningEnv.step (envs/planning_env.py:144-177) assembled from the reference's OWN parts, with the low-level
     GRU PPO actor (whose checkpoint is not in the repository, planning_env.py:16) replaced by the reference's PID
@@ -457,6 +517,9 @@ if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "geodetic":     # regenerate only the geodetic (acmi) fixture
         geodetic_golden("geodetic_golden.npz")
         sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "rollout":      # regenerate only the rollout-buffer fixture
+        rollout_golden("rollout_returns.npz")
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "metrics":      # regenerate only the flight-metrics fixture
         eval_metrics_golden("eval_metrics.npz")
         sys.exit(0)
@@ -483,3 +546,4 @@ if __name__ == "__main__":
     combat_trajectory(24, 30, 18, "combat_traj.npz")
     combat_trajectory(24, 30, 19, "combat_close_traj.npz", close=True)
     geodetic_golden("geodetic_golden.npz")
+    rollout_golden("rollout_returns.npz")
