@@ -50,7 +50,7 @@ __device__ __forceinline__ float rate_out(float* st, const PidGains& G, float de
   float deriv;
   pid_update(st, G, target, rate * scaler * scaler, limit, first, dt, deriv);
   float out = target * G.Kff / (scaler * e2t + 1e-8f) + st[0] * G.Kp + st[1] + deriv * G.Kd;
-  out = 180.0f * out / kPi;
+  out = 180.0f * out / DC(kPi);
   st[2] = out;
   return fminf(fmaxf(out, -45.0f), 45.0f);
 }
@@ -139,17 +139,17 @@ __device__ __forceinline__ void pid_controller(const float* s, float airspeed, f
 
   // ---- TAS loop -> throttle ----------------------------------------------------------------------------------
   float deriv;
-  pid_update(pid + 9, kSpeed, target_vt * 0.3048f / 340.0f, TAS * 0.3048f / 340.0f, fabsf(pid[11]) >= 100.0f, first, dt, deriv);
-  const float sp_out = (target_vt * 0.3048f / 340.0f) * kSpeed.Kff + pid[9] * kSpeed.Kp + pid[10] + deriv * kSpeed.Kd;
+  pid_update(pid + 9, kSpeed, target_vt * 0.3048f / DC(340.0f), TAS * 0.3048f / DC(340.0f), fabsf(pid[11]) >= 100.0f, first, dt, deriv);
+  const float sp_out = (target_vt * 0.3048f / DC(340.0f)) * kSpeed.Kff + pid[9] * kSpeed.Kp + pid[10] + deriv * kSpeed.Kd;
   pid[11] = sp_out;
   const float throttle = fminf(fmaxf(sp_out / 100.0f, 0.0f), 1.0f);
 
   float el, ail, rud;
   pid_stabilize(s, k, dt, roll_dem, target_pitch, yaw_rate_dem, pid, first, el, ail, rud);
   action[0] = throttle;
-  action[1] = -el / 45.0f;
-  action[2] = -ail / 45.0f;
-  action[3] = -rud / 45.0f;
+  action[1] = -el / DC(45.0f);
+  action[2] = -ail / DC(45.0f);
+  action[3] = -rud / DC(45.0f);
 }
 
 // SingleCombatEnv low level (singlecombat_env.py:244-255): the 4-D action [throttle, roll_dem, pitch_dem, yaw] moves
@@ -163,9 +163,9 @@ __device__ __forceinline__ void combat_controller(const float* s, float airspeed
   float el, ail, rud;
   pid_stabilize(s, k, dt, pid[9], pid[10], 0.0f, pid, first, el, ail, rud);
   action[0] = a4[0];
-  action[1] = -el / 45.0f;
-  action[2] = -ail / 45.0f;
-  action[3] = -rud / 45.0f;
+  action[1] = -el / DC(45.0f);
+  action[2] = -ail / DC(45.0f);
+  action[3] = -rud / DC(45.0f);
 }
 
 }  // namespace npl

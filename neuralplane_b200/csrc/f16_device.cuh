@@ -248,6 +248,21 @@ constexpr float kR2D = 57.29577951308232f;   // 180.0 / pi rounded once to f32
 constexpr float kPi = 3.141592653589793f;
 constexpr float kTwoPi = 6.283185307179586f;
 
+// x / d for a compile-time constant d in three instructions instead of the ~10 (FCHK, MUFU.RCP, 4 FFMA, slow-path branch)
+// of div.rn.f32:  q = RN(x * RN(1/d)) is within one ulp, the FMA residual e = x - q*d is exact, and RN(q + e * RN(1/d)) is
+// the correctly rounded quotient (Markstein) -- the very bits of the reference's `tensor / constant`.  Verified by
+// enumeration over EVERY float with 2^-100 <= |x| < 2^100 for every divisor used (oracle/divc_check.c; +-0 -> +0).
+// Written `x / DC(340.0f)` so operator precedence at the call sites stays that of the reference expression.
+struct DC {
+  float d;
+  __host__ __device__ constexpr explicit DC(float v) : d(v) {}
+};
+__device__ __forceinline__ float operator/(float x, DC c) {
+  const float r = 1.0f / c.d;  // folded at compile time
+  const float q = x * r;
+  return fmaf(fmaf(-q, c.d, x), r, q);
+}
+
 __device__ __forceinline__ float tfac_pow(float alt) {  // tfac ** 4.14 (F16_dynamics.py:25,28)
   const float tfac = 1.0f - .703e-5f * alt;
   return powf(tfac, 4.14f);
@@ -440,17 +455,17 @@ __device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
   return ctr;
 }
 __device__ __forceinline__ float u01(uint32_t x) { return (float)(x >> 8) * 5.9604644775390625e-8f; }  // [0,1)
-// Two standard normals from ONE 32-bit word (observation noise only): 16-bit radius and angle uniforms taken at
-// bin midpoints, fast-math log / sqrt / sincos.  |n| <= 4.8; mean 0, variance 1 to < 1e-4.
-__device__ __forceinline__ void box_muller16(uint32_t w, float& n0, float& n1) {
-  const float u1 = ((float)(w >> 16) + 0.5f) * 1.52587890625e-5f;     // (0,1)
-  const float th = ((float)(w & 0xFFFFu) + 0.5f) * (kTwoPi * 1.52587890625e-5f);
-  float r;
-  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(-2.0f * __logf(u1)));
-  float sn, cs;
+// Two normals of standard deviation `sc` from ONE 32-bit word (observation noise only): 16-bit radius and angle
+// uniforms taken at bin midpoints, MUFU log2 / sqrt / sin / cos.  |n| <= 4.8 sc; mean 0, variance sc^2 to < 1e-4.
+// r = sc * sqrt(-2 ln u1) is returned with the two direction cosines so the caller adds the noise with one FMA each.
+__device__ __forceinline__ void box_muller16(uint32_t w, float sc, float& r, float& cs, float& sn) {
+  const float u1 = fmaf((float)(w >> 16), 1.52587890625e-5f, 0.5f * 1.52587890625e-5f);     // (0,1)
+  const float th = fmaf((float)(w & 0xFFFFu), kTwoPi * 1.52587890625e-5f, 0.5f * kTwoPi * 1.52587890625e-5f);
+  float l2, rt;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l2) : "f"(u1));                          // u1 >= 2^-17: never denormal
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(rt) : "f"(l2 * -1.3862943611198906f));  // -2 ln 2 * log2 u1 = -2 ln u1
+  r = rt * sc;
   __sincosf(th, &sn, &cs);
-  n0 = r * cs;
-  n1 = r * sn;
 }
 
 }  // namespace npl

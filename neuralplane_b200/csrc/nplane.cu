@@ -104,6 +104,9 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
@@ -177,8 +180,8 @@ __device__ __forceinline__ void reset_aircraft(const np_env_cfg& c, const Draws&
     tgt[2] = s[6] + 2.0f * (r.d[4] - 0.5f) * c.max_velocities_u_increment;
   } else {
     const float dist = r.d[2] * (c.max_distance - c.min_distance) + c.min_distance;
-    const float th1 = r.d[3] * kPi / 3.0f - (float)(3.141592653589793 / 6.0);
-    const float th2 = r.d[4] * kPi / 3.0f - (float)(3.141592653589793 / 6.0);
+    const float th1 = r.d[3] * kPi / DC(3.0f) - (float)(3.141592653589793 / 6.0);
+    const float th2 = r.d[4] * kPi / DC(3.0f) - (float)(3.141592653589793 / 6.0);
     tgt[0] = s[0] + dist * cosf(th1) * cosf(th2);
     tgt[1] = s[1] + dist * cosf(th1) * sinf(th2);
     tgt[2] = s[2] + dist * sinf(th1);
@@ -189,27 +192,27 @@ __device__ __forceinline__ void reset_aircraft(const np_env_cfg& c, const Draws&
 __device__ __forceinline__ void make_obs(const np_env_cfg& c, const float* s, const float* u, const float* tgt,
                                          const Trig& g, float e2t, float* o) {
   if (c.task == NP_TASK_HEADING) {
-    o[0] = (s[2] - tgt[0]) * 0.3048f / 1000.0f;
+    o[0] = (s[2] - tgt[0]) * 0.3048f / DC(1000.0f);
     o[1] = wrap_pi(s[5] - tgt[1]);
-    o[2] = (s[6] - tgt[2]) * 0.3048f / 340.0f;
+    o[2] = (s[6] - tgt[2]) * 0.3048f / DC(340.0f);
   } else if (c.task == NP_TASK_CONTROL) {
     o[0] = wrap_pi(s[4] - tgt[0]);
     o[1] = wrap_pi(s[5] - tgt[1]);
-    o[2] = (s[6] - tgt[2]) * 0.3048f / 340.0f;
+    o[2] = (s[6] - tgt[2]) * 0.3048f / DC(340.0f);
   } else {
-    o[0] = (s[0] - tgt[0]) * 0.3048f / 1000.0f;
-    o[1] = (s[1] - tgt[1]) * 0.3048f / 1000.0f;
-    o[2] = (s[2] - tgt[2]) * 0.3048f / 1000.0f;
+    o[0] = (s[0] - tgt[0]) * 0.3048f / DC(1000.0f);
+    o[1] = (s[1] - tgt[1]) * 0.3048f / DC(1000.0f);
+    o[2] = (s[2] - tgt[2]) * 0.3048f / DC(1000.0f);
   }
   const float eas = (s[6] + c.airspeed * 1.0f) / e2t;  // F16_model.py:96-103
-  o[3] = s[2] * 0.3048f / 5000.0f;
+  o[3] = s[2] * 0.3048f / DC(5000.0f);
   o[4] = g.sphi; o[5] = g.cphi; o[6] = g.st; o[7] = g.ct;
-  o[8] = eas * 0.3048f / 340.0f;
+  o[8] = eas * 0.3048f / DC(340.0f);
   o[9] = g.sa; o[10] = g.ca; o[11] = g.sb; o[12] = g.cb;
   o[13] = s[9]; o[14] = s[10]; o[15] = s[11];
-  o[16] = u[0] / 0.225f / 76300.0f * 0.3048f;
-  o[17] = u[1] / 45.0f; o[18] = u[2] / 45.0f; o[19] = u[3] / 45.0f;
-  o[20] = 0.0f / 45.0f;  // lef
+  o[16] = u[0] / DC(0.225f) / DC(76300.0f) * 0.3048f;
+  o[17] = u[1] / DC(45.0f); o[18] = u[2] / DC(45.0f); o[19] = u[3] / DC(45.0f);
+  o[20] = 0.0f / DC(45.0f);  // lef
   o[21] = e2t;
 }
 
@@ -229,10 +232,10 @@ __device__ __forceinline__ void add_obs_noise(const StepParams& p, int i, float*
       for (int k = 0; k < 4; ++k) {
         const int j = 8 * q + 2 * k;
         if (j < NP_NUM_OBS) {
-          float n0, n1;
-          box_muller16(w[k], n0, n1);
-          o[j] = o[j] + n0 * sc;
-          o[j + 1] = o[j + 1] + n1 * sc;
+          float r, cs, sn;
+          box_muller16(w[k], sc, r, cs, sn);
+          o[j] = fmaf(r, cs, o[j]);
+          o[j + 1] = fmaf(r, sn, o[j + 1]);
         }
       }
     }
@@ -281,8 +284,8 @@ __device__ __forceinline__ void ao_ta_r(const float* dp, const float* ve, const 
   TA = acosf(fminf(fmaxf(pm / (R * sqrtf(mv) + 1e-8f), -1.0f), 1.0f));
 }
 __device__ __forceinline__ float orientation_reward_v2(float AO, float TA) {  // utils.py:215-217
-  const float t = atanhf(1.0f - fmaxf(1.9f * TA / kPi, 1e-4f * 1.0f)) / (2.0f * kPi);
-  return 1.0f / (50.0f * AO / kPi + 2.0f) + (float)(1.0 / 2) + fminf(t, 0.0f) + 0.5f;
+  const float t = atanhf(1.0f - fmaxf(1.9f * TA / DC(kPi), 1e-4f * 1.0f)) / (2.0f * kPi);
+  return 1.0f / (50.0f * AO / DC(kPi) + 2.0f) + (float)(1.0 / 2) + fminf(t, 0.0f) + 0.5f;
 }
 __device__ __forceinline__ float range_reward_v3(float Rkm) {  // utils.py:230-231
   const float poly = fminf(fmaxf(-0.032f * (Rkm * Rkm) + 0.284f * Rkm + 0.38f, 0.0f), 1.0f);
@@ -291,7 +294,7 @@ __device__ __forceinline__ float range_reward_v3(float Rkm) {  // utils.py:230-2
 __device__ __forceinline__ float orientation_fn(float AO) {  // utils.py:235-243
   constexpr float k6 = (float)(3.141592653589793 / 6);
   const bool m3 = (AO >= 0.0f) & (AO <= k6), m4 = (AO <= 0.0f) & (AO >= -k6);
-  return (1.0f - 6.0f * AO / kPi) * (m3 ? 1.0f : 0.0f) + (1.0f + 6.0f * AO / kPi) * (m4 ? 1.0f : 0.0f);
+  return (1.0f - 6.0f * AO / DC(kPi)) * (m3 ? 1.0f : 0.0f) + (1.0f + 6.0f * AO / DC(kPi)) * (m4 ? 1.0f : 0.0f);
 }
 __device__ __forceinline__ float distance_fn(float Rkm) {  // utils.py:245-249
   return (Rkm <= 1.0f ? 1.0f : 0.0f) + (3.0f - Rkm) / 2.0f * (((Rkm > 1.0f) & (Rkm <= 3.0f)) ? 1.0f : 0.0f);
@@ -322,7 +325,7 @@ __device__ __forceinline__ void combat_outputs(const StepParams& p, float (&s)[2
   ao_ta_r<3>(dp, es[0], es[1], AO, TA, R);
   const float cz = es[0][0] * dp[1] - es[0][1] * dp[0];
   const float side = (cz > 0.0f ? 1.0f : 0.0f) - (cz < 0.0f ? 1.0f : 0.0f);
-  const float Rkm = R * 0.3048f / 1000.0f;
+  const float Rkm = R * 0.3048f / DC(1000.0f);
   const float rr = range_reward_v3(Rkm);
   rew[0] = 0.01f * (orientation_reward_v2(AO, TA) * rr);
   rew[1] = 0.01f * (orientation_reward_v2(kPi - TA, kPi - AO) * rr);
@@ -330,12 +333,12 @@ __device__ __forceinline__ void combat_outputs(const StepParams& p, float (&s)[2
   for (int q = 0; q < 2; ++q) {
     float o[NP_NUM_OBS_COMBAT];
     const int r = 1 - q;
-    o[0] = s[q][2] * 0.3048f / 5000.0f;
+    o[0] = s[q][2] * 0.3048f / DC(5000.0f);
     o[1] = g[q].sphi; o[2] = g[q].cphi; o[3] = g[q].st; o[4] = g[q].ct;
-    o[5] = vel[q][0] * 0.3048f / 340.0f; o[6] = vel[q][1] * 0.3048f / 340.0f; o[7] = vel[q][2] * 0.3048f / 340.0f;
-    o[8] = s[q][6] * 0.3048f / 340.0f;
-    o[9] = (vel[r][0] - vel[q][0]) * 0.3048f / 340.0f;
-    o[10] = (s[r][2] - s[q][2]) * 0.3048f / 1000.0f;
+    o[5] = vel[q][0] * 0.3048f / DC(340.0f); o[6] = vel[q][1] * 0.3048f / DC(340.0f); o[7] = vel[q][2] * 0.3048f / DC(340.0f);
+    o[8] = s[q][6] * 0.3048f / DC(340.0f);
+    o[9] = (vel[r][0] - vel[q][0]) * 0.3048f / DC(340.0f);
+    o[10] = (s[r][2] - s[q][2]) * 0.3048f / DC(1000.0f);
     o[11] = q == 0 ? AO2 : kPi - TA2;
     o[12] = q == 0 ? TA2 : kPi - AO2;
     o[13] = R2 * 0.3048f / 10000.0f;
@@ -545,7 +548,7 @@ __global__ void __launch_bounds__(BS, MINB) f16_step_kernel(const __grid_constan
       if (COMBAT) combat_controller(s[q], c.airspeed, c.dt, a_cmd[q], pid[q], p.pid_first != 0 && sub == 0, a[q]);
 #pragma unroll
       for (int j = 0; j < 4; ++j) a[q][j] = fminf(fmaxf(a[q][j], -1.0f), 1.0f);
-      u[q][0] = 0.9f * u[q][0] + 0.1f * a[q][0] * 0.225f * 76300.0f / 0.3048f;
+      u[q][0] = 0.9f * u[q][0] + 0.1f * a[q][0] * 0.225f * 76300.0f / DC(0.3048f);
       u[q][1] = 0.9f * u[q][1] + 0.1f * a[q][1] * 45.0f;
       u[q][2] = 0.9f * u[q][2] + 0.1f * a[q][2] * 45.0f;
       u[q][3] = 0.9f * u[q][3] + 0.1f * a[q][3] * 45.0f;
@@ -621,10 +624,10 @@ __global__ void __launch_bounds__(BS, MINB) f16_step_kernel(const __grid_constan
           const float acc = sqrtf(ax * ax + ay * ay + az * az);
           const bool overload = (acc - c.acceleration_limit) > 0.0f;            // overload.py:37-42
           const bool low_alt = (sq[2] - c.altitude_limit) < 0.0f;               // low_altitude.py:29-30
-          const float vel = (sq[6] + c.airspeed * 1.0f) * 0.3048f / 340.0f;
+          const float vel = (sq[6] + c.airspeed * 1.0f) * 0.3048f / DC(340.0f);
           const bool hi = (vel - c.max_velocity) >= 0.0f;                       // high_speed.py:29-30
           const bool lo = (vel - c.min_velocity) <= 0.0f;                       // low_speed.py:29-30
-          const float a_deg = sq[7] * 180.0f / kPi, b_deg = sq[8] * 180.0f / kPi;  // extreme_state.py:32-36
+          const float a_deg = sq[7] * 180.0f / DC(kPi), b_deg = sq[8] * 180.0f / DC(kPi);  // extreme_state.py:32-36
           const bool ext = (a_deg < c.min_alpha) | (a_deg > c.max_alpha) | (b_deg < c.min_beta) | (b_deg > c.max_beta);
           const bool late = steps[q] >= c.max_check_interval;
           bool off = false, dn = false;
@@ -636,25 +639,25 @@ __global__ void __launch_bounds__(BS, MINB) f16_step_kernel(const __grid_constan
             off = (fabsf(dpsi) >= (float)(3.141592653589793 / 36.0)) | (fabsf(sq[2] - tq[0]) >= 100.0f) |
                   (fabsf(sq[6] - tq[2]) >= 20.0f);
             dn = !off && !late && (steps[q] >= c.min_check_interval);
-            d0 = (sq[2] - tq[0]) * 0.3048f / 1000.0f;                           // heading_reward.py:26-35
-            d1 = dpsi / kPi;
-            d2 = (sq[6] - tq[2]) * 0.3048f / 340.0f;
+            d0 = (sq[2] - tq[0]) * 0.3048f / DC(1000.0f);                           // heading_reward.py:26-35
+            d1 = dpsi / DC(kPi);
+            d2 = (sq[6] - tq[2]) * 0.3048f / DC(340.0f);
             rw = -(d0 * d0) + -(d1 * d1) + -(d2 * d2);
           } else if (c.task == NP_TASK_CONTROL) {                               // unreach_posture.py:37-55
             const float dpsi = wrap_pi(sq[5] - tq[1]);
             off = (fabsf(dpsi) >= (float)(3.141592653589793 / 36.0)) |
                   (fabsf(sq[4] - tq[0]) >= (float)(3.141592653589793 / 36.0)) | (fabsf(sq[6] - tq[2]) >= 20.0f);
             dn = !off && !late;
-            d0 = wrap_pi(sq[4] - tq[0]) / kPi;                                  // posture_reward.py:26-34
-            d1 = dpsi / kPi;
-            d2 = (sq[6] - tq[2]) * 0.3048f / 340.0f;
+            d0 = wrap_pi(sq[4] - tq[0]) / DC(kPi);                                  // posture_reward.py:26-34
+            d1 = dpsi / DC(kPi);
+            d2 = (sq[6] - tq[2]) * 0.3048f / DC(340.0f);
             rw = -(d0 * d0) + -(d1 * d1) + -(d2 * d2);
           } else {                                                              // unreach_target.py:35-47
             off = (fabsf(sq[0] - tq[0]) >= 100.0f) | (fabsf(sq[1] - tq[1]) >= 100.0f) | (fabsf(sq[2] - tq[2]) >= 100.0f);
             dn = !off && !late;
-            d0 = (sq[0] - tq[0]) * 0.3048f / 1000.0f;                           // position_reward.py:26-34
-            d1 = (sq[1] - tq[1]) * 0.3048f / 1000.0f;
-            d2 = (sq[2] - tq[2]) * 0.3048f / 1000.0f;
+            d0 = (sq[0] - tq[0]) * 0.3048f / DC(1000.0f);                           // position_reward.py:26-34
+            d1 = (sq[1] - tq[1]) * 0.3048f / DC(1000.0f);
+            d2 = (sq[2] - tq[2]) * 0.3048f / DC(1000.0f);
             rw = 0.1f * (-(d0 * d0) + -(d1 * d1) + -(d2 * d2));
           }
           const bool unreach = late && off;
@@ -783,8 +786,8 @@ __device__ __forceinline__ void uav_task_reset(const np_env_cfg& c, const UavVie
     tgt[2] = v.vt + 2.0f * (r.d[4] - 0.5f) * c.max_velocities_u_increment;
   } else {
     const float dist = r.d[2] * (c.max_distance - c.min_distance) + c.min_distance;
-    const float th1 = r.d[3] * kPi / 3.0f - (float)(3.141592653589793 / 6.0);
-    const float th2 = r.d[4] * kPi / 3.0f - (float)(3.141592653589793 / 6.0);
+    const float th1 = r.d[3] * kPi / DC(3.0f) - (float)(3.141592653589793 / 6.0);
+    const float th2 = r.d[4] * kPi / DC(3.0f) - (float)(3.141592653589793 / 6.0);
     tgt[0] = v.npos + dist * cosf(th1) * cosf(th2);
     tgt[1] = v.epos + dist * cosf(th1) * sinf(th2);
     tgt[2] = v.alt + dist * sinf(th1);
@@ -804,36 +807,121 @@ __device__ __forceinline__ void uav_reset_aircraft(const np_env_cfg& c, const Dr
 __device__ __forceinline__ void uav_make_obs(const np_env_cfg& c, const float* s, const UavView& v, const UavTrig& t, const float* tgt,
                                              float* o) {
   if (c.task == NP_TASK_HEADING) {
-    o[0] = (v.alt - tgt[0]) * 0.3048f / 1000.0f;
+    o[0] = (v.alt - tgt[0]) * 0.3048f / DC(1000.0f);
     o[1] = wrap_pi(v.heading - tgt[1]);
-    o[2] = (v.vt - tgt[2]) * 0.3048f / 340.0f;
+    o[2] = (v.vt - tgt[2]) * 0.3048f / DC(340.0f);
   } else if (c.task == NP_TASK_CONTROL) {
     o[0] = wrap_pi(v.pitch - tgt[0]);
     o[1] = wrap_pi(v.heading - tgt[1]);
-    o[2] = (v.vt - tgt[2]) * 0.3048f / 340.0f;
+    o[2] = (v.vt - tgt[2]) * 0.3048f / DC(340.0f);
   } else {
-    o[0] = (v.npos - tgt[0]) * 0.3048f / 1000.0f;
-    o[1] = (v.epos - tgt[1]) * 0.3048f / 1000.0f;
-    o[2] = (v.alt - tgt[2]) * 0.3048f / 1000.0f;
+    o[0] = (v.npos - tgt[0]) * 0.3048f / DC(1000.0f);
+    o[1] = (v.epos - tgt[1]) * 0.3048f / DC(1000.0f);
+    o[2] = (v.alt - tgt[2]) * 0.3048f / DC(1000.0f);
   }
   const float eas = (v.vt + c.airspeed * 1.0f) / v.e2t;  // UAV_model.py:94-102
-  o[3] = v.alt * 0.3048f / 5000.0f;
+  o[3] = v.alt * 0.3048f / DC(5000.0f);
   o[4] = t.sphi; o[5] = t.cphi; o[6] = t.st; o[7] = t.ct;
-  o[8] = eas * 0.3048f / 340.0f;
+  o[8] = eas * 0.3048f / DC(340.0f);
   o[9] = 0.0f; o[10] = 1.0f; o[11] = 0.0f; o[12] = 1.0f;  // sin / cos of get_AOA() = get_AOS() = 0
   o[13] = s[9]; o[14] = s[10]; o[15] = s[11];
-  o[16] = 0.0f / 0.225f / 76300.0f * 0.3048f;             // get_thrust() = 0
-  o[17] = 0.0f / 45.0f; o[18] = 0.0f / 45.0f; o[19] = 0.0f / 45.0f; o[20] = 0.0f / 45.0f;
+  o[16] = 0.0f / DC(0.225f) / DC(76300.0f) * 0.3048f;             // get_thrust() = 0
+  o[17] = 0.0f / DC(45.0f); o[18] = 0.0f / DC(45.0f); o[19] = 0.0f / DC(45.0f); o[20] = 0.0f / DC(45.0f);
   o[21] = v.e2t;
 }
 
+// One aircraft of BaseEnv.step / reset for the UAV plug-in, entirely in registers: masked reset -> (STEP) force
+// low-pass + Euler step -> observation row -> (STEP) terminations + reward.  Shared by the per-thread kernel and the
+// TMA-staged slab kernel below, so both produce identical bits.
 template <bool STEP>
-__global__ void __launch_bounds__(256) uav_env_kernel(const __grid_constant__ StepParams p) {
+__device__ __forceinline__ void uav_aircraft(const StepParams& p, int i, bool rst, const float4 av, float* s, float* F, float* tgt,
+                                             int& steps, float* o, float& rew, bool& done, bool& bad) {
+  const np_env_cfg& c = p.cfg;
+  // ---- BaseEnv.reset (env_base.py:83-97) ---------------------------------------------------------
+  if (rst) {
+    const Draws r = reset_draws(p, i);
+    uav_reset_aircraft(c, r, s, F);
+    uav_task_reset(c, uav_view(s), r, tgt);
+    steps = 0;
+    atomicAdd(&p.counters[7], 1ull);
+  }
+  bad = false; done = false; rew = 0.0f;
+  if (STEP) {
+    // ---- UAVModel.update (UAV_model.py:51-62): clamp, force low-pass, one explicit Euler step ------------
+    const float a[3] = {fminf(fmaxf(av.x, -1.0f), 1.0f), fminf(fmaxf(av.y, -1.0f), 1.0f), fminf(fmaxf(av.z, -1.0f), 1.0f)};
+#pragma unroll
+    for (int j = 0; j < 3; ++j) F[j] = 0.9f * F[j] + 0.1f * a[j] * 27000.0f;
+    float xdot[12];
+    uav_nlplant(s, F, xdot);
+    const float h = c.dt - 0.0f;
+#pragma unroll
+    for (int j = 0; j < 12; ++j) s[j] = s[j] + h * xdot[j];
+    steps += 1;
+  }
+  // ---- obs (env_base.py:103) ----------------------------------------------------------------------
+  const UavView v = uav_view(s);
+  const UavTrig trig = uav_trig(s);   // of the state the observation, the Overload check and the reward all see
+  uav_make_obs(c, s, v, trig, tgt, o);
+  add_obs_noise(p, i, o);
+  if (STEP) {
+    // ---- terminations (task_base.py:75-96) through the getters ------------------------------------------
+    float xdot[12];
+    uav_nlplant(s, F, trig, xdot);                                        // get_acceleration (UAV_model.py:120-130)
+    const float vu = s[6] / DC(0.3048f), vv = s[7] / DC(0.3048f), vw = s[8] / DC(0.3048f);
+    const float ax = xdot[6] / DC(0.3048f) + s[10] * vw - s[11] * vv;
+    const float ay = xdot[7] / DC(0.3048f) + s[11] * vu - s[9] * vw;
+    const float az = xdot[8] / DC(0.3048f) + s[9] * vv - s[10] * vu;
+    const float acc = sqrtf(ax * ax + ay * ay + az * az);
+    const bool overload = (acc - c.acceleration_limit) > 0.0f;
+    const bool low_alt = (v.alt - c.altitude_limit) < 0.0f;
+    const float vel = (v.vt + c.airspeed * 1.0f) * 0.3048f / DC(340.0f);
+    const bool hi = (vel - c.max_velocity) >= 0.0f;
+    const bool lo = (vel - c.min_velocity) <= 0.0f;
+    const float a_deg = 0.0f * 180.0f / DC(kPi);                              // get_AOA() = get_AOS() = 0
+    const bool ext = (a_deg < c.min_alpha) | (a_deg > c.max_alpha) | (a_deg < c.min_beta) | (a_deg > c.max_beta);
+    const bool late = steps >= c.max_check_interval;
+    bool off;
+    float d0, d1, d2;
+    if (c.task == NP_TASK_HEADING) {
+      const float dpsi = wrap_pi(v.heading - tgt[1]);
+      off = (fabsf(dpsi) >= (float)(3.141592653589793 / 36.0)) | (fabsf(v.alt - tgt[0]) >= 100.0f) |
+            (fabsf(v.vt - tgt[2]) >= 20.0f);
+      done = !off && !late && (steps >= c.min_check_interval);
+      d0 = (v.alt - tgt[0]) * 0.3048f / DC(1000.0f); d1 = dpsi / DC(kPi); d2 = (v.vt - tgt[2]) * 0.3048f / DC(340.0f);
+      rew = -(d0 * d0) + -(d1 * d1) + -(d2 * d2);
+    } else if (c.task == NP_TASK_CONTROL) {
+      const float dpsi = wrap_pi(v.heading - tgt[1]);
+      off = (fabsf(dpsi) >= (float)(3.141592653589793 / 36.0)) | (fabsf(v.pitch - tgt[0]) >= (float)(3.141592653589793 / 36.0)) |
+            (fabsf(v.vt - tgt[2]) >= 20.0f);
+      done = !off && !late;
+      d0 = wrap_pi(v.pitch - tgt[0]) / DC(kPi); d1 = dpsi / DC(kPi); d2 = (v.vt - tgt[2]) * 0.3048f / DC(340.0f);
+      rew = -(d0 * d0) + -(d1 * d1) + -(d2 * d2);
+    } else {
+      off = (fabsf(v.npos - tgt[0]) >= 100.0f) | (fabsf(v.epos - tgt[1]) >= 100.0f) | (fabsf(v.alt - tgt[2]) >= 100.0f);
+      done = !off && !late;
+      d0 = (v.npos - tgt[0]) * 0.3048f / DC(1000.0f); d1 = (v.epos - tgt[1]) * 0.3048f / DC(1000.0f);
+      d2 = (v.alt - tgt[2]) * 0.3048f / DC(1000.0f);
+      rew = 0.1f * (-(d0 * d0) + -(d1 * d1) + -(d2 * d2));
+    }
+    const bool unreach = late && off;
+    bad = overload | low_alt | hi | lo | ext | unreach;
+    rew = rew + (float)(-200 * (int)bad + 200 * (int)done);
+    const bool cause[7] = {overload, low_alt, hi, lo, ext, unreach, done};
+#pragma unroll
+    for (int w = 0; w < 7; ++w)
+      if (cause[w]) atomicAdd(&p.counters[w], 1ull);   // ptxas aggregates warp-uniform-address atomics (REDUX + one ATOM)
+  }
+}
+
+// Per-thread variant (reset, unaligned ranges): scalar SoA accesses straight to global memory.
+template <bool STEP>
+__global__ void __launch_bounds__(256, 4) uav_env_kernel(const __grid_constant__ StepParams p) {
   const np_env_cfg& c = p.cfg;
   const int n = c.n, ld = c.ld;
   const int i_end = min(n, 2 * p.pair_end);
   for (int i = 2 * p.pair_begin + blockIdx.x * blockDim.x + threadIdx.x; i < i_end; i += gridDim.x * blockDim.x) {
-    float s[12], F[3], tgt[3];
+    float s[12], F[3], tgt[3], o[NP_NUM_OBS], rew;
+    bool done, bad;
 #pragma unroll
     for (int j = 0; j < 12; ++j) s[j] = p.s[(size_t)j * ld + i];
 #pragma unroll
@@ -842,91 +930,12 @@ __global__ void __launch_bounds__(256) uav_env_kernel(const __grid_constant__ St
     for (int j = 0; j < 3; ++j) tgt[j] = p.tgt[(size_t)j * ld + i];
     int steps = p.step_count[i];
     const bool rst = (p.flags[i] | p.flags[ld + i] | p.flags[2 * (size_t)ld + i]) != 0;
-
-    // ---- BaseEnv.reset (env_base.py:83-97) ---------------------------------------------------------
-    if (rst) {
-      const Draws r = reset_draws(p, i);
-      uav_reset_aircraft(c, r, s, F);
-      uav_task_reset(c, uav_view(s), r, tgt);
-      steps = 0;
-      atomicAdd(&p.counters[7], 1ull);
-    }
-    bool bad = false, done = false;
-    float rew = 0.0f;
-    if (STEP) {
-      // ---- UAVModel.update (UAV_model.py:51-62): clamp, force low-pass, one explicit Euler step ------------
-      const float4 av = reinterpret_cast<const float4*>(p.action)[i];
-      const float a[3] = {fminf(fmaxf(av.x, -1.0f), 1.0f), fminf(fmaxf(av.y, -1.0f), 1.0f), fminf(fmaxf(av.z, -1.0f), 1.0f)};
+    const float4 av = STEP ? reinterpret_cast<const float4*>(p.action)[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+    uav_aircraft<STEP>(p, i, rst, av, s, F, tgt, steps, o, rew, done, bad);
+    float2* orow = reinterpret_cast<float2*>(p.obs + (size_t)i * NP_NUM_OBS);
 #pragma unroll
-      for (int j = 0; j < 3; ++j) F[j] = 0.9f * F[j] + 0.1f * a[j] * 27000.0f;
-      float xdot[12];
-      uav_nlplant(s, F, xdot);
-      const float h = c.dt - 0.0f;
-#pragma unroll
-      for (int j = 0; j < 12; ++j) s[j] = s[j] + h * xdot[j];
-      steps += 1;
-    }
-    // ---- obs (env_base.py:103) ----------------------------------------------------------------------
-    const UavView v = uav_view(s);
-    const UavTrig trig = uav_trig(s);   // of the state the observation, the Overload check and the reward all see
-    {
-      float o[NP_NUM_OBS];
-      uav_make_obs(c, s, v, trig, tgt, o);
-      add_obs_noise(p, i, o);
-      float2* orow = reinterpret_cast<float2*>(p.obs + (size_t)i * NP_NUM_OBS);
-#pragma unroll
-      for (int j = 0; j < NP_NUM_OBS / 2; ++j) orow[j] = make_float2(o[2 * j], o[2 * j + 1]);
-    }
-    if (STEP) {
-      // ---- terminations (task_base.py:75-96) through the getters ------------------------------------------
-      float xdot[12];
-      uav_nlplant(s, F, trig, xdot);                                        // get_acceleration (UAV_model.py:120-130)
-      const float vu = s[6] / 0.3048f, vv = s[7] / 0.3048f, vw = s[8] / 0.3048f;
-      const float ax = xdot[6] / 0.3048f + s[10] * vw - s[11] * vv;
-      const float ay = xdot[7] / 0.3048f + s[11] * vu - s[9] * vw;
-      const float az = xdot[8] / 0.3048f + s[9] * vv - s[10] * vu;
-      const float acc = sqrtf(ax * ax + ay * ay + az * az);
-      const bool overload = (acc - c.acceleration_limit) > 0.0f;
-      const bool low_alt = (v.alt - c.altitude_limit) < 0.0f;
-      const float vel = (v.vt + c.airspeed * 1.0f) * 0.3048f / 340.0f;
-      const bool hi = (vel - c.max_velocity) >= 0.0f;
-      const bool lo = (vel - c.min_velocity) <= 0.0f;
-      const float a_deg = 0.0f * 180.0f / kPi;                              // get_AOA() = get_AOS() = 0
-      const bool ext = (a_deg < c.min_alpha) | (a_deg > c.max_alpha) | (a_deg < c.min_beta) | (a_deg > c.max_beta);
-      const bool late = steps >= c.max_check_interval;
-      bool off;
-      float d0, d1, d2;
-      if (c.task == NP_TASK_HEADING) {
-        const float dpsi = wrap_pi(v.heading - tgt[1]);
-        off = (fabsf(dpsi) >= (float)(3.141592653589793 / 36.0)) | (fabsf(v.alt - tgt[0]) >= 100.0f) |
-              (fabsf(v.vt - tgt[2]) >= 20.0f);
-        done = !off && !late && (steps >= c.min_check_interval);
-        d0 = (v.alt - tgt[0]) * 0.3048f / 1000.0f; d1 = dpsi / kPi; d2 = (v.vt - tgt[2]) * 0.3048f / 340.0f;
-        rew = -(d0 * d0) + -(d1 * d1) + -(d2 * d2);
-      } else if (c.task == NP_TASK_CONTROL) {
-        const float dpsi = wrap_pi(v.heading - tgt[1]);
-        off = (fabsf(dpsi) >= (float)(3.141592653589793 / 36.0)) | (fabsf(v.pitch - tgt[0]) >= (float)(3.141592653589793 / 36.0)) |
-              (fabsf(v.vt - tgt[2]) >= 20.0f);
-        done = !off && !late;
-        d0 = wrap_pi(v.pitch - tgt[0]) / kPi; d1 = dpsi / kPi; d2 = (v.vt - tgt[2]) * 0.3048f / 340.0f;
-        rew = -(d0 * d0) + -(d1 * d1) + -(d2 * d2);
-      } else {
-        off = (fabsf(v.npos - tgt[0]) >= 100.0f) | (fabsf(v.epos - tgt[1]) >= 100.0f) | (fabsf(v.alt - tgt[2]) >= 100.0f);
-        done = !off && !late;
-        d0 = (v.npos - tgt[0]) * 0.3048f / 1000.0f; d1 = (v.epos - tgt[1]) * 0.3048f / 1000.0f;
-        d2 = (v.alt - tgt[2]) * 0.3048f / 1000.0f;
-        rew = 0.1f * (-(d0 * d0) + -(d1 * d1) + -(d2 * d2));
-      }
-      const bool unreach = late && off;
-      bad = overload | low_alt | hi | lo | ext | unreach;
-      rew = rew + (float)(-200 * (int)bad + 200 * (int)done);
-      const bool cause[7] = {overload, low_alt, hi, lo, ext, unreach, done};
-#pragma unroll
-      for (int w = 0; w < 7; ++w)
-        if (cause[w]) atomicAdd(&p.counters[w], 1ull);   // ptxas aggregates warp-uniform-address atomics (REDUX + one ATOM)
-      p.reward[i] = rew;
-    }
-    // ---- store -------------------------------------------------------------------------------------
+    for (int j = 0; j < NP_NUM_OBS / 2; ++j) orow[j] = make_float2(o[2 * j], o[2 * j + 1]);
+    if (STEP) p.reward[i] = rew;
 #pragma unroll
     for (int j = 0; j < 12; ++j) p.s[(size_t)j * ld + i] = s[j];
 #pragma unroll
@@ -938,6 +947,189 @@ __global__ void __launch_bounds__(256) uav_env_kernel(const __grid_constant__ St
     p.flags[ld + i] = bad ? 1 : 0;
     p.flags[2 * (size_t)ld + i] = 0;
   }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K2 (TMA-staged): the HBM-bound UAV step as a persistent slab pipeline.  A CTA owns 256-aircraft slabs; every SoA row
+// segment (1 KB), the action rows (4 KB) and the flag rows arrive in shared memory through TMA bulk copies completing
+// on an mbarrier (23 copies, one per lane of warp 0), and every output -- 19 row segments, flags, reward and the whole
+// 256 x 22 observation block (22.5 KB, contiguous in the row-major obs array) -- leaves through bulk stores, so the
+// LSU sees no global traffic at all (the per-thread variant is LSU-queue / latency limited: 23 scalar loads + 34 stores
+// of 32 separate sectors each per aircraft).  The inputs of slab k+1 are requested as soon as slab k's are in registers and
+// land during slab k's arithmetic; slab k's bulk stores drain during slab k+1's.  68 KB per CTA -> 3 CTAs (24 warps) per SM.
+// The ragged tail slab (< 256 aircraft) goes through guarded per-thread accesses in the same kernel.
+// ------------------------------------------------------------------------------------------------
+namespace uavslab {
+constexpr int kSlab = 256;
+constexpr int IN_S = 0;                            // [12][256] f32
+constexpr int IN_U = IN_S + 12 * kSlab * 4;        // [3][256] f32
+constexpr int IN_T = IN_U + 3 * kSlab * 4;         // [3][256] f32
+constexpr int IN_STEP = IN_T + 3 * kSlab * 4;      // [256] i32
+constexpr int IN_ACT = IN_STEP + kSlab * 4;        // [256][4] f32
+constexpr int IN_FLG = IN_ACT + kSlab * 16;        // [3][256] u8
+constexpr int IN_BYTES = IN_FLG + 3 * kSlab;       // 24 320
+constexpr int OUT_S = IN_BYTES;
+constexpr int OUT_U = OUT_S + 12 * kSlab * 4;
+constexpr int OUT_T = OUT_U + 3 * kSlab * 4;
+constexpr int OUT_STEP = OUT_T + 3 * kSlab * 4;
+constexpr int OUT_REW = OUT_STEP + kSlab * 4;
+constexpr int OUT_FLG = OUT_REW + kSlab * 4;
+constexpr int OUT_OBS = OUT_FLG + 3 * kSlab;       // [256][22] f32
+constexpr int BAR = OUT_OBS + kSlab * NP_NUM_OBS * 4;
+constexpr int SMEM_BYTES = BAR + 32;               // 68 128 (four mbarriers)
+static_assert(OUT_OBS % 16 == 0 && BAR % 8 == 0, "bulk copies need 16-byte aligned shared addresses");
+}  // namespace uavslab
+
+__device__ __forceinline__ void bulk_s2g(void* dst_gmem, const void* src_smem, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem), "r"(smem_u32(src_smem)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// warp 0 requests the inputs of the full slab starting at aircraft i0: lane r fetches row r
+__device__ __forceinline__ void uav_slab_request(const StepParams& p, unsigned char* sm, uint64_t* bar, int i0, int lane) {
+  using namespace uavslab;
+  const size_t ld = (size_t)p.cfg.ld;
+  if (lane == 0) mbar_expect_tx(bar, IN_BYTES);
+  __syncwarp();
+  if (lane < 12) bulk_g2s(sm + IN_S + lane * kSlab * 4, p.s + lane * ld + i0, kSlab * 4, bar);
+  else if (lane < 15) bulk_g2s(sm + IN_U + (lane - 12) * kSlab * 4, p.u + (lane - 12) * ld + i0, kSlab * 4, bar);
+  else if (lane < 18) bulk_g2s(sm + IN_T + (lane - 15) * kSlab * 4, p.tgt + (lane - 15) * ld + i0, kSlab * 4, bar);
+  else if (lane == 18) bulk_g2s(sm + IN_STEP, p.step_count + i0, kSlab * 4, bar);
+  else if (lane == 19) bulk_g2s(sm + IN_ACT, p.action + (size_t)i0 * 4, kSlab * 16, bar);
+  else if (lane < 23) bulk_g2s(sm + IN_FLG + (lane - 20) * kSlab, p.flags + (lane - 20) * ld + i0, kSlab, bar);
+}
+
+// warp 0 sends the results of the full slab starting at aircraft i0: lane r stores row r
+__device__ __forceinline__ void uav_slab_send(const StepParams& p, unsigned char* sm, int i0, int lane) {
+  using namespace uavslab;
+  const size_t ld = (size_t)p.cfg.ld;
+  if (lane < 12) bulk_s2g(p.s + lane * ld + i0, sm + OUT_S + lane * kSlab * 4, kSlab * 4);
+  else if (lane < 15) bulk_s2g(p.u + (lane - 12) * ld + i0, sm + OUT_U + (lane - 12) * kSlab * 4, kSlab * 4);
+  else if (lane < 18) bulk_s2g(p.tgt + (lane - 15) * ld + i0, sm + OUT_T + (lane - 15) * kSlab * 4, kSlab * 4);
+  else if (lane == 18) bulk_s2g(p.step_count + i0, sm + OUT_STEP, kSlab * 4);
+  else if (lane == 19) bulk_s2g(p.reward + i0, sm + OUT_REW, kSlab * 4);
+  else if (lane < 23) bulk_s2g(p.flags + (lane - 20) * ld + i0, sm + OUT_FLG + (lane - 20) * kSlab, kSlab);
+  else if (lane == 23) bulk_s2g(p.obs + (size_t)i0 * NP_NUM_OBS, sm + OUT_OBS, kSlab * NP_NUM_OBS * 4);
+  bulk_commit();
+}
+
+__global__ void __launch_bounds__(uavslab::kSlab, 3) uav_step_slab_kernel(const __grid_constant__ StepParams p) {
+  using namespace uavslab;
+  extern __shared__ __align__(128) unsigned char sm[];
+  const int ld = p.cfg.ld, t = threadIdx.x, lane = t & 31;
+  const bool warp0 = t < 32;
+  const int i_begin = 2 * p.pair_begin, i_end = min(p.cfg.n, 2 * p.pair_end);
+  const int nslab = (i_end - i_begin + kSlab - 1) / kSlab;
+  // No CTA-wide barrier in the slab loop: the eight warps are coupled only through four mbarriers, so a warp that is
+  // ahead keeps issuing (a __syncthreads version measured 3.2 barrier-stall cycles per issued instruction).
+  uint64_t* in_full = reinterpret_cast<uint64_t*>(sm + BAR);  // TMA: the slab's inputs have landed            (tx bytes)
+  uint64_t* in_read = in_full + 1;                            // every warp holds its inputs in registers        (8 warps)
+  uint64_t* written = in_full + 2;                            // every warp has written its results to OUT       (8 warps)
+  uint64_t* out_free = in_full + 3;                           // the previous bulk stores have finished reading OUT  (1)
+  if (t == 0) {
+    mbar_init(in_full, 1);
+    mbar_init(in_read, kSlab / 32);
+    mbar_init(written, kSlab / 32);
+    mbar_init(out_free, 1);
+  }
+  __syncthreads();
+
+  int slab = blockIdx.x;
+  if (warp0 && slab < nslab && i_begin + (slab + 1) * kSlab <= i_end) uav_slab_request(p, sm, in_full, i_begin + slab * kSlab, lane);
+
+  for (int it = 0; slab < nslab; slab += gridDim.x, ++it) {
+    const int i0 = i_begin + slab * kSlab, i = i0 + t;
+    const bool full = i0 + kSlab <= i_end;       // CTA-uniform; only the last slab of the range can be ragged
+    const bool live = full || i < i_end;
+    const uint32_t ph = it & 1;
+    float s[12], F[3], tgt[3], o[NP_NUM_OBS], rew = 0.0f;
+    bool done = false, bad = false, rst = false;
+    int steps = 0;
+    float4 av = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (full) {
+      mbar_wait(in_full, ph);
+#pragma unroll
+      for (int j = 0; j < 12; ++j) s[j] = reinterpret_cast<const float*>(sm + IN_S)[j * kSlab + t];
+#pragma unroll
+      for (int j = 0; j < 3; ++j) F[j] = reinterpret_cast<const float*>(sm + IN_U)[j * kSlab + t];
+#pragma unroll
+      for (int j = 0; j < 3; ++j) tgt[j] = reinterpret_cast<const float*>(sm + IN_T)[j * kSlab + t];
+      steps = reinterpret_cast<const int*>(sm + IN_STEP)[t];
+      av = reinterpret_cast<const float4*>(sm + IN_ACT)[t];
+      rst = (sm[IN_FLG + t] | sm[IN_FLG + kSlab + t] | sm[IN_FLG + 2 * kSlab + t]) != 0;
+      __syncwarp();
+      if (lane == 0) mbar_arrive(in_read);
+      if (warp0) {
+        if (it > 0) {            // the previous slab's stores were issued a whole input wait ago: normally drained by now
+          bulk_wait_read0();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(out_free);
+        }
+        const int next = slab + gridDim.x;
+        if (next < nslab && i_begin + (next + 1) * kSlab <= i_end) {
+          mbar_wait(in_read, ph);   // the input slab is free again: its next contents land during this slab's arithmetic
+          uav_slab_request(p, sm, in_full, i_begin + next * kSlab, lane);
+        }
+      }
+    } else if (live) {
+#pragma unroll
+      for (int j = 0; j < 12; ++j) s[j] = p.s[(size_t)j * ld + i];
+#pragma unroll
+      for (int j = 0; j < 3; ++j) F[j] = p.u[(size_t)j * ld + i];
+#pragma unroll
+      for (int j = 0; j < 3; ++j) tgt[j] = p.tgt[(size_t)j * ld + i];
+      steps = p.step_count[i];
+      av = reinterpret_cast<const float4*>(p.action)[i];
+      rst = (p.flags[i] | p.flags[ld + i] | p.flags[2 * (size_t)ld + i]) != 0;
+    }
+
+    if (live) uav_aircraft<true>(p, i, rst, av, s, F, tgt, steps, o, rew, done, bad);
+
+    if (full) {
+      if (it > 0) mbar_wait(out_free, ph ^ 1);
+#pragma unroll
+      for (int j = 0; j < 12; ++j) reinterpret_cast<float*>(sm + OUT_S)[j * kSlab + t] = s[j];
+#pragma unroll
+      for (int j = 0; j < 3; ++j) reinterpret_cast<float*>(sm + OUT_U)[j * kSlab + t] = F[j];
+#pragma unroll
+      for (int j = 0; j < 3; ++j) reinterpret_cast<float*>(sm + OUT_T)[j * kSlab + t] = tgt[j];
+      reinterpret_cast<int*>(sm + OUT_STEP)[t] = steps;
+      reinterpret_cast<float*>(sm + OUT_REW)[t] = rew;
+      sm[OUT_FLG + t] = done ? 1 : 0;
+      sm[OUT_FLG + kSlab + t] = bad ? 1 : 0;
+      sm[OUT_FLG + 2 * kSlab + t] = 0;
+      float2* orow = reinterpret_cast<float2*>(sm + OUT_OBS) + t * (NP_NUM_OBS / 2);  // 8-byte stride 11: conflict-free
+#pragma unroll
+      for (int j = 0; j < NP_NUM_OBS / 2; ++j) orow[j] = make_float2(o[2 * j], o[2 * j + 1]);
+      fence_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(written);
+      if (warp0) {
+        mbar_wait(written, ph);
+        uav_slab_send(p, sm, i0, lane);
+      }
+    } else if (live) {
+      float2* orow = reinterpret_cast<float2*>(p.obs + (size_t)i * NP_NUM_OBS);
+#pragma unroll
+      for (int j = 0; j < NP_NUM_OBS / 2; ++j) orow[j] = make_float2(o[2 * j], o[2 * j + 1]);
+      p.reward[i] = rew;
+#pragma unroll
+      for (int j = 0; j < 12; ++j) p.s[(size_t)j * ld + i] = s[j];
+#pragma unroll
+      for (int j = 0; j < 3; ++j) p.u[(size_t)j * ld + i] = F[j];
+#pragma unroll
+      for (int j = 0; j < 3; ++j) p.tgt[(size_t)j * ld + i] = tgt[j];
+      p.step_count[i] = steps;
+      p.flags[i] = done ? 1 : 0;
+      p.flags[ld + i] = bad ? 1 : 0;
+      p.flags[2 * (size_t)ld + i] = 0;
+    }
+  }
+  if (warp0) bulk_wait0();  // shared memory must outlive the last bulk stores
 }
 
 __global__ void __launch_bounds__(256) uav_nlplant_kernel(const float* __restrict__ S, const float* __restrict__ U,
@@ -1491,9 +1683,24 @@ static int step_range_impl(np_env* env, const float* action_dev, const float* dr
   if (env->cfg.model == NP_MODEL_UAV) {
     if (count == 0) return NP_OK;
     const int want = (count + 255) / 256;
-    env->grid = want < env->num_sms * 8 ? want : env->num_sms * 8;
-    env->smem = 0;
-    uav_env_kernel<true><<<env->grid, 256, 0, st>>>(p);
+    // TMA bulk copies need 16-byte aligned global addresses: row bases, and the first aircraft a multiple of 16 (u8 flag rows)
+    const uintptr_t bases = (uintptr_t)p.s | (uintptr_t)p.u | (uintptr_t)p.tgt | (uintptr_t)p.step_count | (uintptr_t)p.flags |
+                            (uintptr_t)p.obs | (uintptr_t)p.reward | (uintptr_t)p.action;
+    const bool slab_ok = !(bases & 15) && !(first & 15) && !(env->cfg.ld & 15) && count >= uavslab::kSlab && !getenv("NPLANE_UAV_SCALAR");
+    if (slab_ok) {
+      static bool attr_set = false;
+      if (!attr_set) {
+        NP_CUDA(cudaFuncSetAttribute(uav_step_slab_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, uavslab::SMEM_BYTES));
+        attr_set = true;
+      }
+      env->grid = want < env->num_sms * 3 ? want : env->num_sms * 3;
+      env->smem = uavslab::SMEM_BYTES;
+      uav_step_slab_kernel<<<env->grid, uavslab::kSlab, uavslab::SMEM_BYTES, st>>>(p);
+    } else {
+      env->grid = want < env->num_sms * 8 ? want : env->num_sms * 8;
+      env->smem = 0;
+      uav_env_kernel<true><<<env->grid, 256, 0, st>>>(p);
+    }
     NP_CUDA(cudaGetLastError());
     return NP_OK;
   }
@@ -1594,7 +1801,7 @@ int np_env_counters(np_env* env, uint64_t* out, void* stream) {
 int np_env_launch_info(const np_env* env, int* grid, int* block, int* smem_bytes, int* num_sms) {
   if (!env) return fail(NP_EINVAL, "np_env_launch_info: null env");
   if (grid) *grid = env->grid;
-  if (block) *block = env->tables ? env->tab_block : env->block;
+  if (block) *block = env->cfg.model == NP_MODEL_UAV ? 256 : env->tables ? env->tab_block : env->block;
   if (smem_bytes) *smem_bytes = env->smem;
   if (num_sms) *num_sms = env->num_sms;
   return NP_OK;

@@ -37,9 +37,9 @@ __device__ __forceinline__ void uav_nlplant(const float* s, const float* F, cons
   xdot[3] = P + (R * cphi + Q * sphi) * tt;
   xdot[4] = Q * cphi - R * sphi;
   xdot[5] = (R * cphi + Q * sphi) / ct;
-  xdot[6] = V * R - W * Q - g * st + F[0] / UAV_M;
-  xdot[7] = -U * R + W * P + g * ct * sphi + F[1] / UAV_M;
-  xdot[8] = U * Q - V * P + g * ct * cphi + F[2] / UAV_M;
+  xdot[6] = V * R - W * Q - g * st + F[0] / DC(UAV_M);
+  xdot[7] = -U * R + W * P + g * ct * sphi + F[1] / DC(UAV_M);
+  xdot[8] = U * Q - V * P + g * ct * cphi + F[2] / DC(UAV_M);
   const float b0 = L_bar - Q * R * (I_z - I_y) + P * Q * I_xz;
   const float b1 = N - P * Q * (I_y - I_x) - Q * R * I_xz;
   const float b2 = M - P * R * (I_x - I_z) - (P * P - R * R) * I_xz;
@@ -55,11 +55,11 @@ struct UavView {
 };
 __device__ __forceinline__ UavView uav_view(const float* s) {
   UavView v;
-  v.npos = s[0] / 0.3048f;                                            // get_position
-  v.epos = s[1] / 0.3048f;
-  v.alt = s[2] / 0.3048f;
+  v.npos = s[0] / DC(0.3048f);                                            // get_position
+  v.epos = s[1] / DC(0.3048f);
+  v.alt = s[2] / DC(0.3048f);
   v.roll = s[3]; v.pitch = s[4]; v.heading = s[5];                    // get_posture
-  v.vt = sqrtf(s[6] * s[6] + s[7] * s[7] + s[8] * s[8]) / 0.3048f;    // get_vt
+  v.vt = sqrtf(s[6] * s[6] + s[7] * s[7] + s[8] * s[8]) / DC(0.3048f);    // get_vt
   const float tfac = 1.0f - .703e-5f * v.alt;                         // get_EAS2TAS
   v.e2t = sqrtf(1.0f / powf(tfac, 4.14f));
   return v;
