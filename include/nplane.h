@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define NP_ABI_VERSION 5
+#define NP_ABI_VERSION 6
 
 enum { NP_OK = 0, NP_EINVAL = 1, NP_ECUDA = 2, NP_ESTATE = 3 };
 
@@ -136,6 +136,17 @@ int np_env_step(np_env* env, const float* action_dev, const float* draws_dev, co
  * step, 0 on the others (all ranges then share one RNG counter). */
 int np_env_step_range(np_env* env, const float* action_dev, const float* draws_dev, const float* noise_dev, int first_aircraft,
                       int count, int advance_step_index, void* stream);
+
+/* GPUVecEnv.step with HOST buffers (envs/env_wrappers.py:93-103: numpy actions in, numpy obs / rewards / dones out) in one
+ * call: the population is cut into n_chunks aircraft ranges [edges[c], edges[c+1]) (edges[0] = 0, edges[n_chunks] = n, every
+ * edge even, at most 16 chunks) and staging memcpy -> H2D -> np_env_step_range -> D2H are pipelined over three library-owned
+ * streams, so the observation download (88 of the 95 B/aircraft that cross PCIe) starts after the first small chunk and never
+ * idles.  action_host: [n][4] anywhere in host memory (may equal action_pinned); action_pinned / obs_pinned [n][22] /
+ * reward_pinned [n] / flags_pinned [3][n] (is_done, bad_done, exceed_time_limit rows): page-locked host buffers;
+ * action_dev: [n][4] device scratch.  Ordered after everything queued on `stream`; RETURNS WHEN THE HOST BUFFERS ARE READY.
+ * Bit-identical to np_env_step (all chunks share one RNG counter).  ControlEnv steps only (F16, F16 tables, UAV). */
+int np_env_step_host(np_env* env, const float* action_host, float* action_pinned, float* action_dev, float* obs_pinned,
+                     float* reward_pinned, uint8_t* flags_pinned, const int* edges, int n_chunks, void* stream);
 
 /* PlanningEnv.step(action) (envs/planning_env.py:144-177) as ONE kernel launch: reset -> clamp -> pitch / heading /
  * speed targets from the 3-D high-level action (:146-152) -> n_sub (reference: 50) x { low-level controller ->

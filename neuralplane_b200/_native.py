@@ -71,6 +71,7 @@ SYMBOLS = {
     "np_env_reset": (C.c_int, [_P, _P, _P, _P]),
     "np_env_step": (C.c_int, [_P, _P, _P, _P, _P]),
     "np_env_step_range": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, C.c_int, _P]),
+    "np_env_step_host": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, C.POINTER(C.c_int), C.c_int, _P]),
     "np_env_plan_step": (C.c_int, [_P, _P, C.c_int, _P, _P, _P]),
     "np_env_combat_step": (C.c_int, [_P, _P, C.c_int, _P, _P]),
     "np_env_combat_records": (C.c_int, [_P, _P, _P]),

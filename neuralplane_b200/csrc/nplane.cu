@@ -65,6 +65,10 @@ struct np_env {
   uint32_t step_index = 0;
   bool pid_started = false;  // the fused PID controller has run at least once (PID.reset, pid.py:13)
   int block = 384, tab_block = 384, grid = 0, smem = 0, num_sms = 0;
+  // np_env_step_host: one in-order stream per engine (upload, kernels, download) and the events chaining them
+  static constexpr int kMaxHostChunks = 16;
+  cudaStream_t hs[3] = {nullptr, nullptr, nullptr};
+  cudaEvent_t hev_start = nullptr, hev_done = nullptr, hev_up[kMaxHostChunks] = {}, hev_run[kMaxHostChunks] = {};
 };
 
 struct StepParams {
@@ -1638,6 +1642,12 @@ int np_env_set_cfg(np_env* env, const np_env_cfg* cfg) {
 }
 
 int np_env_destroy(np_env* env) {
+  if (env && env->hs[0]) {
+    for (cudaStream_t st : env->hs) cudaStreamDestroy(st);
+    cudaEventDestroy(env->hev_start);
+    cudaEventDestroy(env->hev_done);
+    for (int c = 0; c < np_env::kMaxHostChunks; ++c) { cudaEventDestroy(env->hev_up[c]); cudaEventDestroy(env->hev_run[c]); }
+  }
   delete env;
   return NP_OK;
 }
@@ -1727,6 +1737,56 @@ static int step_range_impl(np_env* env, const float* action_dev, const float* dr
     case 384: return launch_step<384, 1, MODE_STEP>(env, p, st);
     default: return fail(NP_EINVAL, "np_env_step: block size not compiled in (build with -DNPLANE_ALL_BLOCKS)");
   }
+}
+
+// The numpy boundary of GPUVecEnv.step (env_wrappers.py:93-103) in one native call: host actions in, host observations /
+// rewards / flags out.  The population is cut into chunks (edges[0..n_chunks], whole pairs) and pipelined over three
+// in-order streams, one per engine: chunk c's actions are staged (memcpy into pinned memory) and uploaded while chunk
+// c-1 runs and chunk c-2's 88 B/aircraft observations -- the resource this boundary is bound by -- travel to the host.
+// Issuing a chunk costs a few microseconds here against ~110 us of interpreter time in the Python pipeline it replaces,
+// which is what delayed the start of the download (profiles/r01_variants.txt).  Returns when the host buffers are ready.
+int np_env_step_host(np_env* env, const float* action_host, float* action_pinned, float* action_dev, float* obs_pinned,
+                     float* reward_pinned, uint8_t* flags_pinned, const int* edges, int n_chunks, void* stream) {
+  if (!env || !env->bound) return fail(NP_ESTATE, "np_env_step_host: env not bound");
+  if (!action_host || !action_pinned || !action_dev || !obs_pinned || !reward_pinned || !flags_pinned || !edges || n_chunks < 1 ||
+      n_chunks > np_env::kMaxHostChunks || edges[0] != 0 || edges[n_chunks] != env->cfg.n)
+    return fail(NP_EINVAL, "np_env_step_host: bad argument (1..16 chunks, edges[0] = 0, edges[n_chunks] = n)");
+  for (int c = 0; c < n_chunks; ++c)
+    if (edges[c + 1] <= edges[c] || (edges[c] & 1)) return fail(NP_EINVAL, "np_env_step_host: chunks must be non-empty and start on whole pairs");
+  if (!env->hs[0]) {
+    for (cudaStream_t& st : env->hs) NP_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    NP_CUDA(cudaEventCreateWithFlags(&env->hev_start, cudaEventDisableTiming));
+    NP_CUDA(cudaEventCreateWithFlags(&env->hev_done, cudaEventDisableTiming));
+    for (int c = 0; c < np_env::kMaxHostChunks; ++c) {
+      NP_CUDA(cudaEventCreateWithFlags(&env->hev_up[c], cudaEventDisableTiming));
+      NP_CUDA(cudaEventCreateWithFlags(&env->hev_run[c], cudaEventDisableTiming));
+    }
+  }
+  cudaStream_t main_st = (cudaStream_t)stream, up = env->hs[0], run = env->hs[1], down = env->hs[2];
+  const int n = env->cfg.n, ld = env->cfg.ld, A = 4, D = NP_NUM_OBS;
+  NP_CUDA(cudaEventRecord(env->hev_start, main_st));   // everything already queued on the caller's stream comes first
+  for (cudaStream_t st : env->hs) NP_CUDA(cudaStreamWaitEvent(st, env->hev_start, 0));
+  for (int c = 0; c < n_chunks; ++c) {
+    const int i0 = edges[c], cnt = edges[c + 1] - edges[c];
+    const size_t a_off = (size_t)i0 * A, a_bytes = (size_t)cnt * A * sizeof(float);
+    if (action_host != action_pinned) memcpy(action_pinned + a_off, action_host + a_off, a_bytes);   // overlaps the GPU
+    NP_CUDA(cudaMemcpyAsync(action_dev + a_off, action_pinned + a_off, a_bytes, cudaMemcpyHostToDevice, up));
+    NP_CUDA(cudaEventRecord(env->hev_up[c], up));
+    NP_CUDA(cudaStreamWaitEvent(run, env->hev_up[c], 0));
+    const int rc = step_range_impl(env, action_dev, nullptr, nullptr, i0, cnt, c == 0, run);
+    if (rc != NP_OK) return rc;
+    NP_CUDA(cudaEventRecord(env->hev_run[c], run));
+    NP_CUDA(cudaStreamWaitEvent(down, env->hev_run[c], 0));
+    NP_CUDA(cudaMemcpyAsync(obs_pinned + (size_t)i0 * D, env->buf.obs_dev + (size_t)i0 * D, (size_t)cnt * D * sizeof(float),
+                            cudaMemcpyDeviceToHost, down));
+    NP_CUDA(cudaMemcpyAsync(reward_pinned + i0, env->buf.reward_dev + i0, (size_t)cnt * sizeof(float), cudaMemcpyDeviceToHost, down));
+    NP_CUDA(cudaMemcpy2DAsync(flags_pinned + i0, (size_t)n, env->buf.flags_dev + i0, (size_t)ld, (size_t)cnt, 3,
+                              cudaMemcpyDeviceToHost, down));   // the three flag rows of the chunk in one strided copy
+  }
+  NP_CUDA(cudaEventRecord(env->hev_done, down));
+  NP_CUDA(cudaStreamWaitEvent(main_st, env->hev_done, 0));   // later work on the caller's stream sees the stepped state
+  NP_CUDA(cudaEventSynchronize(env->hev_done));
+  return NP_OK;
 }
 
 int np_env_plan_step(np_env* env, const float* action3_dev, int n_sub, const float* draws_dev, const float* noise_dev,

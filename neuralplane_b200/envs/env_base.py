@@ -221,6 +221,16 @@ class BaseEnv:
                                         1 if advance else 0, self._stream())
         nv.check(st, "np_env_step_range")
 
+    def step_host(self, action_np, act_pinned, act_dev, obs_pinned, rew_pinned, flags_pinned, edges, n_chunks):
+        """The numpy boundary in one native call (np_env_step_host): host actions in, pinned host obs [n, D] / reward [n] /
+        flags [3, n] out, pipelined over `n_chunks` aircraft ranges with edges `edges` (ctypes int array).  Returns when
+        the host buffers are ready."""
+        self._sync_cfg()
+        st = nv.lib().np_env_step_host(self._handle, action_np.ctypes.data, act_pinned.data_ptr(), act_dev.data_ptr(),
+                                       obs_pinned.data_ptr(), rew_pinned.data_ptr(), flags_pinned.data_ptr(), edges,
+                                       int(n_chunks), self._stream())
+        nv.check(st, "np_env_step_host")
+
     def launch_info(self):
         g, b, s, m = C.c_int(), C.c_int(), C.c_int(), C.c_int()
         nv.check(nv.lib().np_env_launch_info(self._handle, C.byref(g), C.byref(b), C.byref(s), C.byref(m)), "np_env_launch_info")

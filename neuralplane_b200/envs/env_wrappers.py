@@ -7,8 +7,14 @@ of different chunks overlap; the 88 B/aircraft observation download is what boun
 synchronise per step.  The returned arrays alias pinned buffers that are reused every OTHER step
 (double-buffered), so a result stays valid until the step after next.
 """
+import ctypes as C
+
 import numpy as np
 import torch
+
+
+
+DEFAULT_PIPELINE = (1, 2, 3, 4, 4, 4)   # relative chunk sizes; see profiles/r01_variants.txt for the sweep
 
 
 class GPUVecEnv:
@@ -36,11 +42,18 @@ class GPUVecEnv:
         if self.device_tensors:
             return
         # pipelined boundary for large single-step envs (ControlEnv): chunks of whole pairs on side streams
-        k = int(pipeline_chunks) if pipeline_chunks is not None else (4 if n >= 200_000 else 1)
+        # pipeline_chunks: a chunk count (equal chunks) or a sequence of relative chunk sizes, e.g. (1, 2, 3, 5, 5): a small
+        # first chunk starts the observation download -- the resource this boundary is bound by -- sooner
+        if pipeline_chunks is None:
+            pipeline_chunks = DEFAULT_PIPELINE if n >= 200_000 else 1
+        w = [1.0] * int(pipeline_chunks) if np.isscalar(pipeline_chunks) else [float(x) for x in pipeline_chunks]
+        k = len(w)
         if k > 1 and hasattr(e, "step_range") and type(e).__name__ == "ControlEnv":
-            edges = [min(n, 2 * ((n // 2 + k - 1) // k) * c) for c in range(k)] + [n]
+            cum = np.cumsum([0.0] + w) / sum(w)
+            # edges on multiples of 256 aircraft: whole pairs, and 16-byte aligned rows for the TMA-staged UAV kernel
+            edges = [min(n, 256 * int(round(n * f / 256))) for f in cum[:-1]] + [n]
             self._chunks = [(edges[c], edges[c + 1]) for c in range(k) if edges[c + 1] > edges[c]]
-            self._streams = [torch.cuda.Stream(device=e.device) for _ in self._chunks]
+            self._edges = (C.c_int * (len(self._chunks) + 1))(*([c[0] for c in self._chunks] + [n]))
         self._act_h = torch.empty((n, A), dtype=torch.float32).pin_memory()
         self._act_d = torch.empty((n, A), dtype=torch.float32, device=e.device)
         self._out = [dict(obs=torch.empty((n, D), dtype=torch.float32).pin_memory(),
@@ -86,28 +99,17 @@ class GPUVecEnv:
                 flags[2].reshape(shp), {})
 
     def _step_pipelined(self, a):
-        """Aircraft are independent, so the step is issued chunk by chunk on side streams: while chunk c's observations
-        travel to the host (the 88 B/aircraft D2H dominates the boundary), chunk c+1 runs and chunk c+2's actions are
-        staged and uploaded.  Same results as the single launch (one RNG counter for all chunks)."""
+        """Aircraft are independent, so the step is pipelined chunk by chunk over three in-order streams -- upload, kernels,
+        download: while chunk c's observations travel to the host (the 88 B/aircraft D2H is what bounds this boundary),
+        chunk c+1 runs and chunk c+2's actions are staged and uploaded.  The whole pipeline is ONE native call
+        (np_env_step_host): issuing a chunk from Python cost ~110 us of interpreter time, which delayed the first download.
+        Same results as the single launch (one RNG counter for all chunks)."""
         e = self.gpu_vec_env
         o = self._out[self._flip]
         self._flip ^= 1
-        main = torch.cuda.current_stream(e.device)
-        start = main.record_event()
-        for c, (i0, i1) in enumerate(self._chunks):
-            st = self._streams[c]
-            st.wait_event(start)
-            self._act_h[i0:i1].copy_(torch.from_numpy(a[i0:i1, :self._A]))          # host memcpy, overlaps the GPU
-            with torch.cuda.stream(st):
-                self._act_d[i0:i1].copy_(self._act_h[i0:i1], non_blocking=True)
-                e.step_range(self._act_d, i0, i1 - i0, advance=(c == 0))
-                o["obs"][i0:i1].copy_(e.last_obs[i0:i1], non_blocking=True)
-                o["rew"][i0:i1].copy_(e.last_reward[i0:i1], non_blocking=True)
-                for j in range(3):
-                    o["flags"][j, i0:i1].copy_(e._flags[j, i0:i1], non_blocking=True)
-        for st in self._streams:
-            main.wait_stream(st)
-        main.synchronize()
+        if a.shape[1] != self._A or not a.flags.c_contiguous:
+            a = np.ascontiguousarray(a[:, :self._A])
+        e.step_host(a, self._act_h, self._act_d, o["obs"], o["rew"], o["flags"], self._edges, len(self._chunks))
         return o
 
     def reset(self):
