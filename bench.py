@@ -155,6 +155,34 @@ def run_reference(args, rank, world):
     }))
 
 
+def side_uav_roofline(dev, hbm_peak, n=8_000_000, K=100, W=20):
+    """Not the headline: the path's HBM-bound kernel (UAV aircraft plug-in, BASELINE configs[2]'s second-model slot) against
+    the same measured HBM peak, timed live with CUDA events after the headline run (outside every timed region above)."""
+    import torch
+    from neuralplane_b200 import ControlEnv
+    try:
+        env = ControlEnv(num_envs=n, config="control", model="UAV", random_seed=0, device=dev)
+        env.reset()
+        acts = [torch.rand((n, 4), device=dev) * 2 - 1 for _ in range(2)]
+        for k in range(W):
+            env.step(acts[k % 2])
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for k in range(K):
+            env.step(acts[k % 2])
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / K
+        achieved = 268.0 * n / (ms * 1e-3) / 1e9
+        return {"kernel": "uav_step_slab_kernel", "workload": f"UAV Control task, ControlEnv, num_agents={n}, random policy, noise_scale "
+                f"{float(env.task.noise_scale)}; working set 2.1 GB per step >> L2", "bound": "hbm", "achieved": achieved, "peak": hbm_peak,
+                "unit": "GB/s", "frac": achieved / hbm_peak, "algorithmic_bytes_per_aircraft_step": 268, "ms_per_step": ms,
+                "aircraft_steps_per_s": n / (ms * 1e-3), "steps": K, "warmup": W, "launch": env.launch_info()}
+    except Exception as e:  # a side line must never take the headline down
+        return {"kernel": "uav_step_slab_kernel", "error": repr(e)}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -167,6 +195,7 @@ def main():
     ap.add_argument("--cpu-budget", type=float, default=12.0)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-cache", action="store_true")
+    ap.add_argument("--no-side", action="store_true", help="skip the side roofline of the HBM-bound UAV step kernel")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -273,6 +302,8 @@ def main():
                          "reference_equivalent_gflops": ALGO_FLOP_PER_STEP * n / per_launch_s / 1e9},
             "termination_counters": counters,
         }
+        if world == 1 and not args.no_side:
+            out["side_rooflines"] = [side_uav_roofline(dev, hbm_peak)]
         if world == 1 and not args.no_cpu:
             v, steps, el, thr = cpu_port_throughput(args.cpu_n, args.cpu_budget)
             out["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": thr, "kind": "port",
