@@ -17,6 +17,24 @@ import torch
 DEFAULT_PIPELINE = (1, 2, 3, 4, 4, 4)   # relative chunk sizes; see profiles/r01_variants.txt for the sweep
 
 
+MAX_PIPELINE_CHUNKS = 16   # np_env_step_host (include/nplane.h)
+
+
+def pipeline_edges(n, pattern):
+    """Aircraft ranges [(i0, i1), ...] of the pipelined numpy step, or None for a single launch.  `pattern` is a chunk
+    count (equal chunks) or a sequence of relative chunk sizes.  Interior edges fall on multiples of 256 aircraft (whole
+    pairs; 16-byte aligned rows for the TMA-staged UAV kernel); empty chunks are dropped."""
+    w = [1.0] * int(pattern) if np.isscalar(pattern) else [float(x) for x in pattern]
+    if len(w) > MAX_PIPELINE_CHUNKS or any(x <= 0 for x in w):
+        raise ValueError(f"pipeline_chunks: 1..{MAX_PIPELINE_CHUNKS} positive chunk sizes, got {pattern!r}")
+    if len(w) <= 1:
+        return None
+    cum = np.cumsum([0.0] + w) / sum(w)
+    edges = [min(n, 256 * int(round(n * f / 256))) for f in cum[:-1]] + [n]
+    chunks = [(edges[c], edges[c + 1]) for c in range(len(w)) if edges[c + 1] > edges[c]]
+    return chunks if len(chunks) > 1 else None
+
+
 class GPUVecEnv:
     def __init__(self, env_fns, device_tensors=False, pipeline_chunks=None):
         """device_tensors=True (SURVEY f-2): step()/reset() take and return torch CUDA tensors in the same
@@ -46,13 +64,8 @@ class GPUVecEnv:
         # first chunk starts the observation download -- the resource this boundary is bound by -- sooner
         if pipeline_chunks is None:
             pipeline_chunks = DEFAULT_PIPELINE if n >= 200_000 else 1
-        w = [1.0] * int(pipeline_chunks) if np.isscalar(pipeline_chunks) else [float(x) for x in pipeline_chunks]
-        k = len(w)
-        if k > 1 and hasattr(e, "step_range") and type(e).__name__ == "ControlEnv":
-            cum = np.cumsum([0.0] + w) / sum(w)
-            # edges on multiples of 256 aircraft: whole pairs, and 16-byte aligned rows for the TMA-staged UAV kernel
-            edges = [min(n, 256 * int(round(n * f / 256))) for f in cum[:-1]] + [n]
-            self._chunks = [(edges[c], edges[c + 1]) for c in range(k) if edges[c + 1] > edges[c]]
+        self._chunks = pipeline_edges(n, pipeline_chunks) if hasattr(e, "step_host") and type(e).__name__ == "ControlEnv" else None
+        if self._chunks is not None:
             self._edges = (C.c_int * (len(self._chunks) + 1))(*([c[0] for c in self._chunks] + [n]))
         self._act_h = torch.empty((n, A), dtype=torch.float32).pin_memory()
         self._act_d = torch.empty((n, A), dtype=torch.float32, device=e.device)
