@@ -174,6 +174,13 @@ int np_env_combat_step(np_env* env, const float* action_dev, int n_sub, const fl
 int np_env_combat_records(np_env* env, float* records_dev, void* stream);
 int np_combat_relgeo(const float* records_dev, const int32_t* ego_idx_dev, const int32_t* enm_idx_dev, float* out_dev, int m,
                      void* stream);
+/* np_combat_relgeo with the exchange fused into the kernel (no gathered array, no NCCL call): slabs_dev is a DEVICE array
+ * of `world` pointers, slabs_dev[r] = rank r's record slab [n_local][8] in peer-mapped memory (NVLink P2P, e.g. the
+ * buffer_ptrs_dev of a torch symmetric-memory tensor); ego / enemy indices address the virtual rank-ordered gathered
+ * array (record g = slabs_dev[g / n_local] + 8 (g % n_local)).  The caller orders it after every rank's
+ * np_env_combat_records with a cross-device barrier.  Same out[m][8] as np_combat_relgeo on the all-gathered array. */
+int np_combat_relgeo_peers(const float* const* slabs_dev, int world, int n_local, const int32_t* ego_idx_dev, const int32_t* enm_idx_dev,
+                           float* out_dev, int m, void* stream);
 /* Byte offset, inside the workspace, of the [ld] f32 blood row (singlecombat_env.py:45). */
 size_t np_env_blood_offset_bytes(const np_env_cfg* cfg);
 

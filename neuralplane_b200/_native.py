@@ -76,6 +76,7 @@ SYMBOLS = {
     "np_env_combat_step": (C.c_int, [_P, _P, C.c_int, _P, _P]),
     "np_env_combat_records": (C.c_int, [_P, _P, _P]),
     "np_combat_relgeo": (C.c_int, [_P, _P, _P, _P, C.c_int, _P]),
+    "np_combat_relgeo_peers": (C.c_int, [_P, C.c_int, C.c_int, _P, _P, _P, C.c_int, _P]),
     "np_env_blood_offset_bytes": (C.c_size_t, [C.POINTER(EnvCfg)]),
     "np_env_pid_offset_bytes": (C.c_size_t, [C.POINTER(EnvCfg)]),
     "np_env_set_pid_started": (C.c_int, [_P, C.c_int]),

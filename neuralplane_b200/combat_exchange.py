@@ -8,8 +8,11 @@ this: the step kernel holds both aircraft of a pair in one thread.
     geo     = relative_geometry(allrec, ego_idx, enm_idx) # [m, 8]: AO TA R AO2 TA2 R2 side dvx
 
 Record = position (3), inertial velocity xdot[0:3] (3), body-axis vx, blood: 32 B per aircraft, so 10^6 aircraft gather
-32 MB per rank per step -- tens of microseconds on NVLink 5, negligible next to the step kernel; plain
-all_gather_into_tensor on the step stream is the right tool (no fused kernel is warranted).
+32 MB per rank per step -- tens of microseconds on NVLink 5, negligible next to the step kernel.
+
+`PeerRecordExchange` is the fused form of the same exchange: the record slabs live in peer-mapped (symmetric) memory and
+np_combat_relgeo_peers pulls the partner records over NVLink with its own loads -- no gathered array, no NCCL call, only
+the 32 B per pair this rank needs cross the link, and the transfer overlaps the geometry arithmetic.
 """
 import torch
 
@@ -54,3 +57,40 @@ def role_sharded_partner_index(n_local_envs, rank, world):
     block = rank % half
     e = torch.arange(n_local_envs, dtype=torch.int64)
     return block * n_local_envs + e, (half + block) * n_local_envs + e
+
+
+class PeerRecordExchange:
+    """Role-sharded exchange over NVLink peer memory.  One symmetric [n_local, 8] record slab per rank:
+
+        ex  = PeerRecordExchange(n_local, device)            # collective: allocates + rendezvous
+        geo = ex.geometry(records_or_env, ego_idx, enm_idx)  # records -> slab, barrier, fused pull + geometry, barrier
+
+    Needs an initialised NCCL process group and P2P access between the ranks' GPUs (one NVSwitch domain)."""
+
+    def __init__(self, n_local, device, group=None):
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm
+        self.group = group if group is not None else dist.group.WORLD
+        self.n_local = int(n_local)
+        self.slab = symm.empty((self.n_local, RECORD_WIDTH), dtype=torch.float32, device=device)
+        self.handle = symm.rendezvous(self.slab, self.group)
+        self.world = self.handle.world_size
+
+    def geometry(self, records, ego_idx, enm_idx):
+        """records: this rank's [n_local, 8] records (copied into the slab), a combat env (its records kernel writes the
+        slab directly) or None (the caller already wrote `self.slab`).  ego_idx / enm_idx index the virtual rank-ordered gathered array.  Returns [m, 8]."""
+        dev = self.slab.device
+        if torch.is_tensor(records):
+            self.slab.copy_(records)
+        elif records is not None:                       # None: the slab already holds this step's records
+            local_records(records, out=self.slab)
+        self.handle.barrier(channel=0)                  # every rank's slab is written and visible to its peers
+        ego_idx = ego_idx.to(device=dev, dtype=torch.int32).contiguous()
+        enm_idx = enm_idx.to(device=dev, dtype=torch.int32).contiguous()
+        m = ego_idx.numel()
+        out = torch.empty((m, 8), dtype=torch.float32, device=dev)
+        st = nv.lib().np_combat_relgeo_peers(self.handle.buffer_ptrs_dev, self.world, self.n_local, ego_idx.data_ptr(),
+                                             enm_idx.data_ptr(), out.data_ptr(), m, torch.cuda.current_stream(dev).cuda_stream)
+        nv.check(st, "np_combat_relgeo_peers")
+        self.handle.barrier(channel=1)                  # peers have read this slab: it may be overwritten by the next step
+        return out

@@ -1181,23 +1181,47 @@ __global__ void __launch_bounds__(256) combat_records_kernel(const float* __rest
   }
 }
 
+// pairwise terms of one (ego, enemy) record pair -> out[i]
+__device__ __forceinline__ void relgeo_pair(const float4 a0, const float4 a1, const float4 b0, const float4 b1, float* __restrict__ out, int i) {
+  const float dp[3] = {b0.x - a0.x, b0.y - a0.y, b0.z - a0.z};
+  const float ve[3] = {a0.w, a1.x, a1.y}, vm[3] = {b0.w, b1.x, b1.y};
+  float AO, TA, R, AO2, TA2, R2;
+  ao_ta_r<3>(dp, ve, vm, AO, TA, R);
+  ao_ta_r<2>(dp, ve, vm, AO2, TA2, R2);
+  const float cz = ve[0] * dp[1] - ve[1] * dp[0];
+  float4 o0, o1;
+  o0.x = AO; o0.y = TA; o0.z = R; o0.w = AO2;
+  o1.x = TA2; o1.y = R2; o1.z = (cz > 0.0f ? 1.0f : 0.0f) - (cz < 0.0f ? 1.0f : 0.0f);
+  o1.w = b1.z - a1.z;   // enemy body-vx minus ego body-vx
+  reinterpret_cast<float4*>(out)[2 * (size_t)i] = o0;
+  reinterpret_cast<float4*>(out)[2 * (size_t)i + 1] = o1;
+}
+
 __global__ void __launch_bounds__(256) combat_relgeo_kernel(const float* __restrict__ rec, const int32_t* __restrict__ ego_idx,
                                                             const int32_t* __restrict__ enm_idx, float* __restrict__ out, int m) {
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < m; i += gridDim.x * blockDim.x) {
     const float4 a0 = reinterpret_cast<const float4*>(rec)[2 * (size_t)ego_idx[i]], a1 = reinterpret_cast<const float4*>(rec)[2 * (size_t)ego_idx[i] + 1];
     const float4 b0 = reinterpret_cast<const float4*>(rec)[2 * (size_t)enm_idx[i]], b1 = reinterpret_cast<const float4*>(rec)[2 * (size_t)enm_idx[i] + 1];
-    const float dp[3] = {b0.x - a0.x, b0.y - a0.y, b0.z - a0.z};
-    const float ve[3] = {a0.w, a1.x, a1.y}, vm[3] = {b0.w, b1.x, b1.y};
-    float AO, TA, R, AO2, TA2, R2;
-    ao_ta_r<3>(dp, ve, vm, AO, TA, R);
-    ao_ta_r<2>(dp, ve, vm, AO2, TA2, R2);
-    const float cz = ve[0] * dp[1] - ve[1] * dp[0];
-    float4 o0, o1;
-    o0.x = AO; o0.y = TA; o0.z = R; o0.w = AO2;
-    o1.x = TA2; o1.y = R2; o1.z = (cz > 0.0f ? 1.0f : 0.0f) - (cz < 0.0f ? 1.0f : 0.0f);
-    o1.w = b1.z - a1.z;   // enemy body-vx minus ego body-vx
-    reinterpret_cast<float4*>(out)[2 * (size_t)i] = o0;
-    reinterpret_cast<float4*>(out)[2 * (size_t)i + 1] = o1;
+    relgeo_pair(a0, a1, b0, b1, out, i);
+  }
+}
+
+// The same terms with the exchange FUSED into the kernel: no gathered array, no NCCL call.  slabs[r] is rank r's record slab
+// ([n_local][8]) in peer-mapped memory (NVLink P2P: torch symmetric memory); global record g lives at slabs[g / n_local] +
+// 8 (g % n_local).  The partner's records are pulled by the kernel's own loads, so the NVLink transfer of one pair
+// overlaps the arithmetic of the others, and only the 32 B per pair this rank needs cross the link (an all-gather moves
+// world x n_local x 32 B to every rank).
+__global__ void __launch_bounds__(256) combat_relgeo_peers_kernel(const float* const* __restrict__ slabs, int n_local,
+                                                                  const int32_t* __restrict__ ego_idx, const int32_t* __restrict__ enm_idx,
+                                                                  float* __restrict__ out, int m) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < m; i += gridDim.x * blockDim.x) {
+    const int ge = ego_idx[i], gm = enm_idx[i];
+    const float4* pe = reinterpret_cast<const float4*>(slabs[ge / n_local]) + 2 * (size_t)(ge % n_local);
+    const float4* pm = reinterpret_cast<const float4*>(slabs[gm / n_local]) + 2 * (size_t)(gm % n_local);
+    // peer memory is written by another GPU between launches: volatile-free plain loads are fine (a new launch after the
+    // cross-device barrier), but they must not come through the non-coherent read-only path
+    const float4 a0 = __ldcg(pe), a1 = __ldcg(pe + 1), b0 = __ldcg(pm), b1 = __ldcg(pm + 1);
+    relgeo_pair(a0, a1, b0, b1, out, i);
   }
 }
 
@@ -1832,6 +1856,17 @@ int np_combat_relgeo(const float* records_dev, const int32_t* ego_idx_dev, const
     return fail(NP_EINVAL, "np_combat_relgeo: bad argument");
   const int want = (m + 255) / 256;
   combat_relgeo_kernel<<<want < 1184 ? want : 1184, 256, 0, (cudaStream_t)stream>>>(records_dev, ego_idx_dev, enm_idx_dev, out_dev, m);
+  NP_CUDA(cudaGetLastError());
+  return NP_OK;
+}
+
+int np_combat_relgeo_peers(const float* const* slabs_dev, int world, int n_local, const int32_t* ego_idx_dev, const int32_t* enm_idx_dev,
+                           float* out_dev, int m, void* stream) {
+  if (!slabs_dev || world < 1 || n_local < 1 || !ego_idx_dev || !enm_idx_dev || !out_dev || m <= 0 || ((uintptr_t)out_dev & 15))
+    return fail(NP_EINVAL, "np_combat_relgeo_peers: bad argument");
+  const int want = (m + 255) / 256;
+  combat_relgeo_peers_kernel<<<want < 1184 ? want : 1184, 256, 0, (cudaStream_t)stream>>>(slabs_dev, n_local, ego_idx_dev, enm_idx_dev,
+                                                                                         out_dev, m);
   NP_CUDA(cudaGetLastError());
   return NP_OK;
 }

@@ -158,3 +158,32 @@ def test_records_and_relgeo_match_the_fused_obs():
     assert torch.allclose(3.141592653589793 - geo[:, 4], o_enm[:, 11], atol=1e-6)
     geo_r = relative_geometry(rec, ego + 1, ego)              # swapped roles: same range, mirrored side
     assert torch.equal(geo_r[:, 2], geo[:, 2]) and torch.equal(geo_r[:, 5], geo[:, 5])
+
+
+def test_relgeo_peers_kernel_equals_relgeo_on_the_gathered_array():
+    """np_combat_relgeo_peers addresses record g at slabs[g / n_local] + 8 (g % n_local): with the slabs of three virtual
+    ranks as ordinary tensors of this GPU (the pointer array a symmetric-memory rendezvous would supply), it must return the
+    bits of np_combat_relgeo on the concatenated array.  The real 2-GPU NVLink run is tools/combat_exchange_check.py
+    (profiles/r01e_combat_exchange_2gpu_p2p.json)."""
+    from neuralplane_b200 import _native as nv
+    from neuralplane_b200.combat_exchange import local_records, relative_geometry
+    num_envs = 3 * 1000
+    env = _env(num_envs)
+    env.reset()
+    g = torch.Generator(device="cuda").manual_seed(5)
+    for k in range(2):
+        env.step(torch.rand((env.n, 4), device="cuda", generator=g) * 2 - 1)
+    rec = local_records(env)                                   # [6000, 8]
+    world, n_local = 3, env.n // 3
+    slabs = [rec[r * n_local:(r + 1) * n_local].clone() for r in range(world)]     # three separate allocations
+    ptrs = torch.tensor([t.data_ptr() for t in slabs], dtype=torch.int64, device="cuda")
+    ego = torch.randint(0, env.n, (5000,), generator=torch.Generator().manual_seed(1))
+    enm = torch.randint(0, env.n, (5000,), generator=torch.Generator().manual_seed(2))
+    want = relative_geometry(rec, ego, enm)
+    got = torch.empty_like(want)
+    e32, m32 = ego.to("cuda", torch.int32), enm.to("cuda", torch.int32)
+    st = nv.lib().np_combat_relgeo_peers(ptrs.data_ptr(), world, n_local, e32.data_ptr(), m32.data_ptr(), got.data_ptr(), ego.numel(),
+                                         torch.cuda.current_stream().cuda_stream)
+    nv.check(st, "np_combat_relgeo_peers")
+    torch.cuda.synchronize()
+    assert torch.equal(got, want)

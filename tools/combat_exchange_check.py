@@ -48,6 +48,31 @@ def main():
     o_ego = obs[0::2]
     ok = bool(torch.equal(geo[:, 3], o_ego[:, 11]) and torch.equal(geo[:, 4], o_ego[:, 12]) and torch.equal(geo[:, 6], o_ego[:, 14])
               and torch.allclose(geo[:, 5] * 0.3048 / 10000, o_ego[:, 13], rtol=1e-6, atol=0))
+    # the NCCL path end to end (gather + geometry kernel), then the fused peer-memory path: same bits, no NCCL call
+    ego_idx, enm_idx = ego_idx.to(device=dev, dtype=torch.int32), enm_idx.to(device=dev, dtype=torch.int32)
+    geo = relative_geometry(allrec, ego_idx, enm_idx)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(10):
+        geo = relative_geometry(allrec, ego_idx, enm_idx)
+    e1.record(); torch.cuda.synchronize()
+    ms_relgeo = e0.elapsed_time(e1) / 10          # the geometry kernel on the gathered array; NCCL path = all-gather + this
+    p2p = {"p2p_ok": None}
+    try:
+        from neuralplane_b200.combat_exchange import PeerRecordExchange
+        ex = PeerRecordExchange(num_envs, dev)
+        geo_p = ex.geometry(mine, ego_idx, enm_idx)
+        torch.cuda.synchronize(); dist.barrier()
+        e0.record()
+        for _ in range(10):
+            geo_p = ex.geometry(None, ego_idx, enm_idx)     # the records are in the slab, as `mine` is for the NCCL path
+        e1.record(); torch.cuda.synchronize()
+        p2p = {"p2p_ok": bool(torch.equal(geo_p, geo)), "p2p_ms": e0.elapsed_time(e1) / 10, "relgeo_on_gathered_ms": ms_relgeo,
+               "p2p_bytes_over_nvlink_per_rank": int(num_envs * 32)}
+    except Exception as e:  # symmetric memory unavailable on this box: report, the NCCL path above stands
+        p2p = {"p2p_ok": None, "p2p_error": repr(e)[:300], "relgeo_on_gathered_ms": ms_relgeo}
+    if p2p["p2p_ok"] is False:
+        ok = False
     t = torch.tensor([1.0 if ok else 0.0, ms], device=dev, dtype=torch.float64)
     dist.all_reduce(t[:1], op=dist.ReduceOp.MIN)
     dist.all_reduce(t[1:], op=dist.ReduceOp.MAX)
@@ -56,7 +81,7 @@ def main():
         print(json.dumps({"check": "role-sharded relgeo from all-gathered records == fused pair-sharded obs columns",
                           "ok": bool(t[0].item() == 1.0), "world": world, "envs_per_block": num_envs,
                           "record_bytes_per_aircraft": 32, "gathered_GB_per_rank": gb, "all_gather_ms": float(t[1].item()),
-                          "gather_GBps_per_rank": gb / (float(t[1].item()) * 1e-3)}), flush=True)
+                          "gather_GBps_per_rank": gb / (float(t[1].item()) * 1e-3), **p2p}), flush=True)
     dist.destroy_process_group()
     sys.exit(0 if t[0].item() == 1.0 else 1)
 
