@@ -972,15 +972,9 @@ constexpr int IN_STEP = IN_T + 3 * kSlab * 4;      // [256] i32
 constexpr int IN_ACT = IN_STEP + kSlab * 4;        // [256][4] f32
 constexpr int IN_FLG = IN_ACT + kSlab * 16;        // [3][256] u8
 constexpr int IN_BYTES = IN_FLG + 3 * kSlab;       // 24 320
-constexpr int OUT_S = IN_BYTES;
-constexpr int OUT_U = OUT_S + 12 * kSlab * 4;
-constexpr int OUT_T = OUT_U + 3 * kSlab * 4;
-constexpr int OUT_STEP = OUT_T + 3 * kSlab * 4;
-constexpr int OUT_REW = OUT_STEP + kSlab * 4;
-constexpr int OUT_FLG = OUT_REW + kSlab * 4;
-constexpr int OUT_OBS = OUT_FLG + 3 * kSlab;       // [256][22] f32
+constexpr int OUT_OBS = IN_BYTES;                  // [256][22] f32: the only output staged in shared memory
 constexpr int BAR = OUT_OBS + kSlab * NP_NUM_OBS * 4;
-constexpr int SMEM_BYTES = BAR + 32;               // 68 128 (four mbarriers)
+constexpr int SMEM_BYTES = BAR + 32;               // 46 880 (four mbarriers) -> 4 CTAs = 32 warps per SM
 static_assert(OUT_OBS % 16 == 0 && BAR % 8 == 0, "bulk copies need 16-byte aligned shared addresses");
 }  // namespace uavslab
 
@@ -1007,21 +1001,16 @@ __device__ __forceinline__ void uav_slab_request(const StepParams& p, unsigned c
   else if (lane < 23) bulk_g2s(sm + IN_FLG + (lane - 20) * kSlab, p.flags + (lane - 20) * ld + i0, kSlab, bar);
 }
 
-// warp 0 sends the results of the full slab starting at aircraft i0: lane r stores row r
+// one lane of warp 0 sends the slab's 256 x 22 observation block (contiguous in the row-major obs array) as one bulk store
 __device__ __forceinline__ void uav_slab_send(const StepParams& p, unsigned char* sm, int i0, int lane) {
   using namespace uavslab;
-  const size_t ld = (size_t)p.cfg.ld;
-  if (lane < 12) bulk_s2g(p.s + lane * ld + i0, sm + OUT_S + lane * kSlab * 4, kSlab * 4);
-  else if (lane < 15) bulk_s2g(p.u + (lane - 12) * ld + i0, sm + OUT_U + (lane - 12) * kSlab * 4, kSlab * 4);
-  else if (lane < 18) bulk_s2g(p.tgt + (lane - 15) * ld + i0, sm + OUT_T + (lane - 15) * kSlab * 4, kSlab * 4);
-  else if (lane == 18) bulk_s2g(p.step_count + i0, sm + OUT_STEP, kSlab * 4);
-  else if (lane == 19) bulk_s2g(p.reward + i0, sm + OUT_REW, kSlab * 4);
-  else if (lane < 23) bulk_s2g(p.flags + (lane - 20) * ld + i0, sm + OUT_FLG + (lane - 20) * kSlab, kSlab);
-  else if (lane == 23) bulk_s2g(p.obs + (size_t)i0 * NP_NUM_OBS, sm + OUT_OBS, kSlab * NP_NUM_OBS * 4);
-  bulk_commit();
+  if (lane == 0) {
+    bulk_s2g(p.obs + (size_t)i0 * NP_NUM_OBS, sm + OUT_OBS, kSlab * NP_NUM_OBS * 4);
+    bulk_commit();
+  }
 }
 
-__global__ void __launch_bounds__(uavslab::kSlab, 3) uav_step_slab_kernel(const __grid_constant__ StepParams p) {
+__global__ void __launch_bounds__(uavslab::kSlab, 4) uav_step_slab_kernel(const __grid_constant__ StepParams p) {
   using namespace uavslab;
   extern __shared__ __align__(128) unsigned char sm[];
   const int ld = p.cfg.ld, t = threadIdx.x, lane = t & 31;
@@ -1094,18 +1083,20 @@ __global__ void __launch_bounds__(uavslab::kSlab, 3) uav_step_slab_kernel(const 
     if (live) uav_aircraft<true>(p, i, rst, av, s, F, tgt, steps, o, rew, done, bad);
 
     if (full) {
+      // SoA rows, reward and flags: fully coalesced 4-byte stores straight from registers (128 B per warp and row)
+#pragma unroll
+      for (int j = 0; j < 12; ++j) p.s[(size_t)j * ld + i] = s[j];
+#pragma unroll
+      for (int j = 0; j < 3; ++j) p.u[(size_t)j * ld + i] = F[j];
+#pragma unroll
+      for (int j = 0; j < 3; ++j) p.tgt[(size_t)j * ld + i] = tgt[j];
+      p.step_count[i] = steps;
+      p.reward[i] = rew;
+      p.flags[i] = done ? 1 : 0;
+      p.flags[ld + i] = bad ? 1 : 0;
+      p.flags[2 * (size_t)ld + i] = 0;
+      // the 88-byte observation rows are the strided part: staged, then one 22.5 KB bulk store per slab
       if (it > 0) mbar_wait(out_free, ph ^ 1);
-#pragma unroll
-      for (int j = 0; j < 12; ++j) reinterpret_cast<float*>(sm + OUT_S)[j * kSlab + t] = s[j];
-#pragma unroll
-      for (int j = 0; j < 3; ++j) reinterpret_cast<float*>(sm + OUT_U)[j * kSlab + t] = F[j];
-#pragma unroll
-      for (int j = 0; j < 3; ++j) reinterpret_cast<float*>(sm + OUT_T)[j * kSlab + t] = tgt[j];
-      reinterpret_cast<int*>(sm + OUT_STEP)[t] = steps;
-      reinterpret_cast<float*>(sm + OUT_REW)[t] = rew;
-      sm[OUT_FLG + t] = done ? 1 : 0;
-      sm[OUT_FLG + kSlab + t] = bad ? 1 : 0;
-      sm[OUT_FLG + 2 * kSlab + t] = 0;
       float2* orow = reinterpret_cast<float2*>(sm + OUT_OBS) + t * (NP_NUM_OBS / 2);  // 8-byte stride 11: conflict-free
 #pragma unroll
       for (int j = 0; j < NP_NUM_OBS / 2; ++j) orow[j] = make_float2(o[2 * j], o[2 * j + 1]);
@@ -1727,7 +1718,7 @@ static int step_range_impl(np_env* env, const float* action_dev, const float* dr
         NP_CUDA(cudaFuncSetAttribute(uav_step_slab_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, uavslab::SMEM_BYTES));
         attr_set = true;
       }
-      env->grid = want < env->num_sms * 3 ? want : env->num_sms * 3;
+      env->grid = want < env->num_sms * 4 ? want : env->num_sms * 4;
       env->smem = uavslab::SMEM_BYTES;
       uav_step_slab_kernel<<<env->grid, uavslab::kSlab, uavslab::SMEM_BYTES, st>>>(p);
     } else {

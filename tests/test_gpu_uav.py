@@ -135,7 +135,7 @@ def test_uav_slab_kernel_is_bit_identical_to_per_thread_kernel(task, monkeypatch
     in-kernel Philox resets and observation noise on, 40 steps of a ragged population (full slabs + a 99-aircraft tail)
     must agree bit for bit in every buffer, as must a step issued as aligned and unaligned ranges."""
     from neuralplane_b200 import ControlEnv
-    n = 148 * 3 * 256 * 2 + 99     # more slabs than resident CTAs: every CTA pipelines >= 2 slabs
+    n = 148 * 4 * 256 * 2 + 99     # more slabs than resident CTAs: every CTA pipelines >= 2 slabs
     envs = []
     for scalar in (False, True):
         e = ControlEnv(num_envs=n, config=task, model="UAV", random_seed=5, device="cuda:0")
@@ -146,7 +146,7 @@ def test_uav_slab_kernel_is_bit_identical_to_per_thread_kernel(task, monkeypatch
         a = torch.rand((n, 4), device="cuda", generator=g) * 2 - 1
         monkeypatch.delenv("NPLANE_UAV_SCALAR", raising=False)
         out_a = envs[0].step(a)
-        assert envs[0].launch_info()["smem_bytes"] > 60000, "slab kernel did not run"
+        assert envs[0].launch_info()["smem_bytes"] > 40000, "slab kernel did not run"
         monkeypatch.setenv("NPLANE_UAV_SCALAR", "1")
         out_b = envs[1].step(a)
         assert envs[1].launch_info()["smem_bytes"] == 0

@@ -10,7 +10,7 @@ for n in (256, 1000, 5000 + 37):
     for task in ("control", "heading", "tracking"):
         e = ControlEnv(num_envs=n, config=task, model="UAV", random_seed=1, device="cuda:0"); e.reset()
         for k in range(4): e.step(torch.rand((n, 4), device="cuda") * 2 - 1)
-        assert e.launch_info()["smem_bytes"] > 60000
+        assert e.launch_info()["smem_bytes"] > 40000
         torch.cuda.synchronize()
 for model, task in (("F16", "heading"), ("UAV", "control"), ("F16_tables", "heading")):
     n = 3000 + 11
