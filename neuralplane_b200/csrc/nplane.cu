@@ -111,16 +111,24 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
-      "WAIT_%=:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"   // %2: suspend-time hint -- the warp sleeps in
-      "@p bra DONE_%=;\n\t"                                              // hardware instead of spinning through issue slots
-      "bra WAIT_%=;\n\t"
-      "DONE_%=:\n\t}" ::"r"(smem_u32(bar)),
-      "r"(parity), "r"(0x989680u)
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"   // %3: suspend-time hint
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(0x989680u)
       : "memory");
+  return ok != 0;
+}
+// A waiting warp backs off with nanosleep between polls: a tight try_wait loop was 21 % of the UAV slab kernel's executed
+// instructions -- issue slots taken from the warps that had work.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  do {
+    __nanosleep(100);
+  } while (!mbar_try_wait(bar, parity));
 }
 __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
@@ -954,13 +962,15 @@ __global__ void __launch_bounds__(256, 4) uav_env_kernel(const __grid_constant__
 }
 
 // ------------------------------------------------------------------------------------------------
-// K2 (TMA-staged): the HBM-bound UAV step as a persistent slab pipeline.  A CTA owns 256-aircraft slabs; every SoA row
-// segment (1 KB), the action rows (4 KB) and the flag rows arrive in shared memory through TMA bulk copies completing
-// on an mbarrier (23 copies, one per lane of warp 0), and every output -- 19 row segments, flags, reward and the whole
-// 256 x 22 observation block (22.5 KB, contiguous in the row-major obs array) -- leaves through bulk stores, so the
-// LSU sees no global traffic at all (the per-thread variant is LSU-queue / latency limited: 23 scalar loads + 34 stores
-// of 32 separate sectors each per aircraft).  The inputs of slab k+1 are requested as soon as slab k's are in registers and
-// land during slab k's arithmetic; slab k's bulk stores drain during slab k+1's.  68 KB per CTA -> 3 CTAs (24 warps) per SM.
+// K2 (TMA-staged): the HBM-bound UAV step as a persistent slab pipeline.  A CTA owns 256-aircraft slabs.
+//   in : every SoA row segment (1 KB), the action block (4 KB) and the flag rows arrive in shared memory through TMA bulk
+//        copies completing on an mbarrier (23 copies, one per lane of warp 0); slab k+1's inputs are requested as soon as
+//        slab k's are in registers and land during slab k's arithmetic;
+//   out: the strided part -- the 256 x 22 observation block (22.5 KB, contiguous in the row-major obs array) -- is staged
+//        and leaves as ONE bulk store that drains during slab k+1's arithmetic; SoA rows, reward and flags are already
+//        coalesced (128 B per warp and row) and go straight from registers.
+// The per-thread variant is LSU-queue / latency limited (23 scalar loads + 34 stores per aircraft, the 11 observation
+// stores touching 32 separate sectors each).  46.9 KB and 64 registers per thread -> 4 CTAs (32 warps) per SM.
 // The ragged tail slab (< 256 aircraft) goes through guarded per-thread accesses in the same kernel.
 // ------------------------------------------------------------------------------------------------
 namespace uavslab {
@@ -1021,8 +1031,8 @@ __global__ void __launch_bounds__(uavslab::kSlab, 4) uav_step_slab_kernel(const 
   // ahead keeps issuing (a __syncthreads version measured 3.2 barrier-stall cycles per issued instruction).
   uint64_t* in_full = reinterpret_cast<uint64_t*>(sm + BAR);  // TMA: the slab's inputs have landed            (tx bytes)
   uint64_t* in_read = in_full + 1;                            // every warp holds its inputs in registers        (8 warps)
-  uint64_t* written = in_full + 2;                            // every warp has written its results to OUT       (8 warps)
-  uint64_t* out_free = in_full + 3;                           // the previous bulk stores have finished reading OUT  (1)
+  uint64_t* written = in_full + 2;                            // every warp has staged its observation rows      (8 warps)
+  uint64_t* out_free = in_full + 3;                           // the previous bulk store has read the obs block      (1)
   if (t == 0) {
     mbar_init(in_full, 1);
     mbar_init(in_read, kSlab / 32);
