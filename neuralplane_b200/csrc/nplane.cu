@@ -1723,10 +1723,12 @@ static int step_range_impl(np_env* env, const float* action_dev, const float* dr
                             (uintptr_t)p.obs | (uintptr_t)p.reward | (uintptr_t)p.action;
     const bool slab_ok = !(bases & 15) && !(first & 15) && !(env->cfg.ld & 15) && count >= uavslab::kSlab && !getenv("NPLANE_UAV_SCALAR");
     if (slab_ok) {
-      static bool attr_set = false;
-      if (!attr_set) {
+      static bool attr_set[64] = {};  // per device: the attribute lives in the device's context
+      int dev = 0;
+      NP_CUDA(cudaGetDevice(&dev));
+      if (!attr_set[dev & 63]) {
         NP_CUDA(cudaFuncSetAttribute(uav_step_slab_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, uavslab::SMEM_BYTES));
-        attr_set = true;
+        attr_set[dev & 63] = true;
       }
       env->grid = want < env->num_sms * 4 ? want : env->num_sms * 4;
       env->smem = uavslab::SMEM_BYTES;
