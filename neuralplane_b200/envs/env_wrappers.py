@@ -59,7 +59,7 @@ class GPUVecEnv:
         self._chunks = None
         if self.device_tensors:
             return
-        # pipelined boundary for large single-step envs (ControlEnv): chunks of whole pairs on side streams
+        # pipelined boundary for large single-step envs (ControlEnv): aircraft chunks through np_env_step_host
         # pipeline_chunks: a chunk count (equal chunks) or a sequence of relative chunk sizes, e.g. (1, 2, 3, 5, 5): a small
         # first chunk starts the observation download -- the resource this boundary is bound by -- sooner
         if pipeline_chunks is None:
