@@ -166,3 +166,36 @@ def test_uav_slab_kernel_is_bit_identical_to_per_thread_kernel(task, monkeypatch
     torch.cuda.synchronize()
     for x, y in zip(_snapshot(envs[0]), _snapshot(envs[1])):
         assert torch.equal(x, y)
+
+
+def test_uav_full_size_sampled_parity_and_invariants():
+    """BASELINE config 3 and beyond (n = 10^6 through the slab kernel): aircraft are independent, so a random sample of
+    the population is replayed through the oracle from the same pre-step state; plus population-wide invariants."""
+    from oracle.uav_oracle import UAVEnvOracle
+    n, m = 1_000_000, 4096
+    env = _env(n, "control")
+    env.reset()
+    g = torch.Generator(device="cuda").manual_seed(1)
+    for _ in range(30):
+        env.step(torch.rand((n, 4), device="cuda", generator=g) * 2 - 1)
+    assert env.launch_info()["smem_bytes"] > 40000                # the TMA-staged slab kernel ran
+    idx = torch.from_numpy(np.sort(np.random.default_rng(0).choice(n, m, replace=False))).cuda()
+    orc = UAVEnvOracle(m, "control")
+    orc.s = env.model.s[idx].cpu(); orc.u = env.model.u[idx].cpu()
+    orc.tgt = env._tgt[:, idx].t().contiguous().cpu()
+    orc.step_count = env.step_count[idx].cpu().long()
+    orc.is_done = env.is_done[idx].cpu().clone(); orc.bad_done = env.bad_done[idx].cpu().clone()
+    orc.exceed_time_limit = env.exceed_time_limit[idx].cpu().clone()
+    a = torch.rand((n, 4), device="cuda", generator=g) * 2 - 1
+    d = torch.rand((n, 5), device="cuda", generator=g)
+    obs, rew, done, bad, exc, _ = env.step(a, reset_draws=d)
+    o_obs, o_rew, o_done, o_bad, o_exc = orc.step(a[idx].cpu(), d[idx].cpu())
+    err = _rel(env.model.s[idx].cpu().numpy(), orc.s.numpy())
+    assert np.percentile(err, 99) <= 2e-6 and err.max() <= 1e-4, (np.percentile(err, 99), err.max())
+    assert np.allclose(obs[idx].cpu().numpy(), o_obs.numpy(), rtol=1e-5, atol=2e-6)
+    near = np.abs(orc.last_accel.numpy() - 300.0) / 300.0 < 1e-5
+    assert ((bad[idx].cpu().numpy() != o_bad.numpy()) & ~near).sum() <= 1
+    assert np.array_equal(env.step_count[idx].cpu().numpy(), orc.step_count.numpy().astype(np.int32))
+    assert torch.isfinite(env.model.s).all() and torch.isfinite(obs).all() and torch.isfinite(rew).all()
+    assert int(env._flags.max()) <= 1 and not bool(exc.any())
+    assert env.termination_counters()["resets"] >= n
