@@ -14,6 +14,9 @@
  *     ld % 4 == 0.  obs is row-major [n][22] (what GPUVecEnv hands to the runners, env_wrappers.py:97).
  *   - `stream` is a cudaStream_t passed as void*; step/reset only ENQUEUE work on it, never synchronise,
  *     and are CUDA-graph capturable.  Handles are not thread-safe; distinct handles are independent.
+ *   - every entry point runs on the device its handle was created on (or that owns its output pointer), whatever the
+ *     caller's current device is, and restores the current device before returning (the reference takes device=
+ *     per env: env_base.py:21).  `stream` must belong to that device.
  */
 #ifndef NPLANE_H_
 #define NPLANE_H_
@@ -25,7 +28,7 @@
 extern "C" {
 #endif
 
-#define NP_ABI_VERSION 6
+#define NP_ABI_VERSION 7
 
 enum { NP_OK = 0, NP_EINVAL = 1, NP_ECUDA = 2, NP_ESTATE = 3 };
 
@@ -111,7 +114,9 @@ int np_aero_pack_host(const float* blob, size_t n_floats, const np_net_desc* des
 
 size_t np_env_workspace_bytes(const np_env_cfg* cfg);
 int np_env_create(const np_env_cfg* cfg, const np_aero* aero, np_env** out);
-int np_env_bind(np_env* env, const np_buffers* bufs);
+/* Binds the device buffers; invalidates the coefficient-cache keys with a memset ENQUEUED ON `stream` (the stream the
+ * caller will step on), never on the legacy default stream. */
+int np_env_bind(np_env* env, const np_buffers* bufs, void* stream);
 /* Replace the task parameters (e.g. task.noise_scale = 0 for parity runs); n, ld and task must not change. */
 int np_env_set_cfg(np_env* env, const np_env_cfg* cfg);
 int np_env_destroy(np_env* env);
@@ -147,6 +152,18 @@ int np_env_step_range(np_env* env, const float* action_dev, const float* draws_d
  * Bit-identical to np_env_step (all chunks share one RNG counter).  ControlEnv steps only (F16, F16 tables, UAV). */
 int np_env_step_host(np_env* env, const float* action_host, float* action_pinned, float* action_dev, float* obs_pinned,
                      float* reward_pinned, uint8_t* flags_pinned, const int* edges, int n_chunks, void* stream);
+
+/* The same boundary with NO copy engine in the path: the step kernel reads the actions from, and writes observation rows,
+ * rewards and flags straight into, MAPPED page-locked host memory (cudaHostAlloc / cudaHostRegister; torch pin_memory()).
+ * The step is compute-bound (~0.46 ms per 10^6 aircraft) while the 95 B/aircraft that cross PCIe need ~1.7 ms, so the
+ * posted writes drain under the arithmetic: one launch, no chunk pipeline.  action_host: [n][4] anywhere in host memory
+ * (may equal action_mapped); action_mapped [n][4], obs_mapped [n][22], reward_mapped [n], flags_mapped [3][flags_ld]
+ * (is_done, bad_done, exceed_time_limit rows; flags_ld even, >= n): page-locked, device-mapped host buffers;
+ * action_dev: NULL (zero-copy action reads) or [n][4] device scratch (explicit H2D copy before the launch).  The env's own
+ * obs / reward device buffers are NOT written by this call.  Ordered after everything queued on `stream`; RETURNS WHEN THE
+ * HOST BUFFERS ARE READY.  Bit-identical to np_env_step.  F16 plug-in (MLP or table back-end) only. */
+int np_env_step_mapped(np_env* env, const float* action_host, float* action_mapped, float* action_dev, float* obs_mapped,
+                       float* reward_mapped, uint8_t* flags_mapped, int flags_ld, void* stream);
 
 /* PlanningEnv.step(action) (envs/planning_env.py:144-177) as ONE kernel launch: reset -> clamp -> pitch / heading /
  * speed targets from the 3-D high-level action (:146-152) -> n_sub (reference: 50) x { low-level controller ->
@@ -217,6 +234,16 @@ int np_env_counters(np_env* env, uint64_t* out, void* stream);
 int np_f16_nlplant(const np_aero* aero, const float* s_dev, const float* u_dev, float* xdot_dev, int n, int ld,
                    void* stream);
 
+/* The aircraft plug-in's stand-alone update(action) (envs/models/F16_model.py:51-67, UAV_model.py:51-62; callers:
+ * planning_env.py:161, example/quick_start.ipynb): clamp -> control low-pass -> ONE explicit Euler step of nlplant
+ * (torchdiffeq fixed-grid euler on t = [0, dt]) on the SoA rows, in place.  recent_s_dev [12][ld] / recent_u_dev [5][ld]
+ * (may be NULL) receive the state / controls the update started from (the reference rebinds recent_s = s first).
+ * action_dev [n][4] row-major (the UAV plug-in reads columns 0..2).  Same arithmetic as the fused env step: bit-identical.
+ * np_f16_table_update is the same for a table-backed F16 plug-in. */
+int np_f16_update(const np_aero* aero, float* s_dev, float* u_dev, float* recent_s_dev, float* recent_u_dev, const float* action_dev,
+                  int n, int ld, double dt, void* stream);
+int np_uav_update(float* s_dev, float* u_dev, float* recent_s_dev, const float* action_dev, int n, int ld, double dt, void* stream);
+
 /* Table aero back-end (SURVEY f-3): the NASA tables the MLP surrogates were fitted to, evaluated by multilinear
  * interpolation as example/train_model/mexndinterp.py:84-110 and combined as example/train_model/hifi_F16_AeroData.py:
  * 406-483.  breakpoints = ALPHA1(20) ALPHA2(14) BETA1(19) DH1(5) DH2(3) concatenated; values / offsets = the 43
@@ -235,6 +262,8 @@ int np_f16_table_coeffs(const np_tables* tables, const float* alpha_deg_dev, con
 int np_env_create_tables(const np_env_cfg* cfg, const np_tables* tables, np_env** out);
 int np_f16_table_nlplant(const np_tables* tables, const float* s_dev, const float* u_dev, float* xdot_dev, int n, int ld,
                          void* stream);
+int np_f16_table_update(const np_tables* tables, float* s_dev, float* u_dev, float* recent_s_dev, float* recent_u_dev,
+                        const float* action_dev, int n, int ld, double dt, void* stream);
 
 /* UAVDynamics.nlplant (envs/models/UAV/UAV_dynamics.py:15-84) on SoA rows: xdot_dev [12][ld] from s_dev [12][ld] and
  * the three body forces u_dev [3+][ld].  Backs UAVModel.get_extended_state and the getters built on it

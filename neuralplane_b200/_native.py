@@ -65,13 +65,17 @@ SYMBOLS = {
                                     C.POINTER(C.c_size_t)]),
     "np_env_workspace_bytes": (C.c_size_t, [C.POINTER(EnvCfg)]),
     "np_env_create": (C.c_int, [C.POINTER(EnvCfg), _P, C.POINTER(_P)]),
-    "np_env_bind": (C.c_int, [_P, C.POINTER(Buffers)]),
+    "np_env_bind": (C.c_int, [_P, C.POINTER(Buffers), _P]),
     "np_env_set_cfg": (C.c_int, [_P, C.POINTER(EnvCfg)]),
     "np_env_destroy": (C.c_int, [_P]),
     "np_env_reset": (C.c_int, [_P, _P, _P, _P]),
     "np_env_step": (C.c_int, [_P, _P, _P, _P, _P]),
     "np_env_step_range": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, C.c_int, _P]),
     "np_env_step_host": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, C.POINTER(C.c_int), C.c_int, _P]),
+    "np_env_step_mapped": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, C.c_int, _P]),
+    "np_f16_update": (C.c_int, [_P, _P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_double, _P]),
+    "np_f16_table_update": (C.c_int, [_P, _P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_double, _P]),
+    "np_uav_update": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, C.c_double, _P]),
     "np_env_plan_step": (C.c_int, [_P, _P, C.c_int, _P, _P, _P]),
     "np_env_combat_step": (C.c_int, [_P, _P, C.c_int, _P, _P]),
     "np_env_combat_records": (C.c_int, [_P, _P, _P]),

@@ -14,6 +14,7 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <memory>
 #include <string>
 #include <vector>
 
@@ -54,7 +55,32 @@ struct np_aero {
 
 struct np_tables {
   float* image_dev = nullptr;  // kTablesFloats (tables_device.cuh)
+  int device = 0;
 };
+
+// Every entry point works on the device its handle (or its pointers) lives on, whatever the caller's current device is
+// (the reference accepts any device= transparently): switch for the duration of the call, restore on the way out.
+struct DeviceGuard {
+  int prev = -1;
+  bool switched = false;
+  explicit DeviceGuard(int dev) {
+    if (dev >= 0 && cudaGetDevice(&prev) == cudaSuccess && prev != dev) switched = cudaSetDevice(dev) == cudaSuccess;
+  }
+  ~DeviceGuard() {
+    if (switched) cudaSetDevice(prev);
+  }
+  DeviceGuard(const DeviceGuard&) = delete;
+  DeviceGuard& operator=(const DeviceGuard&) = delete;
+};
+// device that owns a device pointer (handle-less entry points); -1 = leave the current device alone
+static int device_of(const void* p) {
+  cudaPointerAttributes a;
+  if (!p || cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+    cudaGetLastError();
+    return -1;
+  }
+  return (a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged) ? a.device : -1;
+}
 
 struct np_env {
   np_env_cfg cfg;
@@ -64,7 +90,9 @@ struct np_env {
   bool bound = false;
   uint32_t step_index = 0;
   bool pid_started = false;  // the fused PID controller has run at least once (PID.reset, pid.py:13)
-  int block = 384, tab_block = 384, grid = 0, smem = 0, num_sms = 0;
+  int device = 0;            // the device the env was created on; every entry point switches to it
+  int block = 0;             // 0: chosen per launch (pick_block); else forced by NPLANE_BLOCK
+  int tab_block = 384, grid = 0, smem = 0, num_sms = 0, last_block = 384;
   // np_env_step_host: one in-order stream per engine (upload, kernels, download) and the events chaining them
   static constexpr int kMaxHostChunks = 16;
   cudaStream_t hs[3] = {nullptr, nullptr, nullptr};
@@ -93,6 +121,8 @@ struct StepParams {
   int pair_begin, pair_end;      // aircraft pairs [pair_begin, pair_end) this launch works on (whole population by default)
   const float* draws;            // [n][5] or null
   const float* noise;            // [n][22] or null
+  uint8_t* flags_mirror;         // null, or a second [3][flags_mirror_ld] copy of the new flags (mapped host memory)
+  int flags_mirror_ld;
   uint32_t step_index;
 };
 
@@ -371,7 +401,16 @@ __device__ __forceinline__ void combat_outputs(const StepParams& p, float (&s)[2
 // ------------------------------------------------------------------------------------------------
 // K1: the fused step kernel
 // ------------------------------------------------------------------------------------------------
-static int step_smem_bytes(int aero_bytes, int bs, bool tab = false) { return aero_bytes + (tab ? 0 : kNumSlots * bs * 8) + 16; }
+// Observation rows are 88 B: a thread's two rows are staged in a per-warp tile (64 rows = 5 632 B, contiguous in the
+// row-major obs array) and leave as eleven fully coalesced 16-byte-per-lane stores (512 B per warp instruction, whole
+// 128-B lines).  For HBM this replaces 22 strided 8-byte stores per thread; for MAPPED HOST memory (np_env_step_mapped)
+// it is what makes the PCIe writes full-line posted writes.  Block sizes above 384 have no room for the tiles next to the
+// aero image and the coefficient slots and store their rows directly.
+constexpr int kObsTileFloats = 64 * NP_NUM_OBS;
+constexpr bool stage_obs(int bs, int mode) { return bs <= 384 && mode != 2 /* MODE_COMBAT: 15-D rows, written by combat_outputs */; }
+static int step_smem_bytes(int aero_bytes, int bs, int mode, bool tab = false) {
+  return aero_bytes + (tab ? 0 : kNumSlots * bs * 8) + (stage_obs(bs, mode) ? (bs / 32) * kObsTileFloats * 4 : 0) + 16;
+}
 
 // MODE_STEP  : BaseEnv.step (one FDM step driven by the caller's 4-D action).
 // MODE_COMBAT: SingleCombatEnv.step (singlecombat_env.py:240-274): the thread's two aircraft ARE the pair (ego = 2e,
@@ -390,7 +429,10 @@ __global__ void __launch_bounds__(BS, MINB) f16_step_kernel(const __grid_constan
   extern __shared__ __align__(128) unsigned char smem_raw[];
   float* blob = reinterpret_cast<float*>(smem_raw);
   float2* coef_all = reinterpret_cast<float2*>(smem_raw + p.aero_bytes);     // [kNumSlots][BS] float2 (MLP back-end)
-  uint64_t* bar = reinterpret_cast<uint64_t*>(coef_all + (TAB ? 0 : kNumSlots * BS));
+  constexpr bool STAGE = stage_obs(BS, MODE);
+  float* otile = reinterpret_cast<float*>(coef_all + (TAB ? 0 : kNumSlots * BS)) + (threadIdx.x >> 5) * kObsTileFloats;  // this warp's tile
+  uint64_t* bar = reinterpret_cast<uint64_t*>(reinterpret_cast<float*>(coef_all + (TAB ? 0 : kNumSlots * BS)) +
+                                              (STAGE ? (BS / 32) * kObsTileFloats : 0));
 
   stage_aero(blob, p.aero, (uint32_t)p.aero_bytes, bar);
   uint32_t wb0 = 0;
@@ -420,6 +462,8 @@ __global__ void __launch_bounds__(BS, MINB) f16_step_kernel(const __grid_constan
     const int prl = pr < pend ? pr : pend - 1;  // inactive lanes shadow the last pair and never store
     const bool act[2] = {pr < pend && 2 * pr < n, pr < pend && 2 * pr + 1 < n};
     const int idx[2] = {min(2 * prl, n - 1), min(2 * prl + 1, n - 1)};  // row index into [n][*] arrays
+    // the warp's 64 observation rows leave through its staging tile when all of them exist and the destination is 16-B aligned
+    const bool staged = STAGE && __all_sync(0xffffffffu, act[1]) && ((reinterpret_cast<uintptr_t>(p.obs) & 15) == 0);
 
     // ---- load ----------------------------------------------------------------------------------
     float s[2][12], u[2][4], tgt[2][3], a[2][4];
@@ -624,7 +668,11 @@ __global__ void __launch_bounds__(BS, MINB) f16_step_kernel(const __grid_constan
             float o[NP_NUM_OBS];
             make_obs(c, sq, uq, tq, g, eas2tas_of(tp), o);
             add_obs_noise(p, idx[q], o);
-            if (act[q]) {
+            if (staged) {
+              float2* orow = reinterpret_cast<float2*>(otile + (2 * (threadIdx.x & 31) + q) * NP_NUM_OBS);
+#pragma unroll
+              for (int j = 0; j < NP_NUM_OBS / 2; ++j) orow[j] = make_float2(o[2 * j], o[2 * j + 1]);
+            } else if (act[q]) {
               float2* orow = reinterpret_cast<float2*>(p.obs + (size_t)(2 * pr + q) * NP_NUM_OBS);  // 88-B rows: 8-B aligned
 #pragma unroll
               for (int j = 0; j < NP_NUM_OBS / 2; ++j) orow[j] = make_float2(o[2 * j], o[2 * j + 1]);
@@ -681,6 +729,15 @@ __global__ void __launch_bounds__(BS, MINB) f16_step_kernel(const __grid_constan
                               : 0;
         }
       }
+      if (STAGE && pass == 1 && staged && (!PLAN || sub == nsub - 1)) {   // tile -> obs[64 rows]: 11 x 512 B per warp
+        __syncwarp();
+        const int lane = threadIdx.x & 31;
+        const float4* src = reinterpret_cast<const float4*>(otile);
+        float4* dst = reinterpret_cast<float4*>(p.obs + (size_t)(2 * (pr - lane)) * NP_NUM_OBS);
+#pragma unroll
+        for (int k = 0; k < kObsTileFloats / 128; ++k) dst[lane + 32 * k] = src[lane + 32 * k];
+        __syncwarp();
+      }
       if (COMBAT && pass == 1) {   // pair conditions: Crash (crash.py:29-42) and Shutdown (shutdown.py:30-40)
         const float dn0 = s[0][0] - s[1][0], de0 = s[0][1] - s[1][1], da0 = s[0][2] - s[1][2];
         const bool crash = (dn0 * dn0 + de0 * de0 + da0 * da0) <= c.distance_limit * c.distance_limit;
@@ -725,11 +782,23 @@ __global__ void __launch_bounds__(BS, MINB) f16_step_kernel(const __grid_constan
         reinterpret_cast<uchar2*>(p.flags)[pr] = make_uchar2(done[0] ? 1 : 0, done[1] ? 1 : 0);
         reinterpret_cast<uchar2*>(p.flags + ld)[pr] = make_uchar2(bad[0] ? 1 : 0, bad[1] ? 1 : 0);
         reinterpret_cast<uchar2*>(p.flags + 2 * (size_t)ld)[pr] = make_uchar2(exc[0] ? 1 : 0, exc[1] ? 1 : 0);  // control tasks: Timeout is commented out (heading_task.py:45)
+        if (p.flags_mirror) {   // the numpy boundary's copy, written straight into mapped host memory
+          const size_t ml = (size_t)p.flags_mirror_ld;
+          reinterpret_cast<uchar2*>(p.flags_mirror)[pr] = make_uchar2(done[0] ? 1 : 0, done[1] ? 1 : 0);
+          reinterpret_cast<uchar2*>(p.flags_mirror + ml)[pr] = make_uchar2(bad[0] ? 1 : 0, bad[1] ? 1 : 0);
+          reinterpret_cast<uchar2*>(p.flags_mirror + 2 * ml)[pr] = make_uchar2(exc[0] ? 1 : 0, exc[1] ? 1 : 0);
+        }
       } else {
         p.step_count[2 * pr] = steps[0];
         p.flags[2 * pr] = done[0] ? 1 : 0;
         p.flags[ld + 2 * pr] = bad[0] ? 1 : 0;
         p.flags[2 * (size_t)ld + 2 * pr] = exc[0] ? 1 : 0;
+        if (p.flags_mirror) {
+          const size_t ml = (size_t)p.flags_mirror_ld;
+          p.flags_mirror[2 * pr] = done[0] ? 1 : 0;
+          p.flags_mirror[ml + 2 * pr] = bad[0] ? 1 : 0;
+          p.flags_mirror[2 * ml + 2 * pr] = exc[0] ? 1 : 0;
+        }
       }
     }
   }
@@ -1429,6 +1498,162 @@ __global__ void __launch_bounds__(kAuxBS) f16_coeffs_kernel(const uint32_t* __re
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// The plug-in's stand-alone update(action) (F16_model.py:51-67, UAV_model.py:51-62): clamp -> control low-pass -> one
+// explicit Euler step of nlplant, nothing else (no reset, obs, terminations).  The reference's own PlanningEnv
+// (planning_env.py:161) and example/quick_start.ipynb drive the model this way.  recent_s / recent_u receive the state /
+// controls the update started from (the reference rebinds self.recent_s = self.s before integrating).
+// Same device code and evaluation order as the fused step, so env.step and model.update agree bit for bit.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void lowpass_controls(const float* a_in, float* u) {
+  float a[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) a[j] = fminf(fmaxf(a_in[j], -1.0f), 1.0f);
+  u[0] = 0.9f * u[0] + 0.1f * a[0] * 0.225f * 76300.0f / DC(0.3048f);
+  u[1] = 0.9f * u[1] + 0.1f * a[1] * 45.0f;
+  u[2] = 0.9f * u[2] + 0.1f * a[2] * 45.0f;
+  u[3] = 0.9f * u[3] + 0.1f * a[3] * 45.0f;
+}
+
+__global__ void __launch_bounds__(kAuxBS) f16_update_kernel(const uint32_t* __restrict__ aero, int aero_bytes, float* __restrict__ S,
+                                                            float* __restrict__ U, float* __restrict__ RS, float* __restrict__ RU,
+                                                            const float* __restrict__ action, int n, int ld, float dt) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  float* blob = reinterpret_cast<float*>(smem_raw);
+  float2* coef_all = reinterpret_cast<float2*>(smem_raw + aero_bytes);
+  uint64_t* bar = reinterpret_cast<uint64_t*>(coef_all + kNumSlots * kAuxBS);
+  stage_aero(blob, aero, (uint32_t)aero_bytes, bar);
+  const uint32_t wb0 = aero_base_after_staging(blob);
+  const AeroTabs tabs = aero_tabs(blob, wb0);
+  float2* coef2 = coef_all + threadIdx.x;
+  float* cf = reinterpret_cast<float*>(coef2);
+  constexpr int CS = 2 * kAuxBS;
+  const int npairs = (n + 1) >> 1;
+  for (int pbase = blockIdx.x * kAuxBS; pbase < npairs; pbase += gridDim.x * kAuxBS) {
+    const int pr = pbase + threadIdx.x;
+    const int prl = pr < npairs ? pr : npairs - 1;
+    const bool act0 = pr < npairs, act1 = act0 && 2 * pr + 1 < n;
+    const int idx[2] = {min(2 * prl, n - 1), min(2 * prl + 1, n - 1)};
+    const uint32_t wb = opaque_u32(wb0);
+    float s[2][12], u[2][4];
+#pragma unroll
+    for (int j = 0; j < 12; ++j) {
+      const float2 v = reinterpret_cast<const float2*>(S + (size_t)j * ld)[prl];
+      s[0][j] = v.x; s[1][j] = v.y;
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 v = reinterpret_cast<const float2*>(U + (size_t)j * ld)[prl];
+      u[0][j] = v.x; u[1][j] = v.y;
+    }
+    if (act0 && RS) {
+#pragma unroll
+      for (int j = 0; j < 12; ++j) store_pair(RS + (size_t)j * ld, pr, make_float2(s[0][j], s[1][j]), act1);
+    }
+    if (act0 && RU) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) store_pair(RU + (size_t)j * ld, pr, make_float2(u[0][j], u[1][j]), act1);
+      store_pair(RU + (size_t)4 * ld, pr, make_float2(0.f, 0.f), act1);
+    }
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      const float4 av = reinterpret_cast<const float4*>(action)[idx[q]];
+      const float a[4] = {av.x, av.y, av.z, av.w};
+      lowpass_controls(a, u[q]);
+    }
+    const float2 adeg = make_float2(s[0][7] * kR2D, s[1][7] * kR2D);
+    const float2 bdeg = make_float2(s[0][8] * kR2D, s[1][8] * kR2D);
+    ZIn2 zi;
+    zscores_ab2(blob, adeg, bdeg, zi);
+    zscores_el2(blob, make_float2(u[0][1], u[1][1]), zi);
+    eval_ab2_nets(blob, wb, zi, coef2, kAuxBS);
+    eval_el3_nets(blob, wb, zi, coef2, kAuxBS, 5);
+    uint32_t seg[2];
+    pwl_search2<kLevelsA>(tabs.bp_a, adeg.x, adeg.y, seg[0], seg[1]);
+    coef2[kEtaEl * kAuxBS] = eta_el2(tabs, make_float2(u[0][1], u[1][1]));
+    const float h = dt - 0.0f;
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      float a1[kNumA1], xdot[12];
+      alpha_coefs<kNumUsed - kFirstA1>(blob, tabs, seg[q], q == 0 ? adeg.x : adeg.y, a1);
+      const Trig g = make_trig(s[q]);
+      nlplant_from_coefs(s[q], u[q][0], u[q][2], u[q][3], 0.0f, g, tfac_pow(s[q][2]), cf + q, CS, a1, xdot);
+#pragma unroll
+      for (int j = 0; j < 12; ++j) s[q][j] = s[q][j] + h * xdot[j];
+    }
+    if (act0) {
+#pragma unroll
+      for (int j = 0; j < 12; ++j) store_pair(S + (size_t)j * ld, pr, make_float2(s[0][j], s[1][j]), act1);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) store_pair(U + (size_t)j * ld, pr, make_float2(u[0][j], u[1][j]), act1);
+      store_pair(U + (size_t)4 * ld, pr, make_float2(0.f, 0.f), act1);   // lef = 0 (F16_model.py:57)
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) f16_table_update_kernel(const float* __restrict__ image, float* __restrict__ S, float* __restrict__ U,
+                                                               float* __restrict__ RS, float* __restrict__ RU,
+                                                               const float* __restrict__ action, int n, int ld, float dt) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  float* T = reinterpret_cast<float*>(smem_raw);
+  uint64_t* bar = reinterpret_cast<uint64_t*>(T + kTablesFloats);
+  stage_aero(T, image, (uint32_t)(kTablesFloats * 4), bar);
+  const ZeroCells zc = zero_cells(T);
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    float s[12], u[4], c[kNumSlots], a1[kNumA1], xdot[12];
+#pragma unroll
+    for (int j = 0; j < 12; ++j) s[j] = S[(size_t)j * ld + i];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) u[j] = U[(size_t)j * ld + i];
+    if (RS) {
+#pragma unroll
+      for (int j = 0; j < 12; ++j) RS[(size_t)j * ld + i] = s[j];
+    }
+    if (RU) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) RU[(size_t)j * ld + i] = u[j];
+      RU[(size_t)4 * ld + i] = 0.0f;
+    }
+    const float4 av = reinterpret_cast<const float4*>(action)[i];
+    const float a[4] = {av.x, av.y, av.z, av.w};
+    lowpass_controls(a, u);
+    table_env_coefs(T, zc, s[7] * kR2D, s[8] * kR2D, u[1], true, c, a1);
+    const Trig g = make_trig(s);
+    nlplant_from_coefs(s, u[0], u[2], u[3], 0.0f, g, tfac_pow(s[2]), c, 1, a1, xdot);
+    const float h = dt - 0.0f;
+#pragma unroll
+    for (int j = 0; j < 12; ++j) S[(size_t)j * ld + i] = s[j] + h * xdot[j];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) U[(size_t)j * ld + i] = u[j];
+    U[(size_t)4 * ld + i] = 0.0f;
+  }
+}
+
+__global__ void __launch_bounds__(256) uav_update_kernel(float* __restrict__ S, float* __restrict__ U, float* __restrict__ RS,
+                                                         const float* __restrict__ action, int n, int ld, float dt) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    float s[12], F[3], xdot[12];
+#pragma unroll
+    for (int j = 0; j < 12; ++j) s[j] = S[(size_t)j * ld + i];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) F[j] = U[(size_t)j * ld + i];
+    if (RS) {
+#pragma unroll
+      for (int j = 0; j < 12; ++j) RS[(size_t)j * ld + i] = s[j];
+    }
+    const float4 av = reinterpret_cast<const float4*>(action)[i];
+    const float a[3] = {fminf(fmaxf(av.x, -1.0f), 1.0f), fminf(fmaxf(av.y, -1.0f), 1.0f), fminf(fmaxf(av.z, -1.0f), 1.0f)};
+#pragma unroll
+    for (int j = 0; j < 3; ++j) F[j] = 0.9f * F[j] + 0.1f * a[j] * 27000.0f;
+    uav_nlplant(s, F, xdot);
+    const float h = dt - 0.0f;
+#pragma unroll
+    for (int j = 0; j < 12; ++j) S[(size_t)j * ld + i] = s[j] + h * xdot[j];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) U[(size_t)j * ld + i] = F[j];
+  }
+}
+
 // (alpha,beta)-MLP outputs at alpha = beta = 0, written into the image at np_aero_create (same device code as K1,
 // so a reset lane sees bit-identical values whether it takes the constants or an evaluation).
 __global__ void __launch_bounds__(32) f16_c0_kernel(uint32_t* aero, int aero_bytes) {
@@ -1483,9 +1708,9 @@ int np_aero_create(const float* blob, size_t n_floats, const np_net_desc* descs,
   std::vector<uint32_t> image;
   const std::string err = pack_aero_image(blob, n_floats, descs, norm, n_nets, &image);
   if (!err.empty()) return fail(NP_EINVAL, "np_aero_create: " + err);
-  np_aero* a = new np_aero();
+  std::unique_ptr<np_aero, int (*)(np_aero*)> a(new np_aero(), np_aero_destroy);   // freed on every error return below
   a->bytes = (int)image.size() * 4;
-  cudaGetDevice(&a->device);
+  NP_CUDA(cudaGetDevice(&a->device));
   NP_CUDA(cudaMalloc(&a->image_dev, a->bytes));
   NP_CUDA(cudaMemcpy(a->image_dev, image.data(), a->bytes, cudaMemcpyHostToDevice));
   const int c0_smem = a->bytes + kNumSlots * 32 * 8 + 16;
@@ -1493,12 +1718,13 @@ int np_aero_create(const float* blob, size_t n_floats, const np_net_desc* descs,
   f16_c0_kernel<<<1, 32, c0_smem>>>(a->image_dev, a->bytes);
   NP_CUDA(cudaGetLastError());
   NP_CUDA(cudaDeviceSynchronize());
-  *out = a;
+  *out = a.release();
   return NP_OK;
 }
 
 int np_aero_destroy(np_aero* aero) {
   if (!aero) return NP_OK;
+  DeviceGuard guard(aero->device);
   cudaFree(aero->image_dev);
   delete aero;
   return NP_OK;
@@ -1513,11 +1739,10 @@ size_t np_env_workspace_bytes(const np_env_cfg* cfg) {
 
 template <int BS, int MINB, int MODE, bool TAB = false>
 static int launch_step(np_env* env, const StepParams& p, cudaStream_t st) {
-  const int smem = step_smem_bytes(p.aero_bytes, BS, TAB);
+  const int smem = step_smem_bytes(p.aero_bytes, BS, MODE, TAB);
   static int configured[64] = {};  // per device: the attribute lives in the device's context
   auto kern = f16_step_kernel<BS, MINB, MODE, TAB>;
-  int dev = 0;
-  NP_CUDA(cudaGetDevice(&dev));
+  const int dev = env->device;
   if (configured[dev & 63] < smem) {
     NP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured[dev & 63] = smem;
@@ -1528,9 +1753,24 @@ static int launch_step(np_env* env, const StepParams& p, cudaStream_t st) {
   const int grid = want < env->num_sms * MINB ? want : env->num_sms * MINB;
   env->grid = grid;
   env->smem = smem;
+  env->last_block = BS;
   kern<<<grid, BS, smem, st>>>(p);
   NP_CUDA(cudaGetLastError());
   return NP_OK;
+}
+
+// Block size of the MLP step for a range of `npairs` aircraft pairs.  384 threads (12 warps, 168 registers, no spills) is the
+// fastest shape per SM; 512 (16 warps at 128 registers, a few spills) runs at ~0.93 of its rate but covers a third more aircraft
+// per wave.  A persistent grid of 148 CTAs works in whole waves of 148 x BS pairs, so when the population is a small number
+// of waves (a strong-scaling shard: 125 k aircraft = 1.1 waves of 384) the wider block that saves a whole wave wins.
+static int pick_block(const np_env* env, int npairs) {
+  if (env->block) return env->block;
+  auto cost = [&](int bs, double rate) {
+    const long slabs = (npairs + bs - 1) / bs;
+    const long waves = (slabs + env->num_sms - 1) / env->num_sms;
+    return (double)waves * bs / rate;
+  };
+  return cost(512, 0.93) < cost(384, 1.0) ? 512 : 384;
 }
 
 static StepParams make_params(np_env* env, const float* action, const float* draws, const float* noise) {
@@ -1563,6 +1803,8 @@ static StepParams make_params(np_env* env, const float* action, const float* dra
   p.action = action;
   p.draws = draws;
   p.noise = noise;
+  p.flags_mirror = nullptr;
+  p.flags_mirror_ld = 0;
   p.step_index = env->step_index;
   return p;
 }
@@ -1588,27 +1830,28 @@ static int env_create_impl(const np_env_cfg* cfg, const np_aero* aero, const np_
   if (cfg->n <= 0 || cfg->ld < cfg->n + (cfg->n & 1) || cfg->ld % 4)
     return fail(NP_EINVAL, "np_env_create: need n > 0, ld >= n rounded up to even, ld % 4 == 0");
   if (cfg->task < NP_TASK_HEADING || cfg->task > NP_TASK_TRACKING) return fail(NP_EINVAL, "np_env_create: unknown task");
-  np_env* e = new np_env();
+  std::unique_ptr<np_env> e(new np_env());   // freed on every error return below
   e->cfg = *cfg;
   e->aero = aero;
   e->tables = tables;
   memset(&e->buf, 0, sizeof(e->buf));
-  int dev = 0;
-  NP_CUDA(cudaGetDevice(&dev));
-  NP_CUDA(cudaDeviceGetAttribute(&e->num_sms, cudaDevAttrMultiProcessorCount, dev));
+  NP_CUDA(cudaGetDevice(&e->device));
+  if (aero && aero->device != e->device) return fail(NP_EINVAL, "np_env_create: the np_aero lives on another device");
+  if (tables && tables->device != e->device) return fail(NP_EINVAL, "np_env_create_tables: the np_tables live on another device");
+  NP_CUDA(cudaDeviceGetAttribute(&e->num_sms, cudaDevAttrMultiProcessorCount, e->device));
   // 384 threads x 1 CTA/SM: 12 warps = 3 per scheduler (block sizes whose warp count is not a multiple of 4 load the
-  // four schedulers unevenly and measured 17 % slower), 168 registers -> no spills, and 131 KB of shared memory leaves
-  // the L1 large enough for what little is spilled; 256 x 2 CTA/SM (128 regs, 217 KB smem) measured 1.65e9 vs 2.05e9
-  // aircraft-steps/s (profiles/r01_variants.txt)
-  e->block = 384;
-  if (const char* b = getenv("NPLANE_BLOCK")) e->block = atoi(b);
-  if (e->block % 32 || e->block < 128 || e->block > 512) return fail(NP_EINVAL, "NPLANE_BLOCK must be a multiple of 32 in [128, 512]");
+  // four schedulers unevenly and measured 17 % slower), 168 registers -> no spills; 256 x 2 CTA/SM (128 regs) measured
+  // 1.65e9 vs 2.05e9 aircraft-steps/s (profiles/r01_variants.txt).  pick_block() switches to 512 where that saves a wave.
+  if (const char* b = getenv("NPLANE_BLOCK")) {
+    e->block = atoi(b);
+    if (e->block % 32 || e->block < 128 || e->block > 512) return fail(NP_EINVAL, "NPLANE_BLOCK must be a multiple of 32 in [128, 512]");
+  }
   if (const char* b = getenv("NPLANE_TAB_BLOCK")) e->tab_block = atoi(b);
-  *out = e;
+  *out = e.release();
   return NP_OK;
 }
 
-int np_env_bind(np_env* env, const np_buffers* b) {
+int np_env_bind(np_env* env, const np_buffers* b, void* stream) {
   if (!env || !b) return fail(NP_EINVAL, "np_env_bind: null argument");
   if (!b->s_dev || !b->u_dev || !b->tgt_dev || !b->step_count_dev || !b->flags_dev || !b->obs_dev || !b->reward_dev ||
       !b->workspace_dev)
@@ -1617,11 +1860,13 @@ int np_env_bind(np_env* env, const np_buffers* b) {
       ((uintptr_t)b->u_dev & 15) || ((uintptr_t)b->tgt_dev & 15) || ((uintptr_t)b->reward_dev & 7) ||
       ((uintptr_t)b->step_count_dev & 7) || ((uintptr_t)b->flags_dev & 1))
     return fail(NP_EINVAL, "np_env_bind: buffers must be 16-byte (workspace 128-byte) aligned");
+  DeviceGuard guard(env->device);
   env->buf = *b;
   env->bound = true;
-  // invalidate the coefficient-cache keys: 0xFFFFFFFF is a NaN pattern no stored alpha/beta can equal bitwise
-  NP_CUDA(cudaMemset(reinterpret_cast<float*>(b->workspace_dev) + (size_t)kNumAB2 * env->cfg.ld, 0xFF,
-                     2 * (size_t)env->cfg.ld * sizeof(float)));
+  // invalidate the coefficient-cache keys: 0xFFFFFFFF is a NaN pattern no stored alpha/beta can equal bitwise.  Enqueued
+  // on the caller's stream, like every later step.
+  NP_CUDA(cudaMemsetAsync(reinterpret_cast<float*>(b->workspace_dev) + (size_t)kNumAB2 * env->cfg.ld, 0xFF,
+                          2 * (size_t)env->cfg.ld * sizeof(float), (cudaStream_t)stream));
   return NP_OK;
 }
 
@@ -1639,6 +1884,7 @@ int np_rollout_returns(const float* rewards_dev, float* value_preds_dev, const f
                        void* stream) {
   if (!rewards_dev || !value_preds_dev || !masks_dev || !returns_dev || T <= 0 || M <= 0 || (use_proper_time_limits && !bad_masks_dev))
     return fail(NP_EINVAL, "np_rollout_returns: bad argument");
+  DeviceGuard guard(device_of(returns_dev));
   const int want = (M + 255) / 256;
   rollout_returns_kernel<<<want < 2368 ? want : 2368, 256, 0, (cudaStream_t)stream>>>(
       rewards_dev, value_preds_dev, masks_dev, bad_masks_dev, returns_dev, T, M, (float)gamma, (float)(gamma * gae_lambda), use_gae,
@@ -1651,6 +1897,7 @@ int np_rollout_masks(const uint8_t* flags_dev, int ld, int num_envs, int num_age
                      uint8_t* reset_env_dev, void* stream) {
   if (!flags_dev || !masks_dev || !bad_masks_dev || num_envs <= 0 || num_agents <= 0 || (long long)num_envs * num_agents > ld)
     return fail(NP_EINVAL, "np_rollout_masks: bad argument");
+  DeviceGuard guard(device_of(masks_dev));
   const int want = (num_envs + 255) / 256;
   rollout_masks_kernel<<<want < 2368 ? want : 2368, 256, 0, (cudaStream_t)stream>>>(flags_dev, ld, num_envs, num_agents, masks_dev,
                                                                                    bad_masks_dev, reset_env_dev);
@@ -1667,7 +1914,9 @@ int np_env_set_cfg(np_env* env, const np_env_cfg* cfg) {
 }
 
 int np_env_destroy(np_env* env) {
-  if (env && env->hs[0]) {
+  if (!env) return NP_OK;
+  DeviceGuard guard(env->device);
+  if (env->hs[0]) {
     for (cudaStream_t st : env->hs) cudaStreamDestroy(st);
     cudaEventDestroy(env->hev_start);
     cudaEventDestroy(env->hev_done);
@@ -1679,6 +1928,7 @@ int np_env_destroy(np_env* env) {
 
 int np_env_reset(np_env* env, const float* draws_dev, const float* noise_dev, void* stream) {
   if (!env || !env->bound) return fail(NP_ESTATE, "np_env_reset: env not bound");
+  DeviceGuard guard(env->device);
   StepParams p = make_params(env, nullptr, draws_dev, noise_dev);
   env->step_index++;
   const int want = (env->cfg.n + 255) / 256;
@@ -1694,6 +1944,7 @@ static int step_range_impl(np_env* env, const float* action_dev, const float* dr
 
 int np_env_step(np_env* env, const float* action_dev, const float* draws_dev, const float* noise_dev, void* stream) {
   if (!env || !env->bound) return fail(NP_ESTATE, "np_env_step: env not bound");
+  DeviceGuard guard(env->device);
   return step_range_impl(env, action_dev, draws_dev, noise_dev, 0, env->cfg.n, true, stream);
 }
 
@@ -1703,6 +1954,7 @@ int np_env_step_range(np_env* env, const float* action_dev, const float* draws_d
   if (first_aircraft < 0 || count < 0 || first_aircraft + count > env->cfg.n || (first_aircraft & 1) ||
       ((count & 1) && first_aircraft + count != env->cfg.n))
     return fail(NP_EINVAL, "np_env_step_range: the range must start on an even aircraft and cover whole pairs (except the tail)");
+  DeviceGuard guard(env->device);
   return step_range_impl(env, action_dev, draws_dev, noise_dev, first_aircraft, count, advance_step_index != 0, stream);
 }
 
@@ -1724,8 +1976,7 @@ static int step_range_impl(np_env* env, const float* action_dev, const float* dr
     const bool slab_ok = !(bases & 15) && !(first & 15) && !(env->cfg.ld & 15) && count >= uavslab::kSlab && !getenv("NPLANE_UAV_SCALAR");
     if (slab_ok) {
       static bool attr_set[64] = {};  // per device: the attribute lives in the device's context
-      int dev = 0;
-      NP_CUDA(cudaGetDevice(&dev));
+      const int dev = env->device;
       if (!attr_set[dev & 63]) {
         NP_CUDA(cudaFuncSetAttribute(uav_step_slab_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, uavslab::SMEM_BYTES));
         attr_set[dev & 63] = true;
@@ -1752,16 +2003,16 @@ static int step_range_impl(np_env* env, const float* action_dev, const float* dr
       default: return fail(NP_EINVAL, "np_env_step: table back-end block size not compiled in (build with -DNPLANE_ALL_BLOCKS)");
     }
   }
-  switch (env->block) {
+  switch (pick_block(env, p.pair_end - p.pair_begin)) {
 #ifdef NPLANE_ALL_BLOCKS
     case 128: return launch_step<128, 4, MODE_STEP>(env, p, st);
     case 256: return launch_step<256, 2, MODE_STEP>(env, p, st);
     case 320: return launch_step<320, 1, MODE_STEP>(env, p, st);
     case 352: return launch_step<352, 1, MODE_STEP>(env, p, st);
     case 448: return launch_step<448, 1, MODE_STEP>(env, p, st);
-    case 512: return launch_step<512, 1, MODE_STEP>(env, p, st);
 #endif
     case 384: return launch_step<384, 1, MODE_STEP>(env, p, st);
+    case 512: return launch_step<512, 1, MODE_STEP>(env, p, st);
     default: return fail(NP_EINVAL, "np_env_step: block size not compiled in (build with -DNPLANE_ALL_BLOCKS)");
   }
 }
@@ -1778,6 +2029,7 @@ int np_env_step_host(np_env* env, const float* action_host, float* action_pinned
   if (!action_host || !action_pinned || !action_dev || !obs_pinned || !reward_pinned || !flags_pinned || !edges || n_chunks < 1 ||
       n_chunks > np_env::kMaxHostChunks || edges[0] != 0 || edges[n_chunks] != env->cfg.n)
     return fail(NP_EINVAL, "np_env_step_host: bad argument (1..16 chunks, edges[0] = 0, edges[n_chunks] = n)");
+  DeviceGuard guard(env->device);
   for (int c = 0; c < n_chunks; ++c)
     if (edges[c + 1] <= edges[c] || (edges[c] & 1)) return fail(NP_EINVAL, "np_env_step_host: chunks must be non-empty and start on whole pairs");
   if (!env->hs[0]) {
@@ -1822,6 +2074,7 @@ int np_env_plan_step(np_env* env, const float* action3_dev, int n_sub, const flo
   if (env->cfg.model != NP_MODEL_F16) return fail(NP_EINVAL, "np_env_plan_step: the fused PID controller flies the F16 plug-in");
   if (env->tables) return fail(NP_EINVAL, "np_env_plan_step: not built for the table aero back-end");
   if (!action3_dev || ((uintptr_t)action3_dev & 3) || n_sub < 1) return fail(NP_EINVAL, "np_env_plan_step: bad action pointer or n_sub");
+  DeviceGuard guard(env->device);
   StepParams p = make_params(env, action3_dev, draws_dev, noise_dev);
   p.n_sub = n_sub;
   p.pid_first = env->pid_started ? 0 : 1;
@@ -1835,6 +2088,7 @@ int np_env_combat_step(np_env* env, const float* action_dev, int n_sub, const fl
   if (env->cfg.model != NP_MODEL_F16 || (env->cfg.n & 1)) return fail(NP_EINVAL, "np_env_combat_step: needs the F16 plug-in and an even population (pairs)");
   if (n_sub < 0 || (n_sub > 0 && (!action_dev || ((uintptr_t)action_dev & 15)))) return fail(NP_EINVAL, "np_env_combat_step: bad action pointer or n_sub");
   if (env->tables) return fail(NP_EINVAL, "np_env_combat_step: not built for the table aero back-end");
+  DeviceGuard guard(env->device);
   StepParams p = make_params(env, action_dev ? action_dev : reinterpret_cast<const float*>(env->buf.s_dev), draws_dev, nullptr);
   p.n_sub = n_sub;
   p.pid_first = env->pid_started ? 0 : 1;
@@ -1845,6 +2099,7 @@ int np_env_combat_step(np_env* env, const float* action_dev, int n_sub, const fl
 
 int np_env_combat_records(np_env* env, float* records_dev, void* stream) {
   if (!env || !env->bound || !records_dev || ((uintptr_t)records_dev & 15)) return fail(NP_EINVAL, "np_env_combat_records: bad argument");
+  DeviceGuard guard(env->device);
   StepParams p = make_params(env, nullptr, nullptr, nullptr);
   const int want = (env->cfg.n + 255) / 256;
   combat_records_kernel<<<want < env->num_sms * 8 ? want : env->num_sms * 8, 256, 0, (cudaStream_t)stream>>>(p.s, p.blood, records_dev,
@@ -1857,6 +2112,7 @@ int np_combat_relgeo(const float* records_dev, const int32_t* ego_idx_dev, const
                      void* stream) {
   if (!records_dev || !ego_idx_dev || !enm_idx_dev || !out_dev || m <= 0 || (((uintptr_t)records_dev | (uintptr_t)out_dev) & 15))
     return fail(NP_EINVAL, "np_combat_relgeo: bad argument");
+  DeviceGuard guard(device_of(out_dev));
   const int want = (m + 255) / 256;
   combat_relgeo_kernel<<<want < 1184 ? want : 1184, 256, 0, (cudaStream_t)stream>>>(records_dev, ego_idx_dev, enm_idx_dev, out_dev, m);
   NP_CUDA(cudaGetLastError());
@@ -1867,6 +2123,7 @@ int np_combat_relgeo_peers(const float* const* slabs_dev, int world, int n_local
                            float* out_dev, int m, void* stream) {
   if (!slabs_dev || world < 1 || n_local < 1 || !ego_idx_dev || !enm_idx_dev || !out_dev || m <= 0 || ((uintptr_t)out_dev & 15))
     return fail(NP_EINVAL, "np_combat_relgeo_peers: bad argument");
+  DeviceGuard guard(device_of(out_dev));
   const int want = (m + 255) / 256;
   combat_relgeo_peers_kernel<<<want < 1184 ? want : 1184, 256, 0, (cudaStream_t)stream>>>(slabs_dev, n_local, ego_idx_dev, enm_idx_dev,
                                                                                          out_dev, m);
@@ -1890,6 +2147,7 @@ int np_env_set_pid_started(np_env* env, int started) {
 
 int np_env_counters(np_env* env, uint64_t* out, void* stream) {
   if (!env || !env->bound || !out) return fail(NP_ESTATE, "np_env_counters: env not bound");
+  DeviceGuard guard(env->device);
   StepParams p = make_params(env, nullptr, nullptr, nullptr);
   NP_CUDA(cudaMemcpyAsync(out, p.counters, NP_NUM_COUNTERS * sizeof(uint64_t), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
   NP_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
@@ -1899,7 +2157,7 @@ int np_env_counters(np_env* env, uint64_t* out, void* stream) {
 int np_env_launch_info(const np_env* env, int* grid, int* block, int* smem_bytes, int* num_sms) {
   if (!env) return fail(NP_EINVAL, "np_env_launch_info: null env");
   if (grid) *grid = env->grid;
-  if (block) *block = env->cfg.model == NP_MODEL_UAV ? 256 : env->tables ? env->tab_block : env->block;
+  if (block) *block = env->cfg.model == NP_MODEL_UAV ? 256 : env->tables ? env->tab_block : env->last_block;
   if (smem_bytes) *smem_bytes = env->smem;
   if (num_sms) *num_sms = env->num_sms;
   return NP_OK;
@@ -1909,10 +2167,10 @@ int np_f16_nlplant(const np_aero* aero, const float* s_dev, const float* u_dev, 
   if (!aero || !s_dev || !u_dev || !xdot_dev || n <= 0 || ld < n + (n & 1) || (ld & 1))
     return fail(NP_EINVAL, "np_f16_nlplant: bad argument (need even ld >= n rounded up to even)");
   if (((uintptr_t)s_dev | (uintptr_t)u_dev | (uintptr_t)xdot_dev) & 7) return fail(NP_EINVAL, "np_f16_nlplant: 8-byte alignment");
+  DeviceGuard guard(aero->device);
   const int smem = aux_smem_bytes(aero->bytes);
   static int configured[64] = {};
-  int dev = 0;
-  NP_CUDA(cudaGetDevice(&dev));
+  const int dev = aero->device;
   if (configured[dev & 63] < smem) {
     NP_CUDA(cudaFuncSetAttribute(f16_nlplant_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured[dev & 63] = smem;
@@ -1939,15 +2197,17 @@ int np_tables_create(const float* breakpoints, const int32_t* bp_sizes, const fl
   std::vector<float> host(kTablesFloats, 0.0f);
   memcpy(host.data(), breakpoints, 61 * sizeof(float));
   memcpy(host.data() + kBpFloats, values, (size_t)kTableValues * sizeof(float));
-  np_tables* t = new np_tables();
+  std::unique_ptr<np_tables, int (*)(np_tables*)> t(new np_tables(), np_tables_destroy);   // freed on every error return below
+  NP_CUDA(cudaGetDevice(&t->device));
   NP_CUDA(cudaMalloc(&t->image_dev, kTablesFloats * sizeof(float)));
   NP_CUDA(cudaMemcpy(t->image_dev, host.data(), kTablesFloats * sizeof(float), cudaMemcpyHostToDevice));
-  *out = t;
+  *out = t.release();
   return NP_OK;
 }
 
 int np_tables_destroy(np_tables* t) {
   if (!t) return NP_OK;
+  DeviceGuard guard(t->device);
   cudaFree(t->image_dev);
   delete t;
   return NP_OK;
@@ -1957,10 +2217,10 @@ int np_f16_table_coeffs(const np_tables* tables, const float* alpha_deg_dev, con
                         float* out_dev, int n, int ld, void* stream) {
   if (!tables || !alpha_deg_dev || !beta_deg_dev || !el_deg_dev || !out_dev || n <= 0 || ld < n)
     return fail(NP_EINVAL, "np_f16_table_coeffs: bad argument");
+  DeviceGuard guard(tables->device);
   const int smem = kTablesFloats * 4 + 16;
   static int configured[64] = {};
-  int dev = 0;
-  NP_CUDA(cudaGetDevice(&dev));
+  const int dev = tables->device;
   if (!configured[dev & 63]) {
     NP_CUDA(cudaFuncSetAttribute(f16_table_coeffs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured[dev & 63] = 1;
@@ -1975,10 +2235,10 @@ int np_f16_table_coeffs(const np_tables* tables, const float* alpha_deg_dev, con
 int np_f16_table_nlplant(const np_tables* tables, const float* s_dev, const float* u_dev, float* xdot_dev, int n, int ld,
                          void* stream) {
   if (!tables || !s_dev || !u_dev || !xdot_dev || n <= 0 || ld < n) return fail(NP_EINVAL, "np_f16_table_nlplant: bad argument");
+  DeviceGuard guard(tables->device);
   const int smem = kTablesFloats * 4 + 16;
   static int configured[64] = {};
-  int dev = 0;
-  NP_CUDA(cudaGetDevice(&dev));
+  const int dev = tables->device;
   if (!configured[dev & 63]) {
     NP_CUDA(cudaFuncSetAttribute(f16_table_nlplant_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured[dev & 63] = 1;
@@ -1991,6 +2251,7 @@ int np_f16_table_nlplant(const np_tables* tables, const float* s_dev, const floa
 
 int np_uav_nlplant(const float* s_dev, const float* u_dev, float* xdot_dev, int n, int ld, void* stream) {
   if (!s_dev || !u_dev || !xdot_dev || n <= 0 || ld < n) return fail(NP_EINVAL, "np_uav_nlplant: bad argument");
+  DeviceGuard guard(device_of(xdot_dev));
   const int want = (n + 255) / 256;
   uav_nlplant_kernel<<<want < 1184 ? want : 1184, 256, 0, (cudaStream_t)stream>>>(s_dev, u_dev, xdot_dev, n, ld);
   NP_CUDA(cudaGetLastError());
@@ -2001,10 +2262,10 @@ int np_f16_coeffs(const np_aero* aero, const float* alpha_deg_dev, const float* 
                   float* out_dev, int n, int ld, void* stream) {
   if (!aero || !alpha_deg_dev || !beta_deg_dev || !el_deg_dev || !out_dev || n <= 0 || ld < n)
     return fail(NP_EINVAL, "np_f16_coeffs: bad argument");
+  DeviceGuard guard(aero->device);
   const int smem = aux_smem_bytes(aero->bytes);
   static int configured[64] = {};
-  int dev = 0;
-  NP_CUDA(cudaGetDevice(&dev));
+  const int dev = aero->device;
   if (configured[dev & 63] < smem) {
     NP_CUDA(cudaFuncSetAttribute(f16_coeffs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured[dev & 63] = smem;
@@ -2013,6 +2274,96 @@ int np_f16_coeffs(const np_aero* aero, const float* alpha_deg_dev, const float* 
   f16_coeffs_kernel<<<want < 296 ? want : 296, kAuxBS, smem, (cudaStream_t)stream>>>(aero->image_dev, aero->bytes, alpha_deg_dev,
                                                                                   beta_deg_dev, el_deg_dev, out_dev, n, ld);
   NP_CUDA(cudaGetLastError());
+  return NP_OK;
+}
+
+int np_f16_update(const np_aero* aero, float* s_dev, float* u_dev, float* recent_s_dev, float* recent_u_dev, const float* action_dev,
+                  int n, int ld, double dt, void* stream) {
+  if (!aero || !s_dev || !u_dev || !action_dev || n <= 0 || ld < n + (n & 1) || (ld & 1))
+    return fail(NP_EINVAL, "np_f16_update: bad argument (need even ld >= n rounded up to even)");
+  if ((((uintptr_t)s_dev | (uintptr_t)u_dev | (uintptr_t)recent_s_dev | (uintptr_t)recent_u_dev) & 7) || ((uintptr_t)action_dev & 15))
+    return fail(NP_EINVAL, "np_f16_update: rows 8-byte, action 16-byte aligned");
+  DeviceGuard guard(aero->device);
+  const int smem = aux_smem_bytes(aero->bytes);
+  static int configured[64] = {};
+  const int dev = aero->device;
+  if (configured[dev & 63] < smem) {
+    NP_CUDA(cudaFuncSetAttribute(f16_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured[dev & 63] = smem;
+  }
+  const int want = ((n + 1) / 2 + kAuxBS - 1) / kAuxBS;
+  f16_update_kernel<<<want < 296 ? want : 296, kAuxBS, smem, (cudaStream_t)stream>>>(aero->image_dev, aero->bytes, s_dev, u_dev, recent_s_dev,
+                                                                                  recent_u_dev, action_dev, n, ld, (float)dt);
+  NP_CUDA(cudaGetLastError());
+  return NP_OK;
+}
+
+int np_f16_table_update(const np_tables* tables, float* s_dev, float* u_dev, float* recent_s_dev, float* recent_u_dev,
+                        const float* action_dev, int n, int ld, double dt, void* stream) {
+  if (!tables || !s_dev || !u_dev || !action_dev || n <= 0 || ld < n || ((uintptr_t)action_dev & 15))
+    return fail(NP_EINVAL, "np_f16_table_update: bad argument");
+  DeviceGuard guard(tables->device);
+  const int smem = kTablesFloats * 4 + 16;
+  static int configured[64] = {};
+  const int dev = tables->device;
+  if (!configured[dev & 63]) {
+    NP_CUDA(cudaFuncSetAttribute(f16_table_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured[dev & 63] = 1;
+  }
+  const int want = (n + 255) / 256;
+  f16_table_update_kernel<<<want < 444 ? want : 444, 256, smem, (cudaStream_t)stream>>>(tables->image_dev, s_dev, u_dev, recent_s_dev,
+                                                                                    recent_u_dev, action_dev, n, ld, (float)dt);
+  NP_CUDA(cudaGetLastError());
+  return NP_OK;
+}
+
+int np_uav_update(float* s_dev, float* u_dev, float* recent_s_dev, const float* action_dev, int n, int ld, double dt, void* stream) {
+  if (!s_dev || !u_dev || !action_dev || n <= 0 || ld < n || ((uintptr_t)action_dev & 15)) return fail(NP_EINVAL, "np_uav_update: bad argument");
+  DeviceGuard guard(device_of(s_dev));
+  const int want = (n + 255) / 256;
+  uav_update_kernel<<<want < 1184 ? want : 1184, 256, 0, (cudaStream_t)stream>>>(s_dev, u_dev, recent_s_dev, action_dev, n, ld, (float)dt);
+  NP_CUDA(cudaGetLastError());
+  return NP_OK;
+}
+
+// GPUVecEnv.step with HOST buffers and no copy engine in the path: the step kernel reads the actions from, and writes the
+// observation rows / rewards / flags straight into, MAPPED page-locked host memory.  The kernel is compute-bound at
+// ~0.46 ms per 10^6 aircraft while the 95 B/aircraft need ~1.7 ms of PCIe, so the posted writes (whole 128-B lines, see
+// kObsTileFloats) drain under the arithmetic and the chunked upload / kernel / download pipeline of np_env_step_host
+// disappears.  action_dev != NULL selects an explicit H2D copy of the actions before the launch instead of zero-copy reads.
+int np_env_step_mapped(np_env* env, const float* action_host, float* action_mapped, float* action_dev, float* obs_mapped,
+                       float* reward_mapped, uint8_t* flags_mapped, int flags_ld, void* stream) {
+  if (!env || !env->bound) return fail(NP_ESTATE, "np_env_step_mapped: env not bound");
+  if (env->cfg.model != NP_MODEL_F16) return fail(NP_EINVAL, "np_env_step_mapped: F16 plug-in only (the UAV step is TMA-staged: use np_env_step_host)");
+  const int n = env->cfg.n;
+  if (!action_host || !action_mapped || !obs_mapped || !reward_mapped || !flags_mapped || flags_ld < n + (n & 1) || (flags_ld & 1))
+    return fail(NP_EINVAL, "np_env_step_mapped: null buffer or bad flags pitch (even, >= n rounded up to even)");
+  DeviceGuard guard(env->device);
+  float *act_d = nullptr, *obs_d = nullptr, *rew_d = nullptr;
+  uint8_t* flg_d = nullptr;
+  NP_CUDA(cudaHostGetDevicePointer(reinterpret_cast<void**>(&act_d), action_mapped, 0));
+  NP_CUDA(cudaHostGetDevicePointer(reinterpret_cast<void**>(&obs_d), obs_mapped, 0));
+  NP_CUDA(cudaHostGetDevicePointer(reinterpret_cast<void**>(&rew_d), reward_mapped, 0));
+  NP_CUDA(cudaHostGetDevicePointer(reinterpret_cast<void**>(&flg_d), flags_mapped, 0));
+  if (((uintptr_t)act_d & 15) || ((uintptr_t)obs_d & 15) || ((uintptr_t)rew_d & 7) || ((uintptr_t)flg_d & 1) || ((uintptr_t)action_dev & 15))
+    return fail(NP_EINVAL, "np_env_step_mapped: action / obs 16-byte, reward 8-byte, flags 2-byte aligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (action_host != action_mapped) memcpy(action_mapped, action_host, (size_t)n * NP_NUM_ACT * sizeof(float));
+  const float* act = act_d;
+  if (action_dev) {
+    NP_CUDA(cudaMemcpyAsync(action_dev, action_mapped, (size_t)n * NP_NUM_ACT * sizeof(float), cudaMemcpyHostToDevice, st));
+    act = action_dev;
+  }
+  env->step_index++;
+  StepParams p = make_params(env, act, nullptr, nullptr);
+  p.step_index = env->step_index - 1;
+  p.obs = obs_d;
+  p.reward = rew_d;
+  p.flags_mirror = flg_d;
+  p.flags_mirror_ld = flags_ld;
+  const int rc = env->tables ? launch_step<384, 1, MODE_STEP, true>(env, p, st) : launch_step<384, 1, MODE_STEP>(env, p, st);   // 384: the staged obs path
+  if (rc != NP_OK) return rc;
+  NP_CUDA(cudaStreamSynchronize(st));
   return NP_OK;
 }
 

@@ -98,7 +98,7 @@ class BaseEnv:
             b = nv.Buffers(self.model._s.data_ptr(), self.model._u.data_ptr(), self._tgt.data_ptr(),
                            self._step_count.data_ptr(), self._flags.data_ptr(), self._obs.data_ptr(),
                            self._reward.data_ptr(), self._workspace.data_ptr())
-            nv.check(L.np_env_bind(self._handle, C.byref(b)), "np_env_bind")
+            nv.check(L.np_env_bind(self._handle, C.byref(b), self._stream()), "np_env_bind")
 
     def _sync_cfg(self):
         ns = float(self.task.noise_scale)
@@ -167,11 +167,13 @@ class BaseEnv:
     def get_number_of_agents(self):
         return self.n
 
+    COUNTER_NAMES = nv.COUNTER_NAMES     # what the eight device counters mean for this env (combat renames two)
+
     def termination_counters(self):
         """Per-cause termination counts since construction (device counters; one sync)."""
         out = (C.c_uint64 * nv.NUM_COUNTERS)()
         nv.check(nv.lib().np_env_counters(self._handle, out, self._stream()), "np_env_counters")
-        return dict(zip(nv.COUNTER_NAMES, [int(x) for x in out]))
+        return dict(zip(self.COUNTER_NAMES, [int(x) for x in out]))
 
     # ---- reset / step ---------------------------------------------------------------------------------------
     def _stream(self):
@@ -215,7 +217,9 @@ class BaseEnv:
         """One logical step may be issued as several aircraft ranges (on different streams): `action` is the full
         [n, 4] device tensor, the range is [first, first + count); advance=True on the first range only."""
         self._sync_cfg()
-        st = nv.lib().np_env_step_range(self._handle, action.data_ptr(),
+        if action.device != self.device:
+            raise ValueError(f"action must live on {self.device}, got {action.device}")
+        st = nv.lib().np_env_step_range(self._handle, self._ptr(action, (self.n, 4), "action"),
                                         self._ptr(reset_draws, (self.n, nv.NUM_DRAWS), "reset_draws"),
                                         self._ptr(noise, (self.n, nv.NUM_OBS), "noise"), int(first), int(count),
                                         1 if advance else 0, self._stream())
@@ -226,10 +230,43 @@ class BaseEnv:
         flags [3, n] out, pipelined over `n_chunks` aircraft ranges with edges `edges` (ctypes int array).  Returns when
         the host buffers are ready."""
         self._sync_cfg()
+        n, D = self.n, self.num_observation
+        self._check_host_action(action_np)
+        self._check_pinned(act_pinned, (n, 4), torch.float32, "act_pinned")
+        self._check_pinned(obs_pinned, (n, D), torch.float32, "obs_pinned")
+        self._check_pinned(rew_pinned, (n,), torch.float32, "rew_pinned")
+        self._check_pinned(flags_pinned, (3, n), torch.uint8, "flags_pinned")
+        self._ptr(act_dev, (n, 4), "act_dev")
         st = nv.lib().np_env_step_host(self._handle, action_np.ctypes.data, act_pinned.data_ptr(), act_dev.data_ptr(),
                                        obs_pinned.data_ptr(), rew_pinned.data_ptr(), flags_pinned.data_ptr(), edges,
                                        int(n_chunks), self._stream())
         nv.check(st, "np_env_step_host")
+
+    def _check_host_action(self, a):
+        if not isinstance(a, np.ndarray) or a.dtype != np.float32 or a.shape != (self.n, 4) or not a.flags.c_contiguous:
+            raise ValueError(f"host actions must be a C-contiguous float32 numpy array of shape ({self.n}, 4)")
+
+    @staticmethod
+    def _check_pinned(t, shape, dtype, what):
+        if t.dtype != dtype or tuple(t.shape) != tuple(shape) or not t.is_contiguous() or t.is_cuda or not t.is_pinned():
+            raise ValueError(f"{what} must be a contiguous pinned host tensor of shape {tuple(shape)}, dtype {dtype}")
+
+    def step_mapped(self, action_np, act_pinned, obs_pinned, rew_pinned, flags_pinned, act_dev=None):
+        """The numpy boundary with no copy engine in the path (np_env_step_mapped): the step kernel reads the actions from
+        and writes obs [n, D] / reward [n] / flags [3, ld] straight into pinned (device-mapped) host memory.  Returns when
+        the host buffers are ready.  `last_obs` / `last_reward` (the device buffers) are not updated by this call."""
+        self._sync_cfg()
+        n, D = self.n, self.num_observation
+        self._check_host_action(action_np)
+        self._check_pinned(act_pinned, (n, 4), torch.float32, "act_pinned")
+        self._check_pinned(obs_pinned, (n, D), torch.float32, "obs_pinned")
+        self._check_pinned(rew_pinned, (n,), torch.float32, "rew_pinned")
+        self._check_pinned(flags_pinned, (3, self.ld), torch.uint8, "flags_pinned")
+        st = nv.lib().np_env_step_mapped(self._handle, action_np.ctypes.data, act_pinned.data_ptr(),
+                                         None if act_dev is None else self._ptr(act_dev, (n, 4), "act_dev"),
+                                         obs_pinned.data_ptr(), rew_pinned.data_ptr(), flags_pinned.data_ptr(), self.ld,
+                                         self._stream())
+        nv.check(st, "np_env_step_mapped")
 
     def launch_info(self):
         g, b, s, m = C.c_int(), C.c_int(), C.c_int(), C.c_int()

@@ -1,18 +1,28 @@
 """GPUVecEnv (reference: envs/env_wrappers.py:84-124): the numpy boundary the runners call.
 
 Same shapes as the reference: actions (num_envs, agents, A) in; obs (num_envs, agents, D), rewards / dones /
-bad_dones / exceed_time_limits (num_envs, agents, 1) out.  Host<->device traffic goes through pinned staging
-buffers; large ControlEnv populations are pipelined in aircraft chunks on side streams (upload / kernel / download
-of different chunks overlap; the 88 B/aircraft observation download is what bounds this boundary), with one
-synchronise per step.  The returned arrays alias pinned buffers that are reused every OTHER step
-(double-buffered), so a result stays valid until the step after next.
+bad_dones / exceed_time_limits (num_envs, agents, 1) out.  Three implementations of the host boundary:
+
+  'mapped'    (default for the F16 plug-in) ONE kernel launch that reads the actions from and writes observation rows,
+              rewards and flags straight into pinned, device-mapped host memory (np_env_step_mapped): no copy engine,
+              no chunk pipeline; the 88 B/aircraft of PCIe writes drain under the step's arithmetic.
+  'pipelined' (default for large UAV populations, whose step is TMA-staged) upload / kernel / download of aircraft
+              chunks overlapped on three streams by one native call (np_env_step_host).
+  'copy'      single launch, then a device-to-host copy (small populations of the other kinds).
+
+Lifetime of the returned arrays.  The reference returns fresh arrays every step (`_t2n`).  Here small populations
+(< COPY_BELOW_BYTES of observations) also get fresh arrays; large ones get views of a ring of `ring` pinned buffers
+(default 2: a result stays valid until the step after next) because a 95 MB host memcpy per step would cost more than
+the step itself.  `copy=True` / `copy=False` forces either behaviour.
 """
 import ctypes as C
+import os
 
 import numpy as np
 import torch
 
 
+COPY_BELOW_BYTES = 8 << 20   # observation block size below which step() returns fresh arrays by default
 
 DEFAULT_PIPELINE = (1, 2, 3, 4, 4, 4)   # relative chunk sizes; see profiles/r01_variants.txt for the sweep
 
@@ -36,11 +46,15 @@ def pipeline_edges(n, pattern):
 
 
 class GPUVecEnv:
-    def __init__(self, env_fns, device_tensors=False, pipeline_chunks=None):
+    def __init__(self, env_fns, device_tensors=False, pipeline_chunks=None, boundary=None, copy=None, ring=2):
         """device_tensors=True (SURVEY f-2): step()/reset() take and return torch CUDA tensors in the same
         (num_envs, agents, .) shapes, with no host round trip and no synchronisation -- for policies that live on
-        the same GPU.  The default reproduces the reference's numpy boundary.
-        pipeline_chunks: number of aircraft chunks the numpy step is pipelined over (default 4 from 2x10^5 aircraft)."""
+        the same GPU (the flag tensors are fresh clones, like the reference's; obs / reward are the env's persistent
+        buffers, overwritten by the next step).  The default reproduces the reference's numpy boundary.
+        boundary: 'mapped' | 'pipelined' | 'copy' | None (choose by plug-in and population, see the module docstring).
+        pipeline_chunks: chunk count or relative chunk sizes of the 'pipelined' boundary.
+        copy: return fresh numpy arrays (True), views of the pinned ring (False), or decide by size (None).
+        ring: number of pinned output buffer sets the views rotate through."""
         self.device_tensors = bool(device_tensors)
         assert len(env_fns) == 1, "Number of create env funcitions must be 1!"
         self.gpu_vec_env = env_fns[0]()
@@ -57,73 +71,95 @@ class GPUVecEnv:
         self.h2d_bytes_per_step = 0 if self.device_tensors else n * A * 4
         self.d2h_bytes_per_step = 0 if self.device_tensors else n * D * 4 + n * 4 + 3 * n
         self._chunks = None
+        self.boundary = "device" if self.device_tensors else None
         if self.device_tensors:
             return
-        # pipelined boundary for large single-step envs (ControlEnv): aircraft chunks through np_env_step_host
-        # pipeline_chunks: a chunk count (equal chunks) or a sequence of relative chunk sizes, e.g. (1, 2, 3, 5, 5): a small
-        # first chunk starts the observation download -- the resource this boundary is bound by -- sooner
-        if pipeline_chunks is None:
-            pipeline_chunks = DEFAULT_PIPELINE if n >= 200_000 else 1
-        self._chunks = pipeline_edges(n, pipeline_chunks) if hasattr(e, "step_host") and type(e).__name__ == "ControlEnv" else None
-        if self._chunks is not None:
-            self._edges = (C.c_int * (len(self._chunks) + 1))(*([c[0] for c in self._chunks] + [n]))
+        single_step_env = type(e).__name__ == "ControlEnv"
+        is_f16 = getattr(e.model, "model_id", None) == 0
+        boundary = boundary or os.environ.get("NPLANE_BOUNDARY") or None
+        if boundary is None:
+            if single_step_env and is_f16 and hasattr(e, "step_mapped"):
+                boundary = "mapped"
+            elif single_step_env and hasattr(e, "step_host") and (pipeline_chunks is not None or n >= 200_000):
+                boundary = "pipelined"
+            else:
+                boundary = "copy"
+        if boundary not in ("mapped", "pipelined", "copy"):
+            raise ValueError(f"boundary must be 'mapped', 'pipelined' or 'copy', got {boundary!r}")
+        if boundary == "mapped" and not (single_step_env and is_f16):
+            raise ValueError("the 'mapped' boundary serves ControlEnv with the F16 plug-in")
+        if boundary == "pipelined":
+            if not single_step_env:
+                raise ValueError("the 'pipelined' boundary serves ControlEnv")
+            # a chunk count (equal chunks) or relative chunk sizes, e.g. (1, 2, 3, 5, 5): a small first chunk starts the
+            # observation download -- the resource this boundary is bound by -- sooner
+            self._chunks = pipeline_edges(n, DEFAULT_PIPELINE if pipeline_chunks is None else pipeline_chunks)
+            if self._chunks is None:
+                boundary = "copy"
+            else:
+                self._edges = (C.c_int * (len(self._chunks) + 1))(*([c[0] for c in self._chunks] + [n]))
+        self.boundary = boundary
+        self._copy = (n * D * 4 < COPY_BELOW_BYTES) if copy is None else bool(copy)
+        self._zero_copy_actions = os.environ.get("NPLANE_MAPPED_ACTIONS", "1") != "0"
+        frows = e.ld if boundary == "mapped" else n      # the mapped kernel mirrors the flag rows at the SoA pitch
         self._act_h = torch.empty((n, A), dtype=torch.float32).pin_memory()
         self._act_d = torch.empty((n, A), dtype=torch.float32, device=e.device)
-        self._out = [dict(obs=torch.empty((n, D), dtype=torch.float32).pin_memory(),
-                          rew=torch.empty(n, dtype=torch.float32).pin_memory(),
-                          flags=torch.empty((3, n), dtype=torch.uint8).pin_memory()) for _ in range(2)]
+        self._out = [dict(obs=torch.zeros((n, D), dtype=torch.float32).pin_memory(),
+                          rew=torch.zeros(n, dtype=torch.float32).pin_memory(),
+                          flags=torch.zeros((3, frows), dtype=torch.uint8).pin_memory()) for _ in range(max(1, int(ring)))]
+
+    def _next_out(self):
+        o = self._out[self._flip]
+        self._flip = (self._flip + 1) % len(self._out)
+        return o
 
     def _download(self, with_rest=True):
         e = self.gpu_vec_env
-        o = self._out[self._flip]
-        self._flip ^= 1
+        o = self._next_out()
         o["obs"].copy_(e.last_obs, non_blocking=True)
         if with_rest:
             o["rew"].copy_(e.last_reward, non_blocking=True)
-            o["flags"].copy_(e._flags[:, :e.n], non_blocking=True)
+            o["flags"][:, :e.n].copy_(e._flags[:, :e.n], non_blocking=True)
         torch.cuda.current_stream(e.device).synchronize()
         return o
 
     def _step_device(self, actions):
         e = self.gpu_vec_env
-        import torch as _t
-        a = _t.as_tensor(actions, device=e.device, dtype=_t.float32).reshape(self.num_envs * self.agents, -1)
+        a = torch.as_tensor(actions, device=e.device, dtype=torch.float32).reshape(self.num_envs * self.agents, -1)
         obs, rew, done, bad, exc, info = e.step(a)
         shp = (self.num_envs, self.agents, 1)
-        return (obs.view(self.num_envs, self.agents, e.num_observation), rew.view(shp), done.view(shp), bad.view(shp),
-                exc.view(shp), info)
+        # the reference's `self.is_done = self.is_done + done` yields new tensors every step: callers keep `dones` while stepping
+        return (obs.view(self.num_envs, self.agents, e.num_observation), rew.view(shp), done.clone().view(shp),
+                bad.clone().view(shp), exc.clone().view(shp), info)
 
     def step(self, actions):
         if self.device_tensors:
             return self._step_device(actions)
         e = self.gpu_vec_env
         a = np.asarray(actions, dtype=np.float32).reshape(self.num_envs * self.agents, -1)
-        if self._chunks is None:
+        if self.boundary == "copy":
             self._act_h.copy_(torch.from_numpy(a[:, :self._A]))
             self._act_d.copy_(self._act_h, non_blocking=True)
             e.step(self._act_d)
             o = self._download()
         else:
-            o = self._step_pipelined(a)
+            if a.shape[1] != self._A or not a.flags.c_contiguous:
+                a = np.ascontiguousarray(a[:, :self._A])
+            o = self._next_out()
+            if self.boundary == "mapped":
+                e.step_mapped(a, self._act_h, o["obs"], o["rew"], o["flags"], None if self._zero_copy_actions else self._act_d)
+            else:
+                # Aircraft are independent, so the step is pipelined chunk by chunk over three in-order streams -- upload,
+                # kernels, download -- by ONE native call (issuing a chunk from Python cost ~110 us of interpreter time).
+                # Same results as the single launch (one RNG counter for all chunks).
+                e.step_host(a, self._act_h, self._act_d, o["obs"], o["rew"], o["flags"], self._edges, len(self._chunks))
         shp = (self.num_envs, self.agents, 1)
         obs = o["obs"].numpy().reshape(self.num_envs, self.agents, e.num_observation)
-        flags = o["flags"].numpy().view(np.bool_)
-        return (obs, o["rew"].numpy().reshape(shp), flags[0].reshape(shp), flags[1].reshape(shp),
-                flags[2].reshape(shp), {})
-
-    def _step_pipelined(self, a):
-        """Aircraft are independent, so the step is pipelined chunk by chunk over three in-order streams -- upload, kernels,
-        download: while chunk c's observations travel to the host (the 88 B/aircraft D2H is what bounds this boundary),
-        chunk c+1 runs and chunk c+2's actions are staged and uploaded.  The whole pipeline is ONE native call
-        (np_env_step_host): issuing a chunk from Python cost ~110 us of interpreter time, which delayed the first download.
-        Same results as the single launch (one RNG counter for all chunks)."""
-        e = self.gpu_vec_env
-        o = self._out[self._flip]
-        self._flip ^= 1
-        if a.shape[1] != self._A or not a.flags.c_contiguous:
-            a = np.ascontiguousarray(a[:, :self._A])
-        e.step_host(a, self._act_h, self._act_d, o["obs"], o["rew"], o["flags"], self._edges, len(self._chunks))
-        return o
+        flags = o["flags"].numpy().view(np.bool_)[:, :e.n]
+        rew = o["rew"].numpy().reshape(shp)
+        if self._copy:
+            obs, rew, flags = obs.copy(), rew.copy(), flags.copy()
+        return (obs, rew, flags[0].reshape(shp), flags[1].reshape(shp), flags[2].reshape(shp), {})
 
     def reset(self):
         e = self.gpu_vec_env
@@ -131,7 +167,8 @@ class GPUVecEnv:
             return e.reset().view(self.num_envs, self.agents, e.num_observation)
         e.reset()
         o = self._download(with_rest=False)
-        return o["obs"].numpy().reshape(self.num_envs, self.agents, e.num_observation)
+        obs = o["obs"].numpy().reshape(self.num_envs, self.agents, e.num_observation)
+        return obs.copy() if self._copy else obs
 
     def step_async(self, actions):
         pass

@@ -36,10 +36,12 @@ class F16Model(BaseModel):
         self._xdot = torch.zeros((17, self.ld), device=device)  # rows 12..16 stay 0 (F16_dynamics.py:60)
         self.s = self._s.t()[:n]
         self.u = self._u.t()[:n]
-        # the reference keeps the previous state/control in recent_s / recent_u (aliases, F16_model.py:58,63);
-        # nothing on the control-task path reads them, so they are not materialised per step here.
-        self.recent_s = self.s
-        self.recent_u = self.u
+        # recent_s / recent_u: the state / controls the last update() started from (F16_model.py:58,63).  The fused env step
+        # does not spend HBM traffic on them (nothing on the control-task path reads them); the stand-alone update() does.
+        self._recent_s = torch.zeros((12, self.ld), device=device)
+        self._recent_u = torch.zeros((5, self.ld), device=device)
+        self.recent_s = self._recent_s.t()[:n]
+        self.recent_u = self._recent_u.t()[:n]
 
     def _load_aero(self, device):
         from ...aero import get_aero
@@ -49,8 +51,23 @@ class F16Model(BaseModel):
     def reset(self, env):
         env.reset()
 
+    def _action_ptr(self, action):
+        if not torch.is_tensor(action):
+            action = torch.as_tensor(action, dtype=torch.float32, device=self.device)
+        if action.dim() != 2 or action.shape[0] != self.n or action.shape[1] < 4:
+            raise ValueError(f"action must have shape [{self.n}, >=4], got {tuple(action.shape)}")
+        if action.shape[1] != 4 or action.dtype != torch.float32 or not action.is_contiguous() or action.device != self._s.device:
+            action = action[:, :4].to(device=self._s.device, dtype=torch.float32).contiguous()
+        return action
+
     def update(self, action):
-        raise NotImplementedError("F16Model.update is fused into env.step() (one kernel launch per step)")
+        """F16Model.update (F16_model.py:51-67): clamp, control low-pass, one explicit Euler step of nlplant -- one native
+        launch (np_f16_update), bit-identical to what env.step() does to the same (s, u, action)."""
+        a = self._action_ptr(action)
+        st = nv.lib().np_f16_update(self.aero.handle, self._s.data_ptr(), self._u.data_ptr(), self._recent_s.data_ptr(),
+                                    self._recent_u.data_ptr(), a.data_ptr(), self.n, self.ld, float(self.dt),
+                                    torch.cuda.current_stream(self._s.device).cuda_stream)
+        nv.check(st, "np_f16_update")
 
     def get_extended_state(self):
         """xdot of F16Dynamics.nlplant at the current (s, u): [n,17] view, columns 12..16 zero."""
@@ -167,6 +184,13 @@ class F16TablesModel(F16Model):
     def _load_aero(self, device):
         from ...aero_tables import get_tables
         return get_tables(device)
+
+    def update(self, action):
+        a = self._action_ptr(action)
+        st = nv.lib().np_f16_table_update(self.aero.handle, self._s.data_ptr(), self._u.data_ptr(), self._recent_s.data_ptr(),
+                                          self._recent_u.data_ptr(), a.data_ptr(), self.n, self.ld, float(self.dt),
+                                          torch.cuda.current_stream(self._s.device).cuda_stream)
+        nv.check(st, "np_f16_table_update")
 
     def get_extended_state(self):
         st = nv.lib().np_f16_table_nlplant(self.aero.handle, self._s.data_ptr(), self._u.data_ptr(), self._xdot.data_ptr(),

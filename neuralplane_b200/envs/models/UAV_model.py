@@ -37,13 +37,26 @@ class UAVModel(BaseModel):
         self._xdot = torch.zeros((12, self.ld), device=device)
         self.s = self._s.t()[:n]
         self.u = self._u.t()[:n, :3]
-        self.recent_s = self.s
+        self._recent_s = torch.zeros((12, self.ld), device=device)
+        self.recent_s = self._recent_s.t()[:n]   # the state the last update() started from (UAV_model.py:56)
 
     def reset(self, env):
         env.reset()
 
     def update(self, action):
-        raise NotImplementedError("UAVModel.update is fused into env.step() (one kernel launch per step)")
+        """UAVModel.update (UAV_model.py:51-62): clamp, force low-pass, one explicit Euler step -- one native launch
+        (np_uav_update), bit-identical to what env.step() does to the same (s, u, action)."""
+        if not torch.is_tensor(action):
+            action = torch.as_tensor(action, dtype=torch.float32, device=self.device)
+        if action.dim() != 2 or action.shape[0] != self.n or action.shape[1] < 3:
+            raise ValueError(f"action must have shape [{self.n}, >=3], got {tuple(action.shape)}")
+        if action.shape[1] != 4 or action.dtype != torch.float32 or not action.is_contiguous() or action.device != self._s.device:
+            a4 = torch.zeros((self.n, 4), dtype=torch.float32, device=self._s.device)
+            a4[:, :min(4, action.shape[1])] = action[:, :4].to(device=self._s.device, dtype=torch.float32)
+            action = a4
+        st = nv.lib().np_uav_update(self._s.data_ptr(), self._u.data_ptr(), self._recent_s.data_ptr(), action.data_ptr(), self.n,
+                                    self.ld, float(self.dt), torch.cuda.current_stream(self._s.device).cuda_stream)
+        nv.check(st, "np_uav_update")
 
     def get_extended_state(self):
         """UAVDynamics.nlplant at the current (s, u): [n,12] view (the reference returns 15 columns, the last 3 zero)."""

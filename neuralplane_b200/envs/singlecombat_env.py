@@ -33,6 +33,9 @@ class CombatTask(BaseTask):
 class SingleCombatEnv(BaseEnv):
     native_obs_dim = nv.NUM_OBS_COMBAT
     n_substeps = 5                      # singlecombat_env.py:244
+    # the device counters' cause bits 5 / 6 carry Crash-or-ego-Shutdown / enemy-Shutdown here (crash.py:29-42, shutdown.py:30-40)
+    COUNTER_NAMES = ("overload", "low_altitude", "high_speed", "low_speed", "extreme_state", "crash_or_shutdown",
+                     "enemy_shutdown", "resets")
 
     def __init__(self, num_envs=1, config='selfplay', random_seed=None, device="cuda:0", **kw):
         super().__init__(num_envs, config, 'F16', random_seed, device, **kw)

@@ -127,6 +127,10 @@ class DeviceRolloutBuffer:
         """The env's next reset() writes obs[step] and every step() writes obs[step + 1] / rewards[step] of this buffer."""
         if env.n != self.n_rollout_threads * self.num_agents or env.num_observation != int(np.prod(self.obs.shape[3:])):
             raise ValueError("the env's population / observation width does not match this buffer")
+        if env.n % 2:
+            # rewards[t] starts t * n * 4 bytes into the buffer: with an odd population every odd t is only 4-byte aligned,
+            # and the step kernel stores rewards as 8-byte aircraft pairs (np_env_rebind_outputs would refuse mid-rollout)
+            raise ValueError("attach() needs an even aircraft population (the step kernel writes reward pairs in place)")
         self._env = env
         self._scratch_reward = torch.zeros(env.n, dtype=torch.float32, device=self.device)
         self._retarget(for_reset=True)

@@ -438,21 +438,54 @@ def test_step_is_cuda_graph_capturable_and_stream_ordered(dev):
     assert e_graph.termination_counters() == e_eager.termination_counters()
 
 
-@pytest.mark.parametrize("model,task", [("F16", "heading"), ("UAV", "control")])
+@pytest.mark.parametrize("model,task", [("F16", "heading"), ("F16_tables", "control"), ("UAV", "control")])
 def test_pipelined_numpy_boundary_equals_single_launch(dev, model, task):
-    """GPUVecEnv pipelines large populations in aircraft chunks on side streams (np_env_step_range); results must be
-    bit-identical to the single-launch path, odd population and in-kernel Philox resets / noise included."""
+    """The three host boundaries of GPUVecEnv -- single launch + copy, the chunk pipeline (np_env_step_host) and, for the F16
+    plug-in, the kernel writing straight into mapped pinned memory (np_env_step_mapped, zero-copy action reads or an
+    explicit upload) -- must agree bit for bit, odd population and in-kernel Philox resets / noise included."""
     from neuralplane_b200 import ControlEnv, GPUVecEnv
     ne = 20_001
     mk = lambda: ControlEnv(num_envs=ne, config=task, model=model, random_seed=9, device="cuda:0")
-    v1, v4 = GPUVecEnv([mk], pipeline_chunks=1), GPUVecEnv([mk], pipeline_chunks=4)
+    v1, v4 = GPUVecEnv([mk], boundary="copy"), GPUVecEnv([mk], boundary="pipelined", pipeline_chunks=4)
     assert v1._chunks is None and len(v4._chunks) == 4 and v4._chunks[0][0] == 0 and v4._chunks[-1][1] == ne
     assert all(c[0] % 256 == 0 and c[1] > c[0] for c in v4._chunks) and all(a[1] == b[0] for a, b in zip(v4._chunks, v4._chunks[1:]))
-    assert np.array_equal(v1.reset(), v4.reset())
+    others = [v4]
+    if model != "UAV":
+        vm, vu = GPUVecEnv([mk]), GPUVecEnv([mk], boundary="mapped")
+        assert vm.boundary == "mapped"           # the default for the F16 plug-in
+        vu._zero_copy_actions = False            # explicit H2D copy of the actions before the launch
+        others += [vm, vu]
+    else:
+        with pytest.raises(ValueError):
+            GPUVecEnv([mk], boundary="mapped")
+    o1 = v1.reset()
+    for v in others:
+        assert np.array_equal(o1, v.reset())
+    kept = None
     for k in range(1, 60):
         a = tapes.action_tape(9, k, ne, 1.0).reshape(ne, 1, 4)
-        r1, r4 = v1.step(a), v4.step(a)
-        for x, y in zip(r1[:5], r4[:5]):
-            assert np.array_equal(x, y), k
-    assert v1.gpu_vec_env.termination_counters() == v4.gpu_vec_env.termination_counters()
+        r1 = v1.step(a)
+        for v in others:
+            for x, y in zip(r1[:5], v.step(a)[:5]):
+                assert x.shape == y.shape and np.array_equal(x, y), (k, v.boundary)
+        if k == 10:                              # small populations return fresh arrays, like the reference's _t2n
+            kept = (r1[0], r1[0].copy(), r1[2], r1[2].copy())
+    assert np.array_equal(kept[0], kept[1]) and np.array_equal(kept[2], kept[3])
+    for v in others:
+        assert v1.gpu_vec_env.termination_counters() == v.gpu_vec_env.termination_counters()
     assert v1.gpu_vec_env.termination_counters()["resets"] > ne
+
+
+def test_numpy_boundary_ring_lifetime(dev):
+    """copy=False hands out views of a ring of pinned buffers: a result stays intact for ring - 1 further steps."""
+    from neuralplane_b200 import ControlEnv, GPUVecEnv
+    ne = 4096
+    v = GPUVecEnv([lambda: ControlEnv(num_envs=ne, config="heading", model="F16", random_seed=3, device="cuda:0")], copy=False, ring=3)
+    v.reset()
+    acts = [tapes.action_tape(3, k, ne, 1.0).reshape(ne, 1, 4) for k in range(1, 5)]
+    first = v.step(acts[0])[0]
+    snap = first.copy()
+    v.step(acts[1]); v.step(acts[2])
+    assert np.array_equal(first, snap)           # two more steps: still the ring slot of step 1
+    v.step(acts[3])
+    assert not np.array_equal(first, snap)       # the fourth step reuses it

@@ -1,0 +1,136 @@
+"""GPU tests of the plug-in surface added in ABI v7: the stand-alone model.update() (np_f16_update / np_f16_table_update /
+np_uav_update) against what the fused env step does to the same (s, u, action) and against the oracle; the device guard
+(an env on cuda:1 while the current device is 0); the block-size choice for strong-scaling shards.
+Bit-exact unless stated."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import tapes
+
+pytestmark = pytest.mark.gpu
+
+
+def _cuda(x, dev="cuda:0"):
+    return torch.from_numpy(np.ascontiguousarray(x)).to(dev)
+
+
+@pytest.mark.parametrize("model", ["F16", "F16_tables", "UAV"])
+def test_model_update_equals_fused_step(model):
+    """F16Model.update / UAVModel.update (F16_model.py:51-67, UAV_model.py:51-62; caller planning_env.py:161): the state
+    and controls after model.update(a) are bit-identical to those after env.step(a) from the same start (no aircraft
+    resets inside the compared step), and recent_s / recent_u hold what the update started from."""
+    from neuralplane_b200 import ControlEnv
+    n = 1001                                        # odd: the tail pair path
+    mk = lambda: ControlEnv(num_envs=n, config="control", model=model, random_seed=4, device="cuda:0")
+    e_step, e_upd = mk(), mk()
+    d0 = _cuda(tapes.reset_draw_tape(4, 0, n))
+    e_step.reset(reset_draws=d0)
+    e_upd.reset(reset_draws=d0)
+    assert torch.equal(e_step.model.s, e_upd.model.s)
+    for k in range(1, 6):
+        a = _cuda(tapes.action_tape(4, k, n, 0.3))
+        s_before, u_before = e_upd.model.s.clone(), e_upd.model.u.clone()
+        live = ~(e_step.is_done | e_step.bad_done | e_step.exceed_time_limit)   # aircraft the step will not re-initialise
+        e_step.step(a, reset_draws=_cuda(tapes.reset_draw_tape(4, k, n)))
+        e_upd.model.update(a)
+        assert torch.equal(e_upd.model.recent_s, s_before)
+        if model != "UAV":
+            assert torch.equal(e_upd.model.recent_u[:, :4], u_before[:, :4])
+        assert live.float().mean() > 0.9
+        assert torch.equal(e_upd.model.s[live], e_step.model.s[live]), k
+        assert torch.equal(e_upd.model.u[live], e_step.model.u[live]), k
+        # keep the two populations identical for the next round (the env may have flagged aircraft for reset)
+        e_upd.model.s.copy_(e_step.model.s)
+        e_upd.model.u.copy_(e_step.model.u)
+
+
+def test_f16_update_vs_oracle():
+    """np_f16_update against the CPU oracle's F16 update (oracle/f16_oracle.py, pinned to the reference): 1e-6 relative on
+    the state after one Euler step (fp32; the kernel's libm differs from torch's by an ulp)."""
+    from neuralplane_b200 import ControlEnv
+    from oracle.f16_oracle import F16EnvOracle, euler_step, lowpass_controls
+    n = 512
+    env = ControlEnv(num_envs=n, config="heading", model="F16", random_seed=0, device="cuda:0")
+    orc = F16EnvOracle(n, "heading")
+    d0 = tapes.reset_draw_tape(7, 0, n)
+    env.reset(reset_draws=_cuda(d0))
+    orc.reset(torch.from_numpy(d0))
+    for k in range(1, 4):
+        a = tapes.action_tape(7, k, n, 0.5)
+        env.model.update(_cuda(a))
+        orc.u = lowpass_controls(orc.u, torch.from_numpy(a))          # F16_model.py:51-63
+        orc.s = euler_step(orc.aero, orc.s, orc.u, orc.cfg["dt"])     # :64-67
+    s, so = env.model.s.cpu().numpy().astype(np.float64), orc.s.numpy().astype(np.float64)
+    floor = np.array([10, 10, 100, 0.01, 0.01, 0.01, 10, 0.01, 0.01, 0.01, 0.01, 0.01])
+    assert (np.abs(s - so) / (np.abs(so) + floor)).max() < 2e-6
+    assert np.allclose(env.model.u.cpu().numpy()[:, :4], orc.u.numpy()[:, :4], rtol=1e-6, atol=1e-6)
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
+def test_env_on_another_device_than_current():
+    """an env created with device='cuda:1' must work while the process's current device is 0 (train and eval envs
+    on different GPUs in one process) -- every native entry point switches to the env's device and back."""
+    from neuralplane_b200 import ControlEnv, GPUVecEnv, PlanningEnv
+    torch.cuda.set_device(0)
+    n = 3000
+    e0 = ControlEnv(num_envs=n, config="heading", model="F16", random_seed=5, device="cuda:0")
+    e1 = ControlEnv(num_envs=n, config="heading", model="F16", random_seed=5, device="cuda:1")
+    assert torch.cuda.current_device() == 0
+    o0, o1 = e0.reset(), e1.reset()
+    assert o1.device.index == 1 and torch.equal(o0.cpu(), o1.cpu())
+    for k in range(1, 8):
+        a = tapes.action_tape(5, k, n, 1.0)
+        r0, r1 = e0.step(_cuda(a)), e1.step(_cuda(a, "cuda:1"))
+        assert torch.cuda.current_device() == 0
+        assert torch.equal(r0[0].cpu(), r1[0].cpu()) and torch.equal(r0[3].cpu(), r1[3].cpu())
+    assert e0.termination_counters() == e1.termination_counters()
+    assert torch.equal(e0.model.get_extended_state().cpu(), e1.model.get_extended_state().cpu())
+    v1 = GPUVecEnv([lambda: ControlEnv(num_envs=n, config="heading", model="F16", random_seed=5, device="cuda:1")])
+    v0 = GPUVecEnv([lambda: ControlEnv(num_envs=n, config="heading", model="F16", random_seed=5, device="cuda:0")])
+    assert np.array_equal(v0.reset(), v1.reset())
+    a = tapes.action_tape(5, 1, n, 1.0).reshape(n, 1, 4)
+    assert np.array_equal(v0.step(a)[0], v1.step(a)[0])
+    p1 = PlanningEnv(num_envs=256, config="tracking", random_seed=1, device="cuda:1", n_substeps=3)
+    p1.reset()
+    p1.step(torch.zeros((256, 3), device="cuda:1"))
+    assert torch.isfinite(p1.last_obs).all() and torch.cuda.current_device() == 0
+
+
+def test_block_choice_is_bit_identical_and_saves_a_wave():
+    """A strong-scaling shard of 125 000 aircraft is 1.1 waves of 148 x 384 pairs: pick_block() takes 512-thread CTAs (one
+    wave) there and 384 at 10^6.  The block size must not change a single bit of any output."""
+    import os
+    from neuralplane_b200 import ControlEnv
+    n = 125_000
+    env = ControlEnv(num_envs=n, config="heading", model="F16", random_seed=2, device="cuda:0")
+    os.environ["NPLANE_BLOCK"] = "384"
+    try:
+        ref = ControlEnv(num_envs=n, config="heading", model="F16", random_seed=2, device="cuda:0")
+    finally:
+        del os.environ["NPLANE_BLOCK"]
+    env.reset(); ref.reset()
+    for k in range(1, 6):
+        a = _cuda(tapes.action_tape(2, k, n, 1.0))
+        r, q = env.step(a), ref.step(a)
+        for x, y in zip(r[:5], q[:5]):
+            assert torch.equal(x, y), k
+    assert env.launch_info()["block"] == 512 and ref.launch_info()["block"] == 384
+    assert torch.equal(env.model.s, ref.model.s) and env.termination_counters() == ref.termination_counters()
+    big = ControlEnv(num_envs=1_000_000, config="heading", model="F16", random_seed=2, device="cuda:0")
+    big.reset()
+    big.step(torch.zeros((1_000_000, 4), device="cuda:0"))
+    assert big.launch_info()["block"] == 384
+
+
+def test_rollout_attach_rejects_odd_population():
+    """rewards[t] of an odd population is only 4-byte aligned for odd t; attach() must say so up front."""
+    import types
+    from neuralplane_b200 import ControlEnv
+    from neuralplane_b200.rollout import DeviceRolloutBuffer
+    env = ControlEnv(num_envs=33, config="heading", model="F16", random_seed=0, device="cuda:0")
+    args = types.SimpleNamespace(buffer_size=8, n_rollout_threads=33, gamma=0.99, use_proper_time_limits=False, use_gae=True,
+                                 gae_lambda=0.95, recurrent_hidden_size=8, recurrent_hidden_layers=1)
+    buf = DeviceRolloutBuffer(args, 1, env.observation_space, env.action_space, "cuda:0")
+    with pytest.raises(ValueError, match="even"):
+        buf.attach(env)
