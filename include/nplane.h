@@ -81,6 +81,8 @@ typedef struct np_env_cfg {
   int32_t max_steps;    /* Timeout (timeout.py:16,29); combat only (selfplay.yaml max_steps: 2000) */
   /* combat (envs/configs/selfplay.yaml; singlecombat_env.py:33-44, crash.py:16) */
   float distance_limit, target_dist, max_heading, min_heading, max_npos, min_npos, max_epos, min_epos;
+  int32_t index_stride; /* global aircraft index = index_base + index_stride * local index (0 = 1).  2 in the role-sharded
+                           combat layout, where a rank holds every second aircraft (all egos or all opponents) */
 } np_env_cfg;
 
 /* Device buffers the env works on (replace the tensors of F16_model.py:19-22, heading_task.py:26-28,
@@ -198,6 +200,24 @@ int np_combat_relgeo(const float* records_dev, const int32_t* ego_idx_dev, const
  * np_env_combat_records with a cross-device barrier.  Same out[m][8] as np_combat_relgeo on the all-gathered array. */
 int np_combat_relgeo_peers(const float* const* slabs_dev, int world, int n_local, const int32_t* ego_idx_dev, const int32_t* enm_idx_dev,
                            float* out_dev, int m, void* stream);
+/* ROLE-sharded combat step (BASELINE configs[4]: "NCCL all-gather for opponent relative geometry"): a rank holds
+ * ONE aircraft of every env -- all egos (role 0) or all opponents (role 1); local aircraft i is global aircraft
+ * index_base + 2 i (np_env_cfg.index_stride = 2).  One env step = np_env_combat_role_local (env-level reset from the
+ * pair-reset flags, n_sub <= 5 FDM sub-steps under the attitude controller, per-aircraft terminations; publishes a 28-float
+ * record per aircraft into records_dev [n][28]: final position, inertial velocity, body velocity, blood, own termination
+ * bits, roll / pitch trigonometry, and the position after every sub-step) -> a cross-device barrier (or an all-gather of the
+ * slabs) -> np_env_combat_role_pair (pulls the partner's record from partner_records_dev -- the PEER rank's slab mapped over
+ * NVLink when partner_is_peer = 1, read by the kernel's own loads; or a slice of a gathered array -- and produces Crash at
+ * every sub-step, Shutdown, the 15-D observation, reward, blood, the final flags and the next step's env-level reset flags:
+ * singlecombat_env.py:64-181,207-238,263-271, crash.py:29-42, shutdown.py:30-40).  Every output is bit-identical to
+ * np_env_combat_step on the pair-sharded layout.  n_sub = 0: SingleCombatEnv.reset. */
+int np_env_combat_role_local(np_env* env, const float* action_dev, int n_sub, const float* draws_dev, float* records_dev, void* stream);
+int np_env_combat_role_pair(np_env* env, const float* own_records_dev, const float* partner_records_dev, int partner_is_peer, int role,
+                            int n_sub, void* stream);
+#define NP_COMBAT_RECORD_FLOATS 28
+/* Byte offset, inside the workspace, of the [ld] u8 env-level reset flags of the role-sharded layout (1 = re-initialise). */
+size_t np_env_pair_reset_offset_bytes(const np_env_cfg* cfg);
+
 /* Byte offset, inside the workspace, of the [ld] f32 blood row (singlecombat_env.py:45). */
 size_t np_env_blood_offset_bytes(const np_env_cfg* cfg);
 

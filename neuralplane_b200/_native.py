@@ -22,6 +22,7 @@ TASK_IDS = {"heading": 0, "control": 1, "tracking": 2}
 MODEL_IDS = {"F16": 0, "UAV": 1}
 NUM_NETS, NUM_OBS, NUM_DRAWS, NUM_COUNTERS = 43, 22, 5, 8
 NUM_OBS_COMBAT = 15
+COMBAT_RECORD_FLOATS = 28
 COUNTER_NAMES = ("overload", "low_altitude", "high_speed", "low_speed", "extreme_state", "unreach", "reached", "resets")
 
 
@@ -45,7 +46,7 @@ class EnvCfg(C.Structure):
                 ("max_vt", C.c_float), ("min_vt", C.c_float), ("model", C.c_int32), ("max_steps", C.c_int32),
                 ("distance_limit", C.c_float), ("target_dist", C.c_float), ("max_heading", C.c_float),
                 ("min_heading", C.c_float), ("max_npos", C.c_float), ("min_npos", C.c_float), ("max_epos", C.c_float),
-                ("min_epos", C.c_float)]
+                ("min_epos", C.c_float), ("index_stride", C.c_int32)]
 
 
 class Buffers(C.Structure):
@@ -79,6 +80,9 @@ SYMBOLS = {
     "np_env_plan_step": (C.c_int, [_P, _P, C.c_int, _P, _P, _P]),
     "np_env_combat_step": (C.c_int, [_P, _P, C.c_int, _P, _P]),
     "np_env_combat_records": (C.c_int, [_P, _P, _P]),
+    "np_env_combat_role_local": (C.c_int, [_P, _P, C.c_int, _P, _P, _P]),
+    "np_env_combat_role_pair": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, _P]),
+    "np_env_pair_reset_offset_bytes": (C.c_size_t, [C.POINTER(EnvCfg)]),
     "np_combat_relgeo": (C.c_int, [_P, _P, _P, _P, C.c_int, _P]),
     "np_combat_relgeo_peers": (C.c_int, [_P, C.c_int, C.c_int, _P, _P, _P, C.c_int, _P]),
     "np_env_blood_offset_bytes": (C.c_size_t, [C.POINTER(EnvCfg)]),

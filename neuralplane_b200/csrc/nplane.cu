@@ -46,6 +46,8 @@ static int fail(int code, const std::string& msg) {
 // handles
 // ------------------------------------------------------------------------------------------------
 constexpr int kCacheRows = kNumAB2 + 2;  // 16 (alpha,beta)-MLP outputs + alpha key + beta key
+// workspace rows of [ld] f32: coefficient cache | controller state (kPidRows, ctrl_device.cuh: 12) | blood | pair_reset (u8, one row)
+constexpr int kWorkspaceRows = kCacheRows + 12 + 2;
 
 struct np_aero {
   uint32_t* image_dev = nullptr;
@@ -91,6 +93,7 @@ struct np_env {
   uint32_t step_index = 0;
   bool pid_started = false;  // the fused PID controller has run at least once (PID.reset, pid.py:13)
   int device = 0;            // the device the env was created on; every entry point switches to it
+  int obs_stg = 0;           // NPLANE_OBS_STORE=stg: per-lane stores of the staged observation tile instead of the TMA bulk store
   int block = 0;             // 0: chosen per launch (pick_block); else forced by NPLANE_BLOCK
   int tab_block = 384, grid = 0, smem = 0, num_sms = 0, last_block = 384;
   // np_env_step_host: one in-order stream per engine (upload, kernels, download) and the events chaining them
@@ -121,8 +124,13 @@ struct StepParams {
   int pair_begin, pair_end;      // aircraft pairs [pair_begin, pair_end) this launch works on (whole population by default)
   const float* draws;            // [n][5] or null
   const float* noise;            // [n][22] or null
+  int obs_stg;                   // 1: the staged observation tile leaves through per-lane 16-byte stores instead of a TMA bulk store
   uint8_t* flags_mirror;         // null, or a second [3][flags_mirror_ld] copy of the new flags (mapped host memory)
   int flags_mirror_ld;
+  // role-sharded combat (egos and opponents on different ranks): this rank's two lanes are two DIFFERENT envs' aircraft
+  float* records;                // null (pair-sharded), or this rank's record slab [n][kCombatRecFloats]
+  uint8_t* pair_reset;           // [ld] env-level reset flag of each local aircraft's env (own | partner flags of the last step)
+  int index_stride;              // global aircraft index = index_base + index_stride * local index (RNG streams)
   uint32_t step_index;
 };
 
@@ -167,6 +175,15 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
                : "memory");
 }
 
+__device__ __forceinline__ void bulk_s2g(void* dst_gmem, const void* src_smem, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem), "r"(smem_u32(src_smem)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
 // Stage the aero image into shared memory once per CTA: one elected thread issues TMA bulk copies that
 // complete on an mbarrier; everyone waits on it.
 __device__ __forceinline__ void stage_aero(void* blob_s, const void* aero_g, uint32_t bytes, uint64_t* bar) {
@@ -195,7 +212,7 @@ __device__ __forceinline__ Draws reset_draws(const StepParams& p, int i) {
 #pragma unroll
     for (int j = 0; j < NP_NUM_DRAWS; ++j) r.d[j] = p.draws[(size_t)i * NP_NUM_DRAWS + j];
   } else {
-    const uint64_t gi = p.cfg.index_base + (uint64_t)i;
+    const uint64_t gi = p.cfg.index_base + (uint64_t)p.index_stride * (uint64_t)i;
     const uint2 key = make_uint2((uint32_t)p.cfg.seed, (uint32_t)(p.cfg.seed >> 32));
     const uint4 a = philox4x32_10(make_uint4((uint32_t)gi, (uint32_t)(gi >> 32), p.step_index, 0x5EED0000u), key);
     const uint4 b = philox4x32_10(make_uint4((uint32_t)gi, (uint32_t)(gi >> 32), p.step_index, 0x5EED0001u), key);
@@ -264,7 +281,7 @@ __device__ __forceinline__ void add_obs_noise(const StepParams& p, int i, float*
 #pragma unroll
     for (int j = 0; j < NP_NUM_OBS; ++j) o[j] = o[j] + p.noise[(size_t)i * NP_NUM_OBS + j] * sc;
   } else if (sc != 0.0f) {
-    const uint64_t gi = p.cfg.index_base + (uint64_t)i;
+    const uint64_t gi = p.cfg.index_base + (uint64_t)p.index_stride * (uint64_t)i;
     const uint2 key = make_uint2((uint32_t)p.cfg.seed, (uint32_t)(p.cfg.seed >> 32));
 #pragma unroll
     for (int q = 0; q < 3; ++q) {  // 3 x 4 words -> 12 pairs of normals, 22 used
@@ -342,49 +359,76 @@ __device__ __forceinline__ float distance_fn(float Rkm) {  // utils.py:245-249
   return (Rkm <= 1.0f ? 1.0f : 0.0f) + (3.0f - Rkm) / 2.0f * (((Rkm > 1.0f) & (Rkm <= 3.0f)) ? 1.0f : 0.0f);
 }
 
+// What the pairwise terms need of ONE aircraft at its final state: position, inertial velocity es = xdot[0:3] of nlplant
+// (F16_dynamics.py:104,129-135), body-axis velocity (F16Model.get_velocity), roll / pitch trigonometry and vt.  In the
+// pair-sharded layout both records are built in the thread that owns the pair; in the role-sharded layout each rank builds
+// its own and pulls the partner's from the peer's record slab -- the same code either way, so the outputs agree bit for bit.
+struct CombatRec {
+  float pos[3], es[3], vel[3], sphi, cphi, st, ct, vt;
+};
+__device__ __forceinline__ CombatRec combat_rec(const float* s) {
+  CombatRec r;
+  const Trig t = make_trig(s);
+  const float vt = s[6];
+  r.pos[0] = s[0]; r.pos[1] = s[1]; r.pos[2] = s[2];
+  r.vel[0] = vt * t.cb * t.ca;
+  r.vel[1] = vt * t.sb;
+  r.vel[2] = vt * t.cb * t.sa;
+  const float vtc = vt <= 0.01f ? 0.01f : vt;
+  const BodyVel b = body_vel(vtc, t);
+  r.es[0] = b.U * (t.ct * t.cpsi) + b.V * (t.sphi * t.cpsi * t.st - t.cphi * t.spsi) + b.W * (t.cphi * t.st * t.cpsi + t.sphi * t.spsi);
+  r.es[1] = b.U * (t.ct * t.spsi) + b.V * (t.sphi * t.spsi * t.st + t.cphi * t.cpsi) + b.W * (t.cphi * t.st * t.spsi - t.sphi * t.cpsi);
+  r.es[2] = b.U * t.st - b.V * (t.sphi * t.ct) - b.W * (t.cphi * t.ct);
+  r.sphi = t.sphi; r.cphi = t.cphi; r.st = t.st; r.ct = t.ct; r.vt = vt;
+  return r;
+}
+// pairwise geometry of (ego, enemy): get_AO_TA_R / get2d_AO_TA_R + the side flag (singlecombat_env.py:96-121,142-150)
+struct CombatGeo {
+  float AO, TA, R, AO2, TA2, R2, side, Rkm;
+};
+__device__ __forceinline__ CombatGeo combat_geo(const CombatRec& e, const CombatRec& m) {
+  CombatGeo g;
+  const float dp[3] = {m.pos[0] - e.pos[0], m.pos[1] - e.pos[1], m.pos[2] - e.pos[2]};
+  ao_ta_r<2>(dp, e.es, m.es, g.AO2, g.TA2, g.R2);
+  ao_ta_r<3>(dp, e.es, m.es, g.AO, g.TA, g.R);
+  const float cz = e.es[0] * dp[1] - e.es[1] * dp[0];
+  g.side = (cz > 0.0f ? 1.0f : 0.0f) - (cz < 0.0f ? 1.0f : 0.0f);
+  g.Rkm = g.R * 0.3048f / DC(1000.0f);
+  return g;
+}
+// 15-D observation row of one aircraft (`own`) given its partner and the pair geometry; q = 0: ego, 1: enemy (mirrored)
+__device__ __forceinline__ void combat_obs_row(const CombatRec& own, const CombatRec& other, const CombatGeo& g, int q, float* o) {
+  o[0] = own.pos[2] * 0.3048f / DC(5000.0f);
+  o[1] = own.sphi; o[2] = own.cphi; o[3] = own.st; o[4] = own.ct;
+  o[5] = own.vel[0] * 0.3048f / DC(340.0f); o[6] = own.vel[1] * 0.3048f / DC(340.0f); o[7] = own.vel[2] * 0.3048f / DC(340.0f);
+  o[8] = own.vt * 0.3048f / DC(340.0f);
+  o[9] = (other.vel[0] - own.vel[0]) * 0.3048f / DC(340.0f);
+  o[10] = (other.pos[2] - own.pos[2]) * 0.3048f / DC(1000.0f);
+  o[11] = q == 0 ? g.AO2 : kPi - g.TA2;
+  o[12] = q == 0 ? g.TA2 : kPi - g.AO2;
+  o[13] = g.R2 * 0.3048f / 10000.0f;
+  o[14] = q == 0 ? g.side : -g.side;
+}
+__device__ __forceinline__ float combat_reward(const CombatGeo& g, int q) {   // singlecombat_env.py:140-181
+  const float rr = range_reward_v3(g.Rkm);
+  return q == 0 ? 0.01f * (orientation_reward_v2(g.AO, g.TA) * rr) : 0.01f * (orientation_reward_v2(kPi - g.TA, kPi - g.AO) * rr);
+}
+// blood model (singlecombat_env.py:263-271): what aircraft q loses in this env step
+__device__ __forceinline__ float combat_damage(const CombatGeo& g, int q) {
+  const float df = distance_fn(g.Rkm);
+  return q == 0 ? orientation_fn(kPi - g.TA) * df : orientation_fn(g.AO) * df;
+}
+
 // obs (singlecombat_env.py:64-138), reward (:140-181) and the blood model (:263-271) of one pair at its final state.
 __device__ __forceinline__ void combat_outputs(const StepParams& p, float (&s)[2][12], float (&blood)[2], float (&rew)[2],
                                                int pr, const bool (&act)[2], bool stepped) {
-  float vel[2][3], es[2][3];
-  Trig g[2];
+  const CombatRec rec[2] = {combat_rec(s[0]), combat_rec(s[1])};
+  const CombatGeo g = combat_geo(rec[0], rec[1]);
 #pragma unroll
   for (int q = 0; q < 2; ++q) {
-    g[q] = make_trig(s[q]);
-    const float vt = s[q][6];
-    vel[q][0] = vt * g[q].cb * g[q].ca;                      // F16Model.get_velocity (body axes)
-    vel[q][1] = vt * g[q].sb;
-    vel[q][2] = vt * g[q].cb * g[q].sa;
-    const float vtc = vt <= 0.01f ? 0.01f : vt;              // es[:, :3] = xdot[0:3] of nlplant (F16_dynamics.py:104,129-135)
-    const BodyVel b = body_vel(vtc, g[q]);
-    const Trig& t = g[q];
-    es[q][0] = b.U * (t.ct * t.cpsi) + b.V * (t.sphi * t.cpsi * t.st - t.cphi * t.spsi) + b.W * (t.cphi * t.st * t.cpsi + t.sphi * t.spsi);
-    es[q][1] = b.U * (t.ct * t.spsi) + b.V * (t.sphi * t.spsi * t.st + t.cphi * t.cpsi) + b.W * (t.cphi * t.st * t.spsi - t.sphi * t.cpsi);
-    es[q][2] = b.U * t.st - b.V * (t.sphi * t.ct) - b.W * (t.cphi * t.ct);
-  }
-  const float dp[3] = {s[1][0] - s[0][0], s[1][1] - s[0][1], s[1][2] - s[0][2]};
-  float AO2, TA2, R2, AO, TA, R;
-  ao_ta_r<2>(dp, es[0], es[1], AO2, TA2, R2);
-  ao_ta_r<3>(dp, es[0], es[1], AO, TA, R);
-  const float cz = es[0][0] * dp[1] - es[0][1] * dp[0];
-  const float side = (cz > 0.0f ? 1.0f : 0.0f) - (cz < 0.0f ? 1.0f : 0.0f);
-  const float Rkm = R * 0.3048f / DC(1000.0f);
-  const float rr = range_reward_v3(Rkm);
-  rew[0] = 0.01f * (orientation_reward_v2(AO, TA) * rr);
-  rew[1] = 0.01f * (orientation_reward_v2(kPi - TA, kPi - AO) * rr);
-#pragma unroll
-  for (int q = 0; q < 2; ++q) {
+    rew[q] = combat_reward(g, q);
     float o[NP_NUM_OBS_COMBAT];
-    const int r = 1 - q;
-    o[0] = s[q][2] * 0.3048f / DC(5000.0f);
-    o[1] = g[q].sphi; o[2] = g[q].cphi; o[3] = g[q].st; o[4] = g[q].ct;
-    o[5] = vel[q][0] * 0.3048f / DC(340.0f); o[6] = vel[q][1] * 0.3048f / DC(340.0f); o[7] = vel[q][2] * 0.3048f / DC(340.0f);
-    o[8] = s[q][6] * 0.3048f / DC(340.0f);
-    o[9] = (vel[r][0] - vel[q][0]) * 0.3048f / DC(340.0f);
-    o[10] = (s[r][2] - s[q][2]) * 0.3048f / DC(1000.0f);
-    o[11] = q == 0 ? AO2 : kPi - TA2;
-    o[12] = q == 0 ? TA2 : kPi - AO2;
-    o[13] = R2 * 0.3048f / 10000.0f;
-    o[14] = q == 0 ? side : -side;
+    combat_obs_row(rec[q], rec[1 - q], g, q, o);
     if (act[q]) {
       float* orow = p.obs + (size_t)(2 * pr + q) * NP_NUM_OBS_COMBAT;
 #pragma unroll
@@ -392,10 +436,48 @@ __device__ __forceinline__ void combat_outputs(const StepParams& p, float (&s)[2
     }
   }
   if (stepped) {  // blood model, after obs / reward (singlecombat_env.py:263-271)
-    const float df = distance_fn(Rkm);
-    blood[1] = blood[1] - orientation_fn(AO) * df;
-    blood[0] = blood[0] - orientation_fn(kPi - TA) * df;
+    blood[1] = blood[1] - combat_damage(g, 1);
+    blood[0] = blood[0] - combat_damage(g, 0);
   }
+}
+
+// ---- role-sharded combat records: [n][kCombatRecFloats] f32, 16-byte rows -----------------------------------------------
+//   0..2 final position | 3..5 es | 6 body vx | 7 blood (after the env-level reset, before this step's damage) |
+//   8 this aircraft's own termination bits (1 done, 2 bad, 4 exceed; as an integer bit pattern) | 9 10 body vy vz | 11 vt |
+//   12..15 sin / cos roll, sin / cos pitch | 16..27 position after sub-steps 0..3 (the Crash check runs every sub-step; the
+//   last sub-step's position is the final one)
+constexpr int kCombatRecFloats = 28;
+constexpr int kCombatMaxSub = 5;
+__device__ __forceinline__ void combat_rec_store(float* row, const CombatRec& r, float blood, int bits) {
+  float4* v = reinterpret_cast<float4*>(row);
+  v[0] = make_float4(r.pos[0], r.pos[1], r.pos[2], r.es[0]);
+  v[1] = make_float4(r.es[1], r.es[2], r.vel[0], blood);
+  v[2] = make_float4(__int_as_float(bits), r.vel[1], r.vel[2], r.vt);
+  v[3] = make_float4(r.sphi, r.cphi, r.st, r.ct);
+}
+struct CombatRecFull {
+  CombatRec r;
+  float blood;
+  int bits;
+  float sub_pos[kCombatMaxSub - 1][3];
+};
+template <bool PEER>
+__device__ __forceinline__ CombatRecFull combat_rec_load(const float* row) {
+  const float4* v = reinterpret_cast<const float4*>(row);
+  float4 q[7];
+#pragma unroll
+  for (int j = 0; j < 7; ++j) q[j] = PEER ? __ldcg(v + j) : v[j];   // a peer GPU wrote it: never through the read-only path
+  CombatRecFull f;
+  f.r.pos[0] = q[0].x; f.r.pos[1] = q[0].y; f.r.pos[2] = q[0].z; f.r.es[0] = q[0].w;
+  f.r.es[1] = q[1].x; f.r.es[2] = q[1].y; f.r.vel[0] = q[1].z; f.blood = q[1].w;
+  f.bits = __float_as_int(q[2].x); f.r.vel[1] = q[2].y; f.r.vel[2] = q[2].z; f.r.vt = q[2].w;
+  f.r.sphi = q[3].x; f.r.cphi = q[3].y; f.r.st = q[3].z; f.r.ct = q[3].w;
+  const float sp[12] = {q[4].x, q[4].y, q[4].z, q[4].w, q[5].x, q[5].y, q[5].z, q[5].w, q[6].x, q[6].y, q[6].z, q[6].w};
+#pragma unroll
+  for (int k = 0; k < kCombatMaxSub - 1; ++k)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) f.sub_pos[k][j] = sp[3 * k + j];
+  return f;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -518,7 +600,12 @@ __global__ void __launch_bounds__(BS, MINB) f16_step_kernel(const __grid_constan
     if (COMBAT) {  // env-level reset (singlecombat_env.py:207-238): either flag re-initialises the whole pair
       const float2 bv = reinterpret_cast<const float2*>(p.blood)[prl];
       blood[0] = bv.x; blood[1] = bv.y;
-      rst[0] = rst[1] = rst[0] || rst[1];
+      if (p.records) {   // role-sharded: the two lanes are different envs; their env-level flags were OR-ed by the pair kernel
+        const uchar2 pv = reinterpret_cast<const uchar2*>(p.pair_reset)[prl];
+        rst[0] = pv.x != 0; rst[1] = pv.y != 0;
+      } else {
+        rst[0] = rst[1] = rst[0] || rst[1];
+      }
     }
 #pragma unroll
     for (int q = 0; q < 2; ++q) {
@@ -669,6 +756,10 @@ __global__ void __launch_bounds__(BS, MINB) f16_step_kernel(const __grid_constan
             make_obs(c, sq, uq, tq, g, eas2tas_of(tp), o);
             add_obs_noise(p, idx[q], o);
             if (staged) {
+              if (q == 0 && !p.obs_stg) {   // the tile's previous contents may still be being read by the last bulk store
+                if ((threadIdx.x & 31) == 0) bulk_wait_read0();
+                __syncwarp();
+              }
               float2* orow = reinterpret_cast<float2*>(otile + (2 * (threadIdx.x & 31) + q) * NP_NUM_OBS);
 #pragma unroll
               for (int j = 0; j < NP_NUM_OBS / 2; ++j) orow[j] = make_float2(o[2 * j], o[2 * j + 1]);
@@ -729,16 +820,34 @@ __global__ void __launch_bounds__(BS, MINB) f16_step_kernel(const __grid_constan
                               : 0;
         }
       }
-      if (STAGE && pass == 1 && staged && (!PLAN || sub == nsub - 1)) {   // tile -> obs[64 rows]: 11 x 512 B per warp
-        __syncwarp();
+      if (STAGE && pass == 1 && staged && (!PLAN || sub == nsub - 1)) {   // tile -> obs[64 rows], 5 632 contiguous bytes
         const int lane = threadIdx.x & 31;
-        const float4* src = reinterpret_cast<const float4*>(otile);
-        float4* dst = reinterpret_cast<float4*>(p.obs + (size_t)(2 * (pr - lane)) * NP_NUM_OBS);
+        float* dst = p.obs + (size_t)(2 * (pr - lane)) * NP_NUM_OBS;
+        if (!p.obs_stg) {            // ONE TMA bulk store per warp: no LSU instructions, large write bursts
+          fence_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            bulk_s2g(dst, otile, kObsTileFloats * 4);
+            bulk_commit();
+          }
+        } else {                     // 11 x 512 B per warp through the LSU
+          __syncwarp();
+          const float4* src = reinterpret_cast<const float4*>(otile);
 #pragma unroll
-        for (int k = 0; k < kObsTileFloats / 128; ++k) dst[lane + 32 * k] = src[lane + 32 * k];
-        __syncwarp();
+          for (int k = 0; k < kObsTileFloats / 128; ++k) reinterpret_cast<float4*>(dst)[lane + 32 * k] = src[lane + 32 * k];
+          __syncwarp();
+        }
       }
-      if (COMBAT && pass == 1) {   // pair conditions: Crash (crash.py:29-42) and Shutdown (shutdown.py:30-40)
+      if (COMBAT && pass == 1 && p.records) {   // role-sharded: the partner is on another rank; the pair kernel checks Crash
+        if (sub < nsub - 1 && sub < kCombatMaxSub - 1) {   // against the partner's position after the same sub-step
+#pragma unroll
+          for (int q = 0; q < 2; ++q)
+            if (act[q]) {
+              float* row = p.records + (size_t)(2 * pr + q) * kCombatRecFloats + 16 + 3 * sub;
+              row[0] = s[q][0]; row[1] = s[q][1]; row[2] = s[q][2];
+            }
+        }
+      } else if (COMBAT && pass == 1) {   // pair conditions: Crash (crash.py:29-42) and Shutdown (shutdown.py:30-40)
         const float dn0 = s[0][0] - s[1][0], de0 = s[0][1] - s[1][1], da0 = s[0][2] - s[1][2];
         const bool crash = (dn0 * dn0 + de0 * de0 + da0 * da0) <= c.distance_limit * c.distance_limit;
         const bool m1 = blood[0] <= 0.0f, m2 = blood[1] <= 0.0f;
@@ -754,7 +863,16 @@ __global__ void __launch_bounds__(BS, MINB) f16_step_kernel(const __grid_constan
 
     }  // sub-steps
 
-    if (COMBAT) combat_outputs(p, s, blood, rew, pr, act, nsub > 0);
+    if (COMBAT && p.records) {   // role-sharded: publish this aircraft's record; obs / reward / blood / pair flags follow in
+      rew[0] = rew[1] = 0.0f;    // combat_pair_kernel once the partner's record is visible
+#pragma unroll
+      for (int q = 0; q < 2; ++q)
+        if (act[q])
+          combat_rec_store(p.records + (size_t)(2 * pr + q) * kCombatRecFloats, combat_rec(s[q]), blood[q],
+                           (done[q] ? 1 : 0) | (bad[q] ? 2 : 0) | (exc[q] ? 4 : 0));
+    } else if (COMBAT) {
+      combat_outputs(p, s, blood, rew, pr, act, nsub > 0);
+    }
 
     // ---- termination-cause counters (replace the reference's per-condition print(torch.sum(...)) syncs) --------
 #pragma unroll
@@ -772,7 +890,7 @@ __global__ void __launch_bounds__(BS, MINB) f16_step_kernel(const __grid_constan
       } else {
         store_pair(p.blood, pr, make_float2(blood[0], blood[1]), act[1]);
       }
-      store_pair(p.reward, pr, make_float2(rew[0], rew[1]), act[1]);
+      if (!(COMBAT && p.records)) store_pair(p.reward, pr, make_float2(rew[0], rew[1]), act[1]);
       if (PLAN || COMBAT) {
 #pragma unroll
         for (int j = 0; j < kPidRows; ++j) store_pair(p.pid + (size_t)j * ld, pr, make_float2(pid[0][j], pid[1][j]), act[1]);
@@ -802,6 +920,7 @@ __global__ void __launch_bounds__(BS, MINB) f16_step_kernel(const __grid_constan
       }
     }
   }
+  if (STAGE && (threadIdx.x & 31) == 0) bulk_wait0();   // shared memory must outlive the last bulk stores
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1057,14 +1176,6 @@ constexpr int SMEM_BYTES = BAR + 32;               // 46 880 (four mbarriers) ->
 static_assert(OUT_OBS % 16 == 0 && BAR % 8 == 0, "bulk copies need 16-byte aligned shared addresses");
 }  // namespace uavslab
 
-__device__ __forceinline__ void bulk_s2g(void* dst_gmem, const void* src_smem, uint32_t bytes) {
-  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem), "r"(smem_u32(src_smem)), "r"(bytes)
-               : "memory");
-}
-__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
-__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
-__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // warp 0 requests the inputs of the full slab starting at aircraft i0: lane r fetches row r
 __device__ __forceinline__ void uav_slab_request(const StepParams& p, unsigned char* sm, uint64_t* bar, int i0, int lane) {
@@ -1217,6 +1328,70 @@ __global__ void __launch_bounds__(256) uav_nlplant_kernel(const float* __restric
     uav_nlplant(s, F, xdot);
 #pragma unroll
     for (int j = 0; j < 12; ++j) X[(size_t)j * ld + i] = xdot[j];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K5r: the pair half of the ROLE-sharded combat step (singlecombat_env.py:64-181,207-238,263-271).  The local half
+// (f16_step_kernel<MODE_COMBAT> with p.records) has flown this rank's aircraft -- all egos or all opponents, one per env --
+// through the five sub-steps and published a record each; after a cross-device barrier this kernel pulls the partner's record
+// from the peer rank's slab with its own loads over NVLink (PEER) or from an all-gathered array, and produces everything that
+// needs both aircraft: Crash at every sub-step, Shutdown, the 15-D observation, the reward, the blood model, the final flags
+// and the env-level reset flag of the next step.  One aircraft per thread; 112 B pulled per aircraft.
+// ------------------------------------------------------------------------------------------------
+struct PairParams {
+  const float* own;        // [n][kCombatRecFloats]
+  const float* partner;    // [n][kCombatRecFloats] (peer-mapped or gathered)
+  float* obs;              // [n][15]
+  float* reward;           // [n]
+  float* blood;            // [ld]
+  uint8_t* flags;          // [3][ld]
+  uint8_t* pair_reset;     // [ld]
+  unsigned long long* counters;
+  int n, ld, role, n_sub;
+  float distance_limit;
+};
+template <bool PEER>
+__global__ void __launch_bounds__(256) combat_pair_kernel(const __grid_constant__ PairParams p) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < p.n; i += gridDim.x * blockDim.x) {
+    const CombatRecFull own = combat_rec_load<false>(p.own + (size_t)i * kCombatRecFloats);
+    const CombatRecFull oth = combat_rec_load<PEER>(p.partner + (size_t)i * kCombatRecFloats);
+    const CombatRecFull& ego = p.role == 0 ? own : oth;
+    const CombatRecFull& enm = p.role == 0 ? oth : own;
+    // Crash (crash.py:29-42) after every sub-step, ego - enemy like the pair-sharded kernel
+    bool crash = false;
+    const float lim2 = p.distance_limit * p.distance_limit;
+#pragma unroll
+    for (int sub = 0; sub < kCombatMaxSub; ++sub) {     // constant trip count: the records stay in registers
+      const bool last = sub == p.n_sub - 1;
+      float d[3];
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        const float pe = (sub < kCombatMaxSub - 1 && !last) ? ego.sub_pos[sub < kCombatMaxSub - 1 ? sub : 0][j] : ego.r.pos[j];
+        const float pm = (sub < kCombatMaxSub - 1 && !last) ? enm.sub_pos[sub < kCombatMaxSub - 1 ? sub : 0][j] : enm.r.pos[j];
+        d[j] = pe - pm;
+      }
+      crash |= (sub < p.n_sub) && (d[0] * d[0] + d[1] * d[1] + d[2] * d[2]) <= lim2;
+    }
+    const bool m1 = ego.blood <= 0.0f, m2 = enm.blood <= 0.0f;           // shutdown.py:30-40
+    const bool sd_done = m2 && !m1;
+    const bool stepped = p.n_sub > 0;
+    const int pairbits = stepped ? ((sd_done ? 1 : 0) | ((crash | m1) ? 2 : 0)) : 0;
+    const int mine = own.bits | pairbits, theirs = oth.bits | pairbits;
+    const CombatGeo g = combat_geo(ego.r, enm.r);
+    float o[NP_NUM_OBS_COMBAT];
+    combat_obs_row(own.r, oth.r, g, p.role, o);
+    float* orow = p.obs + (size_t)i * NP_NUM_OBS_COMBAT;
+#pragma unroll
+    for (int j = 0; j < NP_NUM_OBS_COMBAT; ++j) orow[j] = o[j];
+    p.reward[i] = combat_reward(g, p.role);
+    p.blood[i] = stepped ? own.blood - combat_damage(g, p.role) : own.blood;
+    p.flags[i] = (mine & 1) ? 1 : 0;
+    p.flags[p.ld + i] = (mine & 2) ? 1 : 0;
+    p.flags[2 * (size_t)p.ld + i] = (mine & 4) ? 1 : 0;
+    p.pair_reset[i] = (mine | theirs) ? 1 : 0;
+    if (stepped && (crash | m1)) atomicAdd(&p.counters[5], 1ull);
+    if (stepped && sd_done) atomicAdd(&p.counters[6], 1ull);
   }
 }
 
@@ -1732,7 +1907,7 @@ int np_aero_destroy(np_aero* aero) {
 
 size_t np_env_workspace_bytes(const np_env_cfg* cfg) {
   if (!cfg) return 0;
-  return (((size_t)(kCacheRows + kPidRows + 1) * (size_t)cfg->ld * sizeof(float) + 127) / 128) * 128 + 256 /* counters */;
+  return (((size_t)kWorkspaceRows * (size_t)cfg->ld * sizeof(float) + 127) / 128) * 128 + 256 /* counters */;
 }
 
 }  // extern "C"
@@ -1786,12 +1961,14 @@ static StepParams make_params(np_env* env, const float* action, const float* dra
   p.cache = reinterpret_cast<float*>(env->buf.workspace_dev);
   p.pid = p.cache + (size_t)kCacheRows * env->cfg.ld;
   p.blood = p.pid + (size_t)kPidRows * env->cfg.ld;
+  uint8_t* pair_reset_row = reinterpret_cast<uint8_t*>(p.blood + env->cfg.ld);
   p.n_sub = 1;
   p.pid_first = 0;
   p.pair_begin = 0;
   p.pair_end = (env->cfg.n + 1) / 2;
   p.counters = reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(env->buf.workspace_dev) +
-                                                     (((size_t)(kCacheRows + kPidRows + 1) * env->cfg.ld * 4 + 127) / 128) * 128);
+                                                     (((size_t)kWorkspaceRows * env->cfg.ld * 4 + 127) / 128) * 128);
+  static_assert(kWorkspaceRows == kCacheRows + kPidRows + 2, "workspace layout");
   p.aero = env->aero ? env->aero->image_dev : nullptr;
   p.aero_bytes = env->aero ? env->aero->bytes : 0;
   p.tab = 0;
@@ -1805,6 +1982,10 @@ static StepParams make_params(np_env* env, const float* action, const float* dra
   p.noise = noise;
   p.flags_mirror = nullptr;
   p.flags_mirror_ld = 0;
+  p.obs_stg = env->obs_stg;
+  p.records = nullptr;
+  p.pair_reset = pair_reset_row;
+  p.index_stride = env->cfg.index_stride > 0 ? env->cfg.index_stride : 1;
   p.step_index = env->step_index;
   return p;
 }
@@ -1847,6 +2028,7 @@ static int env_create_impl(const np_env_cfg* cfg, const np_aero* aero, const np_
     if (e->block % 32 || e->block < 128 || e->block > 512) return fail(NP_EINVAL, "NPLANE_BLOCK must be a multiple of 32 in [128, 512]");
   }
   if (const char* b = getenv("NPLANE_TAB_BLOCK")) e->tab_block = atoi(b);
+  if (const char* b = getenv("NPLANE_OBS_STORE")) e->obs_stg = strcmp(b, "stg") == 0;
   *out = e.release();
   return NP_OK;
 }
@@ -2095,6 +2277,53 @@ int np_env_combat_step(np_env* env, const float* action_dev, int n_sub, const fl
   if (n_sub > 0) env->pid_started = true;
   env->step_index++;
   return launch_step<384, 1, MODE_COMBAT>(env, p, (cudaStream_t)stream);
+}
+
+// Role-sharded combat step, local half: np_env_combat_step for a rank that holds ONE aircraft of every env (all egos or all
+// opponents): env-level reset from the pair_reset flags, n_sub sub-steps, per-aircraft terminations, and the record the
+// partner rank needs (records_dev [n][28], see kCombatRecFloats) instead of obs / reward.
+int np_env_combat_role_local(np_env* env, const float* action_dev, int n_sub, const float* draws_dev, float* records_dev, void* stream) {
+  if (!env || !env->bound) return fail(NP_ESTATE, "np_env_combat_role_local: env not bound");
+  if (env->cfg.model != NP_MODEL_F16 || (env->cfg.n & 1) || env->tables) return fail(NP_EINVAL, "np_env_combat_role_local: needs the F16 MLP plug-in and an even local population");
+  if (n_sub < 0 || n_sub > kCombatMaxSub || (n_sub > 0 && (!action_dev || ((uintptr_t)action_dev & 15))) || !records_dev || ((uintptr_t)records_dev & 15))
+    return fail(NP_EINVAL, "np_env_combat_role_local: bad action / records pointer or n_sub (0..5)");
+  DeviceGuard guard(env->device);
+  StepParams p = make_params(env, action_dev ? action_dev : reinterpret_cast<const float*>(env->buf.s_dev), draws_dev, nullptr);
+  p.n_sub = n_sub;
+  p.pid_first = env->pid_started ? 0 : 1;
+  if (n_sub > 0) env->pid_started = true;
+  p.records = records_dev;
+  env->step_index++;
+  return launch_step<384, 1, MODE_COMBAT>(env, p, (cudaStream_t)stream);
+}
+
+// Role-sharded combat step, pair half (combat_pair_kernel): to be enqueued after a cross-device barrier that makes the
+// partner rank's records visible.  partner_records_dev: the partner rank's [n][28] slab -- peer-mapped memory
+// (partner_is_peer = 1: pulled over NVLink by the kernel's own loads) or a slice of an all-gathered array (0).
+// role: 0 = this rank holds the egos, 1 = the opponents.  Writes obs [n][15], reward, blood, the final flags and the
+// env-level reset flags of the next step.
+int np_env_combat_role_pair(np_env* env, const float* own_records_dev, const float* partner_records_dev, int partner_is_peer, int role,
+                            int n_sub, void* stream) {
+  if (!env || !env->bound) return fail(NP_ESTATE, "np_env_combat_role_pair: env not bound");
+  if (!own_records_dev || !partner_records_dev || (((uintptr_t)own_records_dev | (uintptr_t)partner_records_dev) & 15) || role < 0 || role > 1 ||
+      n_sub < 0 || n_sub > kCombatMaxSub)
+    return fail(NP_EINVAL, "np_env_combat_role_pair: bad argument");
+  DeviceGuard guard(env->device);
+  StepParams sp = make_params(env, nullptr, nullptr, nullptr);
+  PairParams p;
+  p.own = own_records_dev; p.partner = partner_records_dev;
+  p.obs = sp.obs; p.reward = sp.reward; p.blood = sp.blood; p.flags = sp.flags; p.pair_reset = sp.pair_reset; p.counters = sp.counters;
+  p.n = env->cfg.n; p.ld = env->cfg.ld; p.role = role; p.n_sub = n_sub; p.distance_limit = env->cfg.distance_limit;
+  const int want = (p.n + 255) / 256;
+  const int grid = want < env->num_sms * 8 ? want : env->num_sms * 8;
+  if (partner_is_peer) combat_pair_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(p);
+  else combat_pair_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(p);
+  NP_CUDA(cudaGetLastError());
+  return NP_OK;
+}
+
+size_t np_env_pair_reset_offset_bytes(const np_env_cfg* cfg) {
+  return cfg ? (size_t)(kCacheRows + kPidRows + 1) * (size_t)cfg->ld * sizeof(float) : 0;
 }
 
 int np_env_combat_records(np_env* env, float* records_dev, void* stream) {

@@ -35,10 +35,14 @@ class BaseEnv:
     native_obs_dim = nv.NUM_OBS
 
     def __init__(self, num_envs=10, config='heading', model='F16', random_seed=None, device="cuda:0",
-                 index_base=0, use_coef_cache=True):
+                 index_base=0, use_coef_cache=True, local_agents=None, index_stride=1):
+        """index_base / index_stride: global aircraft index of local aircraft i = index_base + index_stride * i (rank
+        sharding; the in-kernel RNG streams are keyed by global index).  local_agents: agents of each env that live on THIS
+        rank when fewer than the yaml's num_agents do (the role-sharded combat layout keeps one of the two)."""
         self.config = parse_config(config)
         self.num_envs = num_envs
-        self.num_agents = getattr(self.config, 'num_agents', 100)
+        self.num_agents = getattr(self.config, 'num_agents', 100) if local_agents is None else int(local_agents)
+        self.index_stride = int(index_stride)
         self.n = self.num_agents * self.num_envs
         self.device = torch.device(device)
         if self.device.type != "cuda":
@@ -74,6 +78,7 @@ class BaseEnv:
         c.model = self.model.model_id
         c.use_coef_cache = 1 if self.use_coef_cache else 0
         c.seed, c.index_base = self._seed & (2 ** 64 - 1), self.index_base
+        c.index_stride = self.index_stride
         for key, default in _CFG_KEYS:
             setattr(c, key, getattr(self.config, key, default))
         c.noise_scale = self.task.noise_scale

@@ -95,7 +95,7 @@ def test_combat_teacher_forced_vs_oracle():
         events += int(ref[2].sum()) + int(ref[3].sum())
     assert events > 20
     c = env.termination_counters()
-    assert c["unreach"] > 0 and c["reached"] > 0       # combat: slot 5 = crash | shot down, slot 6 = enemy shot down
+    assert c["crash_or_shutdown"] > 0 and c["enemy_shutdown"] > 0 and "unreach" not in c   # combat names its own counters
 
 
 @pytest.mark.parametrize("fixture,close", [("combat_traj.npz", False), ("combat_close_traj.npz", True)])
@@ -129,7 +129,10 @@ def test_combat_full_size_invariants():
         a = torch.rand((env.n, 4), device="cuda", generator=g) * 2 - 1
         obs, rew, done, bad, exc, _ = env.step(a)
         assert obs.shape == (env.n, 15) and torch.isfinite(obs).all() and torch.isfinite(rew).all()
-        assert torch.equal(bad[0::2] | done[0::2] | True, bad[1::2] | done[1::2] | True)
+        # pair-level conditions hit both aircraft of a pair: Shutdown-done (the enemy is shot down) sets `done` on both, so the
+        # done flags agree pairwise; a reset pair starts the next step with both step counts at the same value
+        assert torch.equal(done[0::2], done[1::2])
+        assert torch.equal(env.step_count[0::2], env.step_count[1::2])
         assert bool((obs[0::2, 13] == obs[1::2, 13]).all()) and bool((obs[0::2, 14] == -obs[1::2, 14]).all())
         assert float(env.blood.max()) <= 100.0
         assert int(env.step_count.max()) <= 5 * (k + 1)
@@ -187,3 +190,81 @@ def test_relgeo_peers_kernel_equals_relgeo_on_the_gathered_array():
     nv.check(st, "np_combat_relgeo_peers")
     torch.cuda.synchronize()
     assert torch.equal(got, want)
+
+
+def _role_pair(num_envs, seed=0, first_env=0):
+    from neuralplane_b200 import SingleCombatEnv
+    from neuralplane_b200.combat_exchange import LocalPairExchange
+    mk = lambda r: SingleCombatEnv(num_envs=num_envs, config="selfplay", random_seed=seed, device="cuda:0", layout="role", role=r,
+                                   first_env=first_env)
+    e0, e1 = mk(0), mk(1)
+    return e0, e1, LocalPairExchange(e0, e1)
+
+
+def test_role_sharded_step_is_bit_identical_to_pair_sharded():
+    """SingleCombatEnv(layout='role') -- one aircraft of every env per population, the partner's 28-float record pulled between
+    the local half and the pair half of the step -- against the pair-sharded env on the same envs: obs / reward / flags /
+    state / controls / blood / step counts bit-equal for 20 steps, with Crash, Shutdown and env-level resets occurring, under
+    in-kernel Philox draws keyed by global aircraft index (index_base + 2 i).  Two role populations in one process here
+    (LocalPairExchange); the 2-GPU NVLink / NCCL run is tools/combat_role_check.py."""
+    from neuralplane_b200 import SingleCombatEnv
+    E, first = 3000, 1234
+    pair = SingleCombatEnv(num_envs=E, config="selfplay", random_seed=5, device="cuda:0", index_base=2 * first)
+    e0, e1, ex = _role_pair(E, seed=5, first_env=first)
+    o = pair.reset()
+    o0, o1 = ex.reset_both()
+    assert torch.equal(o[0::2], o0) and torch.equal(o[1::2], o1)
+
+    def force_events():
+        # bring a third of the pairs within the 200 ft crash radius / gun range, with some nearly dead aircraft
+        close = torch.arange(E, device="cuda") % 3 == 0
+        gap = torch.linspace(30.0, 9000.0, E, device="cuda")
+        s = pair.model.s
+        s[1::2][close, 0] = s[0::2][close, 0] + gap[close]
+        s[1::2][close, 1] = s[0::2][close, 1] + 0.03 * gap[close]
+        s[1::2][close, 2] = s[0::2][close, 2] + 15.0
+        s[0::2][close, 5] = 0.0
+        s[1::2][close, 5] = 0.0
+        pair.blood[1::18] = 0.4
+        pair.blood[6::54] = 0.3
+        for r, e in enumerate((e0, e1)):
+            e.model.s.copy_(pair.model.s[r::2])
+            e.blood.copy_(pair.blood[r::2])
+    force_events()
+    g = torch.Generator(device="cuda").manual_seed(3)
+    events = resets = 0
+    for k in range(20):
+        a = torch.rand((2 * E, 4), device="cuda", generator=g) - 0.5
+        before = int(pair.termination_counters()["resets"])
+        rp = pair.step(a)
+        r0, r1 = ex.step_both(a[0::2].contiguous(), a[1::2].contiguous())
+        for r, (rr, e) in enumerate(((r0, e0), (r1, e1))):
+            for x, y, what in zip(rp[:5], rr, ("obs", "reward", "done", "bad", "exc")):
+                assert torch.equal(x[r::2], y), (k, r, what)
+            assert torch.equal(pair.model.s[r::2], e.model.s) and torch.equal(pair.model.u[r::2], e.model.u), (k, r)
+            assert torch.equal(pair.blood[r::2], e.blood) and torch.equal(pair.step_count[r::2], e.step_count), (k, r)
+            assert torch.equal(pair.ctrl_state[r::2], e.ctrl_state), (k, r)
+        events += int(rp[2].sum()) + int(rp[3].sum())
+        resets += int(pair.termination_counters()["resets"]) - before
+        if k == 8:
+            force_events()
+    assert events > 200 and resets > 200          # Crash / Shutdown fired and env-level resets happened inside the compared window
+    cp, c0, c1 = pair.termination_counters(), e0.termination_counters(), e1.termination_counters()
+    for name in ("overload", "low_altitude", "high_speed", "low_speed", "extreme_state", "resets"):
+        assert cp[name] == c0[name] + c1[name], name
+    assert cp["crash_or_shutdown"] == c0["crash_or_shutdown"] + c1["crash_or_shutdown"]
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
+def test_role_sharded_step_two_ranks():
+    """The same comparison across two processes / GPUs with both real exchanges (NVLink peer slabs; NCCL all-gather)."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29631", os.path.join(root, "tools", "combat_role_check.py"), "--envs", "20000", "--steps", "20"],
+                       capture_output=True, text=True, timeout=900, cwd=root)
+    assert r.returncode == 0, r.stderr[-3000:]
+    d = json.loads([ln for ln in r.stdout.splitlines() if ln.startswith("{")][-1])
+    assert d["peer_slabs"]["bit_identical"] and d["all_gather"]["bit_identical"] and d["events"] > 100, d

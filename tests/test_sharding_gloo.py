@@ -76,3 +76,51 @@ def test_role_sharded_partner_index(world):
         assert torch.equal(enm - ego, torch.full_like(ego, (world // 2) * n_envs))
         seen.add((int(ego[0]), int(enm[0])))
     assert len(seen) == world // 2        # rank r and rank r + world/2 look at the same pairs
+
+
+@pytest.mark.parametrize("world,envs", [(2, 500_000), (4, 500_000), (8, 500_000), (8, 100), (2, 6)])
+def test_role_blocks_cover_every_env_once_per_role(world, envs):
+    """SingleCombatEnv(layout='role'): ranks [0, world/2) hold the egos of contiguous env blocks, rank r + world/2 the
+    opponents of the SAME block; global aircraft index of local aircraft i = 2 (first_env + i) + role."""
+    from neuralplane_b200.combat_exchange import partner_rank, role_block
+    cover = {0: [], 1: []}
+    for r in range(world):
+        role, first, n = role_block(envs, r, world)
+        assert role == (0 if r < world // 2 else 1) and n % 2 == 0
+        assert role_block(envs, partner_rank(r, world), world)[1:] == (first, n)       # the partner rank holds the same envs
+        assert partner_rank(partner_rank(r, world), world) == r
+        cover[role] += list(range(first, first + n))
+    assert cover[0] == list(range(envs)) and cover[1] == list(range(envs))
+
+
+def _role_worker(rank, world, port, envs, q):
+    """The all-gather form of the role-sharded exchange over gloo: every rank contributes its [n, 28] record slab; the block
+    the pair kernel reads (gathered[partner * n:]) must be the partner rank's slab, i.e. the other aircraft of MY envs."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from neuralplane_b200.combat_exchange import RECORD_FLOATS, partner_rank, role_block
+        role, first, n = role_block(envs, rank, world)
+        gidx = 2 * (first + torch.arange(n)) + role                       # global aircraft index = index_base + 2 i
+        slab = gidx.to(torch.float32).reshape(-1, 1).repeat(1, RECORD_FLOATS)
+        gathered = torch.empty((world * n, RECORD_FLOATS))
+        dist.all_gather_into_tensor(gathered, slab)
+        part = gathered[partner_rank(rank, world) * n:][:n, 0].to(torch.int64)
+        q.put((rank, bool(torch.equal(part, gidx + (1 - 2 * role)))))       # ego 2e <-> opponent 2e + 1
+    finally:
+        dist.destroy_process_group()
+
+
+def test_role_sharded_all_gather_addresses_the_partner_over_gloo():
+    world, envs = 2, 4096
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_role_worker, args=(r, world, port, envs, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert res == [(0, True), (1, True)]
