@@ -403,6 +403,7 @@ def main():
     ms = e0.elapsed_time(e1)
     ms_max = max_over_ranks(ms)
     info = env.launch_info()
+    venv_boundary = venv.boundary
 
     # end to end through the numpy boundary the runners call (GPUVecEnv.step): host numpy in, host numpy out
     Ke = max(3, min(args.e2e_steps, K))
@@ -472,9 +473,10 @@ def main():
             "launch": dict(info, coef_cache=not args.no_cache),
             "e2e": {"value": e2e_value, "unit": UNIT, "steps": Ke, "ms_per_step": 1e3 * e2e_s / Ke,
                     "h2d_bytes_per_step": n * 4 * 4, "d2h_bytes_per_step": n * 22 * 4 + n * 4 + 3 * n,
-                    "boundary": args.boundary or "mapped",
-                    "how": "GPUVecEnv.step(numpy) -> numpy: the step kernel reads the actions from and writes obs / reward / flags "
-                           "into pinned, device-mapped host memory (bytes counted from those buffers); wall clock, max over ranks"},
+                    "boundary": venv_boundary,
+                    "how": "GPUVecEnv.step(numpy) -> numpy through pinned host buffers (bytes counted from those buffers): 'pipelined' "
+                           "= upload / kernel / download of aircraft chunks on three streams (np_env_step_host), 'mapped' = the "
+                           "kernel reads / writes device-mapped host memory directly; wall clock, max over ranks"},
             "gpu_launches": K,
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",

@@ -3,12 +3,13 @@
 Same shapes as the reference: actions (num_envs, agents, A) in; obs (num_envs, agents, D), rewards / dones /
 bad_dones / exceed_time_limits (num_envs, agents, 1) out.  Three implementations of the host boundary:
 
-  'mapped'    (default for the F16 plug-in) ONE kernel launch that reads the actions from and writes observation rows,
-              rewards and flags straight into pinned, device-mapped host memory (np_env_step_mapped): no copy engine,
-              no chunk pipeline; the 88 B/aircraft of PCIe writes drain under the step's arithmetic.
-  'pipelined' (default for large UAV populations, whose step is TMA-staged) upload / kernel / download of aircraft
-              chunks overlapped on three streams by one native call (np_env_step_host).
-  'copy'      single launch, then a device-to-host copy (small populations of the other kinds).
+  'pipelined' (default from 2 x 10^5 aircraft) upload / kernel / download of aircraft chunks overlapped on three streams by
+              one native call (np_env_step_host); the copy engine moves the 88 B/aircraft observation block at 56 GB/s.
+  'mapped'    (default for smaller F16 populations) ONE kernel launch that reads the actions from and writes observation
+              rows, rewards and flags straight into pinned, device-mapped host memory (np_env_step_mapped): no copy
+              engine, nothing to issue but the launch -- the lowest latency; but SM / TMA posted writes into host memory
+              reach only ~31 GB/s on this platform, so it loses to the pipeline at large n (3.1 vs 2.3 ms at 10^6).
+  'copy'      single launch, then device-to-host copies (small populations of the other kinds).
 
 Lifetime of the returned arrays.  The reference returns fresh arrays every step (`_t2n`).  Here small populations
 (< COPY_BELOW_BYTES of observations) also get fresh arrays; large ones get views of a ring of `ring` pinned buffers
@@ -78,10 +79,13 @@ class GPUVecEnv:
         is_f16 = getattr(e.model, "model_id", None) == 0
         boundary = boundary or os.environ.get("NPLANE_BOUNDARY") or None
         if boundary is None:
-            if single_step_env and is_f16 and hasattr(e, "step_mapped"):
-                boundary = "mapped"
-            elif single_step_env and hasattr(e, "step_host") and (pipeline_chunks is not None or n >= 200_000):
+            # measured on B200 / PCIe Gen5 (profiles/r02_e2e_boundaries.txt): SM- or TMA-issued posted writes into host
+            # memory run at ~31 GB/s, the copy engine at 56 GB/s, so large populations take the chunk pipeline; for small
+            # ones the single mapped launch has the lowest latency (no separate copies to issue)
+            if single_step_env and hasattr(e, "step_host") and (pipeline_chunks is not None or n >= 200_000):
                 boundary = "pipelined"
+            elif single_step_env and is_f16 and hasattr(e, "step_mapped"):
+                boundary = "mapped"
             else:
                 boundary = "copy"
         if boundary not in ("mapped", "pipelined", "copy"):

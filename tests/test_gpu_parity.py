@@ -452,7 +452,7 @@ def test_pipelined_numpy_boundary_equals_single_launch(dev, model, task):
     others = [v4]
     if model != "UAV":
         vm, vu = GPUVecEnv([mk]), GPUVecEnv([mk], boundary="mapped")
-        assert vm.boundary == "mapped"           # the default for the F16 plug-in
+        assert vm.boundary == "mapped"           # the default for F16 populations below 2 x 10^5
         vu._zero_copy_actions = False            # explicit H2D copy of the actions before the launch
         others += [vm, vu]
     else:
