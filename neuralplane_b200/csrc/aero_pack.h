@@ -12,8 +12,7 @@
 //   znorm  [kNumZ][2]           (mean, std) per input-normalisation group
 //   onorm  [43][2]              (mean, std) per net output
 //   weights                     nets 0..21 except eta_el: per layer bias[out], W^T[in][out], padded to 4 words
-//   c0     [16 + 20]            outputs of the 16 (alpha,beta) nets at alpha = beta = 0 and of the 20 consumed alpha-only
-//                               nets at alpha = 0 (what a freshly reset aircraft sees; filled on device)
+//   c0     [16]                 outputs of the 16 (alpha,beta) nets at alpha = beta = 0 (filled on device)
 //   bp_a   [2^La - 1]           merged, sorted alpha breakpoints (deg) of the 21 alpha nets, +inf padded
 //   segmap [(Ma + 1)][24] u8    per merged segment: segment index of each alpha net (21 used bytes)
 //   ent_a  float4[]             per net, per segment: (a0, y0, slope, 0); net k starts at taboff[k]
@@ -219,7 +218,7 @@ inline std::string pack_aero_image(const float* blob, size_t n_floats, const np_
   const size_t Ma = bp_a.size();
 
   std::vector<uint32_t>& im = *image;
-  im.assign(kWeightOff + kWeightFloats + kC0Floats, 0u);
+  im.assign(kWeightOff + kWeightFloats + kNumAB2, 0u);
   memcpy(im.data(), head.data(), head.size() * 4);
   memcpy(im.data() + kWeightOff, weights.data(), weights.size() * 4);
   auto hdr = [&](int i) -> int32_t& { return reinterpret_cast<int32_t*>(im.data())[i]; };  // im reallocates as it grows

@@ -31,8 +31,6 @@ constexpr int kFirstAB2 = kCy;                // the 16 two-input (alpha, beta) 
 constexpr int kNumAB2 = kCxq - kCy;           // 16
 constexpr int kFirstA1 = kCxq;                // the 21 alpha-only nets: [22, 43) -> piecewise-linear tables
 constexpr int kNumA1 = kNumNets - kFirstA1;   // 21
-constexpr int kNumA1Used = kNumUsed - kFirstA1;  // 20 (delta_Czq_lef is never consumed)
-constexpr int kC0Floats = kNumAB2 + kNumA1Used;  // reset-state constants kept in the image: 16 (alpha,beta) + 20 alpha-only
 
 constexpr NetArch arch_of(int k) {
   return k <= kCl ? NetArch{3, 20, 10, 0}

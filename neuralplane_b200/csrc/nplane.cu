@@ -45,15 +45,8 @@ static int fail(int code, const std::string& msg) {
 // ------------------------------------------------------------------------------------------------
 // handles
 // ------------------------------------------------------------------------------------------------
-// Cross-step cache (MODE_STEP): everything the Overload evaluation of step k computes from the NEW state alone is exactly
-// what the Euler derivative of step k + 1 needs -- the 16 (alpha,beta)-MLP outputs, the trigonometry, the atmosphere power
-// and the 20 alpha-only table coefficients.  Rows: 16 outputs | 6 keys (alpha beta phi theta psi alt bit patterns) as SoA
-// rows, then one 32-float record per aircraft (row-major, 128 B: 8 x 16-byte loads): sa ca sb cb st ct sphi cphi spsi cpsi tp
-// a1[20] pad.
-constexpr int kNumKeys = 6;
-constexpr int kXRecFloats = 32;
-constexpr int kCacheRows = kNumAB2 + kNumKeys + kXRecFloats;
-// workspace rows of [ld] f32: cache | controller state (kPidRows, ctrl_device.cuh: 12) | blood | pair_reset (u8, one row)
+constexpr int kCacheRows = kNumAB2 + 2;  // 16 (alpha,beta)-MLP outputs + alpha key + beta key
+// workspace rows of [ld] f32: coefficient cache | controller state (kPidRows, ctrl_device.cuh: 12) | blood | pair_reset (u8, one row)
 constexpr int kWorkspaceRows = kCacheRows + 12 + 2;
 
 struct np_aero {
@@ -487,35 +480,6 @@ __device__ __forceinline__ CombatRecFull combat_rec_load(const float* row) {
   return f;
 }
 
-// ---- cross-step record (see kXRecFloats): trig[11] | tp | a1[20], one 128-byte row per aircraft -------------------------
-__device__ __forceinline__ void xrec_store(float* row, const Trig& g, float tp, const float* a1) {
-  float4* v = reinterpret_cast<float4*>(row);
-  v[0] = make_float4(g.sa, g.ca, g.sb, g.cb);
-  v[1] = make_float4(g.st, g.ct, g.tt, g.sphi);
-  v[2] = make_float4(g.cphi, g.spsi, g.cpsi, tp);
-#pragma unroll
-  for (int j = 0; j < kNumA1Used / 4; ++j) v[3 + j] = make_float4(a1[4 * j], a1[4 * j + 1], a1[4 * j + 2], a1[4 * j + 3]);
-}
-__device__ __forceinline__ void xrec_load(const float* row, Trig& g, float& tp, float* a1) {
-  const float4* v = reinterpret_cast<const float4*>(row);
-  const float4 q0 = v[0], q1 = v[1], q2 = v[2];
-  g.sa = q0.x; g.ca = q0.y; g.sb = q0.z; g.cb = q0.w;
-  g.st = q1.x; g.ct = q1.y; g.tt = q1.z; g.sphi = q1.w;
-  g.cphi = q2.x; g.spsi = q2.y; g.cpsi = q2.z; tp = q2.w;
-#pragma unroll
-  for (int j = 0; j < kNumA1Used / 4; ++j) {
-    const float4 q = v[3 + j];
-    a1[4 * j] = q.x; a1[4 * j + 1] = q.y; a1[4 * j + 2] = q.z; a1[4 * j + 3] = q.w;
-  }
-}
-static_assert(kNumA1Used % 4 == 0 && 12 + kNumA1Used == kXRecFloats, "record layout");
-// what make_trig returns for a freshly reset aircraft (all angles exactly 0)
-__device__ __forceinline__ Trig trig_of_reset() {
-  Trig g;
-  g.sa = 0.f; g.ca = 1.f; g.sb = 0.f; g.cb = 1.f; g.st = 0.f; g.ct = 1.f; g.tt = 0.f; g.sphi = 0.f; g.cphi = 1.f; g.spsi = 0.f; g.cpsi = 1.f;
-  return g;
-}
-
 // ------------------------------------------------------------------------------------------------
 // K1: the fused step kernel
 // ------------------------------------------------------------------------------------------------
@@ -572,8 +536,6 @@ __global__ void __launch_bounds__(BS, MINB) f16_step_kernel(const __grid_constan
   float* cf = reinterpret_cast<float*>(coef2);                  // aircraft a, slot k: cf[a + k * 2 * BS]
   constexpr int CS = TAB ? 1 : 2 * BS;
   constexpr bool PLAN = MODE == MODE_PLAN, COMBAT = MODE == MODE_COMBAT;
-  constexpr bool XC = MODE == MODE_STEP && !TAB;   // cross-step record of the state-only terms (trig, atmosphere, alpha tables)
-  float* const xrec = p.cache + (size_t)(kNumAB2 + kNumKeys) * ld;   // [ld][kXRecFloats]
   const bool use_cache = !TAB && c.use_coef_cache != 0;
 
   const int pend = p.pair_end < npairs ? p.pair_end : npairs;
@@ -615,14 +577,10 @@ __global__ void __launch_bounds__(BS, MINB) f16_step_kernel(const __grid_constan
     }
     // cached (alpha,beta)-MLP outputs and their key: requested with the state rows (one memory round trip, not three)
     // and parked straight in this thread's coefficient slots; reset lanes / misses overwrite them below
-    float2 ka = make_float2(0.f, 0.f), kb = ka, kx[4] = {ka, ka, ka, ka};
+    float2 ka = make_float2(0.f, 0.f), kb = ka;
     if (use_cache) {
       ka = reinterpret_cast<const float2*>(p.cache + (size_t)kNumAB2 * ld)[prl];
       kb = reinterpret_cast<const float2*>(p.cache + (size_t)(kNumAB2 + 1) * ld)[prl];
-      if (XC) {
-#pragma unroll
-        for (int j = 0; j < 4; ++j) kx[j] = reinterpret_cast<const float2*>(p.cache + (size_t)(kNumAB2 + 2 + j) * ld)[prl];
-      }
 #pragma unroll
       for (int k = 0; k < kNumAB2; ++k) coef2[(kFirstAB2 + k) * BS] = reinterpret_cast<const float2*>(p.cache + (size_t)k * ld)[prl];
     }
@@ -701,18 +659,8 @@ __global__ void __launch_bounds__(BS, MINB) f16_step_kernel(const __grid_constan
     if constexpr (!TAB) {
       bool hit[2] = {rst[0], rst[1]};
       if (use_cache) {
-        bool k0 = __float_as_uint(ka.x) == __float_as_uint(s[0][7]) && __float_as_uint(kb.x) == __float_as_uint(s[0][8]);
-        bool k1 = __float_as_uint(ka.y) == __float_as_uint(s[1][7]) && __float_as_uint(kb.y) == __float_as_uint(s[1][8]);
-        if (XC) {   // the record also depends on phi, theta, psi and the altitude
-          constexpr int ks[4] = {3, 4, 5, 2};
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            k0 = k0 && __float_as_uint(kx[j].x) == __float_as_uint(s[0][ks[j]]);
-            k1 = k1 && __float_as_uint(kx[j].y) == __float_as_uint(s[1][ks[j]]);
-          }
-        }
-        hit[0] |= k0;
-        hit[1] |= k1;
+        hit[0] |= __float_as_uint(ka.x) == __float_as_uint(s[0][7]) && __float_as_uint(kb.x) == __float_as_uint(s[0][8]);
+        hit[1] |= __float_as_uint(ka.y) == __float_as_uint(s[1][7]) && __float_as_uint(kb.y) == __float_as_uint(s[1][8]);
       }
       miss = __any_sync(0xffffffffu, !(hit[0] && hit[1])) != 0;
       if (!miss && (rst[0] || rst[1])) {  // a reset lane sits at alpha = beta = 0: constants from the aero image
@@ -766,13 +714,8 @@ __global__ void __launch_bounds__(BS, MINB) f16_step_kernel(const __grid_constan
         for (int k = 0; k < kNumAB2; ++k) store_pair(p.cache + (size_t)k * ld, pr, coef2[(kFirstAB2 + k) * BS], act[1]);
         store_pair(p.cache + (size_t)kNumAB2 * ld, pr, make_float2(s[0][7], s[1][7]), act[1]);
         store_pair(p.cache + (size_t)(kNumAB2 + 1) * ld, pr, make_float2(s[0][8], s[1][8]), act[1]);
-        if (XC) {
-          constexpr int ks[4] = {3, 4, 5, 2};
-#pragma unroll
-          for (int j = 0; j < 4; ++j) store_pair(p.cache + (size_t)(kNumAB2 + 2 + j) * ld, pr, make_float2(s[0][ks[j]], s[1][ks[j]]), act[1]);
-        }
       }
-      if (!(XC && pass == 0 && use_cache && !miss)) pwl_search2<kLevelsA>(tabs.bp_a, adeg.x, adeg.y, seg[0], seg[1]);
+      pwl_search2<kLevelsA>(tabs.bp_a, adeg.x, adeg.y, seg[0], seg[1]);
       if (pass == 0) coef2[kEtaEl * BS] = eta_el2(tabs, make_float2(u[0][1], u[1][1]));
       }
 
@@ -782,29 +725,15 @@ __global__ void __launch_bounds__(BS, MINB) f16_step_kernel(const __grid_constan
         const float* uq = u[q];
         const float* tq = tgt[q];
         const float* cq = cf + q;
-        Trig g;
-        float tp;
+        const Trig g = make_trig(sq);
+        const float tp = tfac_pow(sq[2]);
         float a1[kNumA1];
         float ctab[TAB ? kNumSlots : 1];
-        if (XC && pass == 0 && use_cache && !miss) {   // warp-uniform: the state-only terms of (s) come from the last step's record
-          if (rst[q]) {                                // ... or, for a freshly reset aircraft, are constants
-            g = trig_of_reset();
-            tp = tfac_pow(sq[2]);
-#pragma unroll
-            for (int k = 0; k < kNumA1Used; ++k) a1[k] = c0[kNumAB2 + k];
-          } else {
-            xrec_load(xrec + (size_t)idx[q] * kXRecFloats, g, tp, a1);
-          }
+        if constexpr (TAB) {
+          table_env_coefs(blob, zc, q == 0 ? adeg.x : adeg.y, q == 0 ? bdeg.x : bdeg.y, uq[1], pass == 0, ctab, a1);
+          cq = ctab;
         } else {
-          g = make_trig(sq);
-          tp = tfac_pow(sq[2]);
-          if constexpr (TAB) {
-            table_env_coefs(blob, zc, q == 0 ? adeg.x : adeg.y, q == 0 ? bdeg.x : bdeg.y, uq[1], pass == 0, ctab, a1);
-            cq = ctab;
-          } else {
-            alpha_coefs<kNumUsed - kFirstA1>(blob, tabs, seg[q], q == 0 ? adeg.x : adeg.y, a1);
-          }
-          if (XC && pass == 1 && use_cache && act[q]) xrec_store(xrec + (size_t)(2 * pr + q) * kXRecFloats, g, tp, a1);
+          alpha_coefs<kNumUsed - kFirstA1>(blob, tabs, seg[q], q == 0 ? adeg.x : adeg.y, a1);
         }
         const ForcePart fp = force_part(sq, uq[0], uq[2], uq[3], 0.0f, g, tp, cq, CS, a1);
 
@@ -1017,13 +946,8 @@ __global__ void __launch_bounds__(256) f16_reset_kernel(const __grid_constant__ 
       p.step_count[i] = 0;
       if (c0) {  // the (alpha, beta)-MLP outputs at alpha = beta = 0 (the table back-end keeps no cache)
         for (int k = 0; k < kNumAB2; ++k) p.cache[(size_t)k * ld + i] = c0[k];
-        p.cache[(size_t)kNumAB2 * ld + i] = 0.0f;          // keys: alpha, beta, phi, theta, psi = 0; altitude as drawn
+        p.cache[(size_t)kNumAB2 * ld + i] = 0.0f;
         p.cache[(size_t)(kNumAB2 + 1) * ld + i] = 0.0f;
-        p.cache[(size_t)(kNumAB2 + 2) * ld + i] = 0.0f;
-        p.cache[(size_t)(kNumAB2 + 3) * ld + i] = 0.0f;
-        p.cache[(size_t)(kNumAB2 + 4) * ld + i] = 0.0f;
-        p.cache[(size_t)(kNumAB2 + 5) * ld + i] = s[2];
-        xrec_store(p.cache + (size_t)(kNumAB2 + kNumKeys) * ld + (size_t)i * kXRecFloats, trig_of_reset(), tfac_pow(s[2]), c0 + kNumAB2);
       }
       atomicAdd(&p.counters[7], 1ull);
     } else {
@@ -1917,15 +1841,9 @@ __global__ void __launch_bounds__(32) f16_c0_kernel(uint32_t* aero, int aero_byt
   ZIn2 zi;  // every lane evaluates the same point into its own slots (uniform control flow); lane 0 publishes
   zscores_ab2(blob, make_float2(0.0f * kR2D, 0.0f * kR2D), make_float2(0.0f * kR2D, 0.0f * kR2D), zi);
   eval_ab2_nets(blob, wb, zi, coef2 + threadIdx.x, 32);
-  const AeroTabs tabs = aero_tabs(blob, wb);
-  uint32_t seg0, seg1;
-  pwl_search2<kLevelsA>(tabs.bp_a, 0.0f * kR2D, 0.0f * kR2D, seg0, seg1);
-  float a1[kNumA1];
-  alpha_coefs<kNumA1Used>(blob, tabs, seg0, 0.0f * kR2D, a1);
   if (threadIdx.x == 0) {
     float* c0 = reinterpret_cast<float*>(aero) + reinterpret_cast<const int32_t*>(blob)[kHdrC0];
     for (int k = 0; k < kNumAB2; ++k) c0[k] = coef2[(kFirstAB2 + k) * 32].x;
-    for (int k = 0; k < kNumA1Used; ++k) c0[kNumAB2 + k] = a1[k];
   }
 }
 
@@ -2130,7 +2048,7 @@ int np_env_bind(np_env* env, const np_buffers* b, void* stream) {
   // invalidate the coefficient-cache keys: 0xFFFFFFFF is a NaN pattern no stored alpha/beta can equal bitwise.  Enqueued
   // on the caller's stream, like every later step.
   NP_CUDA(cudaMemsetAsync(reinterpret_cast<float*>(b->workspace_dev) + (size_t)kNumAB2 * env->cfg.ld, 0xFF,
-                          kNumKeys * (size_t)env->cfg.ld * sizeof(float), (cudaStream_t)stream));
+                          2 * (size_t)env->cfg.ld * sizeof(float), (cudaStream_t)stream));
   return NP_OK;
 }
 
