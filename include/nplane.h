@@ -83,6 +83,9 @@ typedef struct np_env_cfg {
   float distance_limit, target_dist, max_heading, min_heading, max_npos, min_npos, max_epos, min_epos;
   int32_t index_stride; /* global aircraft index = index_base + index_stride * local index (0 = 1).  2 in the role-sharded
                            combat layout, where a rank holds every second aircraft (all egos or all opponents) */
+  int32_t combat_pairs_per_env; /* 1: SingleCombat (1-v-1).  2: MultipleCombat (2-v-2, multiple_selfplay.yaml num_agents 4): an
+                           env is two adjacent duels [ego0 enm0 ego1 enm1]; any flag re-initialises all four (0 = 1) */
+  float combat_reward_scale; /* 0.01 (singlecombat_env.py:176-177; the default when 0) or 1 (multiplecombat_env.py:176-177) */
 } np_env_cfg;
 
 /* Device buffers the env works on (replace the tensors of F16_model.py:19-22, heading_task.py:26-28,
@@ -184,6 +187,11 @@ int np_env_plan_step(np_env* env, const float* action3_dev, int n_sub, const flo
  * n_sub = 0 performs only the env-level reset + obs (SingleCombatEnv.reset).  draws_dev [n][5] = npos, epos, altitude,
  * heading, vt uniforms or NULL (Philox).  Per-pair relative geometry needs no exchange in this pair-sharded layout. */
 int np_env_combat_step(np_env* env, const float* action_dev, int n_sub, const float* draws_dev, void* stream);
+/* MultipleCombatEnv.step (envs/multiplecombat_env.py:240-274; envs/configs/multiple_selfplay.yaml) is the same call on an env
+ * created with combat_pairs_per_env = 2, combat_reward_scale = 1 and n_sub = 1 (the reference takes ONE FDM step per env
+ * step there).  The reference file pairs only agents 0 and 1 of each 4-agent env (:100-101,165-166, crash.py:32-33) and its
+ * column stack cannot be built (2 E rows against 4 E aircraft), so the pairing is RESTATED: agents (0,1) and (2,3) of an env
+ * are two duels evaluated with the reference's own 1-v-1 formulas, and the env-level reset (:207-238) spans all four. */
 /* Role-sharded combat layout (egos and opponents on different ranks): each rank writes the 8-float record of
  * its aircraft -- position (3), inertial velocity xdot[0:3] (3), body-axis vx, blood -- into records_dev [n][8] (the
  * all-gather send slab), the ranks all-gather the slabs (NCCL, neuralplane_b200/combat_exchange.py), and

@@ -13,5 +13,6 @@ from .envs.env_base import BaseEnv  # noqa: F401
 from .envs.env_wrappers import GPUVecEnv  # noqa: F401
 from .envs.planning_env import PlanningEnv  # noqa: F401
 from .envs.singlecombat_env import SingleCombatEnv  # noqa: F401
+from .envs.multiplecombat_env import MultipleCombatEnv  # noqa: F401
 
-__all__ = ["ControlEnv", "PlanningEnv", "SingleCombatEnv", "BaseEnv", "GPUVecEnv"]
+__all__ = ["ControlEnv", "PlanningEnv", "SingleCombatEnv", "MultipleCombatEnv", "BaseEnv", "GPUVecEnv"]

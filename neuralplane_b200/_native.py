@@ -46,7 +46,7 @@ class EnvCfg(C.Structure):
                 ("max_vt", C.c_float), ("min_vt", C.c_float), ("model", C.c_int32), ("max_steps", C.c_int32),
                 ("distance_limit", C.c_float), ("target_dist", C.c_float), ("max_heading", C.c_float),
                 ("min_heading", C.c_float), ("max_npos", C.c_float), ("min_npos", C.c_float), ("max_epos", C.c_float),
-                ("min_epos", C.c_float), ("index_stride", C.c_int32)]
+                ("min_epos", C.c_float), ("index_stride", C.c_int32), ("combat_pairs_per_env", C.c_int32), ("combat_reward_scale", C.c_float)]
 
 
 class Buffers(C.Structure):

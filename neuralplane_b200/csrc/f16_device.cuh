@@ -133,35 +133,56 @@ __device__ __forceinline__ float2 denorm2(const float* __restrict__ blob, int k,
   return make_float2(y.x * ms.y + ms.x, y.y * ms.y + ms.x);
 }
 
-// Evaluate MLP nets [K0, K0 + count) of one architecture / normalisation group in a rolled loop; result k goes to
-// out[k * stride] (a float2: both aircraft of this thread).  The loop keeps the code footprint at one body per group.
+// Evaluate MLP nets [K0, K0 + count) of ONE ARCHITECTURE in a rolled loop; result k goes to out[k * stride] (a float2: both
+// aircraft of this thread).  The loop keeps the code footprint at one body per architecture: nets of the same shape but
+// different input normalisation (the "r30 / a20" and the "lef" alpha grids) share it, the alpha z-score being picked per
+// net at run time (warp-uniform) -- two bodies fewer than one per (architecture, normalisation) pair, 0.5 k SASS instructions.
 template <int K0>
 __device__ __forceinline__ void eval_group2(const float* __restrict__ blob, uint32_t wbase, const ZIn2& zi,
                                             float2* __restrict__ out, int stride, int count) {
   constexpr NetArch A = arch_of(K0);
-  constexpr ZSel Z = zsel_of(K0);
   constexpr int NF = net_floats(A);
   static_assert(A.nin >= 2, "one-input nets are table-driven");
-  const float2 z0 = zi.z[Z.a], z1 = zi.z[Z.b];
-  float2 z2 = make_float2(0.f, 0.f);
-  if constexpr (A.nin == 3) z2 = zi.z[Z.e >= 0 ? Z.e : 0];
   uint32_t w = wbase + 4 * mlp_offset(K0);
 #pragma unroll 1
   for (int k = K0; k < K0 + count; ++k, w += 4 * NF) {
+    float2 z0, z1, z2 = make_float2(0.f, 0.f);
+    if constexpr (A.nin == 3) {
+      z0 = zi.z[kZaC]; z1 = zi.z[kZbC]; z2 = zi.z[kZeC];
+    } else {                                   // (alpha, beta) nets: beta is always the "r30" normalisation
+      const bool r_grid = k == kCy || k == kdCl_a20 || (k >= kdCy_r30 && k <= kdCy_a20);
+      z0 = r_grid ? zi.z[kZaR] : zi.z[kZaLef2];
+      z1 = zi.z[kZbR];
+    }
     const float2 y = mlp2<A.nin, A.h1, A.h2, A.h3>(w, z0, z1, z2);
     out[k * stride] = denorm2(blob, k, y);
   }
 }
+// every net the loops above may visit has the architecture and the input selection assumed there
+constexpr bool ab2_groups_ok() {
+  for (int k = kCy; k <= kdCl_a20_lef; ++k) {
+    const ZSel z = zsel_of(k);
+    const bool r_grid = k == kCy || k == kdCl_a20 || (k >= kdCy_r30 && k <= kdCy_a20);
+    if (z.b != kZbR || z.a != (r_grid ? kZaR : kZaLef2)) return false;
+  }
+  for (int k = kCx; k <= kCl; ++k)
+    if (zsel_of(k).a != kZaC || zsel_of(k).b != kZbC || zsel_of(k).e != kZeC) return false;
+  const NetArch a = arch_of(kCy), b = arch_of(kdCz_lef);
+  for (int k = kCy; k <= kdCl_lef; ++k)
+    if (arch_of(k).h2 != a.h2 || arch_of(k).h3 != a.h3) return false;
+  for (int k = kdCz_lef; k <= kdCn_a20; ++k)
+    if (arch_of(k).h2 != b.h2 || arch_of(k).h3 != b.h3) return false;
+  return true;
+}
+static_assert(ab2_groups_ok(), "net table changed: revisit eval_group2 / eval_ab2_nets");
 
-// The 16 two-input (alpha, beta) nets: slots [kFirstAB2, kFirstA1).
+// The 16 two-input (alpha, beta) nets: slots [kFirstAB2, kFirstA1), four architectures.
 __device__ __forceinline__ void eval_ab2_nets(const float* __restrict__ blob, uint32_t wbase, const ZIn2& zi,
                                               float2* __restrict__ out, int stride) {
-  eval_group2<kCy>(blob, wbase, zi, out, stride, 2);           // Cy, delta_Cl_a20
-  eval_group2<kdCx_lef>(blob, wbase, zi, out, stride, 2);      // delta_Cx_lef, delta_Cl_lef
-  eval_group2<kdCz_lef>(blob, wbase, zi, out, stride, 4);
-  eval_group2<kdCy_r30>(blob, wbase, zi, out, stride, 4);
-  eval_group2<kdCy_a20>(blob, wbase, zi, out, stride, 1);
-  eval_group2<kdCy_a20_lef>(blob, wbase, zi, out, stride, 3);
+  eval_group2<kCy>(blob, wbase, zi, out, stride, 4);           // [20,10]:    Cy, delta_Cl_a20, delta_Cx_lef, delta_Cl_lef
+  eval_group2<kdCz_lef>(blob, wbase, zi, out, stride, 8);      // [20,10,5]:  4 x lef, 3 x r30, delta_Cn_a20
+  eval_group2<kdCy_a20>(blob, wbase, zi, out, stride, 1);      // [20,10,10]
+  eval_group2<kdCy_a20_lef>(blob, wbase, zi, out, stride, 3);  // [20,20,10]
 }
 // The three-input nets Cx Cz Cm Cn Cl (alpha, beta, el): `count` = 5 for a full nlplant, 2 (Cx, Cz) when only the
 // force equations are needed (the Overload check).
@@ -230,17 +251,34 @@ __device__ __forceinline__ void alpha_coefs(const void* blob_smem, const AeroTab
 // ------------------------------------------------------------------------------------------------
 // Equations of motion
 // ------------------------------------------------------------------------------------------------
+// ONE copy of each large libm body per kernel (sincosf with its Payne-Hanek slow path is ~80 SASS instructions, powf ~150,
+// Philox ~65): the step kernel's tail is executed once per slab, so every inlined copy is instruction-cache traffic
+// (ncu: 1 100 of the 11 500 static instructions were ten copies of sincosf, stall_no_instruction concentrated in the tail).
+// Values and bits are those of the inlined calls.
+#ifndef NPLANE_INLINE_LIBM
+#define NP_LIBM_INLINE __noinline__
+#else
+#define NP_LIBM_INLINE __forceinline__
+#endif
+__device__ NP_LIBM_INLINE float2 sincos_shared(float x) {
+  float2 r;
+  sincosf(x, &r.x, &r.y);
+  return r;
+}
+__device__ NP_LIBM_INLINE float pow_shared(float x, float y) { return powf(x, y); }
+
 struct Trig {
   float sa, ca, sb, cb, st, ct, tt, sphi, cphi, spsi, cpsi;
 };
 __device__ __forceinline__ Trig make_trig(const float* s) {
   Trig t;
-  sincosf(s[7], &t.sa, &t.ca);
-  sincosf(s[8], &t.sb, &t.cb);
-  sincosf(s[4], &t.st, &t.ct);
+  float2 r;
+  r = sincos_shared(s[7]); t.sa = r.x; t.ca = r.y;
+  r = sincos_shared(s[8]); t.sb = r.x; t.cb = r.y;
+  r = sincos_shared(s[4]); t.st = r.x; t.ct = r.y;
   t.tt = t.st / t.ct;  // tan(theta): one IEEE divide of the two values already needed (<= 3 ulp, like tanf's 4 ulp bound)
-  sincosf(s[3], &t.sphi, &t.cphi);
-  sincosf(s[5], &t.spsi, &t.cpsi);
+  r = sincos_shared(s[3]); t.sphi = r.x; t.cphi = r.y;
+  r = sincos_shared(s[5]); t.spsi = r.x; t.cpsi = r.y;
   return t;
 }
 
@@ -265,7 +303,7 @@ __device__ __forceinline__ float operator/(float x, DC c) {
 
 __device__ __forceinline__ float tfac_pow(float alt) {  // tfac ** 4.14 (F16_dynamics.py:25,28)
   const float tfac = 1.0f - .703e-5f * alt;
-  return powf(tfac, 4.14f);
+  return pow_shared(tfac, 4.14f);
 }
 __device__ __forceinline__ float qbar_of(float tp, float vt) {  // .5 * rho0 * tfac^4.14 * vt^2 (:28,30)
   const float rho = 2.377e-3f * tp;
@@ -275,9 +313,27 @@ __device__ __forceinline__ float eas2tas_of(float tp) {  // F16_model.py:156-162
   return sqrtf(1.0f / tp);
 }
 
+// fmodf(a, 2 pi) in ~10 instructions instead of ~70 (and 13 inlined copies of them): q = trunc(a * RN(1 / 2pi)) is the true
+// truncated quotient or off by one (|a / 2pi| < 2^20: the product's error is < 0.25); r = fma(-q, 2pi, a) is EXACT when q is
+// right (the fmod result is always representable) and has the wrong sign / magnitude >= 2pi when q is off by one, in which
+// case q is corrected and r recomputed from scratch.  Bit-identical to fmodf: enumerated over every float of that range in
+// oracle/fmod_check.c.  Larger arguments (no flying aircraft has them) take the library routine.
+__device__ __noinline__ float fmod_twopi_slow(float a) { return fmodf(a, kTwoPi); }
+__device__ __forceinline__ float fmod_twopi(float a) {
+  if (!(fabsf(a) < 6.0e6f)) return fmod_twopi_slow(a);   // also NaN / inf
+  float q = truncf(a * (float)(1.0 / 6.283185307179586));
+  float r = fmaf(-q, kTwoPi, a);
+  const float sgn = copysignf(1.0f, a);
+  const float rs = r * sgn;                // remainder folded to a's sign: must lie in [0, 2pi)
+  if (rs < 0.0f) q -= sgn;
+  else if (rs >= kTwoPi) q += sgn;
+  else return r == 0.0f ? copysignf(0.0f, a) : r;     // fmod keeps the dividend's sign on an exact zero
+  r = fmaf(-q, kTwoPi, a);
+  return r == 0.0f ? copysignf(0.0f, a) : r;
+}
 // torch `%` (Python-style remainder) then the two wraps of utils.py:144-154.
 __device__ __forceinline__ float wrap_pi(float a) {
-  float r = fmodf(a, kTwoPi);
+  float r = fmod_twopi(a);
   if (r != 0.0f && r < 0.0f) r += kTwoPi;
   if (r < 0.0f) r += kTwoPi;
   if (r > kPi) r -= kTwoPi;
@@ -442,7 +498,7 @@ __device__ __forceinline__ void body_accel(const float* s, const Trig& g, const 
 // ------------------------------------------------------------------------------------------------
 // Counter-based RNG: Philox4x32-10 keyed by the env seed; counter = (global aircraft index, step, stream).
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
+__device__ NP_LIBM_INLINE uint4 philox4x32_10(uint4 ctr, uint2 key) {
   constexpr uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
 #pragma unroll
   for (int r = 0; r < 10; ++r) {

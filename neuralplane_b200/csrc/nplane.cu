@@ -223,17 +223,19 @@ __device__ __forceinline__ Draws reset_draws(const StepParams& p, int i) {
 
 // F16Model.reset (F16_model.py:38-45) + task.reset (heading_task.py:63-69, control_task.py:59-68,
 // tracking_task.py:57-71) for one aircraft.
-__device__ __forceinline__ void reset_aircraft(const np_env_cfg& c, const Draws& r, float* s, float* u, float* tgt) {
+// `task` is a compile-time constant in the step kernel (one instantiation per task: the other two tasks' code -- each with
+// its own wrap / trig calls -- would only be instruction-cache ballast) and c.task in the stand-alone reset kernel.
+__device__ __forceinline__ void reset_aircraft(const np_env_cfg& c, int task, const Draws& r, float* s, float* u, float* tgt) {
 #pragma unroll
   for (int j = 0; j < 12; ++j) s[j] = 0.0f;
   s[2] = r.d[0] * (c.max_altitude - c.min_altitude) + c.min_altitude;
   s[6] = r.d[1] * (c.max_vt - c.min_vt) + c.min_vt;
   u[0] = c.init_T; u[1] = 0.0f; u[2] = 0.0f; u[3] = 0.0f;
-  if (c.task == NP_TASK_HEADING) {
+  if (task == NP_TASK_HEADING) {
     tgt[0] = s[2] + 1000.0f;
     tgt[1] = wrap_pi(s[5] + (float)(2.0 * 3.141592653589793 / 3.0));
     tgt[2] = s[6] + 0.0f;
-  } else if (c.task == NP_TASK_CONTROL) {
+  } else if (task == NP_TASK_CONTROL) {
     tgt[0] = wrap_pi(s[4] + 2.0f * (r.d[2] - 0.5f) * c.max_pitch_increment);
     tgt[1] = wrap_pi(s[5] + 2.0f * (r.d[3] - 0.5f) * c.max_heading_increment);
     tgt[2] = s[6] + 2.0f * (r.d[4] - 0.5f) * c.max_velocities_u_increment;
@@ -241,20 +243,21 @@ __device__ __forceinline__ void reset_aircraft(const np_env_cfg& c, const Draws&
     const float dist = r.d[2] * (c.max_distance - c.min_distance) + c.min_distance;
     const float th1 = r.d[3] * kPi / DC(3.0f) - (float)(3.141592653589793 / 6.0);
     const float th2 = r.d[4] * kPi / DC(3.0f) - (float)(3.141592653589793 / 6.0);
-    tgt[0] = s[0] + dist * cosf(th1) * cosf(th2);
-    tgt[1] = s[1] + dist * cosf(th1) * sinf(th2);
-    tgt[2] = s[2] + dist * sinf(th1);
+    const float2 sc1 = sincos_shared(th1), sc2 = sincos_shared(th2);   // (sin, cos): the bits of sinf / cosf
+    tgt[0] = s[0] + dist * sc1.y * sc2.y;
+    tgt[1] = s[1] + dist * sc1.y * sc2.x;
+    tgt[2] = s[2] + dist * sc1.x;
   }
 }
 
 // 22-D observation row (heading_task.py:113-151; control_task.py:109-111; tracking_task.py:112-114).
-__device__ __forceinline__ void make_obs(const np_env_cfg& c, const float* s, const float* u, const float* tgt,
+__device__ __forceinline__ void make_obs(const np_env_cfg& c, int task, const float* s, const float* u, const float* tgt,
                                          const Trig& g, float e2t, float* o) {
-  if (c.task == NP_TASK_HEADING) {
+  if (task == NP_TASK_HEADING) {
     o[0] = (s[2] - tgt[0]) * 0.3048f / DC(1000.0f);
     o[1] = wrap_pi(s[5] - tgt[1]);
     o[2] = (s[6] - tgt[2]) * 0.3048f / DC(340.0f);
-  } else if (c.task == NP_TASK_CONTROL) {
+  } else if (task == NP_TASK_CONTROL) {
     o[0] = wrap_pi(s[4] - tgt[0]);
     o[1] = wrap_pi(s[5] - tgt[1]);
     o[2] = (s[6] - tgt[2]) * 0.3048f / DC(340.0f);
@@ -409,9 +412,10 @@ __device__ __forceinline__ void combat_obs_row(const CombatRec& own, const Comba
   o[13] = g.R2 * 0.3048f / 10000.0f;
   o[14] = q == 0 ? g.side : -g.side;
 }
-__device__ __forceinline__ float combat_reward(const CombatGeo& g, int q) {   // singlecombat_env.py:140-181
+// singlecombat_env.py:140-181 (scale 0.01) / multiplecombat_env.py:163-181 (scale 1: the product itself)
+__device__ __forceinline__ float combat_reward(const CombatGeo& g, int q, float scale) {
   const float rr = range_reward_v3(g.Rkm);
-  return q == 0 ? 0.01f * (orientation_reward_v2(g.AO, g.TA) * rr) : 0.01f * (orientation_reward_v2(kPi - g.TA, kPi - g.AO) * rr);
+  return q == 0 ? scale * (orientation_reward_v2(g.AO, g.TA) * rr) : scale * (orientation_reward_v2(kPi - g.TA, kPi - g.AO) * rr);
 }
 // blood model (singlecombat_env.py:263-271): what aircraft q loses in this env step
 __device__ __forceinline__ float combat_damage(const CombatGeo& g, int q) {
@@ -426,7 +430,7 @@ __device__ __forceinline__ void combat_outputs(const StepParams& p, float (&s)[2
   const CombatGeo g = combat_geo(rec[0], rec[1]);
 #pragma unroll
   for (int q = 0; q < 2; ++q) {
-    rew[q] = combat_reward(g, q);
+    rew[q] = combat_reward(g, q, p.cfg.combat_reward_scale);
     float o[NP_NUM_OBS_COMBAT];
     combat_obs_row(rec[q], rec[1 - q], g, q, o);
     if (act[q]) {
@@ -506,7 +510,7 @@ enum { MODE_STEP = 0, MODE_PLAN = 1, MODE_COMBAT = 2 };
 // instead of the MLP image; every coefficient is a multilinear interpolation into registers, so the shared coefficient
 // slots and the (alpha, beta) cache do not exist.  Everything around the coefficients is the same code.
 
-template <int BS, int MINB, int MODE, bool TAB = false>
+template <int BS, int MINB, int MODE, bool TAB = false, int TASK = NP_TASK_HEADING>
 __global__ void __launch_bounds__(BS, MINB) f16_step_kernel(const __grid_constant__ StepParams p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   float* blob = reinterpret_cast<float*>(smem_raw);
@@ -604,7 +608,10 @@ __global__ void __launch_bounds__(BS, MINB) f16_step_kernel(const __grid_constan
         const uchar2 pv = reinterpret_cast<const uchar2*>(p.pair_reset)[prl];
         rst[0] = pv.x != 0; rst[1] = pv.y != 0;
       } else {
-        rst[0] = rst[1] = rst[0] || rst[1];
+        bool r = rst[0] || rst[1];
+        // MultipleCombat (multiplecombat_env.py:207-238): an env is TWO adjacent duels = two adjacent lanes; any flag resets all four
+        if (c.combat_pairs_per_env == 2) r |= __shfl_xor_sync(0xffffffffu, (int)r, 1) != 0;
+        rst[0] = rst[1] = r;
       }
     }
 #pragma unroll
@@ -615,7 +622,7 @@ __global__ void __launch_bounds__(BS, MINB) f16_step_kernel(const __grid_constan
           combat_reset_aircraft(c, r, s[q], u[q]);
           blood[q] = 100.0f;
         } else {
-          reset_aircraft(c, r, s[q], u[q], tgt[q]);
+          reset_aircraft(c, TASK, r, s[q], u[q], tgt[q]);
         }
         steps[q] = 0;
       }
@@ -753,7 +760,7 @@ __global__ void __launch_bounds__(BS, MINB) f16_step_kernel(const __grid_constan
           //      planning / combat return only the last sub-step's observation (planning_env.py:177) -------------
           if (!COMBAT && (!PLAN || sub == nsub - 1)) {
             float o[NP_NUM_OBS];
-            make_obs(c, sq, uq, tq, g, eas2tas_of(tp), o);
+            make_obs(c, TASK, sq, uq, tq, g, eas2tas_of(tp), o);
             add_obs_noise(p, idx[q], o);
             if (staged) {
               if (q == 0 && !p.obs_stg) {   // the tile's previous contents may still be being read by the last bulk store
@@ -785,7 +792,7 @@ __global__ void __launch_bounds__(BS, MINB) f16_step_kernel(const __grid_constan
           float d0, d1, d2, rw = 0.0f;
           if (COMBAT) {
             exc[q] |= (steps[q] - c.max_steps) >= 0;                            // timeout.py:29
-          } else if (c.task == NP_TASK_HEADING) {                                      // unreach_heading.py:38-53
+          } else if (TASK == NP_TASK_HEADING) {                                        // unreach_heading.py:38-53
             const float dpsi = wrap_pi(sq[5] - tq[1]);
             off = (fabsf(dpsi) >= (float)(3.141592653589793 / 36.0)) | (fabsf(sq[2] - tq[0]) >= 100.0f) |
                   (fabsf(sq[6] - tq[2]) >= 20.0f);
@@ -794,7 +801,7 @@ __global__ void __launch_bounds__(BS, MINB) f16_step_kernel(const __grid_constan
             d1 = dpsi / DC(kPi);
             d2 = (sq[6] - tq[2]) * 0.3048f / DC(340.0f);
             rw = -(d0 * d0) + -(d1 * d1) + -(d2 * d2);
-          } else if (c.task == NP_TASK_CONTROL) {                               // unreach_posture.py:37-55
+          } else if (TASK == NP_TASK_CONTROL) {                                 // unreach_posture.py:37-55
             const float dpsi = wrap_pi(sq[5] - tq[1]);
             off = (fabsf(dpsi) >= (float)(3.141592653589793 / 36.0)) |
                   (fabsf(sq[4] - tq[0]) >= (float)(3.141592653589793 / 36.0)) | (fabsf(sq[6] - tq[2]) >= 20.0f);
@@ -935,7 +942,7 @@ __global__ void __launch_bounds__(256) f16_reset_kernel(const __grid_constant__ 
     const bool rst = (p.flags[i] | p.flags[ld + i] | p.flags[2 * (size_t)ld + i]) != 0;
     if (rst) {
       const Draws r = reset_draws(p, i);
-      reset_aircraft(c, r, s, u, tgt);
+      reset_aircraft(c, c.task, r, s, u, tgt);
 #pragma unroll
       for (int j = 0; j < 12; ++j) p.s[(size_t)j * ld + i] = s[j];
 #pragma unroll
@@ -961,7 +968,7 @@ __global__ void __launch_bounds__(256) f16_reset_kernel(const __grid_constant__ 
     p.flags[i] = 0; p.flags[ld + i] = 0; p.flags[2 * (size_t)ld + i] = 0;
     const Trig g = make_trig(s);
     float o[NP_NUM_OBS];
-    make_obs(c, s, u, tgt, g, eas2tas_of(tfac_pow(s[2])), o);
+    make_obs(c, c.task, s, u, tgt, g, eas2tas_of(tfac_pow(s[2])), o);
     add_obs_noise(p, i, o);
 #pragma unroll
     for (int j = 0; j < NP_NUM_OBS; ++j) p.obs[(size_t)i * NP_NUM_OBS + j] = o[j];
@@ -1349,7 +1356,7 @@ struct PairParams {
   uint8_t* pair_reset;     // [ld]
   unsigned long long* counters;
   int n, ld, role, n_sub;
-  float distance_limit;
+  float distance_limit, reward_scale;
 };
 template <bool PEER>
 __global__ void __launch_bounds__(256) combat_pair_kernel(const __grid_constant__ PairParams p) {
@@ -1384,7 +1391,7 @@ __global__ void __launch_bounds__(256) combat_pair_kernel(const __grid_constant_
     float* orow = p.obs + (size_t)i * NP_NUM_OBS_COMBAT;
 #pragma unroll
     for (int j = 0; j < NP_NUM_OBS_COMBAT; ++j) orow[j] = o[j];
-    p.reward[i] = combat_reward(g, p.role);
+    p.reward[i] = combat_reward(g, p.role, p.reward_scale);
     p.blood[i] = stepped ? own.blood - combat_damage(g, p.role) : own.blood;
     p.flags[i] = (mine & 1) ? 1 : 0;
     p.flags[p.ld + i] = (mine & 2) ? 1 : 0;
@@ -1912,11 +1919,11 @@ size_t np_env_workspace_bytes(const np_env_cfg* cfg) {
 
 }  // extern "C"
 
-template <int BS, int MINB, int MODE, bool TAB = false>
+template <int BS, int MINB, int MODE, bool TAB = false, int TASK = NP_TASK_HEADING>
 static int launch_step(np_env* env, const StepParams& p, cudaStream_t st) {
   const int smem = step_smem_bytes(p.aero_bytes, BS, MODE, TAB);
   static int configured[64] = {};  // per device: the attribute lives in the device's context
-  auto kern = f16_step_kernel<BS, MINB, MODE, TAB>;
+  auto kern = f16_step_kernel<BS, MINB, MODE, TAB, TASK>;
   const int dev = env->device;
   if (configured[dev & 63] < smem) {
     NP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -1932,6 +1939,16 @@ static int launch_step(np_env* env, const StepParams& p, cudaStream_t st) {
   kern<<<grid, BS, smem, st>>>(p);
   NP_CUDA(cudaGetLastError());
   return NP_OK;
+}
+
+// BaseEnv.step: one instantiation per task (control_env.py:28-35), chosen here
+template <int BS, int MINB, bool TAB = false>
+static int launch_env_step(np_env* env, const StepParams& p, cudaStream_t st) {
+  switch (env->cfg.task) {
+    case NP_TASK_HEADING: return launch_step<BS, MINB, MODE_STEP, TAB, NP_TASK_HEADING>(env, p, st);
+    case NP_TASK_CONTROL: return launch_step<BS, MINB, MODE_STEP, TAB, NP_TASK_CONTROL>(env, p, st);
+    default: return launch_step<BS, MINB, MODE_STEP, TAB, NP_TASK_TRACKING>(env, p, st);
+  }
 }
 
 // Block size of the MLP step for a range of `npairs` aircraft pairs.  384 threads (12 warps, 168 registers, no spills) is the
@@ -2013,6 +2030,9 @@ static int env_create_impl(const np_env_cfg* cfg, const np_aero* aero, const np_
   if (cfg->task < NP_TASK_HEADING || cfg->task > NP_TASK_TRACKING) return fail(NP_EINVAL, "np_env_create: unknown task");
   std::unique_ptr<np_env> e(new np_env());   // freed on every error return below
   e->cfg = *cfg;
+  if (e->cfg.combat_pairs_per_env <= 0) e->cfg.combat_pairs_per_env = 1;
+  if (e->cfg.combat_reward_scale == 0.0f) e->cfg.combat_reward_scale = 0.01f;   // singlecombat_env.py:176-177
+  if (e->cfg.combat_pairs_per_env > 2) return fail(NP_EINVAL, "np_env_create: combat_pairs_per_env must be 1 (1-v-1) or 2 (2-v-2)");
   e->aero = aero;
   e->tables = tables;
   memset(&e->buf, 0, sizeof(e->buf));
@@ -2177,24 +2197,24 @@ static int step_range_impl(np_env* env, const float* action_dev, const float* dr
   if (env->tables) {
     switch (env->tab_block) {
 #if defined(NPLANE_ALL_BLOCKS) || defined(NPLANE_TAB_BLOCKS)
-      case 128: return launch_step<128, 4, MODE_STEP, true>(env, p, st);
-      case 256: return launch_step<256, 2, MODE_STEP, true>(env, p, st);
-      case 512: return launch_step<512, 1, MODE_STEP, true>(env, p, st);
+      case 128: return launch_env_step<128, 4, true>(env, p, st);
+      case 256: return launch_env_step<256, 2, true>(env, p, st);
+      case 512: return launch_env_step<512, 1, true>(env, p, st);
 #endif
-      case 384: return launch_step<384, 1, MODE_STEP, true>(env, p, st);  // 4.36e9 vs 4.16e9 (256 x 2) / 4.20e9 (512) / 4.10e9 (128 x 4) at n = 10^6
+      case 384: return launch_env_step<384, 1, true>(env, p, st);  // 4.36e9 vs 4.16e9 (256 x 2) / 4.20e9 (512) / 4.10e9 (128 x 4) at n = 10^6
       default: return fail(NP_EINVAL, "np_env_step: table back-end block size not compiled in (build with -DNPLANE_ALL_BLOCKS)");
     }
   }
   switch (pick_block(env, p.pair_end - p.pair_begin)) {
 #ifdef NPLANE_ALL_BLOCKS
-    case 128: return launch_step<128, 4, MODE_STEP>(env, p, st);
-    case 256: return launch_step<256, 2, MODE_STEP>(env, p, st);
-    case 320: return launch_step<320, 1, MODE_STEP>(env, p, st);
-    case 352: return launch_step<352, 1, MODE_STEP>(env, p, st);
-    case 448: return launch_step<448, 1, MODE_STEP>(env, p, st);
+    case 128: return launch_env_step<128, 4>(env, p, st);
+    case 256: return launch_env_step<256, 2>(env, p, st);
+    case 320: return launch_env_step<320, 1>(env, p, st);
+    case 352: return launch_env_step<352, 1>(env, p, st);
+    case 448: return launch_env_step<448, 1>(env, p, st);
 #endif
-    case 384: return launch_step<384, 1, MODE_STEP>(env, p, st);
-    case 512: return launch_step<512, 1, MODE_STEP>(env, p, st);
+    case 384: return launch_env_step<384, 1>(env, p, st);
+    case 512: return launch_env_step<512, 1>(env, p, st);
     default: return fail(NP_EINVAL, "np_env_step: block size not compiled in (build with -DNPLANE_ALL_BLOCKS)");
   }
 }
@@ -2255,6 +2275,7 @@ int np_env_plan_step(np_env* env, const float* action3_dev, int n_sub, const flo
   if (!env || !env->bound) return fail(NP_ESTATE, "np_env_plan_step: env not bound");
   if (env->cfg.model != NP_MODEL_F16) return fail(NP_EINVAL, "np_env_plan_step: the fused PID controller flies the F16 plug-in");
   if (env->tables) return fail(NP_EINVAL, "np_env_plan_step: not built for the table aero back-end");
+  if (env->cfg.task != NP_TASK_TRACKING) return fail(NP_EINVAL, "np_env_plan_step: PlanningEnv flies the tracking task (planning_env.py:33)");
   if (!action3_dev || ((uintptr_t)action3_dev & 3) || n_sub < 1) return fail(NP_EINVAL, "np_env_plan_step: bad action pointer or n_sub");
   DeviceGuard guard(env->device);
   StepParams p = make_params(env, action3_dev, draws_dev, noise_dev);
@@ -2262,12 +2283,13 @@ int np_env_plan_step(np_env* env, const float* action3_dev, int n_sub, const flo
   p.pid_first = env->pid_started ? 0 : 1;
   env->pid_started = true;
   env->step_index++;
-  return launch_step<384, 1, MODE_PLAN>(env, p, (cudaStream_t)stream);
+  return launch_step<384, 1, MODE_PLAN, false, NP_TASK_TRACKING>(env, p, (cudaStream_t)stream);
 }
 
 int np_env_combat_step(np_env* env, const float* action_dev, int n_sub, const float* draws_dev, void* stream) {
   if (!env || !env->bound) return fail(NP_ESTATE, "np_env_combat_step: env not bound");
   if (env->cfg.model != NP_MODEL_F16 || (env->cfg.n & 1)) return fail(NP_EINVAL, "np_env_combat_step: needs the F16 plug-in and an even population (pairs)");
+  if (env->cfg.combat_pairs_per_env == 2 && (env->cfg.n & 3)) return fail(NP_EINVAL, "np_env_combat_step: a 2-v-2 population is a multiple of 4 aircraft");
   if (n_sub < 0 || (n_sub > 0 && (!action_dev || ((uintptr_t)action_dev & 15)))) return fail(NP_EINVAL, "np_env_combat_step: bad action pointer or n_sub");
   if (env->tables) return fail(NP_EINVAL, "np_env_combat_step: not built for the table aero back-end");
   DeviceGuard guard(env->device);
@@ -2313,7 +2335,7 @@ int np_env_combat_role_pair(np_env* env, const float* own_records_dev, const flo
   PairParams p;
   p.own = own_records_dev; p.partner = partner_records_dev;
   p.obs = sp.obs; p.reward = sp.reward; p.blood = sp.blood; p.flags = sp.flags; p.pair_reset = sp.pair_reset; p.counters = sp.counters;
-  p.n = env->cfg.n; p.ld = env->cfg.ld; p.role = role; p.n_sub = n_sub; p.distance_limit = env->cfg.distance_limit;
+  p.n = env->cfg.n; p.ld = env->cfg.ld; p.role = role; p.n_sub = n_sub; p.distance_limit = env->cfg.distance_limit; p.reward_scale = env->cfg.combat_reward_scale;
   const int want = (p.n + 255) / 256;
   const int grid = want < env->num_sms * 8 ? want : env->num_sms * 8;
   if (partner_is_peer) combat_pair_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(p);
@@ -2590,7 +2612,7 @@ int np_env_step_mapped(np_env* env, const float* action_host, float* action_mapp
   p.reward = rew_d;
   p.flags_mirror = flg_d;
   p.flags_mirror_ld = flags_ld;
-  const int rc = env->tables ? launch_step<384, 1, MODE_STEP, true>(env, p, st) : launch_step<384, 1, MODE_STEP>(env, p, st);   // 384: the staged obs path
+  const int rc = env->tables ? launch_env_step<384, 1, true>(env, p, st) : launch_env_step<384, 1>(env, p, st);   // 384: the staged obs path
   if (rc != NP_OK) return rc;
   NP_CUDA(cudaStreamSynchronize(st));
   return NP_OK;

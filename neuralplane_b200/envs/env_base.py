@@ -79,6 +79,8 @@ class BaseEnv:
         c.use_coef_cache = 1 if self.use_coef_cache else 0
         c.seed, c.index_base = self._seed & (2 ** 64 - 1), self.index_base
         c.index_stride = self.index_stride
+        c.combat_pairs_per_env = getattr(self, "combat_pairs_per_env", 1)
+        c.combat_reward_scale = getattr(self, "combat_reward_scale", 0.01)
         for key, default in _CFG_KEYS:
             setattr(c, key, getattr(self.config, key, default))
         c.noise_scale = self.task.noise_scale

@@ -39,6 +39,8 @@ class SingleCombatEnv(BaseEnv):
     final flags).  Outputs are bit-identical to the pair layout's.  Connect an exchange with `connect()` before reset()."""
     native_obs_dim = nv.NUM_OBS_COMBAT
     n_substeps = 5                      # singlecombat_env.py:244
+    combat_pairs_per_env = 1            # duels per env (MultipleCombatEnv: 2)
+    combat_reward_scale = 0.01          # singlecombat_env.py:176-177
     # the device counters' cause bits 5 / 6 carry Crash-or-ego-Shutdown / enemy-Shutdown here (crash.py:29-42, shutdown.py:30-40)
     COUNTER_NAMES = ("overload", "low_altitude", "high_speed", "low_speed", "extreme_state", "crash_or_shutdown",
                      "enemy_shutdown", "resets")
@@ -55,7 +57,7 @@ class SingleCombatEnv(BaseEnv):
                 raise ValueError("layout='role' needs an even number of local envs (the step kernel moves aircraft in pairs)")
             kw.update(local_agents=1, index_base=2 * int(first_env) + role, index_stride=2)
         super().__init__(num_envs, config, 'F16', random_seed, device, **kw)
-        if layout == 'pair' and self.num_agents != 2:
+        if layout == 'pair' and self.num_agents != 2 * self.combat_pairs_per_env:
             raise NotImplementedError("Singlecombat number of agents must be 2!")
         off = nv.lib().np_env_blood_offset_bytes(self._cfg)
         self.blood = self._workspace[off: off + self.ld * 4].view(torch.float32)[:self.n]

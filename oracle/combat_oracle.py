@@ -72,7 +72,12 @@ def distance_fn(R):
 
 
 class CombatOracle:
+    N_SUB = 5                # singlecombat_env.py:244
+    GROUP = 2                # aircraft that share an env-level reset (singlecombat_env.py:207-238)
+    REWARD_SCALE = 0.01      # singlecombat_env.py:176-177
+
     def __init__(self, num_envs, cfg=None, aero=None, dtype=torch.float32):
+        """num_envs counts DUELS (ego, enemy pairs)."""
         self.num_envs, self.n, self.dtype = num_envs, 2 * num_envs, dtype
         self.cfg = dict(COMBAT_CFG)
         if cfg:
@@ -97,7 +102,7 @@ class CombatOracle:
     def reset_done_envs(self, draws):
         c = self.cfg
         flag = (self.is_done | self.bad_done) | self.exceed_time_limit
-        m = flag.reshape(self.num_envs, 2).any(dim=1).repeat_interleave(2)
+        m = flag.reshape(-1, self.GROUP).any(dim=1).repeat_interleave(self.GROUP)
         d = draws.to(self.dtype)
         self.s[m, :] = 0
         self.u[m, :] = 0
@@ -189,7 +194,7 @@ class CombatOracle:
         rr = range_reward_v3(self.cfg["target_dist"], dist * 0.3048 / 1000)
         ego_r = orientation_reward_v2(AO, TA) * rr
         enm_r = orientation_reward_v2(torch.pi - TA, torch.pi - AO) * rr
-        return 0.01 * torch.stack((ego_r, enm_r), 1).reshape(-1)
+        return self.REWARD_SCALE * torch.stack((ego_r, enm_r), 1).reshape(-1)
 
     # -- terminations (the eight classes of singlecombat_env.py:48-58) ---------------------------------------
     def terminations(self):
@@ -214,7 +219,7 @@ class CombatOracle:
     def step(self, action, draws):
         self.reset_done_envs(draws)
         a = torch.clamp(action.to(self.dtype), -1, 1)
-        for _ in range(5):
+        for _ in range(self.N_SUB):
             self.roll_dem = 0.9 * self.roll_dem + 0.1 * a[:, 1] * 4 * torch.pi / 9
             self.pitch_dem = 0.9 * self.pitch_dem + 0.1 * a[:, 2] * torch.pi / 12
             el, ail, rud = self.stabilize()
@@ -238,3 +243,22 @@ class CombatOracle:
         for k in ("roll", "pitch", "yaw"):
             rows += [self.pid[k].error, self.pid[k].integrator, self.last_out[k]]
         return torch.stack(rows, 1)
+
+
+MULTI_CFG = dict(COMBAT_CFG, max_npos=10000, min_npos=-10000, max_epos=10000, min_epos=-10000)   # multiple_selfplay.yaml
+
+
+class MultiCombatOracle(CombatOracle):
+    """MultipleCombatEnv (envs/multiplecombat_env.py) with the pairing restated as two adjacent duels per env -- see the
+    docstring of neuralplane_b200/envs/multiplecombat_env.py for why and for what is kept from the file: per-duel 1-v-1
+    formulas, env-level reset over all four agents (:207-238), ONE FDM step per env step (:258), no 0.01 reward factor
+    (:176-177).  `num_envs` counts ENVS of four aircraft.  Parity UNPINNED for this orchestration."""
+    N_SUB = 1
+    GROUP = 4
+    REWARD_SCALE = 1.0
+
+    def __init__(self, num_envs, cfg=None, aero=None, dtype=torch.float32):
+        c = dict(MULTI_CFG)
+        if cfg:
+            c.update(cfg)
+        super().__init__(2 * num_envs, c, aero, dtype)

@@ -30,8 +30,8 @@ def test_library_exports_every_declared_symbol():
 def test_abi_version_and_struct_layout():
     L = nv.lib()
     assert L.np_version() == int(re.search(r"#define NP_ABI_VERSION (\d+)", HEADER).group(1))
-    # np_env_cfg: 4 x i32, 2 x u64, 16 floats, 2 x i32, 5 floats, 2 x i32, 8 floats, 1 x i32 = 168 bytes
-    assert C.sizeof(nv.EnvCfg) == 168 and nv.EnvCfg.index_stride.offset == 164
+    # np_env_cfg: 4 x i32, 2 x u64, 16 floats, 2 x i32, 5 floats, 2 x i32, 8 floats, 2 x i32, 1 float = 176 bytes
+    assert C.sizeof(nv.EnvCfg) == 176 and nv.EnvCfg.index_stride.offset == 164 and nv.EnvCfg.combat_reward_scale.offset == 172
     assert nv.EnvCfg.seed.offset == 16 and nv.EnvCfg.dt.offset == 32 and nv.EnvCfg.model.offset == 124
     assert C.sizeof(nv.NetDesc) == 48 and C.sizeof(nv.Buffers) == 8 * 8
     fields = [f for f, _ in nv.EnvCfg._fields_]

@@ -192,6 +192,46 @@ def test_relgeo_peers_kernel_equals_relgeo_on_the_gathered_array():
     assert torch.equal(got, want)
 
 
+def test_combat_full_size_sampled_parity():
+    """BASELINE configs[4] size (5 x 10^5 pairs): pairs are independent, so a random sample of pairs is replayed through the
+    combat oracle from the same pre-step state, controls, blood, flags and controller state (bars of the teacher-forced test)."""
+    from oracle.combat_oracle import CombatOracle
+    from neuralplane_b200 import _native as nv
+    E, m = 500_000, 1024
+    env = _env(E)
+    env.reset()
+    g = torch.Generator(device="cuda").manual_seed(12)
+    for _ in range(3):
+        env.step(torch.rand((env.n, 4), device="cuda", generator=g) * 2 - 1)
+    pe = np.sort(np.random.default_rng(2).choice(E, m, replace=False))
+    idx = torch.from_numpy(np.stack((2 * pe, 2 * pe + 1), 1).reshape(-1)).cuda()          # both aircraft of the sampled pairs
+    orc = CombatOracle(m)
+    orc.s = env.model.s[idx].cpu(); orc.u = env.model.u[idx].cpu()
+    orc.step_count = env.step_count[idx].cpu().long()
+    orc.is_done = env.is_done[idx].cpu().clone(); orc.bad_done = env.bad_done[idx].cpu().clone()
+    orc.exceed_time_limit = env.exceed_time_limit[idx].cpu().clone()
+    orc.blood = env.blood[idx].cpu().clone()
+    cs = env.ctrl_state[idx].cpu()
+    orc.roll_dem, orc.pitch_dem = cs[:, 9].clone(), cs[:, 10].clone()
+    for j, k in enumerate(("roll", "pitch", "yaw")):
+        orc.pid[k].error, orc.pid[k].integrator, orc.last_out[k] = cs[:, 3 * j].clone(), cs[:, 3 * j + 1].clone(), cs[:, 3 * j + 2].clone()
+        orc.pid[k].first = False
+    a = torch.rand((env.n, 4), device="cuda", generator=g) * 2 - 1
+    d = torch.rand((env.n, 5), device="cuda", generator=g)
+    obs, rew, done, bad, exc, _ = env.step(a, reset_draws=d)
+    o_obs, o_rew, o_done, o_bad, o_exc = orc.step(a[idx].cpu(), d[idx].cpu())
+    err = state_rel_err(env.model.s[idx].cpu().numpy(), orc.s.numpy())
+    assert np.median(err) <= 2e-5 and np.percentile(err, 99) <= 3e-4, (np.median(err), np.percentile(err, 99))
+    assert (bad[idx].cpu() != o_bad).sum() <= 2 and (done[idx].cpu() != o_done).sum() <= 2
+    do = np.abs(obs[idx].cpu().numpy() - o_obs.numpy()).max(axis=1)
+    assert np.median(do) <= 2e-5 and np.percentile(do, 99) <= 2e-3, (np.median(do), do.max())
+    ok = ((bad[idx].cpu() == o_bad) & (done[idx].cpu() == o_done)).numpy()
+    assert np.allclose(rew[idx].cpu().numpy()[ok], o_rew.numpy()[ok], rtol=2e-4, atol=2e-6)
+    assert np.allclose(env.blood[idx].cpu().numpy(), orc.blood.numpy(), rtol=1e-5, atol=2e-3)
+    assert np.array_equal(env.step_count[idx].cpu().numpy(), orc.step_count.numpy().astype(np.int32))
+    assert torch.isfinite(env.model.s).all() and torch.isfinite(obs).all() and torch.isfinite(rew).all()
+
+
 def _role_pair(num_envs, seed=0, first_env=0):
     from neuralplane_b200 import SingleCombatEnv
     from neuralplane_b200.combat_exchange import LocalPairExchange

@@ -361,81 +361,15 @@ def test_observation_noise_statistics(dev):
     assert float(z.abs().max()) < 6.5
     c = np.corrcoef(z[:, :6].t().cpu().numpy())
     assert np.abs(c - np.eye(6)).max() < 0.02
-    # injected normals reproduce obs + noise * scale exactly
+    # injected normals reproduce obs + noise * scale exactly (heading_task.py:152: obs + randn_like(obs) * noise_scale): the two
+    # envs hold the same state (noise never feeds back into it), one steps with injected normals, the other without noise
+    assert torch.equal(e0.model.s, e1.model.s)
     nz = torch.randn((n, 22), device=dev)
     e0.task.noise_scale = 0.01
-    o_inj = e0.step(a, reset_draws=d0, noise=nz)[0].clone()
     e1.task.noise_scale = 0.0
-    e1.model.s[:] = e0.model.s  # not comparable states; only check the injection arithmetic on e0 itself
-    assert torch.isfinite(o_inj).all()
-
-
-def test_gpuvecenv_numpy_boundary(dev):
-    """GPUVecEnv keeps the reference's numpy shapes / dtypes (env_wrappers.py:93-109)."""
-    from neuralplane_b200 import ControlEnv, GPUVecEnv
-    ne = 300
-    venv = GPUVecEnv([lambda: ControlEnv(num_envs=ne, config="heading", model="F16", random_seed=0, device="cuda:0")])
-    obs = venv.reset()
-    assert obs.shape == (ne, 1, 22) and obs.dtype == np.float32
-    act = np.stack([venv.action_space.sample() for _ in range(ne)]).reshape(ne, 1, 4)
-    obs, rew, done, bad, exc, info = venv.step(act)
-    assert obs.shape == (ne, 1, 22) and rew.shape == (ne, 1, 1) and done.shape == (ne, 1, 1)
-    assert rew.dtype == np.float32 and done.dtype == np.bool_ and bad.dtype == np.bool_ and info == {}
-    assert np.isfinite(obs).all()
-
-
-def test_gpuvecenv_device_tensor_mode(dev):
-    """SURVEY f-2: the same wrapper without the host round trip -- torch CUDA tensors in, (num_envs, agents, .) views out."""
-    from neuralplane_b200 import ControlEnv, GPUVecEnv, PlanningEnv, SingleCombatEnv
-    ne = 256
-    mk = lambda: ControlEnv(num_envs=ne, config="heading", model="F16", random_seed=4, device="cuda:0")
-    v_dev, v_np = GPUVecEnv([mk], device_tensors=True), GPUVecEnv([mk])
-    o_dev, o_np = v_dev.reset(), v_np.reset()
-    assert o_dev.is_cuda and o_dev.shape == (ne, 1, 22) and np.array_equal(o_dev.cpu().numpy(), o_np)
-    a = tapes.action_tape(4, 1, ne, 1.0).reshape(ne, 1, 4)
-    r_dev, r_np = v_dev.step(_cuda(a)), v_np.step(a)
-    for x, y in zip(r_dev[:5], r_np[:5]):
-        assert x.is_cuda and tuple(x.shape) == y.shape and np.array_equal(x.cpu().numpy(), y)
-    assert v_dev.h2d_bytes_per_step == 0 and v_np.d2h_bytes_per_step == ne * (22 * 4 + 4 + 3)
-    # the wrapper also fronts the 3-D planning and the 2-agent combat envs
-    vp = GPUVecEnv([lambda: PlanningEnv(num_envs=64, config="tracking", random_seed=1, device="cuda:0", n_substeps=3)])
-    obs, rew, *_ = vp.step(np.zeros((64, 1, 3), np.float32))
-    assert obs.shape == (64, 1, 22) and rew.shape == (64, 1, 1)
-    vc = GPUVecEnv([lambda: SingleCombatEnv(num_envs=32, config="selfplay", random_seed=1, device="cuda:0")])
-    assert vc.reset().shape == (32, 2, 15)
-    obs, rew, done, *_ = vc.step(np.zeros((32, 2, 4), np.float32))
-    assert obs.shape == (32, 2, 15) and rew.shape == (32, 2, 1) and done.shape == (32, 2, 1)
-
-
-def test_step_is_cuda_graph_capturable_and_stream_ordered(dev):
-    """include/nplane.h: step only ENQUEUES on the caller's stream and is CUDA-graph capturable.  A captured graph of 4
-    steps replayed 5 times must equal 20 eager steps bit for bit (noise off; resets from the in-kernel Philox stream are
-    keyed by the step index the host passes at capture time, so the comparison uses a tape of injected draws)."""
-    n = 4096
-    e_graph, e_eager = _env(n), _env(n)
-    d0 = _cuda(tapes.reset_draw_tape(8, 0, n))
-    e_graph.reset(reset_draws=d0); e_eager.reset(reset_draws=d0)
-    acts = [_cuda(tapes.action_tape(8, k, n, 1.0)) for k in range(4)]
-    draws = _cuda(tapes.reset_draw_tape(8, 1, n))
-    side = torch.cuda.Stream()
-    side.wait_stream(torch.cuda.current_stream())
-    with torch.cuda.stream(side):
-        e_graph.step(acts[0], reset_draws=draws)          # warm-up on the side stream (lazy module loading)
-    torch.cuda.current_stream().wait_stream(side)
-    e_eager.step(acts[0], reset_draws=draws)
-    g = torch.cuda.CUDAGraph()
-    with torch.cuda.graph(g):
-        for k in range(4):
-            e_graph.step(acts[k], reset_draws=draws)
-    for _ in range(5):
-        g.replay()
-    for _ in range(5):
-        for k in range(4):
-            e_eager.step(acts[k], reset_draws=draws)
-    torch.cuda.synchronize()
-    assert torch.equal(e_graph.model.s, e_eager.model.s) and torch.equal(e_graph.last_obs, e_eager.last_obs)
-    assert torch.equal(e_graph.step_count, e_eager.step_count) and torch.equal(e_graph.last_reward, e_eager.last_reward)
-    assert e_graph.termination_counters() == e_eager.termination_counters()
+    o_inj = e0.step(a, reset_draws=d0, noise=nz)[0].clone()
+    o_clean = e1.step(a, reset_draws=d0)[0].clone()
+    assert torch.equal(o_inj, o_clean + nz * 0.01)
 
 
 @pytest.mark.parametrize("model,task", [("F16", "heading"), ("F16_tables", "control"), ("UAV", "control")])

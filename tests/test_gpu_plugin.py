@@ -46,25 +46,28 @@ def test_model_update_equals_fused_step(model):
 
 
 def test_f16_update_vs_oracle():
-    """np_f16_update against the CPU oracle's F16 update (oracle/f16_oracle.py, pinned to the reference) after three
-    updates: median state error < 5e-7, worst aircraft < 1e-5 (fp32; the kernel's libm differs from torch's by an ulp)."""
+    """np_f16_update against the CPU oracle's F16 update (oracle/f16_oracle.py, pinned to the reference) from 20000 random
+    in-envelope (s, u): the same bar as the fused step's single-step test -- our distance to the float64 truth is at most
+    2x the reference-fp32 distance (p50 and p99); controls to 1e-6."""
     from neuralplane_b200 import ControlEnv
-    from oracle.f16_oracle import F16EnvOracle, euler_step, lowpass_controls
-    n = 512
+    from oracle.f16_oracle import AeroNets, euler_step, lowpass_controls
+    from _metrics import state_rel_err
+    n = 20000
+    s0, u0 = tapes.random_envelope_states(41, n)
+    a = tapes.action_tape(42, 1, n, 1.0)
     env = ControlEnv(num_envs=n, config="heading", model="F16", random_seed=0, device="cuda:0")
-    orc = F16EnvOracle(n, "heading")
-    d0 = tapes.reset_draw_tape(7, 0, n)
-    env.reset(reset_draws=_cuda(d0))
-    orc.reset(torch.from_numpy(d0))
-    for k in range(1, 4):
-        a = tapes.action_tape(7, k, n, 0.5)
-        env.model.update(_cuda(a))
-        orc.u = lowpass_controls(orc.u, torch.from_numpy(a))          # F16_model.py:51-63
-        orc.s = euler_step(orc.aero, orc.s, orc.u, orc.cfg["dt"])     # :64-67
-    from _metrics import state_rel_err                       # per-component relative error with the suite's floors
-    err = state_rel_err(env.model.s.cpu().numpy(), orc.s.numpy())
-    assert np.median(err) < 5e-7 and err.max() < 1e-5, (np.median(err), err.max())
-    assert np.allclose(env.model.u.cpu().numpy()[:, :4], orc.u.numpy()[:, :4], rtol=1e-6, atol=1e-6)
+    env.model.s[:] = _cuda(s0); env.model.u[:] = _cuda(u0)
+    env.model.update(_cuda(a))
+    res = {}
+    for dt in (torch.float32, torch.float64):
+        u = lowpass_controls(torch.from_numpy(u0).to(dt), torch.from_numpy(a).to(dt))          # F16_model.py:51-63
+        res[dt] = (euler_step(AeroNets(dtype=dt), torch.from_numpy(s0).to(dt), u, 0.02).numpy(), u.numpy())   # :64-67
+    truth = res[torch.float64][0]
+    e_ours, e_ref = state_rel_err(env.model.s.cpu().numpy(), truth), state_rel_err(res[torch.float32][0], truth)
+    assert np.percentile(e_ours, 99) <= 2 * np.percentile(e_ref, 99) and np.median(e_ours) <= 2 * np.median(e_ref), (
+        np.median(e_ours), np.percentile(e_ours, 99), np.median(e_ref), np.percentile(e_ref, 99))
+    assert np.allclose(env.model.u.cpu().numpy()[:, :4], res[torch.float32][1][:, :4], rtol=1e-6, atol=1e-6)
+    assert torch.equal(env.model.recent_s.cpu(), torch.from_numpy(s0))
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")

@@ -62,7 +62,7 @@ def _run(task, fixture, golden_dir, max_steps=None):
 
 
 @pytest.mark.parametrize("task,fixture,max_steps", [
-    ("heading", "heading_traj_a03.npz", 300),
+    ("heading", "heading_traj_a03.npz", 1000),      # config 1 in full: 128 aircraft x 1000 steps
     ("heading", "heading_traj_a10.npz", 300),
     ("control", "control_traj.npz", 300),
     ("tracking", "tracking_traj.npz", 300),
