@@ -312,6 +312,21 @@ def side_combat(dev, rank, world, barrier, max_over_ranks, pairs_total=500_000, 
     return out
 
 
+def side_tables(dev, hbm_peak, barrier, n=4_000_000, K=100, W=20):
+    """The table aero back-end (ControlEnv(model='F16_tables'), SURVEY f-3) through K1t, one aircraft per thread."""
+    import torch
+    from neuralplane_b200 import ControlEnv
+    env = ControlEnv(num_envs=n, config="heading", model="F16_tables", random_seed=0, device=dev)
+    env.reset()
+    acts = [torch.rand((n, 4), device=dev) * 2 - 1 for _ in range(2)]
+    ms = timed_steps(lambda k: env.step(acts[k % 2]), K, W, barrier) / K
+    achieved = 276.0 * n / (ms * 1e-3) / 1e9
+    return {"kernel": "f16_table_step_kernel", "workload": f"F16 Heading task with the table aero back-end, num_agents={n}, random policy",
+            "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+            "algorithmic_bytes_per_aircraft_step": 276, "ms_per_step": ms, "aircraft_steps_per_s": n / (ms * 1e-3), "steps": K,
+            "launch": env.launch_info()}
+
+
 def side_small_n(dev, barrier, n=3000, K=200, W=20):
     """The population the reference trains at (scripts/train_heading.sh:13: 3 000 envs): per-step latency of the device-
     resident step under CUDA-graph replay (no launch overhead from Python)."""
@@ -449,6 +464,7 @@ def main():
         if world == 1:
             jobs += [("uav_roofline", lambda: side_uav_roofline(dev, hbm_peak, barrier)),
                      ("uav_config3", lambda: side_uav_config3(dev, barrier)),
+                     ("table_backend", lambda: side_tables(dev, hbm_peak, barrier)),
                      ("small_n_latency", lambda: side_small_n(dev, barrier))]
         for name, fn in jobs:            # every rank runs the same list (the sharded ones hold collectives)
             try:
@@ -494,8 +510,7 @@ def main():
             "side": side,
             "termination_counters": counters,
         }
-        if "uav_roofline" in side:
-            out["side_rooflines"] = [side["uav_roofline"]]
+        out["side_rooflines"] = [side[k] for k in ("uav_roofline", "table_backend") if k in side and "error" not in side[k]]
         if world == 1 and not args.no_cpu:
             try:
                 nc = n if reference_available() else args.cpu_n

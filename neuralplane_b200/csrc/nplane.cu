@@ -94,6 +94,9 @@ struct np_env {
   bool pid_started = false;  // the fused PID controller has run at least once (PID.reset, pid.py:13)
   int device = 0;            // the device the env was created on; every entry point switches to it
   int obs_stg = 0;           // NPLANE_OBS_STORE=stg: per-lane stores of the staged observation tile instead of the TMA bulk store
+  uint8_t* mirror = nullptr; // set by np_env_step_mapped around a step: second copy of the new flags in mapped host memory
+  int mirror_ld = 0;
+  int tab_pairs = 0;         // NPLANE_TAB_KERNEL=pairs: the table back-end on K1's two-aircraft-per-thread kernel (round 1) instead of K1t
   int block = 0;             // 0: chosen per launch (pick_block); else forced by NPLANE_BLOCK
   int tab_block = 384, grid = 0, smem = 0, num_sms = 0, last_block = 384;
   // np_env_step_host: one in-order stream per engine (upload, kernels, download) and the events chaining them
@@ -484,6 +487,79 @@ __device__ __forceinline__ CombatRecFull combat_rec_load(const float* row) {
   return f;
 }
 
+// F16Model.update's control lag (F16_model.py:52-57): clamp, then first-order low-pass towards the scaled action
+__device__ __forceinline__ void lowpass_controls(const float* a_in, float* u) {
+  float a[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) a[j] = fminf(fmaxf(a_in[j], -1.0f), 1.0f);
+  u[0] = 0.9f * u[0] + 0.1f * a[0] * 0.225f * 76300.0f / DC(0.3048f);
+  u[1] = 0.9f * u[1] + 0.1f * a[1] * 45.0f;
+  u[2] = 0.9f * u[2] + 0.1f * a[2] * 45.0f;
+  u[3] = 0.9f * u[3] + 0.1f * a[3] * 45.0f;
+}
+
+// The six termination predicates (task_base.py:75-96) and the task reward (task_base.py:60-73) of ONE aircraft at its new
+// state; f = the force part of nlplant at that state (Overload needs the body accelerations, F16_model.py:132-148).
+// causes: bit 0 overload, 1 low altitude, 2 high speed, 3 low speed, 4 extreme state, 5 unreach, 6 reached.
+struct Verdict {
+  bool bad, done, exc;
+  float rw;
+  int causes;
+};
+template <bool COMBAT, int TASK>
+__device__ __forceinline__ Verdict judge_state(const np_env_cfg& c, const float* sq, const float* tq, const Trig& g, const ForceOut& f,
+                                               int steps) {
+  float ax, ay, az;
+  body_accel(sq, g, f, ax, ay, az);
+  const float acc = sqrtf(ax * ax + ay * ay + az * az);
+  const bool overload = (acc - c.acceleration_limit) > 0.0f;            // overload.py:37-42
+  const bool low_alt = (sq[2] - c.altitude_limit) < 0.0f;               // low_altitude.py:29-30
+  const float vel = (sq[6] + c.airspeed * 1.0f) * 0.3048f / DC(340.0f);
+  const bool hi = (vel - c.max_velocity) >= 0.0f;                       // high_speed.py:29-30
+  const bool lo = (vel - c.min_velocity) <= 0.0f;                       // low_speed.py:29-30
+  const float a_deg = sq[7] * 180.0f / DC(kPi), b_deg = sq[8] * 180.0f / DC(kPi);  // extreme_state.py:32-36
+  const bool ext = (a_deg < c.min_alpha) | (a_deg > c.max_alpha) | (b_deg < c.min_beta) | (b_deg > c.max_beta);
+  const bool late = steps >= c.max_check_interval;
+  bool off = false, dn = false, exc = false;
+  float d0, d1, d2, rw = 0.0f;
+  if (COMBAT) {
+    exc = (steps - c.max_steps) >= 0;                                   // timeout.py:29
+  } else if (TASK == NP_TASK_HEADING) {                                 // unreach_heading.py:38-53
+    const float dpsi = wrap_pi(sq[5] - tq[1]);
+    off = (fabsf(dpsi) >= (float)(3.141592653589793 / 36.0)) | (fabsf(sq[2] - tq[0]) >= 100.0f) |
+          (fabsf(sq[6] - tq[2]) >= 20.0f);
+    dn = !off && !late && (steps >= c.min_check_interval);
+    d0 = (sq[2] - tq[0]) * 0.3048f / DC(1000.0f);                       // heading_reward.py:26-35
+    d1 = dpsi / DC(kPi);
+    d2 = (sq[6] - tq[2]) * 0.3048f / DC(340.0f);
+    rw = -(d0 * d0) + -(d1 * d1) + -(d2 * d2);
+  } else if (TASK == NP_TASK_CONTROL) {                                 // unreach_posture.py:37-55
+    const float dpsi = wrap_pi(sq[5] - tq[1]);
+    off = (fabsf(dpsi) >= (float)(3.141592653589793 / 36.0)) |
+          (fabsf(sq[4] - tq[0]) >= (float)(3.141592653589793 / 36.0)) | (fabsf(sq[6] - tq[2]) >= 20.0f);
+    dn = !off && !late;
+    d0 = wrap_pi(sq[4] - tq[0]) / DC(kPi);                              // posture_reward.py:26-34
+    d1 = dpsi / DC(kPi);
+    d2 = (sq[6] - tq[2]) * 0.3048f / DC(340.0f);
+    rw = -(d0 * d0) + -(d1 * d1) + -(d2 * d2);
+  } else {                                                              // unreach_target.py:35-47
+    off = (fabsf(sq[0] - tq[0]) >= 100.0f) | (fabsf(sq[1] - tq[1]) >= 100.0f) | (fabsf(sq[2] - tq[2]) >= 100.0f);
+    dn = !off && !late;
+    d0 = (sq[0] - tq[0]) * 0.3048f / DC(1000.0f);                       // position_reward.py:26-34
+    d1 = (sq[1] - tq[1]) * 0.3048f / DC(1000.0f);
+    d2 = (sq[2] - tq[2]) * 0.3048f / DC(1000.0f);
+    rw = 0.1f * (-(d0 * d0) + -(d1 * d1) + -(d2 * d2));
+  }
+  const bool unreach = late && off;
+  Verdict v;
+  v.bad = overload | low_alt | hi | lo | ext | unreach;
+  v.done = dn;
+  v.exc = exc;
+  v.rw = rw;
+  v.causes = (int)overload | ((int)low_alt << 1) | ((int)hi << 2) | ((int)lo << 3) | ((int)ext << 4) | ((int)unreach << 5) | ((int)dn << 6);
+  return v;
+}
+
 // ------------------------------------------------------------------------------------------------
 // K1: the fused step kernel
 // ------------------------------------------------------------------------------------------------
@@ -776,55 +852,13 @@ __global__ void __launch_bounds__(BS, MINB) f16_step_kernel(const __grid_constan
               for (int j = 0; j < NP_NUM_OBS / 2; ++j) orow[j] = make_float2(o[2 * j], o[2 * j + 1]);
             }
           }
-          // ---- terminations (task_base.py:75-96) on the new state --------------------------------------
-          float ax, ay, az;
-          body_accel(sq, g, fp.f, ax, ay, az);
-          const float acc = sqrtf(ax * ax + ay * ay + az * az);
-          const bool overload = (acc - c.acceleration_limit) > 0.0f;            // overload.py:37-42
-          const bool low_alt = (sq[2] - c.altitude_limit) < 0.0f;               // low_altitude.py:29-30
-          const float vel = (sq[6] + c.airspeed * 1.0f) * 0.3048f / DC(340.0f);
-          const bool hi = (vel - c.max_velocity) >= 0.0f;                       // high_speed.py:29-30
-          const bool lo = (vel - c.min_velocity) <= 0.0f;                       // low_speed.py:29-30
-          const float a_deg = sq[7] * 180.0f / DC(kPi), b_deg = sq[8] * 180.0f / DC(kPi);  // extreme_state.py:32-36
-          const bool ext = (a_deg < c.min_alpha) | (a_deg > c.max_alpha) | (b_deg < c.min_beta) | (b_deg > c.max_beta);
-          const bool late = steps[q] >= c.max_check_interval;
-          bool off = false, dn = false;
-          float d0, d1, d2, rw = 0.0f;
-          if (COMBAT) {
-            exc[q] |= (steps[q] - c.max_steps) >= 0;                            // timeout.py:29
-          } else if (TASK == NP_TASK_HEADING) {                                        // unreach_heading.py:38-53
-            const float dpsi = wrap_pi(sq[5] - tq[1]);
-            off = (fabsf(dpsi) >= (float)(3.141592653589793 / 36.0)) | (fabsf(sq[2] - tq[0]) >= 100.0f) |
-                  (fabsf(sq[6] - tq[2]) >= 20.0f);
-            dn = !off && !late && (steps[q] >= c.min_check_interval);
-            d0 = (sq[2] - tq[0]) * 0.3048f / DC(1000.0f);                           // heading_reward.py:26-35
-            d1 = dpsi / DC(kPi);
-            d2 = (sq[6] - tq[2]) * 0.3048f / DC(340.0f);
-            rw = -(d0 * d0) + -(d1 * d1) + -(d2 * d2);
-          } else if (TASK == NP_TASK_CONTROL) {                                 // unreach_posture.py:37-55
-            const float dpsi = wrap_pi(sq[5] - tq[1]);
-            off = (fabsf(dpsi) >= (float)(3.141592653589793 / 36.0)) |
-                  (fabsf(sq[4] - tq[0]) >= (float)(3.141592653589793 / 36.0)) | (fabsf(sq[6] - tq[2]) >= 20.0f);
-            dn = !off && !late;
-            d0 = wrap_pi(sq[4] - tq[0]) / DC(kPi);                                  // posture_reward.py:26-34
-            d1 = dpsi / DC(kPi);
-            d2 = (sq[6] - tq[2]) * 0.3048f / DC(340.0f);
-            rw = -(d0 * d0) + -(d1 * d1) + -(d2 * d2);
-          } else {                                                              // unreach_target.py:35-47
-            off = (fabsf(sq[0] - tq[0]) >= 100.0f) | (fabsf(sq[1] - tq[1]) >= 100.0f) | (fabsf(sq[2] - tq[2]) >= 100.0f);
-            dn = !off && !late;
-            d0 = (sq[0] - tq[0]) * 0.3048f / DC(1000.0f);                           // position_reward.py:26-34
-            d1 = (sq[1] - tq[1]) * 0.3048f / DC(1000.0f);
-            d2 = (sq[2] - tq[2]) * 0.3048f / DC(1000.0f);
-            rw = 0.1f * (-(d0 * d0) + -(d1 * d1) + -(d2 * d2));
-          }
-          const bool unreach = late && off;
-          bad[q] |= overload | low_alt | hi | lo | ext | unreach;               // OR-accumulated (env_base.py:70-75)
-          done[q] |= dn;
-          rew[q] = rw + (float)(-200 * (int)bad[q] + 200 * (int)done[q]);       // event_driven_reward.py:28
-          causes[q] |= act[q] ? ((int)overload | ((int)low_alt << 1) | ((int)hi << 2) | ((int)lo << 3) | ((int)ext << 4) |
-                                 ((int)unreach << 5) | ((int)dn << 6))
-                              : 0;
+          // ---- terminations (task_base.py:75-96) and the task reward on the new state ----------------------
+          const Verdict v = judge_state<COMBAT, TASK>(c, sq, tq, g, fp.f, steps[q]);
+          exc[q] |= v.exc;
+          bad[q] |= v.bad;                                                      // OR-accumulated (env_base.py:70-75)
+          done[q] |= v.done;
+          rew[q] = v.rw + (float)(-200 * (int)bad[q] + 200 * (int)done[q]);     // event_driven_reward.py:28
+          causes[q] |= act[q] ? v.causes : 0;
         }
       }
       if (STAGE && pass == 1 && staged && (!PLAN || sub == nsub - 1)) {   // tile -> obs[64 rows], 5 632 contiguous bytes
@@ -928,6 +962,128 @@ __global__ void __launch_bounds__(BS, MINB) f16_step_kernel(const __grid_constan
     }
   }
   if (STAGE && (threadIdx.x & 31) == 0) bulk_wait0();   // shared memory must outlive the last bulk stores
+}
+
+// ------------------------------------------------------------------------------------------------
+// K1t: BaseEnv.step with the TABLE aero back-end, ONE aircraft per thread.  The table step has no MLP arithmetic to pack
+// two aircraft into (FFMA2), so the pair-per-thread shape of K1 only cost it registers: 168 -> 12 warps per SM, at 50 %
+// issue utilisation on dependent shared-memory gathers.  Here: 384 threads, <= 85 registers, 2 CTAs = 24 warps per SM, the
+// 54 KB table image staged once per CTA, coalesced 4-byte SoA accesses, the 88-byte observation rows staged per warp
+// (32 rows = 2 816 contiguous bytes) and sent with one TMA bulk store.  Same device functions in the same order as K1's
+// TAB instantiation: bit-identical outputs.
+// ------------------------------------------------------------------------------------------------
+constexpr int kTabBS = 384;   // x 2 CTAs per SM = 24 warps; 2 x (54 KB tables + 33 KB observation tiles) of shared memory
+constexpr int kTabTileFloats = 32 * NP_NUM_OBS;
+static int table_step_smem_bytes() { return kTablesFloats * 4 + (kTabBS / 32) * kTabTileFloats * 4 + 16; }
+
+__device__ __forceinline__ void count_cause1(unsigned long long* counters, int which, bool p0) {
+  const int k = __popc(__ballot_sync(0xffffffffu, p0));
+  if (k != 0 && (threadIdx.x & 31) == 0) atomicAdd(&counters[which], (unsigned long long)k);
+}
+
+template <int TASK>
+__global__ void __launch_bounds__(kTabBS, 2) f16_table_step_kernel(const __grid_constant__ StepParams p) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  float* T = reinterpret_cast<float*>(smem_raw);
+  float* otile = T + kTablesFloats + (threadIdx.x >> 5) * kTabTileFloats;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(T + kTablesFloats + (kTabBS / 32) * kTabTileFloats);
+  stage_aero(T, p.aero, (uint32_t)(kTablesFloats * 4), bar);
+  const ZeroCells zc = zero_cells(T);
+  const np_env_cfg& c = p.cfg;
+  const int n = c.n, ld = c.ld, lane = threadIdx.x & 31;
+  const int i_begin = 2 * p.pair_begin, i_end = min(n, 2 * p.pair_end);
+  for (int base = i_begin + blockIdx.x * kTabBS; base < i_end; base += gridDim.x * kTabBS) {
+    const int i = base + threadIdx.x;
+    const bool live = i < i_end;
+    const int il = live ? i : i_end - 1;          // idle lanes shadow the last aircraft and never store
+    float s[12], u[4], tgt[3], a[4];
+#pragma unroll
+    for (int j = 0; j < 12; ++j) s[j] = p.s[(size_t)j * ld + il];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) u[j] = p.u[(size_t)j * ld + il];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) tgt[j] = p.tgt[(size_t)j * ld + il];
+    int steps = p.step_count[il];
+    const bool rst = (p.flags[il] | p.flags[ld + il] | p.flags[2 * (size_t)ld + il]) != 0;
+    {
+      const float4 av = reinterpret_cast<const float4*>(p.action)[il];
+      a[0] = av.x; a[1] = av.y; a[2] = av.z; a[3] = av.w;
+    }
+    if (rst) {                                     // BaseEnv.reset (env_base.py:83-97)
+      reset_aircraft(c, TASK, reset_draws(p, il), s, u, tgt);
+      steps = 0;
+    }
+    count_cause1(p.counters, 7, rst && live);
+    lowpass_controls(a, u);                        // F16_model.py:52-57
+    float rew = 0.0f;
+    bool bad = false, done = false;
+    int causes = 0;
+    const bool staged = __all_sync(0xffffffffu, live) && ((reinterpret_cast<uintptr_t>(p.obs) & 15) == 0);
+#pragma unroll 1
+    for (int pass = 0; pass < 2; ++pass) {
+      float ctab[kNumSlots], a1[kNumA1];
+      table_env_coefs(T, zc, s[7] * kR2D, s[8] * kR2D, u[1], pass == 0, ctab, a1);
+      const Trig g = make_trig(s);
+      const float tp = tfac_pow(s[2]);
+      const ForcePart fp = force_part(s, u[0], u[2], u[3], 0.0f, g, tp, ctab, 1, a1);
+      if (pass == 0) {                             // Euler step (F16_model.py:64-67)
+        float xdot[12];
+        nlplant_kin_moments(s, u[2], u[3], 0.0f, g, fp.qbar, fp.vt, fp.b, fp.t, ctab, 1, a1, xdot);
+        xdot[6] = fp.f.vt_dot; xdot[7] = fp.f.alpha_dot; xdot[8] = fp.f.beta_dot;
+        const float h = c.dt - 0.0f;
+#pragma unroll
+        for (int j = 0; j < 12; ++j) s[j] = s[j] + h * xdot[j];
+        steps += 1;                                // env_base.py:102
+      } else {
+        float o[NP_NUM_OBS];
+        make_obs(c, TASK, s, u, tgt, g, eas2tas_of(tp), o);
+        add_obs_noise(p, il, o);
+        if (staged) {
+          if (lane == 0) bulk_wait_read0();        // the previous slab's bulk store has read the tile
+          __syncwarp();
+          float2* orow = reinterpret_cast<float2*>(otile + lane * NP_NUM_OBS);
+#pragma unroll
+          for (int j = 0; j < NP_NUM_OBS / 2; ++j) orow[j] = make_float2(o[2 * j], o[2 * j + 1]);
+          fence_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            bulk_s2g(p.obs + (size_t)(i - lane) * NP_NUM_OBS, otile, kTabTileFloats * 4);
+            bulk_commit();
+          }
+        } else if (live) {
+          float2* orow = reinterpret_cast<float2*>(p.obs + (size_t)i * NP_NUM_OBS);
+#pragma unroll
+          for (int j = 0; j < NP_NUM_OBS / 2; ++j) orow[j] = make_float2(o[2 * j], o[2 * j + 1]);
+        }
+        const Verdict v = judge_state<false, TASK>(c, s, tgt, g, fp.f, steps);
+        bad = v.bad; done = v.done;
+        rew = v.rw + (float)(-200 * (int)bad + 200 * (int)done);       // event_driven_reward.py:28
+        causes = live ? v.causes : 0;
+      }
+    }
+#pragma unroll
+    for (int w = 0; w < 7; ++w) count_cause1(p.counters, w, (causes >> w) & 1);
+    if (live) {
+#pragma unroll
+      for (int j = 0; j < 12; ++j) p.s[(size_t)j * ld + i] = s[j];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) p.u[(size_t)j * ld + i] = u[j];
+#pragma unroll
+      for (int j = 0; j < 3; ++j) p.tgt[(size_t)j * ld + i] = tgt[j];
+      p.step_count[i] = steps;
+      p.reward[i] = rew;
+      p.flags[i] = done ? 1 : 0;
+      p.flags[ld + i] = bad ? 1 : 0;
+      p.flags[2 * (size_t)ld + i] = 0;             // control tasks: Timeout is commented out (heading_task.py:45)
+      if (p.flags_mirror) {
+        const size_t ml = (size_t)p.flags_mirror_ld;
+        p.flags_mirror[i] = done ? 1 : 0;
+        p.flags_mirror[ml + i] = bad ? 1 : 0;
+        p.flags_mirror[2 * ml + i] = 0;
+      }
+    }
+  }
+  if (lane == 0) bulk_wait0();                     // shared memory must outlive the last bulk stores
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1687,16 +1843,6 @@ __global__ void __launch_bounds__(kAuxBS) f16_coeffs_kernel(const uint32_t* __re
 // controls the update started from (the reference rebinds self.recent_s = self.s before integrating).
 // Same device code and evaluation order as the fused step, so env.step and model.update agree bit for bit.
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void lowpass_controls(const float* a_in, float* u) {
-  float a[4];
-#pragma unroll
-  for (int j = 0; j < 4; ++j) a[j] = fminf(fmaxf(a_in[j], -1.0f), 1.0f);
-  u[0] = 0.9f * u[0] + 0.1f * a[0] * 0.225f * 76300.0f / DC(0.3048f);
-  u[1] = 0.9f * u[1] + 0.1f * a[1] * 45.0f;
-  u[2] = 0.9f * u[2] + 0.1f * a[2] * 45.0f;
-  u[3] = 0.9f * u[3] + 0.1f * a[3] * 45.0f;
-}
-
 __global__ void __launch_bounds__(kAuxBS) f16_update_kernel(const uint32_t* __restrict__ aero, int aero_bytes, float* __restrict__ S,
                                                             float* __restrict__ U, float* __restrict__ RS, float* __restrict__ RU,
                                                             const float* __restrict__ action, int n, int ld, float dt) {
@@ -1957,6 +2103,10 @@ static int launch_env_step(np_env* env, const StepParams& p, cudaStream_t st) {
 // of waves (a strong-scaling shard: 125 k aircraft = 1.1 waves of 384) the wider block that saves a whole wave wins.
 static int pick_block(const np_env* env, int npairs) {
   if (env->block) return env->block;
+  // Small populations (what the reference trains at: 3 000 envs, scripts/train_heading.sh:13) are LATENCY bound: a step is as
+  // long as one warp's pass through the kernel, and that pass is ~2x shorter when the warp has its scheduler to itself.
+  // 128-thread CTAs put one warp on each of an SM's four schedulers and spread the population over 3x as many SMs.
+  if (npairs <= env->num_sms * 128) return 128;
   auto cost = [&](int bs, double rate) {
     const long slabs = (npairs + bs - 1) / bs;
     const long waves = (slabs + env->num_sms - 1) / env->num_sms;
@@ -1997,8 +2147,8 @@ static StepParams make_params(np_env* env, const float* action, const float* dra
   p.action = action;
   p.draws = draws;
   p.noise = noise;
-  p.flags_mirror = nullptr;
-  p.flags_mirror_ld = 0;
+  p.flags_mirror = env->mirror;
+  p.flags_mirror_ld = env->mirror_ld;
   p.obs_stg = env->obs_stg;
   p.records = nullptr;
   p.pair_reset = pair_reset_row;
@@ -2049,6 +2199,7 @@ static int env_create_impl(const np_env_cfg* cfg, const np_aero* aero, const np_
   }
   if (const char* b = getenv("NPLANE_TAB_BLOCK")) e->tab_block = atoi(b);
   if (const char* b = getenv("NPLANE_OBS_STORE")) e->obs_stg = strcmp(b, "stg") == 0;
+  if (const char* b = getenv("NPLANE_TAB_KERNEL")) e->tab_pairs = strcmp(b, "pairs") == 0;
   *out = e.release();
   return NP_OK;
 }
@@ -2194,7 +2345,30 @@ static int step_range_impl(np_env* env, const float* action_dev, const float* dr
     NP_CUDA(cudaGetLastError());
     return NP_OK;
   }
-  if (env->tables) {
+  if (env->tables && !env->tab_pairs) {   // K1t: one aircraft per thread
+    if (count == 0) return NP_OK;
+    const int smem = table_step_smem_bytes();
+    const int want = (count + kTabBS - 1) / kTabBS;
+    env->grid = want < env->num_sms * 2 ? want : env->num_sms * 2;
+    env->smem = smem;
+    env->last_block = kTabBS;
+    static bool attr_set[64][3] = {};
+    auto launch = [&](auto kern, int t) -> int {
+      if (!attr_set[env->device & 63][t]) {
+        NP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        attr_set[env->device & 63][t] = true;
+      }
+      kern<<<env->grid, kTabBS, smem, st>>>(p);
+      NP_CUDA(cudaGetLastError());
+      return NP_OK;
+    };
+    switch (env->cfg.task) {
+      case NP_TASK_HEADING: return launch(f16_table_step_kernel<NP_TASK_HEADING>, 0);
+      case NP_TASK_CONTROL: return launch(f16_table_step_kernel<NP_TASK_CONTROL>, 1);
+      default: return launch(f16_table_step_kernel<NP_TASK_TRACKING>, 2);
+    }
+  }
+  if (env->tables) {                      // NPLANE_TAB_KERNEL=pairs: K1's two-aircraft-per-thread shape with table coefficients
     switch (env->tab_block) {
 #if defined(NPLANE_ALL_BLOCKS) || defined(NPLANE_TAB_BLOCKS)
       case 128: return launch_env_step<128, 4, true>(env, p, st);
@@ -2206,8 +2380,8 @@ static int step_range_impl(np_env* env, const float* action_dev, const float* dr
     }
   }
   switch (pick_block(env, p.pair_end - p.pair_begin)) {
+    case 128: return launch_env_step<128, 1>(env, p, st);
 #ifdef NPLANE_ALL_BLOCKS
-    case 128: return launch_env_step<128, 4>(env, p, st);
     case 256: return launch_env_step<256, 2>(env, p, st);
     case 320: return launch_env_step<320, 1>(env, p, st);
     case 352: return launch_env_step<352, 1>(env, p, st);
@@ -2274,7 +2448,6 @@ int np_env_plan_step(np_env* env, const float* action3_dev, int n_sub, const flo
                      void* stream) {
   if (!env || !env->bound) return fail(NP_ESTATE, "np_env_plan_step: env not bound");
   if (env->cfg.model != NP_MODEL_F16) return fail(NP_EINVAL, "np_env_plan_step: the fused PID controller flies the F16 plug-in");
-  if (env->tables) return fail(NP_EINVAL, "np_env_plan_step: not built for the table aero back-end");
   if (env->cfg.task != NP_TASK_TRACKING) return fail(NP_EINVAL, "np_env_plan_step: PlanningEnv flies the tracking task (planning_env.py:33)");
   if (!action3_dev || ((uintptr_t)action3_dev & 3) || n_sub < 1) return fail(NP_EINVAL, "np_env_plan_step: bad action pointer or n_sub");
   DeviceGuard guard(env->device);
@@ -2283,6 +2456,7 @@ int np_env_plan_step(np_env* env, const float* action3_dev, int n_sub, const flo
   p.pid_first = env->pid_started ? 0 : 1;
   env->pid_started = true;
   env->step_index++;
+  if (env->tables) return launch_step<384, 1, MODE_PLAN, true, NP_TASK_TRACKING>(env, p, (cudaStream_t)stream);
   return launch_step<384, 1, MODE_PLAN, false, NP_TASK_TRACKING>(env, p, (cudaStream_t)stream);
 }
 
@@ -2291,13 +2465,13 @@ int np_env_combat_step(np_env* env, const float* action_dev, int n_sub, const fl
   if (env->cfg.model != NP_MODEL_F16 || (env->cfg.n & 1)) return fail(NP_EINVAL, "np_env_combat_step: needs the F16 plug-in and an even population (pairs)");
   if (env->cfg.combat_pairs_per_env == 2 && (env->cfg.n & 3)) return fail(NP_EINVAL, "np_env_combat_step: a 2-v-2 population is a multiple of 4 aircraft");
   if (n_sub < 0 || (n_sub > 0 && (!action_dev || ((uintptr_t)action_dev & 15)))) return fail(NP_EINVAL, "np_env_combat_step: bad action pointer or n_sub");
-  if (env->tables) return fail(NP_EINVAL, "np_env_combat_step: not built for the table aero back-end");
   DeviceGuard guard(env->device);
   StepParams p = make_params(env, action_dev ? action_dev : reinterpret_cast<const float*>(env->buf.s_dev), draws_dev, nullptr);
   p.n_sub = n_sub;
   p.pid_first = env->pid_started ? 0 : 1;
   if (n_sub > 0) env->pid_started = true;
   env->step_index++;
+  if (env->tables) return launch_step<384, 1, MODE_COMBAT, true>(env, p, (cudaStream_t)stream);
   return launch_step<384, 1, MODE_COMBAT>(env, p, (cudaStream_t)stream);
 }
 
@@ -2408,7 +2582,7 @@ int np_env_counters(np_env* env, uint64_t* out, void* stream) {
 int np_env_launch_info(const np_env* env, int* grid, int* block, int* smem_bytes, int* num_sms) {
   if (!env) return fail(NP_EINVAL, "np_env_launch_info: null env");
   if (grid) *grid = env->grid;
-  if (block) *block = env->cfg.model == NP_MODEL_UAV ? 256 : env->tables ? env->tab_block : env->last_block;
+  if (block) *block = env->cfg.model == NP_MODEL_UAV ? 256 : env->last_block;
   if (smem_bytes) *smem_bytes = env->smem;
   if (num_sms) *num_sms = env->num_sms;
   return NP_OK;
@@ -2612,7 +2786,18 @@ int np_env_step_mapped(np_env* env, const float* action_host, float* action_mapp
   p.reward = rew_d;
   p.flags_mirror = flg_d;
   p.flags_mirror_ld = flags_ld;
-  const int rc = env->tables ? launch_env_step<384, 1, true>(env, p, st) : launch_env_step<384, 1>(env, p, st);   // 384: the staged obs path
+  int rc;
+  if (env->tables) {
+    const float *sobs = env->buf.obs_dev, *srew = env->buf.reward_dev;
+    env->buf.obs_dev = obs_d; env->buf.reward_dev = rew_d;           // step_range_impl builds its parameters from the bound buffers
+    env->mirror = flg_d; env->mirror_ld = flags_ld;
+    env->step_index--;
+    rc = step_range_impl(env, act, nullptr, nullptr, 0, n, true, st);
+    env->buf.obs_dev = const_cast<float*>(sobs); env->buf.reward_dev = const_cast<float*>(srew);
+    env->mirror = nullptr;
+  } else {
+    rc = launch_env_step<384, 1>(env, p, st);   // 384: the staged obs path
+  }
   if (rc != NP_OK) return rc;
   NP_CUDA(cudaStreamSynchronize(st));
   return NP_OK;

@@ -11,7 +11,7 @@ import torch
 
 from .. import _native as nv
 from .env_base import BaseEnv
-from .models.F16_model import F16Model
+from .models.F16_model import F16Model, F16TablesModel
 from .tasks.tracking_task import TrackingTask
 from .utils.utils import wrap_PI
 
@@ -24,9 +24,10 @@ class PlanningEnv(BaseEnv):
         super().__init__(num_envs, config, model, random_seed, device, **kw)
 
     def load(self, random_seed, config, model):
-        if model != 'F16':
-            raise NotImplementedError("the fused PID low-level controller flies the F16 plug-in")
-        self.model = F16Model(self.config, self.n, self.device, random_seed, ld=self.ld)
+        if model not in ('F16', 'F16_tables'):
+            raise NotImplementedError("the fused PID low-level controller flies the F16 plug-in (MLP or table aero back-end)")
+        cls = F16Model if model == 'F16' else F16TablesModel
+        self.model = cls(self.config, self.n, self.device, random_seed, ld=self.ld)
         rows = [self._tgt[j, :self.n] for j in range(3)]
         self.task = TrackingTask(self.config, self.n, self.device, random_seed, rows)
 

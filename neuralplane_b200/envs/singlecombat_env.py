@@ -14,7 +14,7 @@ import torch
 
 from .. import _native as nv
 from .env_base import BaseEnv
-from .models.F16_model import F16Model
+from .models.F16_model import F16Model, F16TablesModel
 from .tasks.task_base import BaseTask
 
 
@@ -46,17 +46,19 @@ class SingleCombatEnv(BaseEnv):
                      "enemy_shutdown", "resets")
 
     def __init__(self, num_envs=1, config='selfplay', random_seed=None, device="cuda:0", layout='pair', role=None,
-                 first_env=0, **kw):
+                 first_env=0, model='F16', **kw):
         if layout not in ('pair', 'role'):
             raise ValueError("layout must be 'pair' or 'role'")
         self.layout, self.role, self.exchange = layout, role, None
+        if model not in ('F16', 'F16_tables') or (model != 'F16' and layout == 'role'):
+            raise NotImplementedError("combat flies the F16 plug-in ('F16'; 'F16_tables' in the pair layout)")
         if layout == 'role':
             if role not in (0, 1):
                 raise ValueError("layout='role' needs role=0 (egos) or role=1 (opponents)")
             if num_envs % 2:
                 raise ValueError("layout='role' needs an even number of local envs (the step kernel moves aircraft in pairs)")
             kw.update(local_agents=1, index_base=2 * int(first_env) + role, index_stride=2)
-        super().__init__(num_envs, config, 'F16', random_seed, device, **kw)
+        super().__init__(num_envs, config, model, random_seed, device, **kw)
         if layout == 'pair' and self.num_agents != 2 * self.combat_pairs_per_env:
             raise NotImplementedError("Singlecombat number of agents must be 2!")
         off = nv.lib().np_env_blood_offset_bytes(self._cfg)
@@ -66,7 +68,8 @@ class SingleCombatEnv(BaseEnv):
         self._pair_reset = self._workspace[off: off + self.ld]
 
     def load(self, random_seed, config, model):
-        self.model = F16Model(self.config, self.n, self.device, random_seed, ld=self.ld)
+        cls = F16Model if model == 'F16' else F16TablesModel
+        self.model = cls(self.config, self.n, self.device, random_seed, ld=self.ld)
         self.task = CombatTask(self.config, self.n, self.device, random_seed, ())
 
     @property

@@ -120,6 +120,21 @@ def test_block_choice_is_bit_identical_and_saves_a_wave():
             assert torch.equal(x, y), k
     assert env.launch_info()["block"] == 512 and ref.launch_info()["block"] == 384
     assert torch.equal(env.model.s, ref.model.s) and env.termination_counters() == ref.termination_counters()
+    # small populations are latency bound: 128-thread CTAs (one warp per scheduler, 3x as many SMs), same bits
+    n = 3000
+    small = ControlEnv(num_envs=n, config="heading", model="F16", random_seed=2, device="cuda:0")
+    os.environ["NPLANE_BLOCK"] = "384"
+    try:
+        ref = ControlEnv(num_envs=n, config="heading", model="F16", random_seed=2, device="cuda:0")
+    finally:
+        del os.environ["NPLANE_BLOCK"]
+    small.reset(); ref.reset()
+    for k in range(1, 60):
+        a = _cuda(tapes.action_tape(2, k, n, 1.0))
+        for x, y in zip(small.step(a)[:5], ref.step(a)[:5]):
+            assert torch.equal(x, y), k
+    assert small.launch_info()["block"] == 128 and small.launch_info()["grid"] == 12 and ref.launch_info()["grid"] == 4
+    assert small.termination_counters() == ref.termination_counters()
     big = ControlEnv(num_envs=1_000_000, config="heading", model="F16", random_seed=2, device="cuda:0")
     big.reset()
     big.step(torch.zeros((1_000_000, 4), device="cuda:0"))

@@ -167,11 +167,73 @@ def test_table_env_full_size_invariants():
     assert c["resets"] >= n and c["overload"] > 0
 
 
-def test_table_env_rejects_planning_and_combat_steps():
-    import ctypes as C
-    from neuralplane_b200 import _native as nv
-    env = _env(64)
-    a = torch.zeros((64, 4), device="cuda")
-    st = torch.cuda.current_stream().cuda_stream
-    assert nv.lib().np_env_plan_step(env._handle, a.data_ptr(), 5, None, None, st) != 0
-    assert nv.lib().np_env_combat_step(env._handle, a.data_ptr(), 5, None, st) != 0
+def test_table_kernel_equals_pair_kernel():
+    """K1t (one aircraft per thread, 24 warps/SM) against the round-1 shape (K1's two-aircraft-per-thread kernel with table
+    coefficients, NPLANE_TAB_KERNEL=pairs): same device functions in the same order -> every output bit for bit, odd
+    population, in-kernel Philox resets and noise included."""
+    import os
+    from neuralplane_b200 import ControlEnv
+    n = 50_001
+    for task in ("heading", "control", "tracking"):
+        new = ControlEnv(num_envs=n, config=task, model="F16_tables", random_seed=6, device="cuda:0")
+        os.environ["NPLANE_TAB_KERNEL"] = "pairs"
+        try:
+            old = ControlEnv(num_envs=n, config=task, model="F16_tables", random_seed=6, device="cuda:0")
+        finally:
+            del os.environ["NPLANE_TAB_KERNEL"]
+        assert torch.equal(new.reset(), old.reset())
+        for k in range(1, 40):
+            a = _cuda(tapes.action_tape(6, k, n, 1.0))
+            rn, ro = new.step(a), old.step(a)
+            for x, y in zip(rn[:5], ro[:5]):
+                assert torch.equal(x, y), (task, k)
+        assert torch.equal(new.model.s, old.model.s) and torch.equal(new.model.u, old.model.u)
+        assert new.termination_counters() == old.termination_counters() and new.termination_counters()["resets"] > n
+        assert new.launch_info()["block"] == 384 and new.launch_info()["grid"] <= 2 * new.launch_info()["num_sms"]
+
+
+def test_table_backend_flies_planning_and_combat():
+    """the planning and combat steps on the table aero back-end, teacher-forced against the planning /
+    combat oracles fed by the table oracle (PlanningOracle / CombatOracle(aero=TableAero())); bars of the MLP-backed tests."""
+    from neuralplane_b200 import PlanningEnv, SingleCombatEnv, _native as nv
+    from oracle.combat_oracle import CombatOracle
+    from oracle.f16_tables_oracle import TableAero
+    from oracle.planning_oracle import PlanningOracle
+    n, seed = 1024, 29
+    env = PlanningEnv(num_envs=n, config="tracking", model="F16_tables", random_seed=0, device="cuda:0", n_substeps=5)
+    orc = PlanningOracle(n, aero=TableAero(dtype=torch.float32))
+    orc.N_SUB = 5
+    d0 = tapes.reset_draw_tape(seed, 0, n)
+    env.reset(reset_draws=_cuda(d0)); orc.reset(torch.from_numpy(d0))
+    for k in range(1, 9):
+        env.model.s[:] = _cuda(orc.s.numpy()); env.model.u[:] = _cuda(orc.u.numpy())
+        env._tgt[:, :n] = _cuda(orc.tgt.numpy().T.copy())
+        env.step_count[:] = _cuda(orc.step_count.numpy().astype(np.int32))
+        env._flags[0, :n] = _cuda(orc.is_done.numpy().astype(np.uint8)); env._flags[1, :n] = _cuda(orc.bad_done.numpy().astype(np.uint8))
+        env._flags[2, :n] = 0
+        env.pid_state[:] = _cuda(orc.pid_state().numpy())
+        nv.check(nv.lib().np_env_set_pid_started(env._handle, 0 if k == 1 else 1), "np_env_set_pid_started")
+        a, d = tapes.action_tape(seed, k, n, 1.0, num_actions=3), tapes.reset_draw_tape(seed, k, n)
+        obs, rew, done, bad, exc, _ = env.step(_cuda(a), reset_draws=_cuda(d))
+        o_obs, o_rew, o_done, o_bad, o_exc = orc.plan_step(torch.from_numpy(a), torch.from_numpy(d))
+        err = state_rel_err(env.model.s.cpu().numpy(), orc.s.numpy())
+        assert np.median(err) <= 2e-5 and np.percentile(err, 99) <= 3e-4, (k, np.median(err), np.percentile(err, 99))
+        assert (bad.cpu().numpy() != o_bad.numpy()).sum() <= 3 and (done.cpu().numpy() != o_done.numpy()).sum() <= 3, k
+        assert np.array_equal(env.step_count.cpu().numpy(), orc.step_count.numpy().astype(np.int32)), k
+    E = 512
+    cenv = SingleCombatEnv(num_envs=E, config="selfplay", model="F16_tables", random_seed=0, device="cuda:0")
+    corc = CombatOracle(E, aero=TableAero(dtype=torch.float32))
+    d0 = tapes.reset_draw_tape(seed, 0, 2 * E)
+    o = cenv.reset(reset_draws=_cuda(d0)); oo = corc.reset(torch.from_numpy(d0))
+    rest = [j for j in range(15) if j not in (11, 12)]
+    assert np.abs(o.cpu().numpy() - oo.numpy())[:, rest].max() < 5e-5
+    a, d = tapes.action_tape(seed, 1, 2 * E, 0.5), tapes.reset_draw_tape(seed, 1, 2 * E)
+    obs, rew, done, bad, exc, _ = cenv.step(_cuda(a), reset_draws=_cuda(d))
+    o_obs, o_rew, o_done, o_bad, o_exc = corc.step(torch.from_numpy(a), torch.from_numpy(d))
+    err = state_rel_err(cenv.model.s.cpu().numpy(), corc.s.numpy())
+    assert np.median(err) <= 2e-5 and np.percentile(err, 99) <= 3e-4, (np.median(err), np.percentile(err, 99))
+    assert np.array_equal(bad.cpu().numpy(), o_bad.numpy()) and np.allclose(rew.cpu().numpy(), o_rew.numpy(), rtol=2e-4, atol=2e-6)
+    # what stays refused: a planning step on an env that is not flying the tracking task
+    henv = _env(64)
+    assert nv.lib().np_env_plan_step(henv._handle, torch.zeros((64, 3), device="cuda").data_ptr(), 5, None, None,
+                                     torch.cuda.current_stream().cuda_stream) != 0
