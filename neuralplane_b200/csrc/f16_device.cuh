@@ -134,9 +134,10 @@ __device__ __forceinline__ float2 denorm2(const float* __restrict__ blob, int k,
 }
 
 // Evaluate MLP nets [K0, K0 + count) of ONE ARCHITECTURE in a rolled loop; result k goes to out[k * stride] (a float2: both
-// aircraft of this thread).  The loop keeps the code footprint at one body per architecture: nets of the same shape but
-// different input normalisation (the "r30 / a20" and the "lef" alpha grids) share it, the alpha z-score being picked per
-// net at run time (warp-uniform) -- two bodies fewer than one per (architecture, normalisation) pair, 0.5 k SASS instructions.
+// aircraft of this thread).  The alpha z-score is picked per net at run time (warp-uniform), so nets of the same shape but
+// different input normalisation (the "r30 / a20" and the "lef" alpha grids) CAN share one body (-DNPLANE_MERGE_GROUPS: two
+// bodies and 0.55 k SASS instructions fewer) -- measured 10 % slower end to end than one loop per (architecture,
+// normalisation) pair (profiles/r02_variants.txt), which therefore stays the default.
 template <int K0>
 __device__ __forceinline__ void eval_group2(const float* __restrict__ blob, uint32_t wbase, const ZIn2& zi,
                                             float2* __restrict__ out, int stride, int count) {
@@ -179,8 +180,15 @@ static_assert(ab2_groups_ok(), "net table changed: revisit eval_group2 / eval_ab
 // The 16 two-input (alpha, beta) nets: slots [kFirstAB2, kFirstA1), four architectures.
 __device__ __forceinline__ void eval_ab2_nets(const float* __restrict__ blob, uint32_t wbase, const ZIn2& zi,
                                               float2* __restrict__ out, int stride) {
+#ifdef NPLANE_MERGE_GROUPS
   eval_group2<kCy>(blob, wbase, zi, out, stride, 4);           // [20,10]:    Cy, delta_Cl_a20, delta_Cx_lef, delta_Cl_lef
   eval_group2<kdCz_lef>(blob, wbase, zi, out, stride, 8);      // [20,10,5]:  4 x lef, 3 x r30, delta_Cn_a20
+#else
+  eval_group2<kCy>(blob, wbase, zi, out, stride, 2);           // [20,10], r30 / a20 alpha grid: Cy, delta_Cl_a20
+  eval_group2<kdCx_lef>(blob, wbase, zi, out, stride, 2);      // [20,10], lef alpha grid:       delta_Cx_lef, delta_Cl_lef
+  eval_group2<kdCz_lef>(blob, wbase, zi, out, stride, 4);      // [20,10,5], lef
+  eval_group2<kdCy_r30>(blob, wbase, zi, out, stride, 4);      // [20,10,5], r30 / a20
+#endif
   eval_group2<kdCy_a20>(blob, wbase, zi, out, stride, 1);      // [20,10,10]
   eval_group2<kdCy_a20_lef>(blob, wbase, zi, out, stride, 3);  // [20,20,10]
 }
@@ -251,11 +259,11 @@ __device__ __forceinline__ void alpha_coefs(const void* blob_smem, const AeroTab
 // ------------------------------------------------------------------------------------------------
 // Equations of motion
 // ------------------------------------------------------------------------------------------------
-// ONE copy of each large libm body per kernel (sincosf with its Payne-Hanek slow path is ~80 SASS instructions, powf ~150,
-// Philox ~65): the step kernel's tail is executed once per slab, so every inlined copy is instruction-cache traffic
-// (ncu: 1 100 of the 11 500 static instructions were ten copies of sincosf, stall_no_instruction concentrated in the tail).
-// Values and bits are those of the inlined calls.
-#ifndef NPLANE_INLINE_LIBM
+// sincosf / powf / Philox bodies.  Sharing ONE copy of each per kernel (__noinline__: -DNPLANE_SHARED_LIBM) takes 1.5 k
+// of the step kernel's SASS instructions away (ten inlined sincosf with their Payne-Hanek slow paths alone are 1.1 k) but
+// MEASURED 10 % slower end to end (0.500 vs 0.451 ms per 10^6-aircraft step, same box, profiles/r02_variants.txt): a call
+// serialises the two aircraft a thread interleaves.  Inlined is the default; the bits are the same either way.
+#ifdef NPLANE_SHARED_LIBM
 #define NP_LIBM_INLINE __noinline__
 #else
 #define NP_LIBM_INLINE __forceinline__
@@ -265,7 +273,11 @@ __device__ NP_LIBM_INLINE float2 sincos_shared(float x) {
   sincosf(x, &r.x, &r.y);
   return r;
 }
+#ifdef NPLANE_SHARED_POW
+__device__ __noinline__ float pow_shared(float x, float y) { return powf(x, y); }
+#else
 __device__ NP_LIBM_INLINE float pow_shared(float x, float y) { return powf(x, y); }
+#endif
 
 struct Trig {
   float sa, ca, sb, cb, st, ct, tt, sphi, cphi, spsi, cpsi;
@@ -498,7 +510,11 @@ __device__ __forceinline__ void body_accel(const float* s, const Trig& g, const 
 // ------------------------------------------------------------------------------------------------
 // Counter-based RNG: Philox4x32-10 keyed by the env seed; counter = (global aircraft index, step, stream).
 // ------------------------------------------------------------------------------------------------
+#ifdef NPLANE_SHARED_PHILOX
+__device__ __noinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
+#else
 __device__ NP_LIBM_INLINE uint4 philox4x32_10(uint4 ctr, uint2 key) {
+#endif
   constexpr uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
 #pragma unroll
   for (int r = 0; r < 10; ++r) {

@@ -569,7 +569,11 @@ __device__ __forceinline__ Verdict judge_state(const np_env_cfg& c, const float*
 // it is what makes the PCIe writes full-line posted writes.  Block sizes above 384 have no room for the tiles next to the
 // aero image and the coefficient slots and store their rows directly.
 constexpr int kObsTileFloats = 64 * NP_NUM_OBS;
+#ifdef NPLANE_NO_STAGE
+constexpr bool stage_obs(int, int) { return false; }
+#else
 constexpr bool stage_obs(int bs, int mode) { return bs <= 384 && mode != 2 /* MODE_COMBAT: 15-D rows, written by combat_outputs */; }
+#endif
 static int step_smem_bytes(int aero_bytes, int bs, int mode, bool tab = false) {
   return aero_bytes + (tab ? 0 : kNumSlots * bs * 8) + (stage_obs(bs, mode) ? (bs / 32) * kObsTileFloats * 4 : 0) + 16;
 }
@@ -779,7 +783,11 @@ __global__ void __launch_bounds__(BS, MINB) f16_step_kernel(const __grid_constan
       u[q][2] = 0.9f * u[q][2] + 0.1f * a[q][2] * 45.0f;
       u[q][3] = 0.9f * u[q][3] + 0.1f * a[q][3] * 45.0f;
     }
+#ifdef NPLANE_UNROLL_PASS
+#pragma unroll
+#else
 #pragma unroll 1
+#endif
     for (int pass = 0; pass < 2; ++pass) {
       const float2 adeg = make_float2(s[0][7] * kR2D, s[1][7] * kR2D);
       const float2 bdeg = make_float2(s[0][8] * kR2D, s[1][8] * kR2D);
@@ -972,9 +980,18 @@ __global__ void __launch_bounds__(BS, MINB) f16_step_kernel(const __grid_constan
 // (32 rows = 2 816 contiguous bytes) and sent with one TMA bulk store.  Same device functions in the same order as K1's
 // TAB instantiation: bit-identical outputs.
 // ------------------------------------------------------------------------------------------------
-constexpr int kTabBS = 384;   // x 2 CTAs per SM = 24 warps; 2 x (54 KB tables + 33 KB observation tiles) of shared memory
+#ifndef NPLANE_TAB_BS
+#define NPLANE_TAB_BS 384     // x 2 CTAs per SM = 24 warps; 2 x (54 KB tables + 33 KB observation tiles) of shared memory
+#define NPLANE_TAB_MINB 2
+#endif
+#ifdef NPLANE_TAB_NOSTAGE
+constexpr bool kTabStage = false;
+#else
+constexpr bool kTabStage = true;
+#endif
+constexpr int kTabBS = NPLANE_TAB_BS, kTabMinB = NPLANE_TAB_MINB;
 constexpr int kTabTileFloats = 32 * NP_NUM_OBS;
-static int table_step_smem_bytes() { return kTablesFloats * 4 + (kTabBS / 32) * kTabTileFloats * 4 + 16; }
+static int table_step_smem_bytes() { return kTablesFloats * 4 + (kTabStage ? (kTabBS / 32) * kTabTileFloats * 4 : 0) + 16; }
 
 __device__ __forceinline__ void count_cause1(unsigned long long* counters, int which, bool p0) {
   const int k = __popc(__ballot_sync(0xffffffffu, p0));
@@ -982,11 +999,11 @@ __device__ __forceinline__ void count_cause1(unsigned long long* counters, int w
 }
 
 template <int TASK>
-__global__ void __launch_bounds__(kTabBS, 2) f16_table_step_kernel(const __grid_constant__ StepParams p) {
+__global__ void __launch_bounds__(kTabBS, kTabMinB) f16_table_step_kernel(const __grid_constant__ StepParams p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   float* T = reinterpret_cast<float*>(smem_raw);
   float* otile = T + kTablesFloats + (threadIdx.x >> 5) * kTabTileFloats;
-  uint64_t* bar = reinterpret_cast<uint64_t*>(T + kTablesFloats + (kTabBS / 32) * kTabTileFloats);
+  uint64_t* bar = reinterpret_cast<uint64_t*>(T + kTablesFloats + (kTabStage ? (kTabBS / 32) * kTabTileFloats : 0));
   stage_aero(T, p.aero, (uint32_t)(kTablesFloats * 4), bar);
   const ZeroCells zc = zero_cells(T);
   const np_env_cfg& c = p.cfg;
@@ -1018,7 +1035,7 @@ __global__ void __launch_bounds__(kTabBS, 2) f16_table_step_kernel(const __grid_
     float rew = 0.0f;
     bool bad = false, done = false;
     int causes = 0;
-    const bool staged = __all_sync(0xffffffffu, live) && ((reinterpret_cast<uintptr_t>(p.obs) & 15) == 0);
+    const bool staged = kTabStage && __all_sync(0xffffffffu, live) && ((reinterpret_cast<uintptr_t>(p.obs) & 15) == 0);
 #pragma unroll 1
     for (int pass = 0; pass < 2; ++pass) {
       float ctab[kNumSlots], a1[kNumA1];
@@ -1083,7 +1100,7 @@ __global__ void __launch_bounds__(kTabBS, 2) f16_table_step_kernel(const __grid_
       }
     }
   }
-  if (lane == 0) bulk_wait0();                     // shared memory must outlive the last bulk stores
+  if (kTabStage && lane == 0) bulk_wait0();        // shared memory must outlive the last bulk stores
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -2349,7 +2366,7 @@ static int step_range_impl(np_env* env, const float* action_dev, const float* dr
     if (count == 0) return NP_OK;
     const int smem = table_step_smem_bytes();
     const int want = (count + kTabBS - 1) / kTabBS;
-    env->grid = want < env->num_sms * 2 ? want : env->num_sms * 2;
+    env->grid = want < env->num_sms * kTabMinB ? want : env->num_sms * kTabMinB;
     env->smem = smem;
     env->last_block = kTabBS;
     static bool attr_set[64][3] = {};
