@@ -2474,6 +2474,8 @@ int np_env_plan_step(np_env* env, const float* action3_dev, int n_sub, const flo
   env->pid_started = true;
   env->step_index++;
   if (env->tables) return launch_step<384, 1, MODE_PLAN, true, NP_TASK_TRACKING>(env, p, (cudaStream_t)stream);
+  // a strong-scaling shard (125 k aircraft = 1.1 waves of 148 x 384 pairs) runs in ONE wave of 512-thread CTAs (pick_block)
+  if (pick_block(env, p.pair_end - p.pair_begin) == 512) return launch_step<512, 1, MODE_PLAN, false, NP_TASK_TRACKING>(env, p, (cudaStream_t)stream);
   return launch_step<384, 1, MODE_PLAN, false, NP_TASK_TRACKING>(env, p, (cudaStream_t)stream);
 }
 
@@ -2489,6 +2491,7 @@ int np_env_combat_step(np_env* env, const float* action_dev, int n_sub, const fl
   if (n_sub > 0) env->pid_started = true;
   env->step_index++;
   if (env->tables) return launch_step<384, 1, MODE_COMBAT, true>(env, p, (cudaStream_t)stream);
+  if (pick_block(env, p.pair_end - p.pair_begin) == 512) return launch_step<512, 1, MODE_COMBAT>(env, p, (cudaStream_t)stream);
   return launch_step<384, 1, MODE_COMBAT>(env, p, (cudaStream_t)stream);
 }
 
@@ -2507,6 +2510,7 @@ int np_env_combat_role_local(np_env* env, const float* action_dev, int n_sub, co
   if (n_sub > 0) env->pid_started = true;
   p.records = records_dev;
   env->step_index++;
+  if (pick_block(env, p.pair_end - p.pair_begin) == 512) return launch_step<512, 1, MODE_COMBAT>(env, p, (cudaStream_t)stream);
   return launch_step<384, 1, MODE_COMBAT>(env, p, (cudaStream_t)stream);
 }
 
