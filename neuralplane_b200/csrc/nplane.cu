@@ -2436,24 +2436,55 @@ int np_env_step_host(np_env* env, const float* action_host, float* action_pinned
   }
   cudaStream_t main_st = (cudaStream_t)stream, up = env->hs[0], run = env->hs[1], down = env->hs[2];
   const int n = env->cfg.n, ld = env->cfg.ld, A = 4, D = NP_NUM_OBS;
+  // F16 plug-in: only the 88 B/aircraft observation block goes through the copy engine.  The range kernels read their actions
+  // straight from the pinned staging buffer (zero-copy: no H2D copy, no upload stream, no per-chunk event chain) and write
+  // reward + flags (7 B/aircraft) straight into the pinned outputs: 2 operations per chunk instead of 8, and the first
+  // download starts one small kernel after the first 1/18 of the actions is staged.  (The whole observation block written
+  // by the kernel instead -- np_env_step_mapped -- loses to the copy engine at this size, profiles/r02_e2e_boundaries.txt.)
+  // The UAV slab kernel fetches its action block with TMA bulk copies and keeps the explicit upload.
+  const bool direct = env->cfg.model == NP_MODEL_F16 && !(n & 1) && !getenv("NPLANE_HOST_PIPE_V1");
+  float* act_src = action_dev;
+  struct Restore {   // the env's own reward buffer / no mirror again on every way out
+    np_env* e;
+    float* rew;
+    ~Restore() { e->buf.reward_dev = rew; e->mirror = nullptr; }
+  } restore_on_exit{env, env->buf.reward_dev};
+  if (direct) {
+    float* rew_d = nullptr;
+    uint8_t* flg_d = nullptr;
+    NP_CUDA(cudaHostGetDevicePointer(reinterpret_cast<void**>(&act_src), action_pinned, 0));
+    NP_CUDA(cudaHostGetDevicePointer(reinterpret_cast<void**>(&rew_d), reward_pinned, 0));
+    NP_CUDA(cudaHostGetDevicePointer(reinterpret_cast<void**>(&flg_d), flags_pinned, 0));
+    env->buf.reward_dev = rew_d;
+    env->mirror = flg_d;
+    env->mirror_ld = n;
+  }
   NP_CUDA(cudaEventRecord(env->hev_start, main_st));   // everything already queued on the caller's stream comes first
   for (cudaStream_t st : env->hs) NP_CUDA(cudaStreamWaitEvent(st, env->hev_start, 0));
   for (int c = 0; c < n_chunks; ++c) {
     const int i0 = edges[c], cnt = edges[c + 1] - edges[c];
     const size_t a_off = (size_t)i0 * A, a_bytes = (size_t)cnt * A * sizeof(float);
     if (action_host != action_pinned) memcpy(action_pinned + a_off, action_host + a_off, a_bytes);   // overlaps the GPU
-    NP_CUDA(cudaMemcpyAsync(action_dev + a_off, action_pinned + a_off, a_bytes, cudaMemcpyHostToDevice, up));
-    NP_CUDA(cudaEventRecord(env->hev_up[c], up));
-    NP_CUDA(cudaStreamWaitEvent(run, env->hev_up[c], 0));
-    const int rc = step_range_impl(env, action_dev, nullptr, nullptr, i0, cnt, c == 0, run);
+    if (!direct) {
+      NP_CUDA(cudaMemcpyAsync(action_dev + a_off, action_pinned + a_off, a_bytes, cudaMemcpyHostToDevice, up));
+      NP_CUDA(cudaEventRecord(env->hev_up[c], up));
+      NP_CUDA(cudaStreamWaitEvent(run, env->hev_up[c], 0));
+    }
+    const int rc = step_range_impl(env, act_src, nullptr, nullptr, i0, cnt, c == 0, run);
     if (rc != NP_OK) return rc;
     NP_CUDA(cudaEventRecord(env->hev_run[c], run));
     NP_CUDA(cudaStreamWaitEvent(down, env->hev_run[c], 0));
     NP_CUDA(cudaMemcpyAsync(obs_pinned + (size_t)i0 * D, env->buf.obs_dev + (size_t)i0 * D, (size_t)cnt * D * sizeof(float),
                             cudaMemcpyDeviceToHost, down));
-    NP_CUDA(cudaMemcpyAsync(reward_pinned + i0, env->buf.reward_dev + i0, (size_t)cnt * sizeof(float), cudaMemcpyDeviceToHost, down));
-    NP_CUDA(cudaMemcpy2DAsync(flags_pinned + i0, (size_t)n, env->buf.flags_dev + i0, (size_t)ld, (size_t)cnt, 3,
-                              cudaMemcpyDeviceToHost, down));   // the three flag rows of the chunk in one strided copy
+    if (!direct) {
+      NP_CUDA(cudaMemcpyAsync(reward_pinned + i0, env->buf.reward_dev + i0, (size_t)cnt * sizeof(float), cudaMemcpyDeviceToHost, down));
+      NP_CUDA(cudaMemcpy2DAsync(flags_pinned + i0, (size_t)n, env->buf.flags_dev + i0, (size_t)ld, (size_t)cnt, 3,
+                                cudaMemcpyDeviceToHost, down));   // the three flag rows of the chunk in one strided copy
+    }
+  }
+  if (direct) {   // the last kernels' direct writes must have landed too (the download stream only covers the observations)
+    NP_CUDA(cudaEventRecord(env->hev_up[0], run));
+    NP_CUDA(cudaStreamWaitEvent(down, env->hev_up[0], 0));
   }
   NP_CUDA(cudaEventRecord(env->hev_done, down));
   NP_CUDA(cudaStreamWaitEvent(main_st, env->hev_done, 0));   // later work on the caller's stream sees the stepped state
