@@ -2436,13 +2436,12 @@ int np_env_step_host(np_env* env, const float* action_host, float* action_pinned
   }
   cudaStream_t main_st = (cudaStream_t)stream, up = env->hs[0], run = env->hs[1], down = env->hs[2];
   const int n = env->cfg.n, ld = env->cfg.ld, A = 4, D = NP_NUM_OBS;
-  // F16 plug-in: only the 88 B/aircraft observation block goes through the copy engine.  The range kernels read their actions
-  // straight from the pinned staging buffer (zero-copy: no H2D copy, no upload stream, no per-chunk event chain) and write
-  // reward + flags (7 B/aircraft) straight into the pinned outputs: 2 operations per chunk instead of 8, and the first
-  // download starts one small kernel after the first 1/18 of the actions is staged.  (The whole observation block written
-  // by the kernel instead -- np_env_step_mapped -- loses to the copy engine at this size, profiles/r02_e2e_boundaries.txt.)
-  // The UAV slab kernel fetches its action block with TMA bulk copies and keeps the explicit upload.
-  const bool direct = env->cfg.model == NP_MODEL_F16 && !(n & 1) && !getenv("NPLANE_HOST_PIPE_V1");
+  // NPLANE_HOST_PIPE_V2=1 (experiment, F16 plug-in): only the 88 B/aircraft observation block goes through the copy engine; the
+  // range kernels read their actions straight from the pinned staging buffer (zero-copy: no H2D copy, no upload stream) and
+  // write reward + flags (7 B/aircraft) straight into the pinned outputs: 2 operations per chunk instead of 8.  MEASURED
+  // SLOWER on the same box (2.34-2.37 vs 2.20-2.26 ms per 10^6-aircraft step, profiles/r02_e2e_boundaries.txt): kernels that
+  // touch host memory run longer, which delays every download behind them.  The explicit upload / download copies stay.
+  const bool direct = env->cfg.model == NP_MODEL_F16 && !(n & 1) && getenv("NPLANE_HOST_PIPE_V2");
   float* act_src = action_dev;
   struct Restore {   // the env's own reward buffer / no mirror again on every way out
     np_env* e;
@@ -2671,6 +2670,8 @@ int np_tables_create(const float* breakpoints, const int32_t* bp_sizes, const fl
   for (int j = 0, o = 0; j < 5; o += want_sizes[j], ++j)
     for (int i = 1; i < want_sizes[j]; ++i)
       if (!(breakpoints[o + i] > breakpoints[o + i - 1])) return fail(NP_EINVAL, "np_tables_create: breakpoints must increase");
+  for (int i = 0; i < kNA2; ++i)   // the step kernels derive the ALPHA2 cell from the ALPHA1 cell (tables_device.cuh)
+    if (breakpoints[kBpA2 + i] != breakpoints[kBpA1 + i]) return fail(NP_EINVAL, "np_tables_create: ALPHA2 must be the first 14 points of ALPHA1");
   std::vector<float> host(kTablesFloats, 0.0f);
   memcpy(host.data(), breakpoints, 61 * sizeof(float));
   memcpy(host.data() + kBpFloats, values, (size_t)kTableValues * sizeof(float));

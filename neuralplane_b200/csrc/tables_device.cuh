@@ -73,6 +73,38 @@ __device__ __forceinline__ Cell find_cell_u(const float* bp, float x) {
   c.lam = (x - bp[i]) / (bp[i + 1] - bp[i]);
   return c;
 }
+// The same cell -- i = #{interior breakpoints <= x}, lam -- from a GUESS of i that is then walked to the exact cell with
+// compares against the grid itself: any guess gives the scan's result on any increasing grid (the walk is a loop), a good
+// guess makes the walk 0 or 1 step.  ~15 instructions instead of ~60 for the 20-point alpha grid (the scan loads every
+// breakpoint and compares it); the guesses below are for the NASA grids of example/data (ALPHA1 = -20..60 step 5, 70, 80,
+// 90; BETA1 = -30..-10 step 5, -10..10 step 2, 10..30 step 5).
+template <int N>
+__device__ __forceinline__ Cell cell_from_guess(const float* bp, float x, int i) {
+  x = fminf(fmaxf(x, bp[0]), bp[N - 1]);
+  i = min(max(i, 0), N - 2);
+  while (i > 0 && x < bp[i]) --i;
+  while (i < N - 2 && x >= bp[i + 1]) ++i;
+  Cell c;
+  c.i = i;
+  c.lam = (x - bp[i]) / (bp[i + 1] - bp[i]);
+  return c;
+}
+__device__ __forceinline__ Cell find_cell_alpha1(const float* bp, float x) {
+  const int guess = x < 60.0f ? (int)((x + 20.0f) * 0.2f) : 16 + (x >= 70.0f) + (x >= 80.0f);
+  return cell_from_guess<kNA1>(bp, x, guess);
+}
+// ALPHA2 (-20..45 step 5) is the first 14 points of ALPHA1: below 45 deg the cell is ALPHA1's, at and above it the clamped
+// point sits on the last breakpoint (i = 12, lam = (45 - 40) / (45 - 40) = 1) -- what find_cell_u<kNA2> returns, without a scan
+__device__ __forceinline__ Cell cell_alpha2_from_alpha1(const float* bp2, const Cell& a1, float x) {
+  Cell c = a1;
+  if (!(x < bp2[kNA2 - 1])) { c.i = kNA2 - 2; c.lam = 1.0f; }
+  return c;
+}
+__device__ __forceinline__ Cell find_cell_beta1(const float* bp, float x) {
+  const int guess = x < -10.0f ? (int)((x + 30.0f) * 0.2f) : x < 10.0f ? 4 + (int)((x + 10.0f) * 0.5f) : 14 + (int)((x - 10.0f) * 0.2f);
+  return cell_from_guess<kNB1>(bp, x, guess);
+}
+
 // successive linear interpolation, alpha first (mexndinterp.py:50-81): lambda * f2 + (1 - lambda) * f1
 // (the second product is fused: one rounding fewer than the fp32 restatement, and FMUL + FFMA instead of FMUL, FMUL, FADD --
 // the table path is checked against the float64 oracle, tests/test_gpu_tables*.py)
@@ -138,7 +170,11 @@ __device__ __forceinline__ ZeroCells zero_cells(const float* T) {
 // full = false: only what the force equations read (Cx_tot, Cy_tot, Cz_tot: the Overload evaluation, F16_model.py:132-148).
 __device__ __forceinline__ void table_env_coefs(const float* T, const ZeroCells& z, float alpha, float beta, float el, bool full,
                                                 float* __restrict__ c, float* __restrict__ a1) {
+#ifdef NPLANE_TAB_SCAN
   const Cell ca = find_cell_u<kNA1>(T + kBpA1, alpha), cl = find_cell_u<kNA2>(T + kBpA2, alpha), cb = find_cell_u<kNB1>(T + kBpB1, beta);
+#else
+  const Cell ca = find_cell_alpha1(T + kBpA1, alpha), cl = cell_alpha2_from_alpha1(T + kBpA2, ca, alpha), cb = find_cell_beta1(T + kBpB1, beta);
+#endif
   const Cell d1 = find_cell_u<kND1>(T + kBpD1, el);
 #define T3(t, d) tab3(T + table_offset(t), kNA1, kNB1, ca, cb, d)
 #define T2(t) tab2(T + table_offset(t), kNA1, ca, cb)
