@@ -343,8 +343,22 @@ def side_small_n(dev, barrier, n=3000, K=200, W=20):
         for _ in range(10):
             env.step(a)
     ms = timed_steps(lambda k: g.replay(), K // 10, 2, barrier) / (K // 10 * 10)
-    return {"workload": f"F16 Heading task, ControlEnv, num_agents={n} (the reference's training population), CUDA-graph replay",
-            "us_per_step": ms * 1e3, "aircraft_steps_per_s": n / (ms * 1e-3), "launch": env.launch_info()}
+    # the same population through the numpy boundary the reference's runners call (host actions in, host obs out: one mapped launch)
+    import numpy as np
+    from neuralplane_b200 import GPUVecEnv
+    venv = GPUVecEnv([lambda: ControlEnv(num_envs=n, config="heading", model="F16", random_seed=0, device=dev)])
+    venv.reset()
+    ha = (np.random.default_rng(0).random((n, 1, 4), dtype=np.float32) * 2 - 1)
+    for _ in range(20):
+        venv.step(ha)
+    t0 = time.perf_counter()
+    for _ in range(K):
+        venv.step(ha)
+    e2e_us = 1e6 * (time.perf_counter() - t0) / K
+    return {"workload": f"F16 Heading task, ControlEnv, num_agents={n} (the reference's training population)",
+            "us_per_step": ms * 1e3, "aircraft_steps_per_s": n / (ms * 1e-3), "how": "device-resident step under CUDA-graph replay",
+            "e2e_us_per_step": e2e_us, "e2e_aircraft_steps_per_s": n / (e2e_us * 1e-6), "e2e_boundary": venv.boundary,
+            "launch": env.launch_info()}
 
 
 def main():
@@ -514,7 +528,7 @@ def main():
         if world == 1 and not args.no_cpu:
             try:
                 nc = n if reference_available() else args.cpu_n
-                v, el, kind, thr, sample = cpu_arm(nc, 1, 3 if reference_available() else 30)
+                v, el, kind, thr, sample = cpu_arm(nc, 1, 5 if reference_available() else 50)
                 out["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": thr, "kind": kind, "sample": sample}
             except Exception as e:
                 out["cpu_baseline"] = {"error": repr(e)[:300]}

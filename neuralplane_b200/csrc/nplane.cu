@@ -24,6 +24,11 @@
 #include "uav_device.cuh"
 #include "ctrl_device.cuh"
 #include "tables_device.cuh"
+#include "ptx_device.cuh"
+#include "env_device.cuh"
+#include "combat_device.cuh"
+#include "uav_kernels.cuh"
+#include "aux_kernels.cuh"
 
 using namespace npl;
 
@@ -104,461 +109,6 @@ struct np_env {
   cudaStream_t hs[3] = {nullptr, nullptr, nullptr};
   cudaEvent_t hev_start = nullptr, hev_done = nullptr, hev_up[kMaxHostChunks] = {}, hev_run[kMaxHostChunks] = {};
 };
-
-struct StepParams {
-  np_env_cfg cfg;
-  float* s;
-  float* u;
-  float* tgt;
-  int32_t* step_count;
-  uint8_t* flags;
-  float* obs;
-  float* reward;
-  float* cache;                  // [kCacheRows][ld]
-  unsigned long long* counters;  // [NP_NUM_COUNTERS]
-  const uint32_t* aero;          // device image, aero_bytes
-  int aero_bytes;
-  int tab;                       // 1: `aero` is the table image (tables_device.cuh), not the MLP image
-  const float* action;           // [n][4]; planning step: [n][3]
-  float* pid;                    // [kPidRows][ld] controller state (planning / combat step)
-  float* blood;                  // [ld] combat damage state (singlecombat_env.py:45)
-  int n_sub;                     // FDM sub-steps per env step (planning: 50, planning_env.py:153)
-  int pid_first;                 // 1: the controllers have never run (PID.reset, pid.py:13)
-  int pair_begin, pair_end;      // aircraft pairs [pair_begin, pair_end) this launch works on (whole population by default)
-  const float* draws;            // [n][5] or null
-  const float* noise;            // [n][22] or null
-  int obs_stg;                   // 1: the staged observation tile leaves through per-lane 16-byte stores instead of a TMA bulk store
-  uint8_t* flags_mirror;         // null, or a second [3][flags_mirror_ld] copy of the new flags (mapped host memory)
-  int flags_mirror_ld;
-  // role-sharded combat (egos and opponents on different ranks): this rank's two lanes are two DIFFERENT envs' aircraft
-  float* records;                // null (pair-sharded), or this rank's record slab [n][kCombatRecFloats]
-  uint8_t* pair_reset;           // [ld] env-level reset flag of each local aircraft's env (own | partner flags of the last step)
-  int index_stride;              // global aircraft index = index_base + index_stride * local index (RNG streams)
-  uint32_t step_index;
-};
-
-// ------------------------------------------------------------------------------------------------
-// small PTX wrappers (TMA 1-D bulk copies + mbarrier)
-// ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"   // %3: suspend-time hint
-      "selp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity), "r"(0x989680u)
-      : "memory");
-  return ok != 0;
-}
-// A waiting warp backs off with nanosleep between polls: a tight try_wait loop was 21 % of the UAV slab kernel's executed
-// instructions -- issue slots taken from the warps that had work.
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  if (mbar_try_wait(bar, parity)) return;
-  do {
-    __nanosleep(100);
-  } while (!mbar_try_wait(bar, parity));
-}
-__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                   smem_u32(dst_smem)),
-               "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
-               : "memory");
-}
-
-__device__ __forceinline__ void bulk_s2g(void* dst_gmem, const void* src_smem, uint32_t bytes) {
-  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem), "r"(smem_u32(src_smem)), "r"(bytes)
-               : "memory");
-}
-__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
-__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
-__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-
-// Stage the aero image into shared memory once per CTA: one elected thread issues TMA bulk copies that
-// complete on an mbarrier; everyone waits on it.
-__device__ __forceinline__ void stage_aero(void* blob_s, const void* aero_g, uint32_t bytes, uint64_t* bar) {
-  if (threadIdx.x == 0) {
-    mbar_init(bar, 1);
-    mbar_expect_tx(bar, bytes);
-    constexpr uint32_t kChunk = 16384;
-    for (uint32_t off = 0; off < bytes; off += kChunk) {
-      const uint32_t nb = min(kChunk, bytes - off);
-      bulk_g2s(reinterpret_cast<char*>(blob_s) + off, reinterpret_cast<const char*>(aero_g) + off, nb, bar);
-    }
-  }
-  __syncthreads();
-  mbar_wait(bar, 0);
-}
-
-// ------------------------------------------------------------------------------------------------
-// shared pieces of reset / obs / task logic (one aircraft)
-// ------------------------------------------------------------------------------------------------
-struct Draws {
-  float d[NP_NUM_DRAWS];
-};
-__device__ __forceinline__ Draws reset_draws(const StepParams& p, int i) {
-  Draws r;
-  if (p.draws) {
-#pragma unroll
-    for (int j = 0; j < NP_NUM_DRAWS; ++j) r.d[j] = p.draws[(size_t)i * NP_NUM_DRAWS + j];
-  } else {
-    const uint64_t gi = p.cfg.index_base + (uint64_t)p.index_stride * (uint64_t)i;
-    const uint2 key = make_uint2((uint32_t)p.cfg.seed, (uint32_t)(p.cfg.seed >> 32));
-    const uint4 a = philox4x32_10(make_uint4((uint32_t)gi, (uint32_t)(gi >> 32), p.step_index, 0x5EED0000u), key);
-    const uint4 b = philox4x32_10(make_uint4((uint32_t)gi, (uint32_t)(gi >> 32), p.step_index, 0x5EED0001u), key);
-    r.d[0] = u01(a.x); r.d[1] = u01(a.y); r.d[2] = u01(a.z); r.d[3] = u01(a.w); r.d[4] = u01(b.x);
-  }
-  return r;
-}
-
-// F16Model.reset (F16_model.py:38-45) + task.reset (heading_task.py:63-69, control_task.py:59-68,
-// tracking_task.py:57-71) for one aircraft.
-// `task` is a compile-time constant in the step kernel (one instantiation per task: the other two tasks' code -- each with
-// its own wrap / trig calls -- would only be instruction-cache ballast) and c.task in the stand-alone reset kernel.
-__device__ __forceinline__ void reset_aircraft(const np_env_cfg& c, int task, const Draws& r, float* s, float* u, float* tgt) {
-#pragma unroll
-  for (int j = 0; j < 12; ++j) s[j] = 0.0f;
-  s[2] = r.d[0] * (c.max_altitude - c.min_altitude) + c.min_altitude;
-  s[6] = r.d[1] * (c.max_vt - c.min_vt) + c.min_vt;
-  u[0] = c.init_T; u[1] = 0.0f; u[2] = 0.0f; u[3] = 0.0f;
-  if (task == NP_TASK_HEADING) {
-    tgt[0] = s[2] + 1000.0f;
-    tgt[1] = wrap_pi(s[5] + (float)(2.0 * 3.141592653589793 / 3.0));
-    tgt[2] = s[6] + 0.0f;
-  } else if (task == NP_TASK_CONTROL) {
-    tgt[0] = wrap_pi(s[4] + 2.0f * (r.d[2] - 0.5f) * c.max_pitch_increment);
-    tgt[1] = wrap_pi(s[5] + 2.0f * (r.d[3] - 0.5f) * c.max_heading_increment);
-    tgt[2] = s[6] + 2.0f * (r.d[4] - 0.5f) * c.max_velocities_u_increment;
-  } else {
-    const float dist = r.d[2] * (c.max_distance - c.min_distance) + c.min_distance;
-    const float th1 = r.d[3] * kPi / DC(3.0f) - (float)(3.141592653589793 / 6.0);
-    const float th2 = r.d[4] * kPi / DC(3.0f) - (float)(3.141592653589793 / 6.0);
-    const float2 sc1 = sincos_shared(th1), sc2 = sincos_shared(th2);   // (sin, cos): the bits of sinf / cosf
-    tgt[0] = s[0] + dist * sc1.y * sc2.y;
-    tgt[1] = s[1] + dist * sc1.y * sc2.x;
-    tgt[2] = s[2] + dist * sc1.x;
-  }
-}
-
-// 22-D observation row (heading_task.py:113-151; control_task.py:109-111; tracking_task.py:112-114).
-__device__ __forceinline__ void make_obs(const np_env_cfg& c, int task, const float* s, const float* u, const float* tgt,
-                                         const Trig& g, float e2t, float* o) {
-  if (task == NP_TASK_HEADING) {
-    o[0] = (s[2] - tgt[0]) * 0.3048f / DC(1000.0f);
-    o[1] = wrap_pi(s[5] - tgt[1]);
-    o[2] = (s[6] - tgt[2]) * 0.3048f / DC(340.0f);
-  } else if (task == NP_TASK_CONTROL) {
-    o[0] = wrap_pi(s[4] - tgt[0]);
-    o[1] = wrap_pi(s[5] - tgt[1]);
-    o[2] = (s[6] - tgt[2]) * 0.3048f / DC(340.0f);
-  } else {
-    o[0] = (s[0] - tgt[0]) * 0.3048f / DC(1000.0f);
-    o[1] = (s[1] - tgt[1]) * 0.3048f / DC(1000.0f);
-    o[2] = (s[2] - tgt[2]) * 0.3048f / DC(1000.0f);
-  }
-  const float eas = (s[6] + c.airspeed * 1.0f) / e2t;  // F16_model.py:96-103
-  o[3] = s[2] * 0.3048f / DC(5000.0f);
-  o[4] = g.sphi; o[5] = g.cphi; o[6] = g.st; o[7] = g.ct;
-  o[8] = eas * 0.3048f / DC(340.0f);
-  o[9] = g.sa; o[10] = g.ca; o[11] = g.sb; o[12] = g.cb;
-  o[13] = s[9]; o[14] = s[10]; o[15] = s[11];
-  o[16] = u[0] / DC(0.225f) / DC(76300.0f) * 0.3048f;
-  o[17] = u[1] / DC(45.0f); o[18] = u[2] / DC(45.0f); o[19] = u[3] / DC(45.0f);
-  o[20] = 0.0f / DC(45.0f);  // lef
-  o[21] = e2t;
-}
-
-__device__ __forceinline__ void add_obs_noise(const StepParams& p, int i, float* o) {
-  const float sc = p.cfg.noise_scale;
-  if (p.noise) {  // injected standard normals (parity runs): obs + randn * noise_scale (heading_task.py:152)
-#pragma unroll
-    for (int j = 0; j < NP_NUM_OBS; ++j) o[j] = o[j] + p.noise[(size_t)i * NP_NUM_OBS + j] * sc;
-  } else if (sc != 0.0f) {
-    const uint64_t gi = p.cfg.index_base + (uint64_t)p.index_stride * (uint64_t)i;
-    const uint2 key = make_uint2((uint32_t)p.cfg.seed, (uint32_t)(p.cfg.seed >> 32));
-#pragma unroll
-    for (int q = 0; q < 3; ++q) {  // 3 x 4 words -> 12 pairs of normals, 22 used
-      const uint4 r = philox4x32_10(make_uint4((uint32_t)gi, (uint32_t)(gi >> 32), p.step_index, 0x0B5E0000u + q), key);
-      const uint32_t w[4] = {r.x, r.y, r.z, r.w};
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const int j = 8 * q + 2 * k;
-        if (j < NP_NUM_OBS) {
-          float r, cs, sn;
-          box_muller16(w[k], sc, r, cs, sn);
-          o[j] = fmaf(r, cs, o[j]);
-          o[j + 1] = fmaf(r, sn, o[j + 1]);
-        }
-      }
-    }
-  }
-}
-
-// one aircraft pair of an SoA row: a single 8-byte store, or only the first aircraft for the odd tail
-__device__ __forceinline__ void store_pair(float* row, int pr, float2 v, bool both) {
-  if (both) reinterpret_cast<float2*>(row)[pr] = v;
-  else row[2 * pr] = v.x;
-}
-
-// one atomic per warp per cause: the thread's two aircraft contribute p0 and p1
-__device__ __forceinline__ void count_cause2(unsigned long long* counters, int which, bool p0, bool p1) {
-  const int k = __popc(__ballot_sync(0xffffffffu, p0)) + __popc(__ballot_sync(0xffffffffu, p1));
-  if (k != 0 && (threadIdx.x & 31) == 0) atomicAdd(&counters[which], (unsigned long long)k);
-}
-
-// ------------------------------------------------------------------------------------------------
-// K5 helpers: 1-v-1 combat (singlecombat_env.py; envs/utils/utils.py:156-249).  The pair lives in one thread.
-// ------------------------------------------------------------------------------------------------
-// SingleCombatEnv.reset_done_envs re-initialisation of one aircraft (:219-225): draws npos, epos, altitude, heading, vt
-__device__ __forceinline__ void combat_reset_aircraft(const np_env_cfg& c, const Draws& r, float* s, float* u) {
-#pragma unroll
-  for (int j = 0; j < 12; ++j) s[j] = 0.0f;
-  s[0] = r.d[0] * (c.max_npos - c.min_npos) + c.min_npos;
-  s[1] = r.d[1] * (c.max_epos - c.min_epos) + c.min_epos;
-  s[2] = r.d[2] * (c.max_altitude - c.min_altitude) + c.min_altitude;
-  s[5] = r.d[3] * (c.max_heading - c.min_heading) + c.min_heading;
-  s[6] = r.d[4] * (c.max_vt - c.min_vt) + c.min_vt;
-  u[0] = c.init_T; u[1] = 0.0f; u[2] = 0.0f; u[3] = 0.0f;
-}
-
-// AO / TA / R of get_AO_TA_R (3-D) or get2d_AO_TA_R (utils.py:156-206): dp = enemy - ego position, ve / vm = ego / enemy
-// inertial velocity (xdot[0:3]); DIM = 3 or 2.
-template <int DIM>
-__device__ __forceinline__ void ao_ta_r(const float* dp, const float* ve, const float* vm, float& AO, float& TA, float& R) {
-  float ev = 0.f, mv = 0.f, d2 = 0.f, pe = 0.f, pm = 0.f;
-#pragma unroll
-  for (int j = 0; j < DIM; ++j) {
-    ev = ev + ve[j] * ve[j]; mv = mv + vm[j] * vm[j]; d2 = d2 + dp[j] * dp[j];
-    pe = pe + dp[j] * ve[j]; pm = pm + dp[j] * vm[j];
-  }
-  R = sqrtf(d2);
-  AO = acosf(fminf(fmaxf(pe / (R * sqrtf(ev) + 1e-8f), -1.0f), 1.0f));
-  TA = acosf(fminf(fmaxf(pm / (R * sqrtf(mv) + 1e-8f), -1.0f), 1.0f));
-}
-__device__ __forceinline__ float orientation_reward_v2(float AO, float TA) {  // utils.py:215-217
-  const float t = atanhf(1.0f - fmaxf(1.9f * TA / DC(kPi), 1e-4f * 1.0f)) / (2.0f * kPi);
-  return 1.0f / (50.0f * AO / DC(kPi) + 2.0f) + (float)(1.0 / 2) + fminf(t, 0.0f) + 0.5f;
-}
-__device__ __forceinline__ float range_reward_v3(float Rkm) {  // utils.py:230-231
-  const float poly = fminf(fmaxf(-0.032f * (Rkm * Rkm) + 0.284f * Rkm + 0.38f, 0.0f), 1.0f);
-  return (Rkm < 5.0f ? 1.0f : 0.0f) + (Rkm >= 5.0f ? 1.0f : 0.0f) * poly + fminf(fmaxf(expf(-0.16f * Rkm), 0.0f), 0.2f);
-}
-__device__ __forceinline__ float orientation_fn(float AO) {  // utils.py:235-243
-  constexpr float k6 = (float)(3.141592653589793 / 6);
-  const bool m3 = (AO >= 0.0f) & (AO <= k6), m4 = (AO <= 0.0f) & (AO >= -k6);
-  return (1.0f - 6.0f * AO / DC(kPi)) * (m3 ? 1.0f : 0.0f) + (1.0f + 6.0f * AO / DC(kPi)) * (m4 ? 1.0f : 0.0f);
-}
-__device__ __forceinline__ float distance_fn(float Rkm) {  // utils.py:245-249
-  return (Rkm <= 1.0f ? 1.0f : 0.0f) + (3.0f - Rkm) / 2.0f * (((Rkm > 1.0f) & (Rkm <= 3.0f)) ? 1.0f : 0.0f);
-}
-
-// What the pairwise terms need of ONE aircraft at its final state: position, inertial velocity es = xdot[0:3] of nlplant
-// (F16_dynamics.py:104,129-135), body-axis velocity (F16Model.get_velocity), roll / pitch trigonometry and vt.  In the
-// pair-sharded layout both records are built in the thread that owns the pair; in the role-sharded layout each rank builds
-// its own and pulls the partner's from the peer's record slab -- the same code either way, so the outputs agree bit for bit.
-struct CombatRec {
-  float pos[3], es[3], vel[3], sphi, cphi, st, ct, vt;
-};
-__device__ __forceinline__ CombatRec combat_rec(const float* s) {
-  CombatRec r;
-  const Trig t = make_trig(s);
-  const float vt = s[6];
-  r.pos[0] = s[0]; r.pos[1] = s[1]; r.pos[2] = s[2];
-  r.vel[0] = vt * t.cb * t.ca;
-  r.vel[1] = vt * t.sb;
-  r.vel[2] = vt * t.cb * t.sa;
-  const float vtc = vt <= 0.01f ? 0.01f : vt;
-  const BodyVel b = body_vel(vtc, t);
-  r.es[0] = b.U * (t.ct * t.cpsi) + b.V * (t.sphi * t.cpsi * t.st - t.cphi * t.spsi) + b.W * (t.cphi * t.st * t.cpsi + t.sphi * t.spsi);
-  r.es[1] = b.U * (t.ct * t.spsi) + b.V * (t.sphi * t.spsi * t.st + t.cphi * t.cpsi) + b.W * (t.cphi * t.st * t.spsi - t.sphi * t.cpsi);
-  r.es[2] = b.U * t.st - b.V * (t.sphi * t.ct) - b.W * (t.cphi * t.ct);
-  r.sphi = t.sphi; r.cphi = t.cphi; r.st = t.st; r.ct = t.ct; r.vt = vt;
-  return r;
-}
-// pairwise geometry of (ego, enemy): get_AO_TA_R / get2d_AO_TA_R + the side flag (singlecombat_env.py:96-121,142-150)
-struct CombatGeo {
-  float AO, TA, R, AO2, TA2, R2, side, Rkm;
-};
-__device__ __forceinline__ CombatGeo combat_geo(const CombatRec& e, const CombatRec& m) {
-  CombatGeo g;
-  const float dp[3] = {m.pos[0] - e.pos[0], m.pos[1] - e.pos[1], m.pos[2] - e.pos[2]};
-  ao_ta_r<2>(dp, e.es, m.es, g.AO2, g.TA2, g.R2);
-  ao_ta_r<3>(dp, e.es, m.es, g.AO, g.TA, g.R);
-  const float cz = e.es[0] * dp[1] - e.es[1] * dp[0];
-  g.side = (cz > 0.0f ? 1.0f : 0.0f) - (cz < 0.0f ? 1.0f : 0.0f);
-  g.Rkm = g.R * 0.3048f / DC(1000.0f);
-  return g;
-}
-// 15-D observation row of one aircraft (`own`) given its partner and the pair geometry; q = 0: ego, 1: enemy (mirrored)
-__device__ __forceinline__ void combat_obs_row(const CombatRec& own, const CombatRec& other, const CombatGeo& g, int q, float* o) {
-  o[0] = own.pos[2] * 0.3048f / DC(5000.0f);
-  o[1] = own.sphi; o[2] = own.cphi; o[3] = own.st; o[4] = own.ct;
-  o[5] = own.vel[0] * 0.3048f / DC(340.0f); o[6] = own.vel[1] * 0.3048f / DC(340.0f); o[7] = own.vel[2] * 0.3048f / DC(340.0f);
-  o[8] = own.vt * 0.3048f / DC(340.0f);
-  o[9] = (other.vel[0] - own.vel[0]) * 0.3048f / DC(340.0f);
-  o[10] = (other.pos[2] - own.pos[2]) * 0.3048f / DC(1000.0f);
-  o[11] = q == 0 ? g.AO2 : kPi - g.TA2;
-  o[12] = q == 0 ? g.TA2 : kPi - g.AO2;
-  o[13] = g.R2 * 0.3048f / 10000.0f;
-  o[14] = q == 0 ? g.side : -g.side;
-}
-// singlecombat_env.py:140-181 (scale 0.01) / multiplecombat_env.py:163-181 (scale 1: the product itself)
-__device__ __forceinline__ float combat_reward(const CombatGeo& g, int q, float scale) {
-  const float rr = range_reward_v3(g.Rkm);
-  return q == 0 ? scale * (orientation_reward_v2(g.AO, g.TA) * rr) : scale * (orientation_reward_v2(kPi - g.TA, kPi - g.AO) * rr);
-}
-// blood model (singlecombat_env.py:263-271): what aircraft q loses in this env step
-__device__ __forceinline__ float combat_damage(const CombatGeo& g, int q) {
-  const float df = distance_fn(g.Rkm);
-  return q == 0 ? orientation_fn(kPi - g.TA) * df : orientation_fn(g.AO) * df;
-}
-
-// obs (singlecombat_env.py:64-138), reward (:140-181) and the blood model (:263-271) of one pair at its final state.
-__device__ __forceinline__ void combat_outputs(const StepParams& p, float (&s)[2][12], float (&blood)[2], float (&rew)[2],
-                                               int pr, const bool (&act)[2], bool stepped) {
-  const CombatRec rec[2] = {combat_rec(s[0]), combat_rec(s[1])};
-  const CombatGeo g = combat_geo(rec[0], rec[1]);
-#pragma unroll
-  for (int q = 0; q < 2; ++q) {
-    rew[q] = combat_reward(g, q, p.cfg.combat_reward_scale);
-    float o[NP_NUM_OBS_COMBAT];
-    combat_obs_row(rec[q], rec[1 - q], g, q, o);
-    if (act[q]) {
-      float* orow = p.obs + (size_t)(2 * pr + q) * NP_NUM_OBS_COMBAT;
-#pragma unroll
-      for (int j = 0; j < NP_NUM_OBS_COMBAT; ++j) orow[j] = o[j];
-    }
-  }
-  if (stepped) {  // blood model, after obs / reward (singlecombat_env.py:263-271)
-    blood[1] = blood[1] - combat_damage(g, 1);
-    blood[0] = blood[0] - combat_damage(g, 0);
-  }
-}
-
-// ---- role-sharded combat records: [n][kCombatRecFloats] f32, 16-byte rows -----------------------------------------------
-//   0..2 final position | 3..5 es | 6 body vx | 7 blood (after the env-level reset, before this step's damage) |
-//   8 this aircraft's own termination bits (1 done, 2 bad, 4 exceed; as an integer bit pattern) | 9 10 body vy vz | 11 vt |
-//   12..15 sin / cos roll, sin / cos pitch | 16..27 position after sub-steps 0..3 (the Crash check runs every sub-step; the
-//   last sub-step's position is the final one)
-constexpr int kCombatRecFloats = 28;
-constexpr int kCombatMaxSub = 5;
-__device__ __forceinline__ void combat_rec_store(float* row, const CombatRec& r, float blood, int bits) {
-  float4* v = reinterpret_cast<float4*>(row);
-  v[0] = make_float4(r.pos[0], r.pos[1], r.pos[2], r.es[0]);
-  v[1] = make_float4(r.es[1], r.es[2], r.vel[0], blood);
-  v[2] = make_float4(__int_as_float(bits), r.vel[1], r.vel[2], r.vt);
-  v[3] = make_float4(r.sphi, r.cphi, r.st, r.ct);
-}
-struct CombatRecFull {
-  CombatRec r;
-  float blood;
-  int bits;
-  float sub_pos[kCombatMaxSub - 1][3];
-};
-template <bool PEER>
-__device__ __forceinline__ CombatRecFull combat_rec_load(const float* row) {
-  const float4* v = reinterpret_cast<const float4*>(row);
-  float4 q[7];
-#pragma unroll
-  for (int j = 0; j < 7; ++j) q[j] = PEER ? __ldcg(v + j) : v[j];   // a peer GPU wrote it: never through the read-only path
-  CombatRecFull f;
-  f.r.pos[0] = q[0].x; f.r.pos[1] = q[0].y; f.r.pos[2] = q[0].z; f.r.es[0] = q[0].w;
-  f.r.es[1] = q[1].x; f.r.es[2] = q[1].y; f.r.vel[0] = q[1].z; f.blood = q[1].w;
-  f.bits = __float_as_int(q[2].x); f.r.vel[1] = q[2].y; f.r.vel[2] = q[2].z; f.r.vt = q[2].w;
-  f.r.sphi = q[3].x; f.r.cphi = q[3].y; f.r.st = q[3].z; f.r.ct = q[3].w;
-  const float sp[12] = {q[4].x, q[4].y, q[4].z, q[4].w, q[5].x, q[5].y, q[5].z, q[5].w, q[6].x, q[6].y, q[6].z, q[6].w};
-#pragma unroll
-  for (int k = 0; k < kCombatMaxSub - 1; ++k)
-#pragma unroll
-    for (int j = 0; j < 3; ++j) f.sub_pos[k][j] = sp[3 * k + j];
-  return f;
-}
-
-// F16Model.update's control lag (F16_model.py:52-57): clamp, then first-order low-pass towards the scaled action
-__device__ __forceinline__ void lowpass_controls(const float* a_in, float* u) {
-  float a[4];
-#pragma unroll
-  for (int j = 0; j < 4; ++j) a[j] = fminf(fmaxf(a_in[j], -1.0f), 1.0f);
-  u[0] = 0.9f * u[0] + 0.1f * a[0] * 0.225f * 76300.0f / DC(0.3048f);
-  u[1] = 0.9f * u[1] + 0.1f * a[1] * 45.0f;
-  u[2] = 0.9f * u[2] + 0.1f * a[2] * 45.0f;
-  u[3] = 0.9f * u[3] + 0.1f * a[3] * 45.0f;
-}
-
-// The six termination predicates (task_base.py:75-96) and the task reward (task_base.py:60-73) of ONE aircraft at its new
-// state; f = the force part of nlplant at that state (Overload needs the body accelerations, F16_model.py:132-148).
-// causes: bit 0 overload, 1 low altitude, 2 high speed, 3 low speed, 4 extreme state, 5 unreach, 6 reached.
-struct Verdict {
-  bool bad, done, exc;
-  float rw;
-  int causes;
-};
-template <bool COMBAT, int TASK>
-__device__ __forceinline__ Verdict judge_state(const np_env_cfg& c, const float* sq, const float* tq, const Trig& g, const ForceOut& f,
-                                               int steps) {
-  float ax, ay, az;
-  body_accel(sq, g, f, ax, ay, az);
-  const float acc = sqrtf(ax * ax + ay * ay + az * az);
-  const bool overload = (acc - c.acceleration_limit) > 0.0f;            // overload.py:37-42
-  const bool low_alt = (sq[2] - c.altitude_limit) < 0.0f;               // low_altitude.py:29-30
-  const float vel = (sq[6] + c.airspeed * 1.0f) * 0.3048f / DC(340.0f);
-  const bool hi = (vel - c.max_velocity) >= 0.0f;                       // high_speed.py:29-30
-  const bool lo = (vel - c.min_velocity) <= 0.0f;                       // low_speed.py:29-30
-  const float a_deg = sq[7] * 180.0f / DC(kPi), b_deg = sq[8] * 180.0f / DC(kPi);  // extreme_state.py:32-36
-  const bool ext = (a_deg < c.min_alpha) | (a_deg > c.max_alpha) | (b_deg < c.min_beta) | (b_deg > c.max_beta);
-  const bool late = steps >= c.max_check_interval;
-  bool off = false, dn = false, exc = false;
-  float d0, d1, d2, rw = 0.0f;
-  if (COMBAT) {
-    exc = (steps - c.max_steps) >= 0;                                   // timeout.py:29
-  } else if (TASK == NP_TASK_HEADING) {                                 // unreach_heading.py:38-53
-    const float dpsi = wrap_pi(sq[5] - tq[1]);
-    off = (fabsf(dpsi) >= (float)(3.141592653589793 / 36.0)) | (fabsf(sq[2] - tq[0]) >= 100.0f) |
-          (fabsf(sq[6] - tq[2]) >= 20.0f);
-    dn = !off && !late && (steps >= c.min_check_interval);
-    d0 = (sq[2] - tq[0]) * 0.3048f / DC(1000.0f);                       // heading_reward.py:26-35
-    d1 = dpsi / DC(kPi);
-    d2 = (sq[6] - tq[2]) * 0.3048f / DC(340.0f);
-    rw = -(d0 * d0) + -(d1 * d1) + -(d2 * d2);
-  } else if (TASK == NP_TASK_CONTROL) {                                 // unreach_posture.py:37-55
-    const float dpsi = wrap_pi(sq[5] - tq[1]);
-    off = (fabsf(dpsi) >= (float)(3.141592653589793 / 36.0)) |
-          (fabsf(sq[4] - tq[0]) >= (float)(3.141592653589793 / 36.0)) | (fabsf(sq[6] - tq[2]) >= 20.0f);
-    dn = !off && !late;
-    d0 = wrap_pi(sq[4] - tq[0]) / DC(kPi);                              // posture_reward.py:26-34
-    d1 = dpsi / DC(kPi);
-    d2 = (sq[6] - tq[2]) * 0.3048f / DC(340.0f);
-    rw = -(d0 * d0) + -(d1 * d1) + -(d2 * d2);
-  } else {                                                              // unreach_target.py:35-47
-    off = (fabsf(sq[0] - tq[0]) >= 100.0f) | (fabsf(sq[1] - tq[1]) >= 100.0f) | (fabsf(sq[2] - tq[2]) >= 100.0f);
-    dn = !off && !late;
-    d0 = (sq[0] - tq[0]) * 0.3048f / DC(1000.0f);                       // position_reward.py:26-34
-    d1 = (sq[1] - tq[1]) * 0.3048f / DC(1000.0f);
-    d2 = (sq[2] - tq[2]) * 0.3048f / DC(1000.0f);
-    rw = 0.1f * (-(d0 * d0) + -(d1 * d1) + -(d2 * d2));
-  }
-  const bool unreach = late && off;
-  Verdict v;
-  v.bad = overload | low_alt | hi | lo | ext | unreach;
-  v.done = dn;
-  v.exc = exc;
-  v.rw = rw;
-  v.causes = (int)overload | ((int)low_alt << 1) | ((int)hi << 2) | ((int)lo << 3) | ((int)ext << 4) | ((int)unreach << 5) | ((int)dn << 6);
-  return v;
-}
 
 // ------------------------------------------------------------------------------------------------
 // K1: the fused step kernel
@@ -1149,369 +699,6 @@ __global__ void __launch_bounds__(256) f16_reset_kernel(const __grid_constant__ 
 }
 
 // ------------------------------------------------------------------------------------------------
-// K2: the UAV plug-in (envs/models/UAV_model.py, UAV/UAV_dynamics.py) behind the same tasks.  Trivial arithmetic,
-// HBM-bound: one aircraft per thread, coalesced SoA rows, one launch per BaseEnv.step().
-// Algorithmic bytes per aircraft-step: 268 = read 96 (s 48, F 12, tgt 12, step 4, flags 4, action 16) +
-// write 172 (s 48, F 12, tgt 12, step 4, flags 4, obs 88, reward 4).
-// ------------------------------------------------------------------------------------------------
-// task.reset on the getter view (heading_task.py:49-69, control_task.py:49-68, tracking_task.py:48-71)
-__device__ __forceinline__ void uav_task_reset(const np_env_cfg& c, const UavView& v, const Draws& r, float* tgt) {
-  if (c.task == NP_TASK_HEADING) {
-    tgt[0] = v.alt + 1000.0f;
-    tgt[1] = wrap_pi(v.heading + (float)(2.0 * 3.141592653589793 / 3.0));
-    tgt[2] = v.vt + 0.0f;
-  } else if (c.task == NP_TASK_CONTROL) {
-    tgt[0] = wrap_pi(v.pitch + 2.0f * (r.d[2] - 0.5f) * c.max_pitch_increment);
-    tgt[1] = wrap_pi(v.heading + 2.0f * (r.d[3] - 0.5f) * c.max_heading_increment);
-    tgt[2] = v.vt + 2.0f * (r.d[4] - 0.5f) * c.max_velocities_u_increment;
-  } else {
-    const float dist = r.d[2] * (c.max_distance - c.min_distance) + c.min_distance;
-    const float th1 = r.d[3] * kPi / DC(3.0f) - (float)(3.141592653589793 / 6.0);
-    const float th2 = r.d[4] * kPi / DC(3.0f) - (float)(3.141592653589793 / 6.0);
-    tgt[0] = v.npos + dist * cosf(th1) * cosf(th2);
-    tgt[1] = v.epos + dist * cosf(th1) * sinf(th2);
-    tgt[2] = v.alt + dist * sinf(th1);
-  }
-}
-
-// UAVModel.reset (UAV_model.py:32-45): SI state, zero forces except u[0] = init_T
-__device__ __forceinline__ void uav_reset_aircraft(const np_env_cfg& c, const Draws& r, float* s, float* F) {
-#pragma unroll
-  for (int j = 0; j < 12; ++j) s[j] = 0.0f;
-  s[2] = (r.d[0] * (c.max_altitude - c.min_altitude) + c.min_altitude) * 0.3048f;
-  s[6] = (r.d[1] * (c.max_vt - c.min_vt) + c.min_vt) * 0.3048f;
-  F[0] = c.init_T; F[1] = 0.0f; F[2] = 0.0f;
-}
-
-// 22-D observation through the getters (heading_task.py:93-152): AOA = AOS = thrust = surfaces = 0 for this model
-__device__ __forceinline__ void uav_make_obs(const np_env_cfg& c, const float* s, const UavView& v, const UavTrig& t, const float* tgt,
-                                             float* o) {
-  if (c.task == NP_TASK_HEADING) {
-    o[0] = (v.alt - tgt[0]) * 0.3048f / DC(1000.0f);
-    o[1] = wrap_pi(v.heading - tgt[1]);
-    o[2] = (v.vt - tgt[2]) * 0.3048f / DC(340.0f);
-  } else if (c.task == NP_TASK_CONTROL) {
-    o[0] = wrap_pi(v.pitch - tgt[0]);
-    o[1] = wrap_pi(v.heading - tgt[1]);
-    o[2] = (v.vt - tgt[2]) * 0.3048f / DC(340.0f);
-  } else {
-    o[0] = (v.npos - tgt[0]) * 0.3048f / DC(1000.0f);
-    o[1] = (v.epos - tgt[1]) * 0.3048f / DC(1000.0f);
-    o[2] = (v.alt - tgt[2]) * 0.3048f / DC(1000.0f);
-  }
-  const float eas = (v.vt + c.airspeed * 1.0f) / v.e2t;  // UAV_model.py:94-102
-  o[3] = v.alt * 0.3048f / DC(5000.0f);
-  o[4] = t.sphi; o[5] = t.cphi; o[6] = t.st; o[7] = t.ct;
-  o[8] = eas * 0.3048f / DC(340.0f);
-  o[9] = 0.0f; o[10] = 1.0f; o[11] = 0.0f; o[12] = 1.0f;  // sin / cos of get_AOA() = get_AOS() = 0
-  o[13] = s[9]; o[14] = s[10]; o[15] = s[11];
-  o[16] = 0.0f / DC(0.225f) / DC(76300.0f) * 0.3048f;             // get_thrust() = 0
-  o[17] = 0.0f / DC(45.0f); o[18] = 0.0f / DC(45.0f); o[19] = 0.0f / DC(45.0f); o[20] = 0.0f / DC(45.0f);
-  o[21] = v.e2t;
-}
-
-// One aircraft of BaseEnv.step / reset for the UAV plug-in, entirely in registers: masked reset -> (STEP) force
-// low-pass + Euler step -> observation row -> (STEP) terminations + reward.  Shared by the per-thread kernel and the
-// TMA-staged slab kernel below, so both produce identical bits.
-template <bool STEP>
-__device__ __forceinline__ void uav_aircraft(const StepParams& p, int i, bool rst, const float4 av, float* s, float* F, float* tgt,
-                                             int& steps, float* o, float& rew, bool& done, bool& bad) {
-  const np_env_cfg& c = p.cfg;
-  // ---- BaseEnv.reset (env_base.py:83-97) ---------------------------------------------------------
-  if (rst) {
-    const Draws r = reset_draws(p, i);
-    uav_reset_aircraft(c, r, s, F);
-    uav_task_reset(c, uav_view(s), r, tgt);
-    steps = 0;
-    atomicAdd(&p.counters[7], 1ull);
-  }
-  bad = false; done = false; rew = 0.0f;
-  if (STEP) {
-    // ---- UAVModel.update (UAV_model.py:51-62): clamp, force low-pass, one explicit Euler step ------------
-    const float a[3] = {fminf(fmaxf(av.x, -1.0f), 1.0f), fminf(fmaxf(av.y, -1.0f), 1.0f), fminf(fmaxf(av.z, -1.0f), 1.0f)};
-#pragma unroll
-    for (int j = 0; j < 3; ++j) F[j] = 0.9f * F[j] + 0.1f * a[j] * 27000.0f;
-    float xdot[12];
-    uav_nlplant(s, F, xdot);
-    const float h = c.dt - 0.0f;
-#pragma unroll
-    for (int j = 0; j < 12; ++j) s[j] = s[j] + h * xdot[j];
-    steps += 1;
-  }
-  // ---- obs (env_base.py:103) ----------------------------------------------------------------------
-  const UavView v = uav_view(s);
-  const UavTrig trig = uav_trig(s);   // of the state the observation, the Overload check and the reward all see
-  uav_make_obs(c, s, v, trig, tgt, o);
-  add_obs_noise(p, i, o);
-  if (STEP) {
-    // ---- terminations (task_base.py:75-96) through the getters ------------------------------------------
-    float xdot[12];
-    uav_nlplant(s, F, trig, xdot);                                        // get_acceleration (UAV_model.py:120-130)
-    const float vu = s[6] / DC(0.3048f), vv = s[7] / DC(0.3048f), vw = s[8] / DC(0.3048f);
-    const float ax = xdot[6] / DC(0.3048f) + s[10] * vw - s[11] * vv;
-    const float ay = xdot[7] / DC(0.3048f) + s[11] * vu - s[9] * vw;
-    const float az = xdot[8] / DC(0.3048f) + s[9] * vv - s[10] * vu;
-    const float acc = sqrtf(ax * ax + ay * ay + az * az);
-    const bool overload = (acc - c.acceleration_limit) > 0.0f;
-    const bool low_alt = (v.alt - c.altitude_limit) < 0.0f;
-    const float vel = (v.vt + c.airspeed * 1.0f) * 0.3048f / DC(340.0f);
-    const bool hi = (vel - c.max_velocity) >= 0.0f;
-    const bool lo = (vel - c.min_velocity) <= 0.0f;
-    const float a_deg = 0.0f * 180.0f / DC(kPi);                              // get_AOA() = get_AOS() = 0
-    const bool ext = (a_deg < c.min_alpha) | (a_deg > c.max_alpha) | (a_deg < c.min_beta) | (a_deg > c.max_beta);
-    const bool late = steps >= c.max_check_interval;
-    bool off;
-    float d0, d1, d2;
-    if (c.task == NP_TASK_HEADING) {
-      const float dpsi = wrap_pi(v.heading - tgt[1]);
-      off = (fabsf(dpsi) >= (float)(3.141592653589793 / 36.0)) | (fabsf(v.alt - tgt[0]) >= 100.0f) |
-            (fabsf(v.vt - tgt[2]) >= 20.0f);
-      done = !off && !late && (steps >= c.min_check_interval);
-      d0 = (v.alt - tgt[0]) * 0.3048f / DC(1000.0f); d1 = dpsi / DC(kPi); d2 = (v.vt - tgt[2]) * 0.3048f / DC(340.0f);
-      rew = -(d0 * d0) + -(d1 * d1) + -(d2 * d2);
-    } else if (c.task == NP_TASK_CONTROL) {
-      const float dpsi = wrap_pi(v.heading - tgt[1]);
-      off = (fabsf(dpsi) >= (float)(3.141592653589793 / 36.0)) | (fabsf(v.pitch - tgt[0]) >= (float)(3.141592653589793 / 36.0)) |
-            (fabsf(v.vt - tgt[2]) >= 20.0f);
-      done = !off && !late;
-      d0 = wrap_pi(v.pitch - tgt[0]) / DC(kPi); d1 = dpsi / DC(kPi); d2 = (v.vt - tgt[2]) * 0.3048f / DC(340.0f);
-      rew = -(d0 * d0) + -(d1 * d1) + -(d2 * d2);
-    } else {
-      off = (fabsf(v.npos - tgt[0]) >= 100.0f) | (fabsf(v.epos - tgt[1]) >= 100.0f) | (fabsf(v.alt - tgt[2]) >= 100.0f);
-      done = !off && !late;
-      d0 = (v.npos - tgt[0]) * 0.3048f / DC(1000.0f); d1 = (v.epos - tgt[1]) * 0.3048f / DC(1000.0f);
-      d2 = (v.alt - tgt[2]) * 0.3048f / DC(1000.0f);
-      rew = 0.1f * (-(d0 * d0) + -(d1 * d1) + -(d2 * d2));
-    }
-    const bool unreach = late && off;
-    bad = overload | low_alt | hi | lo | ext | unreach;
-    rew = rew + (float)(-200 * (int)bad + 200 * (int)done);
-    const bool cause[7] = {overload, low_alt, hi, lo, ext, unreach, done};
-#pragma unroll
-    for (int w = 0; w < 7; ++w)
-      if (cause[w]) atomicAdd(&p.counters[w], 1ull);   // ptxas aggregates warp-uniform-address atomics (REDUX + one ATOM)
-  }
-}
-
-// Per-thread variant (reset, unaligned ranges): scalar SoA accesses straight to global memory.
-template <bool STEP>
-__global__ void __launch_bounds__(256, 4) uav_env_kernel(const __grid_constant__ StepParams p) {
-  const np_env_cfg& c = p.cfg;
-  const int n = c.n, ld = c.ld;
-  const int i_end = min(n, 2 * p.pair_end);
-  for (int i = 2 * p.pair_begin + blockIdx.x * blockDim.x + threadIdx.x; i < i_end; i += gridDim.x * blockDim.x) {
-    float s[12], F[3], tgt[3], o[NP_NUM_OBS], rew;
-    bool done, bad;
-#pragma unroll
-    for (int j = 0; j < 12; ++j) s[j] = p.s[(size_t)j * ld + i];
-#pragma unroll
-    for (int j = 0; j < 3; ++j) F[j] = p.u[(size_t)j * ld + i];
-#pragma unroll
-    for (int j = 0; j < 3; ++j) tgt[j] = p.tgt[(size_t)j * ld + i];
-    int steps = p.step_count[i];
-    const bool rst = (p.flags[i] | p.flags[ld + i] | p.flags[2 * (size_t)ld + i]) != 0;
-    const float4 av = STEP ? reinterpret_cast<const float4*>(p.action)[i] : make_float4(0.f, 0.f, 0.f, 0.f);
-    uav_aircraft<STEP>(p, i, rst, av, s, F, tgt, steps, o, rew, done, bad);
-    float2* orow = reinterpret_cast<float2*>(p.obs + (size_t)i * NP_NUM_OBS);
-#pragma unroll
-    for (int j = 0; j < NP_NUM_OBS / 2; ++j) orow[j] = make_float2(o[2 * j], o[2 * j + 1]);
-    if (STEP) p.reward[i] = rew;
-#pragma unroll
-    for (int j = 0; j < 12; ++j) p.s[(size_t)j * ld + i] = s[j];
-#pragma unroll
-    for (int j = 0; j < 3; ++j) p.u[(size_t)j * ld + i] = F[j];
-#pragma unroll
-    for (int j = 0; j < 3; ++j) p.tgt[(size_t)j * ld + i] = tgt[j];
-    p.step_count[i] = steps;
-    p.flags[i] = done ? 1 : 0;
-    p.flags[ld + i] = bad ? 1 : 0;
-    p.flags[2 * (size_t)ld + i] = 0;
-  }
-}
-
-// ------------------------------------------------------------------------------------------------
-// K2 (TMA-staged): the HBM-bound UAV step as a persistent slab pipeline.  A CTA owns 256-aircraft slabs.
-//   in : every SoA row segment (1 KB), the action block (4 KB) and the flag rows arrive in shared memory through TMA bulk
-//        copies completing on an mbarrier (23 copies, one per lane of warp 0); slab k+1's inputs are requested as soon as
-//        slab k's are in registers and land during slab k's arithmetic;
-//   out: the strided part -- the 256 x 22 observation block (22.5 KB, contiguous in the row-major obs array) -- is staged
-//        and leaves as ONE bulk store that drains during slab k+1's arithmetic; SoA rows, reward and flags are already
-//        coalesced (128 B per warp and row) and go straight from registers.
-// The per-thread variant is LSU-queue / latency limited (23 scalar loads + 34 stores per aircraft, the 11 observation
-// stores touching 32 separate sectors each).  46.9 KB and 64 registers per thread -> 4 CTAs (32 warps) per SM.
-// The ragged tail slab (< 256 aircraft) goes through guarded per-thread accesses in the same kernel.
-// ------------------------------------------------------------------------------------------------
-namespace uavslab {
-constexpr int kSlab = 256;
-constexpr int IN_S = 0;                            // [12][256] f32
-constexpr int IN_U = IN_S + 12 * kSlab * 4;        // [3][256] f32
-constexpr int IN_T = IN_U + 3 * kSlab * 4;         // [3][256] f32
-constexpr int IN_STEP = IN_T + 3 * kSlab * 4;      // [256] i32
-constexpr int IN_ACT = IN_STEP + kSlab * 4;        // [256][4] f32
-constexpr int IN_FLG = IN_ACT + kSlab * 16;        // [3][256] u8
-constexpr int IN_BYTES = IN_FLG + 3 * kSlab;       // 24 320
-constexpr int OUT_OBS = IN_BYTES;                  // [256][22] f32: the only output staged in shared memory
-constexpr int BAR = OUT_OBS + kSlab * NP_NUM_OBS * 4;
-constexpr int SMEM_BYTES = BAR + 32;               // 46 880 (four mbarriers) -> 4 CTAs = 32 warps per SM
-static_assert(OUT_OBS % 16 == 0 && BAR % 8 == 0, "bulk copies need 16-byte aligned shared addresses");
-}  // namespace uavslab
-
-
-// warp 0 requests the inputs of the full slab starting at aircraft i0: lane r fetches row r
-__device__ __forceinline__ void uav_slab_request(const StepParams& p, unsigned char* sm, uint64_t* bar, int i0, int lane) {
-  using namespace uavslab;
-  const size_t ld = (size_t)p.cfg.ld;
-  if (lane == 0) mbar_expect_tx(bar, IN_BYTES);
-  __syncwarp();
-  if (lane < 12) bulk_g2s(sm + IN_S + lane * kSlab * 4, p.s + lane * ld + i0, kSlab * 4, bar);
-  else if (lane < 15) bulk_g2s(sm + IN_U + (lane - 12) * kSlab * 4, p.u + (lane - 12) * ld + i0, kSlab * 4, bar);
-  else if (lane < 18) bulk_g2s(sm + IN_T + (lane - 15) * kSlab * 4, p.tgt + (lane - 15) * ld + i0, kSlab * 4, bar);
-  else if (lane == 18) bulk_g2s(sm + IN_STEP, p.step_count + i0, kSlab * 4, bar);
-  else if (lane == 19) bulk_g2s(sm + IN_ACT, p.action + (size_t)i0 * 4, kSlab * 16, bar);
-  else if (lane < 23) bulk_g2s(sm + IN_FLG + (lane - 20) * kSlab, p.flags + (lane - 20) * ld + i0, kSlab, bar);
-}
-
-// one lane of warp 0 sends the slab's 256 x 22 observation block (contiguous in the row-major obs array) as one bulk store
-__device__ __forceinline__ void uav_slab_send(const StepParams& p, unsigned char* sm, int i0, int lane) {
-  using namespace uavslab;
-  if (lane == 0) {
-    bulk_s2g(p.obs + (size_t)i0 * NP_NUM_OBS, sm + OUT_OBS, kSlab * NP_NUM_OBS * 4);
-    bulk_commit();
-  }
-}
-
-__global__ void __launch_bounds__(uavslab::kSlab, 4) uav_step_slab_kernel(const __grid_constant__ StepParams p) {
-  using namespace uavslab;
-  extern __shared__ __align__(128) unsigned char sm[];
-  const int ld = p.cfg.ld, t = threadIdx.x, lane = t & 31;
-  const bool warp0 = t < 32;
-  const int i_begin = 2 * p.pair_begin, i_end = min(p.cfg.n, 2 * p.pair_end);
-  const int nslab = (i_end - i_begin + kSlab - 1) / kSlab;
-  // No CTA-wide barrier in the slab loop: the eight warps are coupled only through four mbarriers, so a warp that is
-  // ahead keeps issuing (a __syncthreads version measured 3.2 barrier-stall cycles per issued instruction).
-  uint64_t* in_full = reinterpret_cast<uint64_t*>(sm + BAR);  // TMA: the slab's inputs have landed            (tx bytes)
-  uint64_t* in_read = in_full + 1;                            // every warp holds its inputs in registers        (8 warps)
-  uint64_t* written = in_full + 2;                            // every warp has staged its observation rows      (8 warps)
-  uint64_t* out_free = in_full + 3;                           // the previous bulk store has read the obs block      (1)
-  if (t == 0) {
-    mbar_init(in_full, 1);
-    mbar_init(in_read, kSlab / 32);
-    mbar_init(written, kSlab / 32);
-    mbar_init(out_free, 1);
-  }
-  __syncthreads();
-
-  int slab = blockIdx.x;
-  if (warp0 && slab < nslab && i_begin + (slab + 1) * kSlab <= i_end) uav_slab_request(p, sm, in_full, i_begin + slab * kSlab, lane);
-
-  for (int it = 0; slab < nslab; slab += gridDim.x, ++it) {
-    const int i0 = i_begin + slab * kSlab, i = i0 + t;
-    const bool full = i0 + kSlab <= i_end;       // CTA-uniform; only the last slab of the range can be ragged
-    const bool live = full || i < i_end;
-    const uint32_t ph = it & 1;
-    float s[12], F[3], tgt[3], o[NP_NUM_OBS], rew = 0.0f;
-    bool done = false, bad = false, rst = false;
-    int steps = 0;
-    float4 av = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (full) {
-      mbar_wait(in_full, ph);
-#pragma unroll
-      for (int j = 0; j < 12; ++j) s[j] = reinterpret_cast<const float*>(sm + IN_S)[j * kSlab + t];
-#pragma unroll
-      for (int j = 0; j < 3; ++j) F[j] = reinterpret_cast<const float*>(sm + IN_U)[j * kSlab + t];
-#pragma unroll
-      for (int j = 0; j < 3; ++j) tgt[j] = reinterpret_cast<const float*>(sm + IN_T)[j * kSlab + t];
-      steps = reinterpret_cast<const int*>(sm + IN_STEP)[t];
-      av = reinterpret_cast<const float4*>(sm + IN_ACT)[t];
-      rst = (sm[IN_FLG + t] | sm[IN_FLG + kSlab + t] | sm[IN_FLG + 2 * kSlab + t]) != 0;
-      __syncwarp();
-      if (lane == 0) mbar_arrive(in_read);
-      if (warp0) {
-        if (it > 0) {            // the previous slab's stores were issued a whole input wait ago: normally drained by now
-          bulk_wait_read0();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(out_free);
-        }
-        const int next = slab + gridDim.x;
-        if (next < nslab && i_begin + (next + 1) * kSlab <= i_end) {
-          mbar_wait(in_read, ph);   // the input slab is free again: its next contents land during this slab's arithmetic
-          uav_slab_request(p, sm, in_full, i_begin + next * kSlab, lane);
-        }
-      }
-    } else if (live) {
-#pragma unroll
-      for (int j = 0; j < 12; ++j) s[j] = p.s[(size_t)j * ld + i];
-#pragma unroll
-      for (int j = 0; j < 3; ++j) F[j] = p.u[(size_t)j * ld + i];
-#pragma unroll
-      for (int j = 0; j < 3; ++j) tgt[j] = p.tgt[(size_t)j * ld + i];
-      steps = p.step_count[i];
-      av = reinterpret_cast<const float4*>(p.action)[i];
-      rst = (p.flags[i] | p.flags[ld + i] | p.flags[2 * (size_t)ld + i]) != 0;
-    }
-
-    if (live) uav_aircraft<true>(p, i, rst, av, s, F, tgt, steps, o, rew, done, bad);
-
-    if (full) {
-      // SoA rows, reward and flags: fully coalesced 4-byte stores straight from registers (128 B per warp and row)
-#pragma unroll
-      for (int j = 0; j < 12; ++j) p.s[(size_t)j * ld + i] = s[j];
-#pragma unroll
-      for (int j = 0; j < 3; ++j) p.u[(size_t)j * ld + i] = F[j];
-#pragma unroll
-      for (int j = 0; j < 3; ++j) p.tgt[(size_t)j * ld + i] = tgt[j];
-      p.step_count[i] = steps;
-      p.reward[i] = rew;
-      p.flags[i] = done ? 1 : 0;
-      p.flags[ld + i] = bad ? 1 : 0;
-      p.flags[2 * (size_t)ld + i] = 0;
-      // the 88-byte observation rows are the strided part: staged, then one 22.5 KB bulk store per slab
-      if (it > 0) mbar_wait(out_free, ph ^ 1);
-      float2* orow = reinterpret_cast<float2*>(sm + OUT_OBS) + t * (NP_NUM_OBS / 2);  // 8-byte stride 11: conflict-free
-#pragma unroll
-      for (int j = 0; j < NP_NUM_OBS / 2; ++j) orow[j] = make_float2(o[2 * j], o[2 * j + 1]);
-      fence_async_smem();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(written);
-      if (warp0) {
-        mbar_wait(written, ph);
-        uav_slab_send(p, sm, i0, lane);
-      }
-    } else if (live) {
-      float2* orow = reinterpret_cast<float2*>(p.obs + (size_t)i * NP_NUM_OBS);
-#pragma unroll
-      for (int j = 0; j < NP_NUM_OBS / 2; ++j) orow[j] = make_float2(o[2 * j], o[2 * j + 1]);
-      p.reward[i] = rew;
-#pragma unroll
-      for (int j = 0; j < 12; ++j) p.s[(size_t)j * ld + i] = s[j];
-#pragma unroll
-      for (int j = 0; j < 3; ++j) p.u[(size_t)j * ld + i] = F[j];
-#pragma unroll
-      for (int j = 0; j < 3; ++j) p.tgt[(size_t)j * ld + i] = tgt[j];
-      p.step_count[i] = steps;
-      p.flags[i] = done ? 1 : 0;
-      p.flags[ld + i] = bad ? 1 : 0;
-      p.flags[2 * (size_t)ld + i] = 0;
-    }
-  }
-  if (warp0) bulk_wait0();  // shared memory must outlive the last bulk stores
-}
-
-__global__ void __launch_bounds__(256) uav_nlplant_kernel(const float* __restrict__ S, const float* __restrict__ U,
-                                                          float* __restrict__ X, int n, int ld) {
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    float s[12], F[3], xdot[12];
-#pragma unroll
-    for (int j = 0; j < 12; ++j) s[j] = S[(size_t)j * ld + i];
-#pragma unroll
-    for (int j = 0; j < 3; ++j) F[j] = U[(size_t)j * ld + i];
-    uav_nlplant(s, F, xdot);
-#pragma unroll
-    for (int j = 0; j < 12; ++j) X[(size_t)j * ld + i] = xdot[j];
-  }
-}
-
-// ------------------------------------------------------------------------------------------------
 // K5r: the pair half of the ROLE-sharded combat step (singlecombat_env.py:64-181,207-238,263-271).  The local half
 // (f16_step_kernel<MODE_COMBAT> with p.records) has flown this rank's aircraft -- all egos or all opponents, one per env --
 // through the five sub-steps and published a record each; after a cross-device barrier this kernel pulls the partner's record
@@ -1647,373 +834,6 @@ __global__ void __launch_bounds__(256) combat_relgeo_peers_kernel(const float* c
     // cross-device barrier), but they must not come through the non-coherent read-only path
     const float4 a0 = __ldcg(pe), a1 = __ldcg(pe + 1), b0 = __ldcg(pm), b1 = __ldcg(pm + 1);
     relgeo_pair(a0, a1, b0, b1, out, i);
-  }
-}
-
-// ------------------------------------------------------------------------------------------------
-// K7: device-resident rollout buffer (SURVEY f-2).  ReplayBuffer.compute_returns (algorithms/utils/buffer.py:139-172) as a
-// backward scan, one thread per (env, agent) column -- rows are [T(+1)][M] so every load / store is coalesced; and the
-// mask derivation of F16SimRunner.insert (runner/F16sim_runner.py:141-157) straight from the env's flag rows.
-// Arithmetic order == numpy's fp32 evaluation of the reference expressions (built with -fmad=false): bit-exact.
-// ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) rollout_returns_kernel(const float* __restrict__ R, float* __restrict__ V,
-                                                              const float* __restrict__ Mk, const float* __restrict__ Bm,
-                                                              float* __restrict__ Ret, int T, int M, float gamma, float gl,
-                                                              int use_gae, int proper) {
-  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < M; j += gridDim.x * blockDim.x) {
-    if (use_gae) {
-      float gae = 0.0f, vnext = V[(size_t)T * M + j];   // value_preds[-1] = next_value was written by the caller
-#pragma unroll 4
-      for (int t = T - 1; t >= 0; --t) {
-        const size_t i = (size_t)t * M + j, i1 = i + M;
-        const float v = V[i], m = Mk[i1];
-        const float td = R[i] + gamma * vnext * m - v;                    // buffer.py:151 / :163
-        gae = td + gl * m * gae;                                          // :152 / :166  (gl = f32(gamma * gae_lambda))
-        if (proper) gae = gae * Bm[i1];                                   // :153
-        Ret[i] = gae + v;                                                 // :154 / :167
-        vnext = v;
-      }
-    } else {
-      float ret = Ret[(size_t)T * M + j];                // returns[-1] = next_value was written by the caller
-#pragma unroll 4
-      for (int t = T - 1; t >= 0; --t) {
-        const size_t i = (size_t)t * M + j, i1 = i + M;
-        const float m = Mk[i1];
-        if (proper) {                                                     // :158-159
-          const float bm = Bm[i1];
-          ret = (ret * gamma * m + R[i]) * bm + (1.0f - bm) * V[i];
-        } else {
-          ret = ret * gamma * m + R[i];                                   // :171
-        }
-        Ret[i] = ret;
-      }
-    }
-  }
-}
-
-// masks[e, a] = 0 where ANY agent of env e is done, bad_masks likewise for bad_done, reset_env[e] = any flag of any agent
-// (F16sim_runner.py:144-155); one thread per env.
-__global__ void __launch_bounds__(256) rollout_masks_kernel(const uint8_t* __restrict__ flags, int ld, int num_envs, int agents,
-                                                            float* __restrict__ masks, float* __restrict__ bad_masks,
-                                                            uint8_t* __restrict__ reset_env) {
-  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < num_envs; e += gridDim.x * blockDim.x) {
-    unsigned d = 0, b = 0, x = 0;
-    for (int a = 0; a < agents; ++a) {
-      const size_t i = (size_t)e * agents + a;
-      d |= flags[i]; b |= flags[ld + i]; x |= flags[2 * (size_t)ld + i];
-    }
-    const float mk = d ? 0.0f : 1.0f, bk = b ? 0.0f : 1.0f;
-    for (int a = 0; a < agents; ++a) {
-      masks[(size_t)e * agents + a] = mk;
-      bad_masks[(size_t)e * agents + a] = bk;
-    }
-    if (reset_env) reset_env[e] = (d | b | x) ? 1 : 0;
-  }
-}
-
-// ------------------------------------------------------------------------------------------------
-// K6: table aero back-end (tables_device.cuh): 44 coefficients per (alpha, beta, el) point from the NASA tables
-// ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) f16_table_coeffs_kernel(const float* __restrict__ image, const float* __restrict__ A,
-                                                               const float* __restrict__ Bd, const float* __restrict__ E,
-                                                               float* __restrict__ out, int n, int ld) {
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  float* T = reinterpret_cast<float*>(smem_raw);
-  uint64_t* bar = reinterpret_cast<uint64_t*>(T + kTablesFloats);
-  stage_aero(T, image, (uint32_t)(kTablesFloats * 4), bar);
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
-    table_coefficients(T, A[i], Bd[i], E[i], out + i, ld);
-}
-
-// nlplant with the table back-end (the getters of a table-backed F16 plug-in): one aircraft per thread
-__global__ void __launch_bounds__(256) f16_table_nlplant_kernel(const float* __restrict__ image, const float* __restrict__ S,
-                                                                const float* __restrict__ U, float* __restrict__ X, int n, int ld) {
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  float* T = reinterpret_cast<float*>(smem_raw);
-  uint64_t* bar = reinterpret_cast<uint64_t*>(T + kTablesFloats);
-  stage_aero(T, image, (uint32_t)(kTablesFloats * 4), bar);
-  const ZeroCells zc = zero_cells(T);
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    float s[12], u[5], c[kNumSlots], a1[kNumA1], xdot[12];
-#pragma unroll
-    for (int j = 0; j < 12; ++j) s[j] = S[(size_t)j * ld + i];
-#pragma unroll
-    for (int j = 0; j < 5; ++j) u[j] = U[(size_t)j * ld + i];
-    table_env_coefs(T, zc, s[7] * kR2D, s[8] * kR2D, u[1], true, c, a1);
-    const Trig g = make_trig(s);
-    nlplant_from_coefs(s, u[0], u[2], u[3], u[4], g, tfac_pow(s[2]), c, 1, a1, xdot);
-#pragma unroll
-    for (int j = 0; j < 12; ++j) X[(size_t)j * ld + i] = xdot[j];
-  }
-}
-
-// ------------------------------------------------------------------------------------------------
-// stand-alone nlplant / coefficient kernels (model plug-in getters, parity tests): same device code as K1,
-// two points per thread
-// ------------------------------------------------------------------------------------------------
-constexpr int kAuxBS = 128;
-static int aux_smem_bytes(int aero_bytes) { return aero_bytes + kNumSlots * kAuxBS * 8 + 16; }
-
-__global__ void __launch_bounds__(kAuxBS) f16_nlplant_kernel(const uint32_t* __restrict__ aero, int aero_bytes,
-                                                             const float* __restrict__ S, const float* __restrict__ U,
-                                                             float* __restrict__ X, int n, int ld) {
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  float* blob = reinterpret_cast<float*>(smem_raw);
-  float2* coef_all = reinterpret_cast<float2*>(smem_raw + aero_bytes);
-  uint64_t* bar = reinterpret_cast<uint64_t*>(coef_all + kNumSlots * kAuxBS);
-  stage_aero(blob, aero, (uint32_t)aero_bytes, bar);
-  const uint32_t wb0 = aero_base_after_staging(blob);
-  const AeroTabs tabs = aero_tabs(blob, wb0);
-  float2* coef2 = coef_all + threadIdx.x;
-  float* cf = reinterpret_cast<float*>(coef2);
-  constexpr int CS = 2 * kAuxBS;
-  const int npairs = (n + 1) >> 1;
-  for (int pbase = blockIdx.x * kAuxBS; pbase < npairs; pbase += gridDim.x * kAuxBS) {
-    const int pr = pbase + threadIdx.x;
-    const int prl = pr < npairs ? pr : npairs - 1;
-    const uint32_t wb = opaque_u32(wb0);
-    float s[2][12], u[2][5];
-#pragma unroll
-    for (int j = 0; j < 12; ++j) {
-      const float2 v = reinterpret_cast<const float2*>(S + (size_t)j * ld)[prl];
-      s[0][j] = v.x; s[1][j] = v.y;
-    }
-#pragma unroll
-    for (int j = 0; j < 5; ++j) {
-      const float2 v = reinterpret_cast<const float2*>(U + (size_t)j * ld)[prl];
-      u[0][j] = v.x; u[1][j] = v.y;
-    }
-    const float2 adeg = make_float2(s[0][7] * kR2D, s[1][7] * kR2D);
-    const float2 bdeg = make_float2(s[0][8] * kR2D, s[1][8] * kR2D);
-    ZIn2 zi;
-    zscores_ab2(blob, adeg, bdeg, zi);
-    zscores_el2(blob, make_float2(u[0][1], u[1][1]), zi);
-    eval_ab2_nets(blob, wb, zi, coef2, kAuxBS);
-    eval_el3_nets(blob, wb, zi, coef2, kAuxBS, 5);
-    float xdot[2][12];
-    uint32_t seg[2];
-    pwl_search2<kLevelsA>(tabs.bp_a, adeg.x, adeg.y, seg[0], seg[1]);
-    coef2[kEtaEl * kAuxBS] = eta_el2(tabs, make_float2(u[0][1], u[1][1]));
-#pragma unroll
-    for (int q = 0; q < 2; ++q) {
-      float a1[kNumA1];
-      alpha_coefs<kNumUsed - kFirstA1>(blob, tabs, seg[q], q == 0 ? adeg.x : adeg.y, a1);
-      const Trig g = make_trig(s[q]);
-      nlplant_from_coefs(s[q], u[q][0], u[q][2], u[q][3], u[q][4], g, tfac_pow(s[q][2]), cf + q, CS, a1, xdot[q]);
-    }
-    if (pr < npairs) {  // rows are ld >= n + (n & 1) floats long
-#pragma unroll
-      for (int j = 0; j < 12; ++j)
-        reinterpret_cast<float2*>(X + (size_t)j * ld)[pr] = make_float2(xdot[0][j], xdot[1][j]);
-    }
-  }
-}
-
-__global__ void __launch_bounds__(kAuxBS) f16_coeffs_kernel(const uint32_t* __restrict__ aero, int aero_bytes,
-                                                            const float* __restrict__ A, const float* __restrict__ Bd,
-                                                            const float* __restrict__ E, float* __restrict__ out, int n,
-                                                            int ld) {
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  float* blob = reinterpret_cast<float*>(smem_raw);
-  float2* coef_all = reinterpret_cast<float2*>(smem_raw + aero_bytes);
-  uint64_t* bar = reinterpret_cast<uint64_t*>(coef_all + kNumSlots * kAuxBS);
-  stage_aero(blob, aero, (uint32_t)aero_bytes, bar);
-  const uint32_t wb0 = aero_base_after_staging(blob);
-  const AeroTabs tabs = aero_tabs(blob, wb0);
-  float2* coef2 = coef_all + threadIdx.x;
-  float* cf = reinterpret_cast<float*>(coef2);
-  constexpr int CS = 2 * kAuxBS;
-  const int npairs = (n + 1) >> 1;
-  for (int pbase = blockIdx.x * kAuxBS; pbase < npairs; pbase += gridDim.x * kAuxBS) {
-    const int pr = pbase + threadIdx.x;
-    const int prl = pr < npairs ? pr : npairs - 1;
-    const int i0 = min(2 * prl, n - 1), i1 = min(2 * prl + 1, n - 1);
-    const uint32_t wb = opaque_u32(wb0);
-    const float2 adeg = make_float2(A[i0], A[i1]), bdeg = make_float2(Bd[i0], Bd[i1]), edeg = make_float2(E[i0], E[i1]);
-    ZIn2 zi;
-    zscores_ab2(blob, adeg, bdeg, zi);
-    zscores_el2(blob, edeg, zi);
-    eval_ab2_nets(blob, wb, zi, coef2, kAuxBS);
-    eval_el3_nets(blob, wb, zi, coef2, kAuxBS, 5);
-    uint32_t seg[2];
-    pwl_search2<kLevelsA>(tabs.bp_a, adeg.x, adeg.y, seg[0], seg[1]);
-    const float2 eta2 = eta_el2(tabs, edeg);
-#pragma unroll
-    for (int q = 0; q < 2; ++q) {
-      const int i = 2 * pr + q;
-      float a1[kNumA1];
-      alpha_coefs<kNumA1>(blob, tabs, seg[q], q == 0 ? adeg.x : adeg.y, a1);
-      const float eta = q == 0 ? eta2.x : eta2.y;
-      if (i < n) {
-        for (int k = 0; k < kNumSlots; ++k) out[(size_t)k * ld + i] = k == kEtaEl ? eta : cf[q + k * CS];
-#pragma unroll
-        for (int k = 0; k < kNumA1; ++k) out[(size_t)(kFirstA1 + k) * ld + i] = a1[k];
-      }
-    }
-  }
-}
-
-// ------------------------------------------------------------------------------------------------
-// The plug-in's stand-alone update(action) (F16_model.py:51-67, UAV_model.py:51-62): clamp -> control low-pass -> one
-// explicit Euler step of nlplant, nothing else (no reset, obs, terminations).  The reference's own PlanningEnv
-// (planning_env.py:161) and example/quick_start.ipynb drive the model this way.  recent_s / recent_u receive the state /
-// controls the update started from (the reference rebinds self.recent_s = self.s before integrating).
-// Same device code and evaluation order as the fused step, so env.step and model.update agree bit for bit.
-// ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kAuxBS) f16_update_kernel(const uint32_t* __restrict__ aero, int aero_bytes, float* __restrict__ S,
-                                                            float* __restrict__ U, float* __restrict__ RS, float* __restrict__ RU,
-                                                            const float* __restrict__ action, int n, int ld, float dt) {
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  float* blob = reinterpret_cast<float*>(smem_raw);
-  float2* coef_all = reinterpret_cast<float2*>(smem_raw + aero_bytes);
-  uint64_t* bar = reinterpret_cast<uint64_t*>(coef_all + kNumSlots * kAuxBS);
-  stage_aero(blob, aero, (uint32_t)aero_bytes, bar);
-  const uint32_t wb0 = aero_base_after_staging(blob);
-  const AeroTabs tabs = aero_tabs(blob, wb0);
-  float2* coef2 = coef_all + threadIdx.x;
-  float* cf = reinterpret_cast<float*>(coef2);
-  constexpr int CS = 2 * kAuxBS;
-  const int npairs = (n + 1) >> 1;
-  for (int pbase = blockIdx.x * kAuxBS; pbase < npairs; pbase += gridDim.x * kAuxBS) {
-    const int pr = pbase + threadIdx.x;
-    const int prl = pr < npairs ? pr : npairs - 1;
-    const bool act0 = pr < npairs, act1 = act0 && 2 * pr + 1 < n;
-    const int idx[2] = {min(2 * prl, n - 1), min(2 * prl + 1, n - 1)};
-    const uint32_t wb = opaque_u32(wb0);
-    float s[2][12], u[2][4];
-#pragma unroll
-    for (int j = 0; j < 12; ++j) {
-      const float2 v = reinterpret_cast<const float2*>(S + (size_t)j * ld)[prl];
-      s[0][j] = v.x; s[1][j] = v.y;
-    }
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const float2 v = reinterpret_cast<const float2*>(U + (size_t)j * ld)[prl];
-      u[0][j] = v.x; u[1][j] = v.y;
-    }
-    if (act0 && RS) {
-#pragma unroll
-      for (int j = 0; j < 12; ++j) store_pair(RS + (size_t)j * ld, pr, make_float2(s[0][j], s[1][j]), act1);
-    }
-    if (act0 && RU) {
-#pragma unroll
-      for (int j = 0; j < 4; ++j) store_pair(RU + (size_t)j * ld, pr, make_float2(u[0][j], u[1][j]), act1);
-      store_pair(RU + (size_t)4 * ld, pr, make_float2(0.f, 0.f), act1);
-    }
-#pragma unroll
-    for (int q = 0; q < 2; ++q) {
-      const float4 av = reinterpret_cast<const float4*>(action)[idx[q]];
-      const float a[4] = {av.x, av.y, av.z, av.w};
-      lowpass_controls(a, u[q]);
-    }
-    const float2 adeg = make_float2(s[0][7] * kR2D, s[1][7] * kR2D);
-    const float2 bdeg = make_float2(s[0][8] * kR2D, s[1][8] * kR2D);
-    ZIn2 zi;
-    zscores_ab2(blob, adeg, bdeg, zi);
-    zscores_el2(blob, make_float2(u[0][1], u[1][1]), zi);
-    eval_ab2_nets(blob, wb, zi, coef2, kAuxBS);
-    eval_el3_nets(blob, wb, zi, coef2, kAuxBS, 5);
-    uint32_t seg[2];
-    pwl_search2<kLevelsA>(tabs.bp_a, adeg.x, adeg.y, seg[0], seg[1]);
-    coef2[kEtaEl * kAuxBS] = eta_el2(tabs, make_float2(u[0][1], u[1][1]));
-    const float h = dt - 0.0f;
-#pragma unroll
-    for (int q = 0; q < 2; ++q) {
-      float a1[kNumA1], xdot[12];
-      alpha_coefs<kNumUsed - kFirstA1>(blob, tabs, seg[q], q == 0 ? adeg.x : adeg.y, a1);
-      const Trig g = make_trig(s[q]);
-      nlplant_from_coefs(s[q], u[q][0], u[q][2], u[q][3], 0.0f, g, tfac_pow(s[q][2]), cf + q, CS, a1, xdot);
-#pragma unroll
-      for (int j = 0; j < 12; ++j) s[q][j] = s[q][j] + h * xdot[j];
-    }
-    if (act0) {
-#pragma unroll
-      for (int j = 0; j < 12; ++j) store_pair(S + (size_t)j * ld, pr, make_float2(s[0][j], s[1][j]), act1);
-#pragma unroll
-      for (int j = 0; j < 4; ++j) store_pair(U + (size_t)j * ld, pr, make_float2(u[0][j], u[1][j]), act1);
-      store_pair(U + (size_t)4 * ld, pr, make_float2(0.f, 0.f), act1);   // lef = 0 (F16_model.py:57)
-    }
-  }
-}
-
-__global__ void __launch_bounds__(256) f16_table_update_kernel(const float* __restrict__ image, float* __restrict__ S, float* __restrict__ U,
-                                                               float* __restrict__ RS, float* __restrict__ RU,
-                                                               const float* __restrict__ action, int n, int ld, float dt) {
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  float* T = reinterpret_cast<float*>(smem_raw);
-  uint64_t* bar = reinterpret_cast<uint64_t*>(T + kTablesFloats);
-  stage_aero(T, image, (uint32_t)(kTablesFloats * 4), bar);
-  const ZeroCells zc = zero_cells(T);
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    float s[12], u[4], c[kNumSlots], a1[kNumA1], xdot[12];
-#pragma unroll
-    for (int j = 0; j < 12; ++j) s[j] = S[(size_t)j * ld + i];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) u[j] = U[(size_t)j * ld + i];
-    if (RS) {
-#pragma unroll
-      for (int j = 0; j < 12; ++j) RS[(size_t)j * ld + i] = s[j];
-    }
-    if (RU) {
-#pragma unroll
-      for (int j = 0; j < 4; ++j) RU[(size_t)j * ld + i] = u[j];
-      RU[(size_t)4 * ld + i] = 0.0f;
-    }
-    const float4 av = reinterpret_cast<const float4*>(action)[i];
-    const float a[4] = {av.x, av.y, av.z, av.w};
-    lowpass_controls(a, u);
-    table_env_coefs(T, zc, s[7] * kR2D, s[8] * kR2D, u[1], true, c, a1);
-    const Trig g = make_trig(s);
-    nlplant_from_coefs(s, u[0], u[2], u[3], 0.0f, g, tfac_pow(s[2]), c, 1, a1, xdot);
-    const float h = dt - 0.0f;
-#pragma unroll
-    for (int j = 0; j < 12; ++j) S[(size_t)j * ld + i] = s[j] + h * xdot[j];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) U[(size_t)j * ld + i] = u[j];
-    U[(size_t)4 * ld + i] = 0.0f;
-  }
-}
-
-__global__ void __launch_bounds__(256) uav_update_kernel(float* __restrict__ S, float* __restrict__ U, float* __restrict__ RS,
-                                                         const float* __restrict__ action, int n, int ld, float dt) {
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    float s[12], F[3], xdot[12];
-#pragma unroll
-    for (int j = 0; j < 12; ++j) s[j] = S[(size_t)j * ld + i];
-#pragma unroll
-    for (int j = 0; j < 3; ++j) F[j] = U[(size_t)j * ld + i];
-    if (RS) {
-#pragma unroll
-      for (int j = 0; j < 12; ++j) RS[(size_t)j * ld + i] = s[j];
-    }
-    const float4 av = reinterpret_cast<const float4*>(action)[i];
-    const float a[3] = {fminf(fmaxf(av.x, -1.0f), 1.0f), fminf(fmaxf(av.y, -1.0f), 1.0f), fminf(fmaxf(av.z, -1.0f), 1.0f)};
-#pragma unroll
-    for (int j = 0; j < 3; ++j) F[j] = 0.9f * F[j] + 0.1f * a[j] * 27000.0f;
-    uav_nlplant(s, F, xdot);
-    const float h = dt - 0.0f;
-#pragma unroll
-    for (int j = 0; j < 12; ++j) S[(size_t)j * ld + i] = s[j] + h * xdot[j];
-#pragma unroll
-    for (int j = 0; j < 3; ++j) U[(size_t)j * ld + i] = F[j];
-  }
-}
-
-// (alpha,beta)-MLP outputs at alpha = beta = 0, written into the image at np_aero_create (same device code as K1,
-// so a reset lane sees bit-identical values whether it takes the constants or an evaluation).
-__global__ void __launch_bounds__(32) f16_c0_kernel(uint32_t* aero, int aero_bytes) {
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  float* blob = reinterpret_cast<float*>(smem_raw);
-  float2* coef2 = reinterpret_cast<float2*>(smem_raw + aero_bytes);
-  uint64_t* bar = reinterpret_cast<uint64_t*>(coef2 + kNumSlots * 32);
-  stage_aero(blob, aero, (uint32_t)aero_bytes, bar);
-  const uint32_t wb = aero_base_after_staging(blob);
-  ZIn2 zi;  // every lane evaluates the same point into its own slots (uniform control flow); lane 0 publishes
-  zscores_ab2(blob, make_float2(0.0f * kR2D, 0.0f * kR2D), make_float2(0.0f * kR2D, 0.0f * kR2D), zi);
-  eval_ab2_nets(blob, wb, zi, coef2 + threadIdx.x, 32);
-  if (threadIdx.x == 0) {
-    float* c0 = reinterpret_cast<float*>(aero) + reinterpret_cast<const int32_t*>(blob)[kHdrC0];
-    for (int k = 0; k < kNumAB2; ++k) c0[k] = coef2[(kFirstAB2 + k) * 32].x;
   }
 }
 

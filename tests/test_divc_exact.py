@@ -20,8 +20,9 @@ def test_constant_division_is_correctly_rounded():
 def test_every_kernel_divisor_is_enumerated():
     """Every DC(...) divisor in the device code is in the checker's list."""
     src = ""
-    for f in ("nplane.cu", "f16_device.cuh", "uav_device.cuh", "ctrl_device.cuh", "tables_device.cuh"):
-        src += open(os.path.join(ROOT, "neuralplane_b200", "csrc", f)).read()
+    csrc = os.path.join(ROOT, "neuralplane_b200", "csrc")
+    for f in sorted(os.listdir(csrc)):
+        src += open(os.path.join(csrc, f)).read()
     used = set(re.findall(r"/ DC\(([^)]+)\)", src))
     names = {"kPi": "3.14159265358979323846f", "UAV_M": "300.0f"}
     chk = open(os.path.join(ROOT, "oracle", "divc_check.c")).read()
