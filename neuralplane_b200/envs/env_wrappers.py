@@ -97,6 +97,8 @@ class GPUVecEnv:
                 raise ValueError("the 'pipelined' boundary serves ControlEnv")
             # a chunk count (equal chunks) or relative chunk sizes, e.g. (1, 2, 3, 5, 5): a small first chunk starts the
             # observation download -- the resource this boundary is bound by -- sooner
+            if pipeline_chunks is None and os.environ.get("NPLANE_PIPELINE"):       # e.g. "1,2,3,4,4,4" (experiments)
+                pipeline_chunks = tuple(float(x) for x in os.environ["NPLANE_PIPELINE"].split(","))
             self._chunks = pipeline_edges(n, DEFAULT_PIPELINE if pipeline_chunks is None else pipeline_chunks)
             if self._chunks is None:
                 boundary = "copy"
