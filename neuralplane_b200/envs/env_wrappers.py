@@ -113,6 +113,11 @@ class GPUVecEnv:
         self._out = [dict(obs=torch.zeros((n, D), dtype=torch.float32).pin_memory(),
                           rew=torch.zeros(n, dtype=torch.float32).pin_memory(),
                           flags=torch.zeros((3, frows), dtype=torch.uint8).pin_memory()) for _ in range(max(1, int(ring)))]
+        shp = (self.num_envs, self.agents, 1)
+        for o in self._out:      # numpy views of the pinned buffers in the shapes the runners expect, built once
+            fl = o["flags"].numpy().view(np.bool_)[:, :n]
+            o["views"] = (o["obs"].numpy().reshape(self.num_envs, self.agents, D), o["rew"].numpy().reshape(shp),
+                          fl[0].reshape(shp), fl[1].reshape(shp), fl[2].reshape(shp))
 
     def _next_out(self):
         o = self._out[self._flip]
@@ -159,13 +164,10 @@ class GPUVecEnv:
                 # kernels, download -- by ONE native call (issuing a chunk from Python cost ~110 us of interpreter time).
                 # Same results as the single launch (one RNG counter for all chunks).
                 e.step_host(a, self._act_h, self._act_d, o["obs"], o["rew"], o["flags"], self._edges, len(self._chunks))
-        shp = (self.num_envs, self.agents, 1)
-        obs = o["obs"].numpy().reshape(self.num_envs, self.agents, e.num_observation)
-        flags = o["flags"].numpy().view(np.bool_)[:, :e.n]
-        rew = o["rew"].numpy().reshape(shp)
+        v = o["views"]
         if self._copy:
-            obs, rew, flags = obs.copy(), rew.copy(), flags.copy()
-        return (obs, rew, flags[0].reshape(shp), flags[1].reshape(shp), flags[2].reshape(shp), {})
+            return (v[0].copy(), v[1].copy(), v[2].copy(), v[3].copy(), v[4].copy(), {})
+        return (v[0], v[1], v[2], v[3], v[4], {})
 
     def reset(self):
         e = self.gpu_vec_env
@@ -173,7 +175,7 @@ class GPUVecEnv:
             return e.reset().view(self.num_envs, self.agents, e.num_observation)
         e.reset()
         o = self._download(with_rest=False)
-        obs = o["obs"].numpy().reshape(self.num_envs, self.agents, e.num_observation)
+        obs = o["views"][0]
         return obs.copy() if self._copy else obs
 
     def step_async(self, actions):
