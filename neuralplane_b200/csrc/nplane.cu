@@ -1652,25 +1652,17 @@ int np_env_step_mapped(np_env* env, const float* action_host, float* action_mapp
     NP_CUDA(cudaMemcpyAsync(action_dev, action_mapped, (size_t)n * NP_NUM_ACT * sizeof(float), cudaMemcpyHostToDevice, st));
     act = action_dev;
   }
-  env->step_index++;
-  StepParams p = make_params(env, act, nullptr, nullptr);
-  p.step_index = env->step_index - 1;
-  p.obs = obs_d;
-  p.reward = rew_d;
-  p.flags_mirror = flg_d;
-  p.flags_mirror_ld = flags_ld;
-  int rc;
-  if (env->tables) {
-    const float *sobs = env->buf.obs_dev, *srew = env->buf.reward_dev;
-    env->buf.obs_dev = obs_d; env->buf.reward_dev = rew_d;           // step_range_impl builds its parameters from the bound buffers
-    env->mirror = flg_d; env->mirror_ld = flags_ld;
-    env->step_index--;
-    rc = step_range_impl(env, act, nullptr, nullptr, 0, n, true, st);
-    env->buf.obs_dev = const_cast<float*>(sobs); env->buf.reward_dev = const_cast<float*>(srew);
-    env->mirror = nullptr;
-  } else {
-    rc = launch_env_step<384, 1>(env, p, st);   // 384: the staged obs path
-  }
+  // the ordinary step, with the env's obs / reward outputs and a flag mirror pointed at the mapped host buffers for its duration
+  struct Redirect {
+    np_env* e;
+    float *obs, *rew;
+    ~Redirect() { e->buf.obs_dev = obs; e->buf.reward_dev = rew; e->mirror = nullptr; }
+  } redirect{env, env->buf.obs_dev, env->buf.reward_dev};
+  env->buf.obs_dev = obs_d;
+  env->buf.reward_dev = rew_d;
+  env->mirror = flg_d;
+  env->mirror_ld = flags_ld;
+  const int rc = step_range_impl(env, act, nullptr, nullptr, 0, n, true, st);
   if (rc != NP_OK) return rc;
   NP_CUDA(cudaStreamSynchronize(st));
   return NP_OK;
