@@ -1,4 +1,10 @@
 #!/bin/bash
+# the GPU suite and smoke(), as the driver runs them at round end
+cd "$GRAFT_REPO_ROOT" 2>/dev/null || cd /root/repo
 mkdir -p gpurun_out
-timeout 2000 python -m pytest tests -q -m gpu -s "$@" > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_gpu.log
-grep -E "passed|failed|rc=|Error|assert|k= *(1|10|100|300|1000) |vs fp64" gpurun_out/pytest_gpu.log | tail -n 60
+timeout 1800 python -m pytest tests -x -q -m gpu > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -3 gpurun_out/pytest_gpu.log
+timeout 600 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
+timeout 300 python bench.py --steps 20 --warmup 5 --no-cpu > gpurun_out/bench_quick.json 2> gpurun_out/bench_quick.err; python - <<'PY'
+import json
+d=json.loads(open('gpurun_out/bench_quick.json').read().strip().splitlines()[-1]); print('value %.4g e2e %.4g'%(d['value'], d['e2e']['value']), json.dumps(d['side']['small_n_latency'])[:400])
+PY
