@@ -942,8 +942,10 @@ static int pick_block(const np_env* env, int npairs) {
   if (env->block) return env->block;
   // Small populations (what the reference trains at: 3 000 envs, scripts/train_heading.sh:13) are LATENCY bound: a step is as
   // long as one warp's pass through the kernel, and that pass is ~2x shorter when the warp has its scheduler to itself.
-  // 128-thread CTAs put one warp on each of an SM's four schedulers and spread the population over 3x as many SMs.
-  if (npairs <= env->num_sms * 128) return 128;
+  // 128-thread CTAs put one warp on each of an SM's four schedulers and spread the population over 3x as many SMs; up to two of
+  // them share an SM (measured, tools/small_n_sweep.py: n = 3 000 ... 37 888: 29 us vs 48 us with 384-thread CTAs; 50 000 / 75 000:
+  // 37 / 40 vs 49 us; from 100 000 the 384-thread shape wins again).
+  if (npairs <= env->num_sms * 128 * 2) return 128;
   auto cost = [&](int bs, double rate) {
     const long slabs = (npairs + bs - 1) / bs;
     const long waves = (slabs + env->num_sms - 1) / env->num_sms;
@@ -1217,7 +1219,7 @@ static int step_range_impl(np_env* env, const float* action_dev, const float* dr
     }
   }
   switch (pick_block(env, p.pair_end - p.pair_begin)) {
-    case 128: return launch_env_step<128, 1>(env, p, st);
+    case 128: return launch_env_step<128, 2>(env, p, st);   // two CTAs may share an SM (2 x 110 KB of shared memory)
 #ifdef NPLANE_ALL_BLOCKS
     case 256: return launch_env_step<256, 2>(env, p, st);
     case 320: return launch_env_step<320, 1>(env, p, st);
