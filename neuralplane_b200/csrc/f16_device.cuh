@@ -138,15 +138,17 @@ __device__ __forceinline__ float2 denorm2(const float* __restrict__ blob, int k,
 // different input normalisation (the "r30 / a20" and the "lef" alpha grids) CAN share one body (-DNPLANE_MERGE_GROUPS: two
 // bodies and 0.55 k SASS instructions fewer) -- measured 10 % slower end to end than one loop per (architecture,
 // normalisation) pair (profiles/r02_variants.txt), which therefore stays the default.
+// `first` / `count` select nets [K0 + first, K0 + first + count) of the group (the cooperative small-population kernel splits a
+// group over the warps of a CTA).
 template <int K0>
 __device__ __forceinline__ void eval_group2(const float* __restrict__ blob, uint32_t wbase, const ZIn2& zi,
-                                            float2* __restrict__ out, int stride, int count) {
+                                            float2* __restrict__ out, int stride, int count, int first = 0) {
   constexpr NetArch A = arch_of(K0);
   constexpr int NF = net_floats(A);
   static_assert(A.nin >= 2, "one-input nets are table-driven");
-  uint32_t w = wbase + 4 * mlp_offset(K0);
+  uint32_t w = wbase + 4 * mlp_offset(K0) + 4 * NF * first;
 #pragma unroll 1
-  for (int k = K0; k < K0 + count; ++k, w += 4 * NF) {
+  for (int k = K0 + first; k < K0 + first + count; ++k, w += 4 * NF) {
     float2 z0, z1, z2 = make_float2(0.f, 0.f);
     if constexpr (A.nin == 3) {
       z0 = zi.z[kZaC]; z1 = zi.z[kZbC]; z2 = zi.z[kZeC];
@@ -195,8 +197,23 @@ __device__ __forceinline__ void eval_ab2_nets(const float* __restrict__ blob, ui
 // The three-input nets Cx Cz Cm Cn Cl (alpha, beta, el): `count` = 5 for a full nlplant, 2 (Cx, Cz) when only the
 // force equations are needed (the Overload check).
 __device__ __forceinline__ void eval_el3_nets(const float* __restrict__ blob, uint32_t wbase, const ZIn2& zi,
-                                              float2* __restrict__ out, int stride, int count) {
-  eval_group2<kCx>(blob, wbase, zi, out, stride, count);
+                                              float2* __restrict__ out, int stride, int count, int first = 0) {
+  eval_group2<kCx>(blob, wbase, zi, out, stride, count, first);
+}
+// Warp `w` of 4's share of the 16 (alpha, beta) nets (1 190 ... 1 490 MACs each) and of the three-input nets.
+__device__ __forceinline__ void eval_ab2_nets_quarter(const float* __restrict__ blob, uint32_t wbase, const ZIn2& zi,
+                                                      float2* __restrict__ out, int stride, int w) {
+  if (w < 2) eval_group2<kCy>(blob, wbase, zi, out, stride, 1, w);
+  else eval_group2<kdCx_lef>(blob, wbase, zi, out, stride, 1, w - 2);
+  eval_group2<kdCz_lef>(blob, wbase, zi, out, stride, 1, w);
+  eval_group2<kdCy_r30>(blob, wbase, zi, out, stride, 1, w);
+  if (w == 0) eval_group2<kdCy_a20>(blob, wbase, zi, out, stride, 1, 0);
+  else eval_group2<kdCy_a20_lef>(blob, wbase, zi, out, stride, 1, w - 1);
+}
+__device__ __forceinline__ void eval_el3_nets_quarter(const float* __restrict__ blob, uint32_t wbase, const ZIn2& zi,
+                                                      float2* __restrict__ out, int stride, int w, bool full) {
+  if (full) eval_el3_nets(blob, wbase, zi, out, stride, w == 0 ? 2 : 1, w == 0 ? 0 : w + 1);   // Cx Cz | Cm | Cn | Cl
+  else if (w < 2) eval_el3_nets(blob, wbase, zi, out, stride, 1, w);                            // Cx | Cz
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -103,6 +103,7 @@ struct np_env {
   int mirror_ld = 0;
   int tab_pairs = 0;         // NPLANE_TAB_KERNEL=pairs: the table back-end on K1's two-aircraft-per-thread kernel (round 1) instead of K1t
   int block = 0;             // 0: chosen per launch (pick_block); else forced by NPLANE_BLOCK
+  int coop_pairs = 0;        // ranges of up to this many pairs run on K1c (NPLANE_COOP_PAIRS; 0 = never)
   int tab_block = 384, grid = 0, smem = 0, num_sms = 0, last_block = 384;
   // np_env_step_host: one in-order stream per engine (upload, kernels, download) and the events chaining them
   static constexpr int kMaxHostChunks = 16;
@@ -548,6 +549,8 @@ __device__ __forceinline__ void count_cause1(unsigned long long* counters, int w
   if (k != 0 && (threadIdx.x & 31) == 0) atomicAdd(&counters[which], (unsigned long long)k);
 }
 
+#include "coop_step_kernel.cuh"   // K1c: the small-population (latency) shape of K1
+
 template <int TASK>
 __global__ void __launch_bounds__(kTabBS, kTabMinB) f16_table_step_kernel(const __grid_constant__ StepParams p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -940,6 +943,7 @@ static int launch_env_step(np_env* env, const StepParams& p, cudaStream_t st) {
 // of waves (a strong-scaling shard: 125 k aircraft = 1.1 waves of 384) the wider block that saves a whole wave wins.
 static int pick_block(const np_env* env, int npairs) {
   if (env->block) return env->block;
+  // (Up to 18 944 aircraft the step does not come here at all: K1c, coop_step_kernel.cuh.)
   // Small populations (what the reference trains at: 3 000 envs, scripts/train_heading.sh:13) are LATENCY bound: a step is as
   // long as one warp's pass through the kernel, and that pass is ~2x shorter when the warp has its scheduler to itself.
   // 128-thread CTAs put one warp on each of an SM's four schedulers and spread the population over 3x as many SMs; up to two of
@@ -1036,6 +1040,8 @@ static int env_create_impl(const np_env_cfg* cfg, const np_aero* aero, const np_
     e->block = atoi(b);
     if (e->block % 32 || e->block < 128 || e->block > 512) return fail(NP_EINVAL, "NPLANE_BLOCK must be a multiple of 32 in [128, 512]");
   }
+  e->coop_pairs = e->num_sms * 2 * kCoopPairs;   // one wave of K1c CTAs
+  if (const char* b = getenv("NPLANE_COOP_PAIRS")) e->coop_pairs = atoi(b);
   if (const char* b = getenv("NPLANE_TAB_BLOCK")) e->tab_block = atoi(b);
   if (const char* b = getenv("NPLANE_OBS_STORE")) e->obs_stg = strcmp(b, "stg") == 0;
   if (const char* b = getenv("NPLANE_TAB_KERNEL")) e->tab_pairs = strcmp(b, "pairs") == 0;
@@ -1216,6 +1222,30 @@ static int step_range_impl(np_env* env, const float* action_dev, const float* dr
 #endif
       case 384: return launch_env_step<384, 1, true>(env, p, st);  // 4.36e9 vs 4.16e9 (256 x 2) / 4.20e9 (512) / 4.10e9 (128 x 4) at n = 10^6
       default: return fail(NP_EINVAL, "np_env_step: table back-end block size not compiled in (build with -DNPLANE_ALL_BLOCKS)");
+    }
+  }
+  if (env->coop_pairs > 0 && !env->block && p.pair_end - p.pair_begin <= env->coop_pairs) {   // K1c: four warps share each pair's MLPs
+    const int npairs = p.pair_end - p.pair_begin;
+    if (npairs <= 0) return NP_OK;
+    const int smem = coop_smem_bytes(p.aero_bytes);
+    const int want = (npairs + kCoopPairs - 1) / kCoopPairs;
+    env->grid = want < env->num_sms * 2 ? want : env->num_sms * 2;
+    env->smem = smem;
+    env->last_block = kCoopBS;
+    static int configured[64][3] = {};
+    auto launch = [&](auto kern, int t) -> int {
+      if (configured[env->device & 63][t] < smem) {
+        NP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        configured[env->device & 63][t] = smem;
+      }
+      kern<<<env->grid, kCoopBS, smem, st>>>(p);
+      NP_CUDA(cudaGetLastError());
+      return NP_OK;
+    };
+    switch (env->cfg.task) {
+      case NP_TASK_HEADING: return launch(f16_step_coop_kernel<NP_TASK_HEADING>, 0);
+      case NP_TASK_CONTROL: return launch(f16_step_coop_kernel<NP_TASK_CONTROL>, 1);
+      default: return launch(f16_step_coop_kernel<NP_TASK_TRACKING>, 2);
     }
   }
   switch (pick_block(env, p.pair_end - p.pair_begin)) {

@@ -120,8 +120,8 @@ def test_block_choice_is_bit_identical_and_saves_a_wave():
             assert torch.equal(x, y), k
     assert env.launch_info()["block"] == 512 and ref.launch_info()["block"] == 384
     assert torch.equal(env.model.s, ref.model.s) and env.termination_counters() == ref.termination_counters()
-    # small populations are latency bound: 128-thread CTAs (one warp per scheduler, 3x as many SMs), same bits
-    n = 3000
+    # mid-size populations are latency bound: 128-thread CTAs (one warp per scheduler, 3x as many SMs), same bits
+    n = 30_000
     small = ControlEnv(num_envs=n, config="heading", model="F16", random_seed=2, device="cuda:0")
     os.environ["NPLANE_BLOCK"] = "384"
     try:
@@ -133,12 +133,49 @@ def test_block_choice_is_bit_identical_and_saves_a_wave():
         a = _cuda(tapes.action_tape(2, k, n, 1.0))
         for x, y in zip(small.step(a)[:5], ref.step(a)[:5]):
             assert torch.equal(x, y), k
-    assert small.launch_info()["block"] == 128 and small.launch_info()["grid"] == 12 and ref.launch_info()["grid"] == 4
+    assert small.launch_info()["block"] == 128 and small.launch_info()["grid"] == 118 and ref.launch_info()["grid"] == 40
     assert small.termination_counters() == ref.termination_counters()
     big = ControlEnv(num_envs=1_000_000, config="heading", model="F16", random_seed=2, device="cuda:0")
     big.reset()
     big.step(torch.zeros((1_000_000, 4), device="cuda:0"))
     assert big.launch_info()["block"] == 384
+
+
+@pytest.mark.parametrize("config,n", [("heading", 3000), ("heading", 1), ("heading", 63), ("control", 2999), ("tracking", 18_944),
+                                      ("heading", 18_945)])
+def test_cooperative_small_population_kernel_is_bit_identical(config, n):
+    """K1c (coop_step_kernel.cuh) deals a pair's 21 MLP evaluations over the four warps of a CTA to cut the latency of a step
+    at the reference's training sizes (3 000 envs).  Same device functions on the same operands: every output, the state, the
+    coefficient cache (through the following steps) and the counters must equal K1's bit for bit -- across episodic resets
+    (terminations of the random actions plus flags raised by hand), ragged and odd populations, all three tasks."""
+    import os
+    from neuralplane_b200 import ControlEnv
+    kw = dict(num_envs=n, config=config, model="F16", random_seed=5, device="cuda:0")
+    coop = ControlEnv(**kw)
+    os.environ["NPLANE_COOP_PAIRS"] = "0"
+    try:
+        ref = ControlEnv(**kw)
+    finally:
+        del os.environ["NPLANE_COOP_PAIRS"]
+    coop.reset(); ref.reset()
+    for k in range(1, 80):
+        a = _cuda(tapes.action_tape(5, k, n, 1.5))
+        for x, y in zip(coop.step(a)[:5], ref.step(a)[:5]):
+            assert torch.equal(x, y), k
+        if k % 20 == 0:                                     # some lanes of a warp reset, the others hit the coefficient cache
+            for e in (coop, ref):
+                e.is_done[::7] = True
+                e.bad_done[3::64] = True
+    li, lr = coop.launch_info(), ref.launch_info()
+    if n <= 18_944:
+        assert li["block"] == 128 and li["grid"] == min(296, (n + 63) // 64), li
+        assert lr["grid"] == (n + 255) // 256, lr          # K1's 128-thread CTAs: 256 aircraft each
+    else:
+        assert li == lr                                     # above one wave of K1c CTAs both run K1
+    assert torch.equal(coop.model.s, ref.model.s) and torch.equal(coop.model.u, ref.model.u)
+    assert torch.equal(coop.step_count, ref.step_count)
+    assert coop.termination_counters() == ref.termination_counters()
+    assert coop.termination_counters()["resets"] > 0
 
 
 def test_rollout_attach_rejects_odd_population():

@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """us per step of the device-resident F16 heading step (CUDA-graph replay) over small and mid populations, by CTA shape
-(NPLANE_BLOCK = 128 / 384 / auto): where should pick_block() switch?"""
+(NPLANE_BLOCK = 128 / 384, K1c = the cooperative kernel forced, auto = the library's choice): where should the dispatch switch?"""
 import json
 import os
 import sys
@@ -12,13 +12,16 @@ from neuralplane_b200 import ControlEnv  # noqa: E402
 
 dev = torch.device("cuda:0")
 out = {}
-for n in (1000, 3000, 10_000, 20_000, 37_888, 50_000, 75_000, 100_000, 150_000, 200_000):
+for n in (256, 1000, 3000, 10_000, 18_944, 25_000, 37_888, 50_000, 75_000, 100_000, 150_000, 200_000):
     row = {}
-    for blk in ("128", "384", "auto"):
-        if blk != "auto":
+    for blk in ("128", "384", "K1c", "auto"):
+        if blk in ("128", "384"):
             os.environ["NPLANE_BLOCK"] = blk
+        if blk == "K1c":
+            os.environ["NPLANE_COOP_PAIRS"] = "100000000"
         env = ControlEnv(num_envs=n, config="heading", model="F16", random_seed=0, device=dev)
         os.environ.pop("NPLANE_BLOCK", None)
+        os.environ.pop("NPLANE_COOP_PAIRS", None)
         env.reset()
         a = torch.rand((n, 4), device=dev) * 2 - 1
         for _ in range(3):
