@@ -2,28 +2,98 @@
 // is latency bound: its duration is one warp's pass through ~24 000 dependent instructions of K1, not a throughput.
 // Included by nplane.cu after K1 (uses its StepParams, tile constants and device functions).
 //
-// The cure is to cut the pass, not to add warps: a CTA of FOUR warps flies 32 aircraft pairs (one pair per lane, as K1), and
-// the 21 MLP evaluations of a step -- >90 % of the instructions -- are dealt out over the four warps (each lane of every
-// warp holds the same pair, so every warp can evaluate any net for it):
-//   warp w: the (alpha, beta) nets {w, w+4, w+8, w+12} (Cy dCz_lef dCy_r30 dCy_a20 | dCl_a20 dCm_lef dCn_r30 dCy_a20_lef | ...),
-//           pass 0: three-input nets Cx Cz | Cm | Cn | Cl (+ eta_el on warp 3), pass 1: Cx | Cz | - | -.
-// Outputs meet in the CTA's coefficient slots ([kNumSlots][32] float2 of shared memory); after a __syncthreads warp 0 flies
-// aircraft 2*pair and warp 1 aircraft 2*pair+1 through the scalar tail (trig, atmosphere, PWL coefficients, forces, moments,
-// Euler, observation, terminations, reward), and hands the new (alpha, beta) back through shared memory for pass 1.
-// The prologue (loads, episodic reset, control lag, cache-hit test) is recomputed by all four warps: it is short and
-// CTA-uniform, which keeps every branch around the barriers uniform.
+// The cure is to cut the pass, not to add aircraft: a CTA of NW = 4 or 8 warps flies 32 aircraft pairs (one pair per lane, as
+// K1), and the 21 MLP evaluations of a step -- most of the instructions -- are dealt out over the warps (each lane of every warp
+// holds the same pair, so every warp can evaluate any net for it): kCoopShare below.  Outputs meet in the CTA's coefficient
+// slots ([kNumSlots][32] float2 of shared memory); after a __syncthreads warp 0 flies aircraft 2*pair and warp 1 aircraft
+// 2*pair+1 through the scalar tail (forces, moments, Euler; terminations, reward), and hands the new (alpha, beta) back through
+// shared memory for pass 1.  Warps 0 / 1 get a small MLP share and use the slack for everything in the tail that needs no MLP
+// output -- trig, atmosphere, the PWL alpha coefficients, and in pass 1 the whole observation row with its noise -- so that
+// only forces / moments / Euler / verdict remain behind the barriers.
+// The prologue (loads, episodic reset, control lag, cache-hit test) is recomputed by all warps: it is short and CTA-uniform,
+// which keeps every branch around the barriers uniform.
+//   NW = 8 (one CTA per SM, two warps per scheduler): up to 148 x 64 = 9 472 aircraft in one wave;
+//   NW = 4 (two CTAs per SM): up to 18 944.
 //
 // Every value is produced by the same device function on the same operands as in K1 (the two halves of an FFMA2 are
 // independent), so the step is BIT-IDENTICAL to K1's: tests/test_gpu_plugin.py compares them directly.
 #pragma once
+#include <type_traits>
 
-constexpr int kCoopBS = 128, kCoopPairs = 32;
+constexpr int kCoopPairs = 32;
+// Net groups of one architecture and z-score selection (f16_device.cuh eval_ab2_nets): first (alpha, beta) net, nets in the group
+constexpr int kCoopGroupK0[6] = {kCy, kdCx_lef, kdCz_lef, kdCy_r30, kdCy_a20, kdCy_a20_lef};
+constexpr int kCoopGroupN[6] = {2, 2, 4, 4, 1, 3};
+// kCoopShare[NW == 8][warp][g] = {first, count}: the nets [first, first + count) of group g this warp evaluates; g = 6: the
+// three-input nets Cx Cz Cm Cn Cl in pass 0 (all five), g = 7: in pass 1 (Cx Cz).  MACs per net: 250 250 295 295 350 650 | 270.
+//   NW = 4, pass 1:  1 190 | 1 490 | 1 760 | 1 760   (warps 0 / 1 also prepare their aircraft's tail)
+//   NW = 8, pass 1:    545 |   295 | 900 | 900 | 900 | 885 | 885 | 890
+struct CoopRange { signed char first, count; };
+#define NP_COOP_SHARE_TABLE { \
+    {   /* NW = 4 */ \
+        {{0, 1}, {0, 0}, {0, 1}, {0, 1}, {0, 1}, {0, 0}, {4, 1}, {0, 0}}, \
+        {{1, 1}, {0, 0}, {1, 1}, {1, 1}, {0, 0}, {0, 1}, {0, 0}, {0, 0}}, \
+        {{0, 0}, {0, 1}, {2, 1}, {2, 1}, {0, 0}, {1, 1}, {0, 2}, {0, 1}}, \
+        {{0, 0}, {1, 1}, {3, 1}, {3, 1}, {0, 0}, {2, 1}, {2, 2}, {1, 1}}, \
+        {}, {}, {}, {}, \
+    }, \
+    {   /* NW = 8 */ \
+        {{0, 1}, {0, 0}, {0, 1}, {0, 0}, {0, 0}, {0, 0}, {0, 0}, {0, 0}}, \
+        {{0, 0}, {0, 0}, {1, 1}, {0, 0}, {0, 0}, {0, 0}, {0, 0}, {0, 0}}, \
+        {{1, 1}, {0, 0}, {0, 0}, {0, 0}, {0, 0}, {0, 1}, {0, 1}, {0, 0}}, \
+        {{0, 0}, {0, 1}, {0, 0}, {0, 0}, {0, 0}, {1, 1}, {1, 1}, {0, 0}}, \
+        {{0, 0}, {1, 1}, {0, 0}, {0, 0}, {0, 0}, {2, 1}, {2, 1}, {0, 0}}, \
+        {{0, 0}, {0, 0}, {2, 2}, {0, 1}, {0, 0}, {0, 0}, {3, 1}, {0, 0}}, \
+        {{0, 0}, {0, 0}, {0, 0}, {1, 3}, {0, 0}, {0, 0}, {4, 1}, {0, 0}}, \
+        {{0, 0}, {0, 0}, {0, 0}, {0, 0}, {0, 1}, {0, 0}, {0, 0}, {0, 2}}, \
+    }}
+constexpr CoopRange kCoopShare[2][8][8] = NP_COOP_SHARE_TABLE;          // compile-time uses (ownership, checks)
+__constant__ CoopRange kCoopShareDev[2][8][8] = NP_COOP_SHARE_TABLE;      // the kernel's warp-indexed copy
+constexpr int coop_eta_warp(int v) { return v ? 7 : 1; }   // eta_el (a PWL lookup) in pass 0
+// which warp owns (alpha, beta) net k (0 ... 15): it loads / patches / evaluates that slot, so no two warps write one slot
+constexpr int coop_owner(int v, int k) {
+  int g = 0, base = 0;
+  while (k >= base + kCoopGroupN[g]) { base += kCoopGroupN[g]; ++g; }
+  for (int w = 0; w < 8; ++w)
+    if (k - base >= kCoopShare[v][w][g].first && k - base < kCoopShare[v][w][g].first + kCoopShare[v][w][g].count) return w;
+  return -1;
+}
+constexpr bool coop_shares_ok(int v, int nw) {
+  for (int k = 0; k < kNumAB2; ++k)
+    if (coop_owner(v, k) < 0 || coop_owner(v, k) >= nw) return false;
+  for (int g = 0; g < 8; ++g) {   // every net of every group exactly once
+    int total = 0;
+    for (int w = 0; w < nw; ++w) total += kCoopShare[v][w][g].count;
+    if (total != (g < 6 ? kCoopGroupN[g] : g == 6 ? 5 : 2)) return false;
+  }
+  return true;
+}
+static_assert(coop_shares_ok(0, 4) && coop_shares_ok(1, 8), "K1c: the MLP shares must cover every net exactly once");
+template <int K, int N, class F>
+__device__ __forceinline__ void coop_static_for(F&& f) {
+  if constexpr (K < N) {
+    f(std::integral_constant<int, K>{});
+    coop_static_for<K + 1, N>(f);
+  }
+}
+static_assert(kCoopGroupK0[0] - kFirstAB2 == 0 && kCoopGroupK0[5] + 3 - kFirstAB2 == kNumAB2, "K1c: group table vs net enum");
+#ifdef NPLANE_COOP_TIMING   // debug build (tools/k1c_phases.py): per-warp clock stamps of CTA 0, left in the first obs rows
+#define NP_COOP_STAMP_INIT() __shared__ long long np_stamps[8][10]; long long* stamps = np_stamps[warp]; const long long t_start = clock64()
+#define NP_COOP_STAMP(i) do { if (lane == 0) stamps[i] = clock64() - t_start; } while (0)
+#define NP_COOP_STAMP_FLUSH() do { NP_COOP_STAMP(9); __syncthreads(); if (blockIdx.x == 0 && lane < 10) p.obs[warp * 10 + lane] = (float)np_stamps[warp][lane]; } while (0)
+#else
+#define NP_COOP_STAMP_INIT() do { } while (0)
+#define NP_COOP_STAMP(i) do { } while (0)
+#define NP_COOP_STAMP_FLUSH() do { } while (0)
+#endif
 static int coop_smem_bytes(int aero_bytes) {
   return aero_bytes + kNumSlots * kCoopPairs * 8 + kObsTileFloats * 4 + 4 * kCoopPairs * 4 + 16;
 }
 
-template <int TASK>
-__global__ void __launch_bounds__(kCoopBS, 2) f16_step_coop_kernel(const __grid_constant__ StepParams p) {
+template <int TASK, int NW>
+__global__ void __launch_bounds__(NW * 32, NW == 4 ? 2 : 1) f16_step_coop_kernel(const __grid_constant__ StepParams p) {
+  static_assert(NW == 4 || NW == 8, "K1c: four or eight warps");
+  constexpr int V = NW == 8 ? 1 : 0;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   float* blob = reinterpret_cast<float*>(smem_raw);
   float2* coef_all = reinterpret_cast<float2*>(smem_raw + p.aero_bytes);     // [kNumSlots][32] float2
@@ -32,10 +102,12 @@ __global__ void __launch_bounds__(kCoopBS, 2) f16_step_coop_kernel(const __grid_
   float* xb = xa + 2 * kCoopPairs;                                           // [2][32]: beta'
   uint64_t* bar = reinterpret_cast<uint64_t*>(xb + 2 * kCoopPairs);
 
-  stage_aero(blob, p.aero, (uint32_t)p.aero_bytes, bar);
-  const uint32_t wb0 = aero_base_after_staging(blob);
-  const AeroTabs tabs = aero_tabs(blob, wb0);
-  const float* c0 = blob + reinterpret_cast<const int32_t*>(blob)[kHdrC0];
+  stage_aero_issue(blob, p.aero, (uint32_t)p.aero_bytes, bar);   // waited for below, behind the first state loads
+  // Launched with programmatic stream serialisation: everything above (CTA start-up, the image copies: immutable data) may
+  // overlap the tail of the previous kernel in the stream -- e.g. the previous env step.  Nothing that kernel wrote is read, and
+  // nothing is written, before this wait; the next kernel may then start its own prologue behind us.
+  grid_dependency_wait();
+  grid_launch_dependents();
 
   const np_env_cfg& c = p.cfg;
   const int n = c.n, ld = c.ld;
@@ -43,6 +115,7 @@ __global__ void __launch_bounds__(kCoopBS, 2) f16_step_coop_kernel(const __grid_
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const bool owner = warp < 2;   // warps 0 / 1 fly aircraft 0 / 1 of each pair through the scalar tail
   const bool q1 = (warp & 1) != 0;
+  NP_COOP_STAMP_INIT();
   float2* coef2 = coef_all + lane;                                           // slot k of this lane's pair: coef2[k * 32]
   const float* cq = reinterpret_cast<const float*>(coef2) + (q1 ? 1 : 0);
   constexpr int CS = 2 * kCoopPairs;
@@ -90,14 +163,22 @@ __global__ void __launch_bounds__(kCoopBS, 2) f16_step_coop_kernel(const __grid_
     if (use_cache) {
       ka = reinterpret_cast<const float2*>(p.cache + (size_t)kNumAB2 * ld)[prl];
       kb = reinterpret_cast<const float2*>(p.cache + (size_t)(kNumAB2 + 1) * ld)[prl];
-#pragma unroll
-      for (int k = warp; k < kNumAB2; k += 4) coef2[(kFirstAB2 + k) * kCoopPairs] = reinterpret_cast<const float2*>(p.cache + (size_t)k * ld)[prl];
+      coop_static_for<0, kNumAB2>([&](auto kc) {
+        constexpr int k = decltype(kc)::value, ow = coop_owner(V, k);
+        if (ow == warp) coef2[(kFirstAB2 + k) * kCoopPairs] = reinterpret_cast<const float2*>(p.cache + (size_t)k * ld)[prl];
+      });
     }
 #pragma unroll
     for (int q = 0; q < 2; ++q) {
       const float4 av = reinterpret_cast<const float4*>(p.action)[idx[q]];
       a[q][0] = av.x; a[q][1] = av.y; a[q][2] = av.z; a[q][3] = av.w;
     }
+
+    // the aero image (64 KB, TMA) has been arriving while the loads above were issued; later iterations pass straight through
+    mbar_wait(bar, 0);
+    const uint32_t wb0 = aero_base_after_staging(blob);
+    const AeroTabs tabs = aero_tabs(blob, wb0);
+    const float* c0 = blob + reinterpret_cast<const int32_t*>(blob)[kHdrC0];
 
     // ---- episodic reset (env_base.py:83-97) -----------------------------------------------------------------------
 #pragma unroll
@@ -118,13 +199,15 @@ __global__ void __launch_bounds__(kCoopBS, 2) f16_step_coop_kernel(const __grid_
     }
     const bool miss = __any_sync(0xffffffffu, !(hit[0] && hit[1])) != 0;
     if (!miss && (rst[0] || rst[1])) {
-#pragma unroll
-      for (int k = warp; k < kNumAB2; k += 4) {
-        float2 v = coef2[(kFirstAB2 + k) * kCoopPairs];
-        if (rst[0]) v.x = c0[k];
-        if (rst[1]) v.y = c0[k];
-        coef2[(kFirstAB2 + k) * kCoopPairs] = v;
-      }
+      coop_static_for<0, kNumAB2>([&](auto kc) {
+        constexpr int k = decltype(kc)::value, ow = coop_owner(V, k);
+        if (ow == warp) {
+          float2 v = coef2[(kFirstAB2 + k) * kCoopPairs];
+          if (rst[0]) v.x = c0[k];
+          if (rst[1]) v.y = c0[k];
+          coef2[(kFirstAB2 + k) * kCoopPairs] = v;
+        }
+      });
     }
 
     // ---- control lag (F16_model.py:52-57) -----------------------------------------------------------------------
@@ -160,6 +243,7 @@ __global__ void __launch_bounds__(kCoopBS, 2) f16_step_coop_kernel(const __grid_
     first_iter = false;
 
 #pragma unroll 1
+    NP_COOP_STAMP(0);
     for (int pass = 0; pass < 2; ++pass) {
       const float2 adeg = make_float2(al.x * kR2D, al.y * kR2D);
       const float2 bdeg = make_float2(be.x * kR2D, be.y * kR2D);
@@ -167,38 +251,28 @@ __global__ void __launch_bounds__(kCoopBS, 2) f16_step_coop_kernel(const __grid_
       ZIn2 zi;
       zscores_ab2(blob, adeg, bdeg, zi);
       zscores_el2(blob, el, zi);
-      if (pass == 1 || miss) eval_ab2_nets_quarter(blob, wb, zi, coef2, kCoopPairs, warp);
-      eval_el3_nets_quarter(blob, wb, zi, coef2, kCoopPairs, warp, pass == 0);
-      if (pass == 0 && warp == 3) coef2[kEtaEl * kCoopPairs] = eta_el2(tabs, el);
-      __syncthreads();   // all 22 slots of the 32 pairs are in place
-
-      if (pass == 1 && use_cache && act[0]) {   // the next step's Euler derivative needs exactly these
-#pragma unroll
-        for (int k = warp; k < kNumAB2; k += 4) store_pair(p.cache + (size_t)k * ld, pr, coef2[(kFirstAB2 + k) * kCoopPairs], act[1]);
-        if (warp == 2) store_pair(p.cache + (size_t)kNumAB2 * ld, pr, al, act[1]);
-        if (warp == 3) store_pair(p.cache + (size_t)(kNumAB2 + 1) * ld, pr, be, act[1]);
+      const CoopRange* share = kCoopShareDev[V][warp];
+      if (pass == 1 || miss) {
+        eval_group2<kCy>(blob, wb, zi, coef2, kCoopPairs, share[0].count, share[0].first);
+        eval_group2<kdCx_lef>(blob, wb, zi, coef2, kCoopPairs, share[1].count, share[1].first);
+        eval_group2<kdCz_lef>(blob, wb, zi, coef2, kCoopPairs, share[2].count, share[2].first);
+        eval_group2<kdCy_r30>(blob, wb, zi, coef2, kCoopPairs, share[3].count, share[3].first);
+        eval_group2<kdCy_a20>(blob, wb, zi, coef2, kCoopPairs, share[4].count, share[4].first);
+        eval_group2<kdCy_a20_lef>(blob, wb, zi, coef2, kCoopPairs, share[5].count, share[5].first);
       }
-
+      eval_el3_nets(blob, wb, zi, coef2, kCoopPairs, share[6 + pass].count, share[6 + pass].first);
+      if (pass == 0 && warp == coop_eta_warp(V)) coef2[kEtaEl * kCoopPairs] = eta_el2(tabs, el);
+      // the part of the tail that needs no MLP output, done by the (lightly loaded) owner warps while the others finish
+      const float aq = q1 ? adeg.y : adeg.x;
+      Trig g;
+      float tp = 0.0f, a1[kNumA1];
       if (owner) {
-        const float aq = q1 ? adeg.y : adeg.x;
         uint32_t seg, seg_unused;
         pwl_search2<kLevelsA>(tabs.bp_a, aq, aq, seg, seg_unused);
-        const Trig g = make_trig(sq);
-        const float tp = tfac_pow(sq[2]);
-        float a1[kNumA1];
+        g = make_trig(sq);
+        tp = tfac_pow(sq[2]);
         alpha_coefs<kNumUsed - kFirstA1>(blob, tabs, seg, aq, a1);
-        const ForcePart fp = force_part(sq, uq[0], uq[2], uq[3], 0.0f, g, tp, cq, CS, a1);
-        if (pass == 0) {
-          float xdot[12];
-          nlplant_kin_moments(sq, uq[2], uq[3], 0.0f, g, fp.qbar, fp.vt, fp.b, fp.t, cq, CS, a1, xdot);
-          xdot[6] = fp.f.vt_dot; xdot[7] = fp.f.alpha_dot; xdot[8] = fp.f.beta_dot;
-          const float h = c.dt - 0.0f;
-#pragma unroll
-          for (int j = 0; j < 12; ++j) sq[j] = sq[j] + h * xdot[j];
-          stepq += 1;
-          xa[(q1 ? kCoopPairs : 0) + lane] = sq[7];
-          xb[(q1 ? kCoopPairs : 0) + lane] = sq[8];
-        } else {
+        if (pass == 1) {   // the observation of the new state (env_base.py:103) needs no coefficient at all
           float o[NP_NUM_OBS];
           make_obs(c, TASK, sq, uq, tq, g, eas2tas_of(tp), o);
           add_obs_noise(p, idxq, o);
@@ -212,6 +286,33 @@ __global__ void __launch_bounds__(kCoopBS, 2) f16_step_coop_kernel(const __grid_
 #pragma unroll
             for (int j = 0; j < NP_NUM_OBS / 2; ++j) orow[j] = make_float2(o[2 * j], o[2 * j + 1]);
           }
+        }
+      }
+      NP_COOP_STAMP(pass == 0 ? 1 : 5);
+      __syncthreads();   // all 22 slots of the 32 pairs are in place
+      NP_COOP_STAMP(pass == 0 ? 2 : 5 + 3);
+
+      if (pass == 1 && use_cache && act[0]) {   // the next step's Euler derivative needs exactly these
+#pragma unroll
+        for (int k = 0; k < kNumAB2; ++k)   // warps 0 / 1 have the tail to fly: the others store
+          if (2 + k % (NW - 2) == warp) store_pair(p.cache + (size_t)k * ld, pr, coef2[(kFirstAB2 + k) * kCoopPairs], act[1]);
+        if (warp == 2) store_pair(p.cache + (size_t)kNumAB2 * ld, pr, al, act[1]);
+        if (warp == 3) store_pair(p.cache + (size_t)(kNumAB2 + 1) * ld, pr, be, act[1]);
+      }
+
+      if (owner) {
+        const ForcePart fp = force_part(sq, uq[0], uq[2], uq[3], 0.0f, g, tp, cq, CS, a1);
+        if (pass == 0) {
+          float xdot[12];
+          nlplant_kin_moments(sq, uq[2], uq[3], 0.0f, g, fp.qbar, fp.vt, fp.b, fp.t, cq, CS, a1, xdot);
+          xdot[6] = fp.f.vt_dot; xdot[7] = fp.f.alpha_dot; xdot[8] = fp.f.beta_dot;
+          const float h = c.dt - 0.0f;
+#pragma unroll
+          for (int j = 0; j < 12; ++j) sq[j] = sq[j] + h * xdot[j];
+          stepq += 1;
+          xa[(q1 ? kCoopPairs : 0) + lane] = sq[7];
+          xb[(q1 ? kCoopPairs : 0) + lane] = sq[8];
+        } else {
           const Verdict v = judge_state<false, TASK>(c, sq, tq, g, fp.f, stepq);
           excq = v.exc; badq = v.bad; doneq = v.done;
           rewq = v.rw + (float)(-200 * (int)badq + 200 * (int)doneq);
@@ -219,7 +320,9 @@ __global__ void __launch_bounds__(kCoopBS, 2) f16_step_coop_kernel(const __grid_
         }
       }
       if (pass == 0) {
+        NP_COOP_STAMP(3);
         __syncthreads();   // the new (alpha, beta) of both aircraft, for every warp's share of pass 1
+        NP_COOP_STAMP(4);
         al = make_float2(xa[lane], xa[kCoopPairs + lane]);
         be = make_float2(xb[lane], xb[kCoopPairs + lane]);
       }
@@ -248,7 +351,9 @@ __global__ void __launch_bounds__(kCoopBS, 2) f16_step_coop_kernel(const __grid_
         }
       }
     }
+    NP_COOP_STAMP(6);
     __syncthreads();   // tile complete; slots and exchange rows free for the next 32 pairs
+    NP_COOP_STAMP(7);
     if (staged) {      // tile -> obs[64 rows], 5 632 contiguous bytes
       float* dst = p.obs + (size_t)(2 * pbase) * NP_NUM_OBS;
       if (!p.obs_stg) {
@@ -258,10 +363,11 @@ __global__ void __launch_bounds__(kCoopBS, 2) f16_step_coop_kernel(const __grid_
         }
       } else {
         const float4* src = reinterpret_cast<const float4*>(otile);
-        for (int k = threadIdx.x; k < kObsTileFloats / 4; k += kCoopBS) reinterpret_cast<float4*>(dst)[k] = src[k];
+        for (int k = threadIdx.x; k < kObsTileFloats / 4; k += NW * 32) reinterpret_cast<float4*>(dst)[k] = src[k];
         __syncthreads();
       }
     }
   }
   if (threadIdx.x == 0) bulk_wait0();   // shared memory must outlive the last bulk store
+  NP_COOP_STAMP_FLUSH();
 }

@@ -200,21 +200,6 @@ __device__ __forceinline__ void eval_el3_nets(const float* __restrict__ blob, ui
                                               float2* __restrict__ out, int stride, int count, int first = 0) {
   eval_group2<kCx>(blob, wbase, zi, out, stride, count, first);
 }
-// Warp `w` of 4's share of the 16 (alpha, beta) nets (1 190 ... 1 490 MACs each) and of the three-input nets.
-__device__ __forceinline__ void eval_ab2_nets_quarter(const float* __restrict__ blob, uint32_t wbase, const ZIn2& zi,
-                                                      float2* __restrict__ out, int stride, int w) {
-  if (w < 2) eval_group2<kCy>(blob, wbase, zi, out, stride, 1, w);
-  else eval_group2<kdCx_lef>(blob, wbase, zi, out, stride, 1, w - 2);
-  eval_group2<kdCz_lef>(blob, wbase, zi, out, stride, 1, w);
-  eval_group2<kdCy_r30>(blob, wbase, zi, out, stride, 1, w);
-  if (w == 0) eval_group2<kdCy_a20>(blob, wbase, zi, out, stride, 1, 0);
-  else eval_group2<kdCy_a20_lef>(blob, wbase, zi, out, stride, 1, w - 1);
-}
-__device__ __forceinline__ void eval_el3_nets_quarter(const float* __restrict__ blob, uint32_t wbase, const ZIn2& zi,
-                                                      float2* __restrict__ out, int stride, int w, bool full) {
-  if (full) eval_el3_nets(blob, wbase, zi, out, stride, w == 0 ? 2 : 1, w == 0 ? 0 : w + 1);   // Cx Cz | Cm | Cn | Cl
-  else if (w < 2) eval_el3_nets(blob, wbase, zi, out, stride, 1, w);                            // Cx | Cz
-}
 
 // ------------------------------------------------------------------------------------------------
 // One-input nets as exact piecewise-linear tables (aero_pack.h): binary search of the merged breakpoint list,

@@ -104,6 +104,9 @@ struct np_env {
   int tab_pairs = 0;         // NPLANE_TAB_KERNEL=pairs: the table back-end on K1's two-aircraft-per-thread kernel (round 1) instead of K1t
   int block = 0;             // 0: chosen per launch (pick_block); else forced by NPLANE_BLOCK
   int coop_pairs = 0;        // ranges of up to this many pairs run on K1c (NPLANE_COOP_PAIRS; 0 = never)
+  int coop_warps = 0;        // NPLANE_COOP_WARPS = 4 / 8: force K1c's CTA shape (0: by population)
+  int coop_grid = 0;         // NPLANE_COOP_GRID: cap on K1c's grid (experiments: how much of a step is cold start)
+  int pdl = 1;               // K1c is launched with programmatic stream serialisation (NPLANE_PDL=0: ordinary launch)
   int tab_block = 384, grid = 0, smem = 0, num_sms = 0, last_block = 384;
   // np_env_step_host: one in-order stream per engine (upload, kernels, download) and the events chaining them
   static constexpr int kMaxHostChunks = 16;
@@ -1042,6 +1045,12 @@ static int env_create_impl(const np_env_cfg* cfg, const np_aero* aero, const np_
   }
   e->coop_pairs = e->num_sms * 2 * kCoopPairs;   // one wave of K1c CTAs
   if (const char* b = getenv("NPLANE_COOP_PAIRS")) e->coop_pairs = atoi(b);
+  if (const char* b = getenv("NPLANE_PDL")) e->pdl = atoi(b) != 0;
+  if (const char* b = getenv("NPLANE_COOP_GRID")) e->coop_grid = atoi(b);
+  if (const char* b = getenv("NPLANE_COOP_WARPS")) {
+    e->coop_warps = atoi(b);
+    if (e->coop_warps != 0 && e->coop_warps != 4 && e->coop_warps != 8) return fail(NP_EINVAL, "NPLANE_COOP_WARPS must be 4 or 8");
+  }
   if (const char* b = getenv("NPLANE_TAB_BLOCK")) e->tab_block = atoi(b);
   if (const char* b = getenv("NPLANE_OBS_STORE")) e->obs_stg = strcmp(b, "stg") == 0;
   if (const char* b = getenv("NPLANE_TAB_KERNEL")) e->tab_pairs = strcmp(b, "pairs") == 0;
@@ -1224,28 +1233,49 @@ static int step_range_impl(np_env* env, const float* action_dev, const float* dr
       default: return fail(NP_EINVAL, "np_env_step: table back-end block size not compiled in (build with -DNPLANE_ALL_BLOCKS)");
     }
   }
-  if (env->coop_pairs > 0 && !env->block && p.pair_end - p.pair_begin <= env->coop_pairs) {   // K1c: four warps share each pair's MLPs
+  if (env->coop_pairs > 0 && !env->block && p.pair_end - p.pair_begin <= env->coop_pairs) {   // K1c: the warps of a CTA share each pair's MLPs
     const int npairs = p.pair_end - p.pair_begin;
     if (npairs <= 0) return NP_OK;
     const int smem = coop_smem_bytes(p.aero_bytes);
     const int want = (npairs + kCoopPairs - 1) / kCoopPairs;
-    env->grid = want < env->num_sms * 2 ? want : env->num_sms * 2;
+    // eight warps while one CTA per SM covers the population (9 472 aircraft), four (two CTAs per SM) up to 18 944
+    const int nw = env->coop_warps ? env->coop_warps : (want <= env->num_sms ? 8 : 4);
+    const int per_sm = nw == 8 ? 1 : 2;
+    env->grid = want < env->num_sms * per_sm ? want : env->num_sms * per_sm;
+    if (env->coop_grid > 0 && env->grid > env->coop_grid) env->grid = env->coop_grid;
     env->smem = smem;
-    env->last_block = kCoopBS;
-    static int configured[64][3] = {};
+    env->last_block = nw * 32;
+    static int configured[64][6] = {};
     auto launch = [&](auto kern, int t) -> int {
       if (configured[env->device & 63][t] < smem) {
         NP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         configured[env->device & 63][t] = smem;
       }
-      kern<<<env->grid, kCoopBS, smem, st>>>(p);
-      NP_CUDA(cudaGetLastError());
+      // programmatic dependent launch: the CTAs may start (and stage the aero image) while the previous kernel of the stream drains
+      cudaLaunchConfig_t lc = {};
+      lc.gridDim = dim3(env->grid);
+      lc.blockDim = dim3(nw * 32);
+      lc.dynamicSmemBytes = smem;
+      lc.stream = st;
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      at[0].val.programmaticStreamSerializationAllowed = 1;
+      lc.attrs = at;
+      lc.numAttrs = env->pdl ? 1 : 0;
+      NP_CUDA(cudaLaunchKernelEx(&lc, kern, p));
       return NP_OK;
     };
+    if (nw == 8) {
+      switch (env->cfg.task) {
+        case NP_TASK_HEADING: return launch(f16_step_coop_kernel<NP_TASK_HEADING, 8>, 3);
+        case NP_TASK_CONTROL: return launch(f16_step_coop_kernel<NP_TASK_CONTROL, 8>, 4);
+        default: return launch(f16_step_coop_kernel<NP_TASK_TRACKING, 8>, 5);
+      }
+    }
     switch (env->cfg.task) {
-      case NP_TASK_HEADING: return launch(f16_step_coop_kernel<NP_TASK_HEADING>, 0);
-      case NP_TASK_CONTROL: return launch(f16_step_coop_kernel<NP_TASK_CONTROL>, 1);
-      default: return launch(f16_step_coop_kernel<NP_TASK_TRACKING>, 2);
+      case NP_TASK_HEADING: return launch(f16_step_coop_kernel<NP_TASK_HEADING, 4>, 0);
+      case NP_TASK_CONTROL: return launch(f16_step_coop_kernel<NP_TASK_CONTROL, 4>, 1);
+      default: return launch(f16_step_coop_kernel<NP_TASK_TRACKING, 4>, 2);
     }
   }
   switch (pick_block(env, p.pair_end - p.pair_begin)) {

@@ -53,7 +53,9 @@ __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.a
 
 // Stage the aero image into shared memory once per CTA: one elected thread issues TMA bulk copies that
 // complete on an mbarrier; everyone waits on it.
-__device__ __forceinline__ void stage_aero(void* blob_s, const void* aero_g, uint32_t bytes, uint64_t* bar) {
+// stage_aero_issue() only starts the copies (the caller overlaps its first global loads with them and waits with
+// mbar_wait(bar, 0) before the first use of the image).
+__device__ __forceinline__ void stage_aero_issue(void* blob_s, const void* aero_g, uint32_t bytes, uint64_t* bar) {
   if (threadIdx.x == 0) {
     mbar_init(bar, 1);
     mbar_expect_tx(bar, bytes);
@@ -64,6 +66,14 @@ __device__ __forceinline__ void stage_aero(void* blob_s, const void* aero_g, uin
     }
   }
   __syncthreads();
+}
+__device__ __forceinline__ void stage_aero(void* blob_s, const void* aero_g, uint32_t bytes, uint64_t* bar) {
+  stage_aero_issue(blob_s, aero_g, bytes, bar);
   mbar_wait(bar, 0);
 }
 
+// Programmatic dependent launch (sm_90+): a kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may start
+// before the kernel ahead of it in the stream has finished; grid_dependency_wait() blocks until that kernel has completed and
+// its writes are visible (a no-op for an ordinary launch), grid_launch_dependents() lets the NEXT kernel of the stream start.
+__device__ __forceinline__ void grid_dependency_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void grid_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }

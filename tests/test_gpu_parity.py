@@ -32,6 +32,15 @@ def dev():
     return torch.device("cuda:0")
 
 
+@pytest.fixture(params=["K1c", "K1"])
+def step_kernel(request, monkeypatch):
+    """Populations up to 18 944 aircraft step on K1c (coop_step_kernel.cuh) by default; the tests that hold the step against the
+    oracle / the reference fixtures at such sizes run once on it and once on K1 (the kernel of the headline number)."""
+    if request.param == "K1":
+        monkeypatch.setenv("NPLANE_COOP_PAIRS", "0")
+    return request.param
+
+
 def _env(n, task="heading", **kw):
     from neuralplane_b200 import ControlEnv
     env = ControlEnv(num_envs=n, config=task, model="F16", random_seed=0, device="cuda:0", **kw)
@@ -152,25 +161,25 @@ def _trajectory(task, fixture):
     assert abs(got_bad - ref_bad) <= max(5, 0.03 * ref_bad), (got_bad, ref_bad)
 
 
-def test_heading_1000_steps_small_actions(dev):
+def test_heading_1000_steps_small_actions(dev, step_kernel):
     """BASELINE config 1: F16 heading, n=128, 1000 steps, actions 0.3*U(-1,1)."""
     _trajectory("heading", "heading_traj_a03.npz")
 
 
-def test_heading_1000_steps_full_actions(dev):
+def test_heading_1000_steps_full_actions(dev, step_kernel):
     """Same with full-scale actions (the reset-exercising tape): ~2200 terminations/resets in 1000 steps."""
     _trajectory("heading", "heading_traj_a10.npz")
 
 
-def test_control_task_trajectory(dev):
+def test_control_task_trajectory(dev, step_kernel):
     _trajectory("control", "control_traj.npz")
 
 
-def test_tracking_task_trajectory(dev):
+def test_tracking_task_trajectory(dev, step_kernel):
     _trajectory("tracking", "tracking_traj.npz")
 
 
-def test_done_branch(dev):
+def test_done_branch(dev, step_kernel):
     """Target reached -> done, +200, and the reset at the top of the next step (unreach_heading.py:49-53)."""
     g = np.load(os.path.join(GOLDEN, "heading_done_branch.npz"))
     n, steps, seed = [int(x) for x in g["meta"]]
@@ -282,7 +291,7 @@ def test_coef_cache_is_bit_identical(dev):
 
 
 @pytest.mark.parametrize("n", [1, 31, 77, 257])
-def test_ragged_population_sizes(dev, n):
+def test_ragged_population_sizes(dev, n, step_kernel):
     """n not a multiple of the warp / block size: tail lanes must neither read nor write out of range."""
     from oracle.f16_oracle import F16EnvOracle
     env, orc = _env(n, "heading"), F16EnvOracle(n, "heading")

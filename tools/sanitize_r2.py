@@ -23,6 +23,16 @@ for n in (257, 3000 + 11, 60_000 + 1):          # 128-thread latency shape, 128,
                 e.step(torch.rand((n, 4), device=dev) * 2 - 1)
             e.model.update(torch.rand((n, 4), device=dev) * 2 - 1)
             torch.cuda.synchronize()
+# n = 257 / 3011 above ran on K1c (the cooperative small-population kernel); K1c over several waves (tile / slot reuse across
+# iterations), and K1's 128-thread shape it replaced at these sizes
+for var, val, n in (("NPLANE_COOP_PAIRS", "100000000", 40_001), ("NPLANE_COOP_PAIRS", "0", 3011)):
+    os.environ[var] = val
+    e = ControlEnv(num_envs=n, config="tracking", model="F16", random_seed=1, device=dev)
+    del os.environ[var]
+    e.reset()
+    for k in range(3):
+        e.step(torch.rand((n, 4), device=dev) * 2 - 1)
+    torch.cuda.synchronize()
 os.environ["NPLANE_BLOCK"] = "512"
 e = ControlEnv(num_envs=5000, config="heading", model="F16", random_seed=1, device=dev)
 del os.environ["NPLANE_BLOCK"]
