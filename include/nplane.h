@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define NP_ABI_VERSION 7
+#define NP_ABI_VERSION 8
 
 enum { NP_OK = 0, NP_EINVAL = 1, NP_ECUDA = 2, NP_ESTATE = 3 };
 
@@ -256,6 +256,14 @@ int np_rollout_returns(const float* rewards_dev, float* value_preds_dev, const f
  * print(torch.sum(bad_done)) host syncs, e.g. overload.py:32-34).  Synchronises `stream`.
  * out[0..7] = overload, low_altitude, high_speed, low_speed, extreme_state, unreach, reached(done), resets. */
 int np_env_counters(np_env* env, uint64_t* out, void* stream);
+
+/* (no reference counterpart: the reference draws from torch's global generator on the host, env_base.py:83-97,
+ * heading_task.py:152.)  Every step call advances the env's RNG counter on the HOST, so a captured CUDA graph replays
+ * with frozen counters -- the same reset / observation-noise draws on every replay.  This enqueues a one-thread kernel
+ * that adds `delta` to a device-side epoch word all kernels add to their counter: capture it at the end of a graph of K
+ * step calls with delta = K and replay r continues exactly where an eager loop of r*K steps would be (the results are
+ * bit-identical to that loop).  Zero at bind. */
+int np_env_rng_advance(np_env* env, uint32_t delta, void* stream);
 
 /* F16Dynamics.nlplant (F16_dynamics.py:37-229) on SoA rows: xdot_dev [12][ld] from s_dev [12][ld], u_dev [5][ld].
  * Backs F16Model.get_extended_state and the getters built on it (F16_model.py:47-49,75-91,132-182). */

@@ -89,6 +89,7 @@ SYMBOLS = {
     "np_env_pid_offset_bytes": (C.c_size_t, [C.POINTER(EnvCfg)]),
     "np_env_set_pid_started": (C.c_int, [_P, C.c_int]),
     "np_env_counters": (C.c_int, [_P, C.POINTER(C.c_uint64), _P]),
+    "np_env_rng_advance": (C.c_int, [_P, C.c_uint32, _P]),
     "np_env_launch_info": (C.c_int, [_P, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "np_f16_nlplant": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, _P]),
     "np_tables_create": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_size_t, C.POINTER(_P)]),

@@ -174,6 +174,9 @@ __global__ void __launch_bounds__(NW * 32, NW == 4 ? 2 : 1) f16_step_coop_kernel
       a[q][0] = av.x; a[q][1] = av.y; a[q][2] = av.z; a[q][3] = av.w;
     }
 
+    // the RNG counter of this launch: one more L2 round trip in flight with the state loads (requested AFTER them: its first
+    // consumer is an add the compiler places right behind the load, and a warp issues in order)
+    const uint32_t rng = rng_step(p);
     // the aero image (64 KB, TMA) has been arriving while the loads above were issued; later iterations pass straight through
     mbar_wait(bar, 0);
     const uint32_t wb0 = aero_base_after_staging(blob);
@@ -184,7 +187,7 @@ __global__ void __launch_bounds__(NW * 32, NW == 4 ? 2 : 1) f16_step_coop_kernel
 #pragma unroll
     for (int q = 0; q < 2; ++q) {
       if (rst[q]) {
-        const Draws r = reset_draws(p, idx[q]);
+        const Draws r = reset_draws(p, idx[q], rng);
         reset_aircraft(c, TASK, r, s[q], u[q], tgt[q]);
         steps[q] = 0;
       }
@@ -275,7 +278,7 @@ __global__ void __launch_bounds__(NW * 32, NW == 4 ? 2 : 1) f16_step_coop_kernel
         if (pass == 1) {   // the observation of the new state (env_base.py:103) needs no coefficient at all
           float o[NP_NUM_OBS];
           make_obs(c, TASK, sq, uq, tq, g, eas2tas_of(tp), o);
-          add_obs_noise(p, idxq, o);
+          add_obs_noise(p, idxq, o, rng);
           if (staged) {
             float2* orow = reinterpret_cast<float2*>(otile + (2 * lane + (q1 ? 1 : 0)) * NP_NUM_OBS);
 #pragma unroll

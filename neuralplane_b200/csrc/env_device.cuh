@@ -38,13 +38,24 @@ struct StepParams {
   uint8_t* pair_reset;           // [ld] env-level reset flag of each local aircraft's env (own | partner flags of the last step)
   int index_stride;              // global aircraft index = index_base + index_stride * local index (RNG streams)
   uint32_t step_index;
+  const uint32_t* rng_epoch;     // device word added to step_index (np_env_rng_advance): fresh RNG streams for each replay of a CUDA graph
 };
+
+// The RNG counter of this launch.  step_index is advanced on the host by every step call, i.e. it is a constant of a captured
+// CUDA graph; the epoch word lives on the device and is advanced by np_env_rng_advance (capturable), 0 otherwise.
+// (read through L2: the word may have been written by the kernel just ahead in the stream)
+#ifdef NPLANE_NO_EPOCH   // experiment: what the epoch read costs
+__device__ __forceinline__ uint32_t rng_step(const StepParams& p) { return p.step_index; }
+#else
+__device__ __forceinline__ uint32_t rng_step(const StepParams& p) { return p.step_index + __ldcg(p.rng_epoch); }
+#endif
 
 
 struct Draws {
   float d[NP_NUM_DRAWS];
 };
-__device__ __forceinline__ Draws reset_draws(const StepParams& p, int i) {
+// `step` = rng_step(p); the latency kernel reads it once up front, the others where it is needed (rare / hidden by other warps)
+__device__ __forceinline__ Draws reset_draws(const StepParams& p, int i, uint32_t step) {
   Draws r;
   if (p.draws) {
 #pragma unroll
@@ -52,8 +63,8 @@ __device__ __forceinline__ Draws reset_draws(const StepParams& p, int i) {
   } else {
     const uint64_t gi = p.cfg.index_base + (uint64_t)p.index_stride * (uint64_t)i;
     const uint2 key = make_uint2((uint32_t)p.cfg.seed, (uint32_t)(p.cfg.seed >> 32));
-    const uint4 a = philox4x32_10(make_uint4((uint32_t)gi, (uint32_t)(gi >> 32), p.step_index, 0x5EED0000u), key);
-    const uint4 b = philox4x32_10(make_uint4((uint32_t)gi, (uint32_t)(gi >> 32), p.step_index, 0x5EED0001u), key);
+    const uint4 a = philox4x32_10(make_uint4((uint32_t)gi, (uint32_t)(gi >> 32), step, 0x5EED0000u), key);
+    const uint4 b = philox4x32_10(make_uint4((uint32_t)gi, (uint32_t)(gi >> 32), step, 0x5EED0001u), key);
     r.d[0] = u01(a.x); r.d[1] = u01(a.y); r.d[2] = u01(a.z); r.d[3] = u01(a.w); r.d[4] = u01(b.x);
   }
   return r;
@@ -116,7 +127,9 @@ __device__ __forceinline__ void make_obs(const np_env_cfg& c, int task, const fl
   o[21] = e2t;
 }
 
-__device__ __forceinline__ void add_obs_noise(const StepParams& p, int i, float* o) {
+__device__ __forceinline__ Draws reset_draws(const StepParams& p, int i) { return reset_draws(p, i, p.draws ? 0u : rng_step(p)); }
+
+__device__ __forceinline__ void add_obs_noise(const StepParams& p, int i, float* o, uint32_t step) {
   const float sc = p.cfg.noise_scale;
   if (p.noise) {  // injected standard normals (parity runs): obs + randn * noise_scale (heading_task.py:152)
 #pragma unroll
@@ -126,7 +139,7 @@ __device__ __forceinline__ void add_obs_noise(const StepParams& p, int i, float*
     const uint2 key = make_uint2((uint32_t)p.cfg.seed, (uint32_t)(p.cfg.seed >> 32));
 #pragma unroll
     for (int q = 0; q < 3; ++q) {  // 3 x 4 words -> 12 pairs of normals, 22 used
-      const uint4 r = philox4x32_10(make_uint4((uint32_t)gi, (uint32_t)(gi >> 32), p.step_index, 0x0B5E0000u + q), key);
+      const uint4 r = philox4x32_10(make_uint4((uint32_t)gi, (uint32_t)(gi >> 32), step, 0x0B5E0000u + q), key);
       const uint32_t w[4] = {r.x, r.y, r.z, r.w};
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
@@ -140,6 +153,9 @@ __device__ __forceinline__ void add_obs_noise(const StepParams& p, int i, float*
       }
     }
   }
+}
+__device__ __forceinline__ void add_obs_noise(const StepParams& p, int i, float* o) {
+  add_obs_noise(p, i, o, (p.noise || p.cfg.noise_scale == 0.0f) ? 0u : rng_step(p));
 }
 
 // one aircraft pair of an SoA row: a single 8-byte store, or only the first aircraft for the odd tail

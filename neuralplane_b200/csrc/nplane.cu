@@ -154,6 +154,10 @@ __global__ void __launch_bounds__(BS, MINB) f16_step_kernel(const __grid_constan
   uint64_t* bar = reinterpret_cast<uint64_t*>(reinterpret_cast<float*>(coef_all + (TAB ? 0 : kNumSlots * BS)) +
                                               (STAGE ? (BS / 32) * kObsTileFloats : 0));
 
+  // the RNG counter of this launch (host counter + device epoch, env_device.cuh rng_step): one L2 read per CTA, parked in
+  // shared memory (a read per aircraft measured -2.5 %; a register held through the kernel is what K1 has none of to spare)
+  uint32_t& rng_s = reinterpret_cast<uint32_t*>(bar)[2];   // the spare word behind the staging barrier
+  if (threadIdx.x == 32) rng_s = rng_step(p);
   stage_aero(blob, p.aero, (uint32_t)p.aero_bytes, bar);
   uint32_t wb0 = 0;
   AeroTabs tabs{};
@@ -251,7 +255,7 @@ __global__ void __launch_bounds__(BS, MINB) f16_step_kernel(const __grid_constan
 #pragma unroll
     for (int q = 0; q < 2; ++q) {
       if (rst[q]) {
-        const Draws r = reset_draws(p, idx[q]);
+        const Draws r = reset_draws(p, idx[q], rng_s);
         if (COMBAT) {
           combat_reset_aircraft(c, r, s[q], u[q]);
           blood[q] = 100.0f;
@@ -399,7 +403,7 @@ __global__ void __launch_bounds__(BS, MINB) f16_step_kernel(const __grid_constan
           if (!COMBAT && (!PLAN || sub == nsub - 1)) {
             float o[NP_NUM_OBS];
             make_obs(c, TASK, sq, uq, tq, g, eas2tas_of(tp), o);
-            add_obs_noise(p, idx[q], o);
+            add_obs_noise(p, idx[q], o, rng_s);
             if (staged) {
               if (q == 0 && !p.obs_stg) {   // the tile's previous contents may still be being read by the last bulk store
                 if ((threadIdx.x & 31) == 0) bulk_wait_read0();
@@ -560,6 +564,8 @@ __global__ void __launch_bounds__(kTabBS, kTabMinB) f16_table_step_kernel(const 
   float* T = reinterpret_cast<float*>(smem_raw);
   float* otile = T + kTablesFloats + (threadIdx.x >> 5) * kTabTileFloats;
   uint64_t* bar = reinterpret_cast<uint64_t*>(T + kTablesFloats + (kTabStage ? (kTabBS / 32) * kTabTileFloats : 0));
+  uint32_t& rng_s = reinterpret_cast<uint32_t*>(bar)[2];   // as in K1
+  if (threadIdx.x == 32) rng_s = rng_step(p);
   stage_aero(T, p.aero, (uint32_t)(kTablesFloats * 4), bar);
   const ZeroCells zc = zero_cells(T);
   const np_env_cfg& c = p.cfg;
@@ -583,7 +589,7 @@ __global__ void __launch_bounds__(kTabBS, kTabMinB) f16_table_step_kernel(const 
       a[0] = av.x; a[1] = av.y; a[2] = av.z; a[3] = av.w;
     }
     if (rst) {                                     // BaseEnv.reset (env_base.py:83-97)
-      reset_aircraft(c, TASK, reset_draws(p, il), s, u, tgt);
+      reset_aircraft(c, TASK, reset_draws(p, il, rng_s), s, u, tgt);
       steps = 0;
     }
     count_cause1(p.counters, 7, rst && live);
@@ -610,7 +616,7 @@ __global__ void __launch_bounds__(kTabBS, kTabMinB) f16_table_step_kernel(const 
       } else {
         float o[NP_NUM_OBS];
         make_obs(c, TASK, s, u, tgt, g, eas2tas_of(tp), o);
-        add_obs_noise(p, il, o);
+        add_obs_noise(p, il, o, rng_s);
         if (staged) {
           if (lane == 0) bulk_wait_read0();        // the previous slab's bulk store has read the tile
           __syncwarp();
@@ -982,6 +988,7 @@ static StepParams make_params(np_env* env, const float* action, const float* dra
   p.counters = reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(env->buf.workspace_dev) +
                                                      (((size_t)kWorkspaceRows * env->cfg.ld * 4 + 127) / 128) * 128);
   static_assert(kWorkspaceRows == kCacheRows + kPidRows + 2, "workspace layout");
+  p.rng_epoch = reinterpret_cast<const uint32_t*>(p.counters + 16);   // second 128-B line of the 256-B block: not the line the counter atomics hit
   p.aero = env->aero ? env->aero->image_dev : nullptr;
   p.aero_bytes = env->aero ? env->aero->bytes : 0;
   p.tab = 0;
@@ -1074,6 +1081,9 @@ int np_env_bind(np_env* env, const np_buffers* b, void* stream) {
   // on the caller's stream, like every later step.
   NP_CUDA(cudaMemsetAsync(reinterpret_cast<float*>(b->workspace_dev) + (size_t)kNumAB2 * env->cfg.ld, 0xFF,
                           2 * (size_t)env->cfg.ld * sizeof(float), (cudaStream_t)stream));
+  // termination counters and the RNG epoch word (np_env_rng_advance) start at zero
+  NP_CUDA(cudaMemsetAsync(reinterpret_cast<char*>(b->workspace_dev) + (((size_t)kWorkspaceRows * env->cfg.ld * 4 + 127) / 128) * 128, 0, 256,
+                          (cudaStream_t)stream));
   return NP_OK;
 }
 
@@ -1509,6 +1519,20 @@ int np_env_counters(np_env* env, uint64_t* out, void* stream) {
   StepParams p = make_params(env, nullptr, nullptr, nullptr);
   NP_CUDA(cudaMemcpyAsync(out, p.counters, NP_NUM_COUNTERS * sizeof(uint64_t), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
   NP_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+  return NP_OK;
+}
+
+// CUDA-graph capture freezes every host-side launch argument, including the RNG counter the step calls advance: each replay
+// would draw the same reset / noise streams.  This adds `delta` to a DEVICE word that every kernel adds to its counter; captured
+// at the end of a graph of K steps with delta = K, every replay continues the sequence an eager loop would have produced.
+__global__ void rng_epoch_add_kernel(uint32_t* epoch, uint32_t delta) { *epoch += delta; }
+
+int np_env_rng_advance(np_env* env, uint32_t delta, void* stream) {
+  if (!env || !env->bound) return fail(NP_ESTATE, "np_env_rng_advance: env not bound");
+  DeviceGuard guard(env->device);
+  StepParams p = make_params(env, nullptr, nullptr, nullptr);
+  rng_epoch_add_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(const_cast<uint32_t*>(p.rng_epoch), delta);
+  NP_CUDA(cudaGetLastError());
   return NP_OK;
 }
 

@@ -70,12 +70,12 @@ __device__ __forceinline__ void uav_make_obs(const np_env_cfg& c, const float* s
 // low-pass + Euler step -> observation row -> (STEP) terminations + reward.  Shared by the per-thread kernel and the
 // TMA-staged slab kernel below, so both produce identical bits.
 template <bool STEP>
-__device__ __forceinline__ void uav_aircraft(const StepParams& p, int i, bool rst, const float4 av, float* s, float* F, float* tgt,
+__device__ __forceinline__ void uav_aircraft(const StepParams& p, uint32_t rng, int i, bool rst, const float4 av, float* s, float* F, float* tgt,
                                              int& steps, float* o, float& rew, bool& done, bool& bad) {
   const np_env_cfg& c = p.cfg;
   // ---- BaseEnv.reset (env_base.py:83-97) ---------------------------------------------------------
   if (rst) {
-    const Draws r = reset_draws(p, i);
+    const Draws r = reset_draws(p, i, rng);
     uav_reset_aircraft(c, r, s, F);
     uav_task_reset(c, uav_view(s), r, tgt);
     steps = 0;
@@ -98,7 +98,7 @@ __device__ __forceinline__ void uav_aircraft(const StepParams& p, int i, bool rs
   const UavView v = uav_view(s);
   const UavTrig trig = uav_trig(s);   // of the state the observation, the Overload check and the reward all see
   uav_make_obs(c, s, v, trig, tgt, o);
-  add_obs_noise(p, i, o);
+  add_obs_noise(p, i, o, rng);
   if (STEP) {
     // ---- terminations (task_base.py:75-96) through the getters ------------------------------------------
     float xdot[12];
@@ -155,6 +155,7 @@ __global__ void __launch_bounds__(256, 4) uav_env_kernel(const __grid_constant__
   const np_env_cfg& c = p.cfg;
   const int n = c.n, ld = c.ld;
   const int i_end = min(n, 2 * p.pair_end);
+  const uint32_t rng = rng_step(p);   // the RNG counter of this launch: read once per thread, not once per aircraft
   for (int i = 2 * p.pair_begin + blockIdx.x * blockDim.x + threadIdx.x; i < i_end; i += gridDim.x * blockDim.x) {
     float s[12], F[3], tgt[3], o[NP_NUM_OBS], rew;
     bool done, bad;
@@ -167,7 +168,7 @@ __global__ void __launch_bounds__(256, 4) uav_env_kernel(const __grid_constant__
     int steps = p.step_count[i];
     const bool rst = (p.flags[i] | p.flags[ld + i] | p.flags[2 * (size_t)ld + i]) != 0;
     const float4 av = STEP ? reinterpret_cast<const float4*>(p.action)[i] : make_float4(0.f, 0.f, 0.f, 0.f);
-    uav_aircraft<STEP>(p, i, rst, av, s, F, tgt, steps, o, rew, done, bad);
+    uav_aircraft<STEP>(p, rng, i, rst, av, s, F, tgt, steps, o, rew, done, bad);
     float2* orow = reinterpret_cast<float2*>(p.obs + (size_t)i * NP_NUM_OBS);
 #pragma unroll
     for (int j = 0; j < NP_NUM_OBS / 2; ++j) orow[j] = make_float2(o[2 * j], o[2 * j + 1]);
@@ -257,6 +258,7 @@ __global__ void __launch_bounds__(uavslab::kSlab, 4) uav_step_slab_kernel(const 
   }
   __syncthreads();
 
+  const uint32_t rng = rng_step(p);   // the RNG counter of this launch: read once per thread, not once per aircraft
   int slab = blockIdx.x;
   if (warp0 && slab < nslab && i_begin + (slab + 1) * kSlab <= i_end) uav_slab_request(p, sm, in_full, i_begin + slab * kSlab, lane);
 
@@ -306,7 +308,7 @@ __global__ void __launch_bounds__(uavslab::kSlab, 4) uav_step_slab_kernel(const 
       rst = (p.flags[i] | p.flags[ld + i] | p.flags[2 * (size_t)ld + i]) != 0;
     }
 
-    if (live) uav_aircraft<true>(p, i, rst, av, s, F, tgt, steps, o, rew, done, bad);
+    if (live) uav_aircraft<true>(p, rng, i, rst, av, s, F, tgt, steps, o, rew, done, bad);
 
     if (full) {
       // SoA rows, reward and flags: fully coalesced 4-byte stores straight from registers (128 B per warp and row)

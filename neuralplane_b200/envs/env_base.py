@@ -182,6 +182,12 @@ class BaseEnv:
         nv.check(nv.lib().np_env_counters(self._handle, out, self._stream()), "np_env_counters")
         return dict(zip(self.COUNTER_NAMES, [int(x) for x in out]))
 
+    def advance_rng(self, delta):
+        """CUDA-graph capture freezes the host-side RNG counter that every reset() / step() call advances, so each replay of a
+        captured graph would draw the same reset states and observation noise.  Capture `env.advance_rng(K)` at the end of a
+        graph of K step calls: replay r then continues exactly the sequence an eager loop of r * K steps produces."""
+        nv.check(nv.lib().np_env_rng_advance(self._handle, int(delta), self._stream()), "np_env_rng_advance")
+
     # ---- reset / step ---------------------------------------------------------------------------------------
     def _stream(self):
         return torch.cuda.current_stream(self.device).cuda_stream

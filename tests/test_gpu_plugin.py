@@ -178,6 +178,44 @@ def test_cooperative_small_population_kernel_is_bit_identical(config, n):
     assert coop.termination_counters()["resets"] > 0
 
 
+@pytest.mark.parametrize("n", [3000, 40_000])
+def test_cuda_graph_replay_equals_eager_loop(n):
+    """A rollout loop captured in a CUDA graph: K1c (n = 3 000) is launched with programmatic stream serialisation (the next
+    step's CTAs start behind this step's dependency wait), K1 (n = 40 000) with ordinary launches.  The RNG counter the step
+    calls advance is a host-side launch argument, frozen by the capture; env.advance_rng(K), captured at the end of the K
+    steps, moves a device-side epoch instead.  Three replays of a 10-step graph must leave exactly the state, outputs (with
+    in-kernel observation noise and reset draws) and counters of 30 eager steps with ordinary launches (NPLANE_PDL=0)."""
+    import os
+    from neuralplane_b200 import ControlEnv
+    kw = dict(num_envs=n, config="heading", model="F16", random_seed=9, device="cuda:0")
+    env = ControlEnv(**kw)
+    os.environ["NPLANE_PDL"] = "0"
+    try:
+        ref = ControlEnv(**kw)
+    finally:
+        del os.environ["NPLANE_PDL"]
+    env.reset(); ref.reset()
+    a = _cuda(tapes.action_tape(9, 1, n, 1.0))
+    for e in (env, ref):                     # warm-up outside the capture (first launch sets the kernel attributes)
+        e.step(a)
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        for _ in range(10):
+            out = env.step(a)
+        env.advance_rng(10)
+    for _ in range(3):
+        g.replay()
+    for _ in range(30):
+        exp = ref.step(a)
+    torch.cuda.synchronize()
+    for x, y in zip(out[:5], exp[:5]):
+        assert torch.equal(x, y)
+    assert torch.equal(env.model.s, ref.model.s) and torch.equal(env.step_count, ref.step_count)
+    c = env.termination_counters()
+    assert c == ref.termination_counters() and c["resets"] > n      # full-scale actions: episodes end, fresh draws each replay
+
+
 def test_rollout_attach_rejects_odd_population():
     """rewards[t] of an odd population is only 4-byte aligned for odd t; attach() must say so up front."""
     import types
