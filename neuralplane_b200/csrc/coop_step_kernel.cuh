@@ -77,6 +77,11 @@ __device__ __forceinline__ void coop_static_for(F&& f) {
   }
 }
 static_assert(kCoopGroupK0[0] - kFirstAB2 == 0 && kCoopGroupK0[5] + 3 - kFirstAB2 == kNumAB2, "K1c: group table vs net enum");
+#ifdef NPLANE_COOP_ROLLED   // experiment: keep the two passes rolled (smaller code)
+#define NP_COOP_UNROLL_PASS _Pragma("unroll 1")
+#else
+#define NP_COOP_UNROLL_PASS
+#endif
 #ifdef NPLANE_COOP_TIMING   // debug build (tools/k1c_phases.py): per-warp clock stamps of CTA 0, left in the first obs rows
 #define NP_COOP_STAMP_INIT() __shared__ long long np_stamps[8][10]; long long* stamps = np_stamps[warp]; const long long t_start = clock64()
 #define NP_COOP_STAMP(i) do { if (lane == 0) stamps[i] = clock64() - t_start; } while (0)
@@ -87,10 +92,15 @@ static_assert(kCoopGroupK0[0] - kFirstAB2 == 0 && kCoopGroupK0[5] + 3 - kFirstAB
 #define NP_COOP_STAMP_FLUSH() do { } while (0)
 #endif
 static int coop_smem_bytes(int aero_bytes) {
-  return aero_bytes + kNumSlots * kCoopPairs * 8 + kObsTileFloats * 4 + 4 * kCoopPairs * 4 + 16;
+  return aero_bytes + kNumSlots * kCoopPairs * 8 + kObsTileFloats * 4 + 6 * kCoopPairs * 4 + 16;
 }
 
-template <int TASK, int NW>
+// PLAN = true: PlanningEnv.step (planning_env.py:144-177) -- K1's MODE_PLAN on the same CTA shape.  train_tracking.sh runs it
+// at 10 000 envs: 50 FDM sub-steps per env step under the fused PID controller, so the pass that K1c shortens is walked 100
+// times per launch.  Warps 0 / 1 run their aircraft's controller and control lag at the top of every sub-step and publish the
+// new elevator deflection (the one control the nets see) through shared memory; state, controller state and flags stay in
+// their registers for the whole env step; the observation row is produced in the last sub-step only.
+template <int TASK, int NW, bool PLAN = false>
 __global__ void __launch_bounds__(NW * 32, NW == 4 ? 2 : 1) f16_step_coop_kernel(const __grid_constant__ StepParams p) {
   static_assert(NW == 4 || NW == 8, "K1c: four or eight warps");
   constexpr int V = NW == 8 ? 1 : 0;
@@ -100,7 +110,8 @@ __global__ void __launch_bounds__(NW * 32, NW == 4 ? 2 : 1) f16_step_coop_kernel
   float* otile = reinterpret_cast<float*>(coef_all + kNumSlots * kCoopPairs);  // the CTA's 64 observation rows
   float* xa = otile + kObsTileFloats;                                        // [2][32]: alpha' of aircraft q of pair `lane`
   float* xb = xa + 2 * kCoopPairs;                                           // [2][32]: beta'
-  uint64_t* bar = reinterpret_cast<uint64_t*>(xb + 2 * kCoopPairs);
+  float* xe = xb + 2 * kCoopPairs;                                           // [2][32]: elevator after the control lag (PLAN)
+  uint64_t* bar = reinterpret_cast<uint64_t*>(xe + 2 * kCoopPairs);
 
   stage_aero_issue(blob, p.aero, (uint32_t)p.aero_bytes, bar);   // waited for below, behind the first state loads
   // Launched with programmatic stream serialisation: everything above (CTA start-up, the image copies: immutable data) may
@@ -168,10 +179,12 @@ __global__ void __launch_bounds__(NW * 32, NW == 4 ? 2 : 1) f16_step_coop_kernel
         if (ow == warp) coef2[(kFirstAB2 + k) * kCoopPairs] = reinterpret_cast<const float2*>(p.cache + (size_t)k * ld)[prl];
       });
     }
+    if constexpr (!PLAN) {
 #pragma unroll
-    for (int q = 0; q < 2; ++q) {
-      const float4 av = reinterpret_cast<const float4*>(p.action)[idx[q]];
-      a[q][0] = av.x; a[q][1] = av.y; a[q][2] = av.z; a[q][3] = av.w;
+      for (int q = 0; q < 2; ++q) {
+        const float4 av = reinterpret_cast<const float4*>(p.action)[idx[q]];
+        a[q][0] = av.x; a[q][1] = av.y; a[q][2] = av.z; a[q][3] = av.w;
+      }
     }
 
     // the RNG counter of this launch: one more L2 round trip in flight with the state loads (requested AFTER them: its first
@@ -213,15 +226,17 @@ __global__ void __launch_bounds__(NW * 32, NW == 4 ? 2 : 1) f16_step_coop_kernel
       });
     }
 
-    // ---- control lag (F16_model.py:52-57) -----------------------------------------------------------------------
+    // ---- control lag (F16_model.py:52-57); PLAN: per sub-step, by the warp that flies the aircraft ---------------------
+    if constexpr (!PLAN) {
 #pragma unroll
-    for (int q = 0; q < 2; ++q) {
+      for (int q = 0; q < 2; ++q) {
 #pragma unroll
-      for (int j = 0; j < 4; ++j) a[q][j] = fminf(fmaxf(a[q][j], -1.0f), 1.0f);
-      u[q][0] = 0.9f * u[q][0] + 0.1f * a[q][0] * 0.225f * 76300.0f / DC(0.3048f);
-      u[q][1] = 0.9f * u[q][1] + 0.1f * a[q][1] * 45.0f;
-      u[q][2] = 0.9f * u[q][2] + 0.1f * a[q][2] * 45.0f;
-      u[q][3] = 0.9f * u[q][3] + 0.1f * a[q][3] * 45.0f;
+        for (int j = 0; j < 4; ++j) a[q][j] = fminf(fmaxf(a[q][j], -1.0f), 1.0f);
+        u[q][0] = 0.9f * u[q][0] + 0.1f * a[q][0] * 0.225f * 76300.0f / DC(0.3048f);
+        u[q][1] = 0.9f * u[q][1] + 0.1f * a[q][1] * 45.0f;
+        u[q][2] = 0.9f * u[q][2] + 0.1f * a[q][2] * 45.0f;
+        u[q][3] = 0.9f * u[q][3] + 0.1f * a[q][3] * 45.0f;
+      }
     }
 
     // ---- the aircraft this warp flies through the tail ----------------------------------------------------------------
@@ -237,16 +252,48 @@ __global__ void __launch_bounds__(NW * 32, NW == 4 ? 2 : 1) f16_step_coop_kernel
     const int idxq = q1 ? idx[1] : idx[0];
     const int row = 2 * pr + (q1 ? 1 : 0);
     float2 al = make_float2(s[0][7], s[1][7]), be = make_float2(s[0][8], s[1][8]);
-    const float2 el = make_float2(u[0][1], u[1][1]);
+    float2 el = make_float2(u[0][1], u[1][1]);
     bool badq = false, doneq = false, excq = false;
     float rewq = 0.0f;
     int causesq = 0;
+    // planning step: targets from the high-level action (planning_env.py:146-152) and the controller state, owner warps only
+    float plan_tgt[3] = {0.f, 0.f, 0.f}, pid[PLAN ? kPidRows : 1];
+    if constexpr (PLAN) {
+      if (owner) {
+        float a3[3];
+#pragma unroll
+        for (int j = 0; j < 3; ++j) a3[j] = fminf(fmaxf(p.action[(size_t)idxq * 3 + j], -1.0f), 1.0f);
+        plan_tgt[0] = sq[4] + a3[0] * 0.3f;
+        plan_tgt[1] = sq[5] + a3[1] * 0.3f;
+        plan_tgt[2] = sq[6] + a3[2] * 30.0f;
+#pragma unroll
+        for (int j = 0; j < kPidRows; ++j) pid[j] = p.pid[(size_t)j * ld + idxq];
+      }
+    }
+    const int nsub = PLAN ? p.n_sub : 1;
 
     if (!first_iter && threadIdx.x == 0) bulk_wait_read0();   // the tile may still be being read by the previous bulk store
     first_iter = false;
 
-#pragma unroll 1
     NP_COOP_STAMP(0);
+#pragma unroll 1
+    for (int sub = 0; sub < nsub; ++sub) {
+    if constexpr (PLAN) {
+      if (owner) {   // the PID stack (ctrl_device.cuh) and the control lag of this FDM sub-step
+        float a4[4];
+        pid_controller(sq, c.airspeed, c.dt, plan_tgt[0], plan_tgt[1], plan_tgt[2], pid, p.pid_first != 0 && sub == 0, a4);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) a4[j] = fminf(fmaxf(a4[j], -1.0f), 1.0f);
+        uq[0] = 0.9f * uq[0] + 0.1f * a4[0] * 0.225f * 76300.0f / DC(0.3048f);
+        uq[1] = 0.9f * uq[1] + 0.1f * a4[1] * 45.0f;
+        uq[2] = 0.9f * uq[2] + 0.1f * a4[2] * 45.0f;
+        uq[3] = 0.9f * uq[3] + 0.1f * a4[3] * 45.0f;
+        xe[(q1 ? kCoopPairs : 0) + lane] = uq[1];
+      }
+      __syncthreads();   // the new elevator of both aircraft; the verdict of the last sub-step has read its slots
+      el = make_float2(xe[lane], xe[kCoopPairs + lane]);
+    }
+    NP_COOP_UNROLL_PASS
     for (int pass = 0; pass < 2; ++pass) {
       const float2 adeg = make_float2(al.x * kR2D, al.y * kR2D);
       const float2 bdeg = make_float2(be.x * kR2D, be.y * kR2D);
@@ -255,7 +302,8 @@ __global__ void __launch_bounds__(NW * 32, NW == 4 ? 2 : 1) f16_step_coop_kernel
       zscores_ab2(blob, adeg, bdeg, zi);
       zscores_el2(blob, el, zi);
       const CoopRange* share = kCoopShareDev[V][warp];
-      if (pass == 1 || miss) {
+      // after the first sub-step the slots already hold the outputs at the current (alpha, beta): pass 1 left them there
+      if (pass == 1 || (miss && sub == 0)) {
         eval_group2<kCy>(blob, wb, zi, coef2, kCoopPairs, share[0].count, share[0].first);
         eval_group2<kdCx_lef>(blob, wb, zi, coef2, kCoopPairs, share[1].count, share[1].first);
         eval_group2<kdCz_lef>(blob, wb, zi, coef2, kCoopPairs, share[2].count, share[2].first);
@@ -275,7 +323,7 @@ __global__ void __launch_bounds__(NW * 32, NW == 4 ? 2 : 1) f16_step_coop_kernel
         g = make_trig(sq);
         tp = tfac_pow(sq[2]);
         alpha_coefs<kNumUsed - kFirstA1>(blob, tabs, seg, aq, a1);
-        if (pass == 1) {   // the observation of the new state (env_base.py:103) needs no coefficient at all
+        if (pass == 1 && sub == nsub - 1) {   // the observation of the new state (env_base.py:103) needs no coefficient at all
           float o[NP_NUM_OBS];
           make_obs(c, TASK, sq, uq, tq, g, eas2tas_of(tp), o);
           add_obs_noise(p, idxq, o, rng);
@@ -295,7 +343,7 @@ __global__ void __launch_bounds__(NW * 32, NW == 4 ? 2 : 1) f16_step_coop_kernel
       __syncthreads();   // all 22 slots of the 32 pairs are in place
       NP_COOP_STAMP(pass == 0 ? 2 : 5 + 3);
 
-      if (pass == 1 && use_cache && act[0]) {   // the next step's Euler derivative needs exactly these
+      if (pass == 1 && use_cache && act[0] && sub == nsub - 1) {   // the next step's Euler derivative needs exactly these
 #pragma unroll
         for (int k = 0; k < kNumAB2; ++k)   // warps 0 / 1 have the tail to fly: the others store
           if (2 + k % (NW - 2) == warp) store_pair(p.cache + (size_t)k * ld, pr, coef2[(kFirstAB2 + k) * kCoopPairs], act[1]);
@@ -310,16 +358,17 @@ __global__ void __launch_bounds__(NW * 32, NW == 4 ? 2 : 1) f16_step_coop_kernel
           nlplant_kin_moments(sq, uq[2], uq[3], 0.0f, g, fp.qbar, fp.vt, fp.b, fp.t, cq, CS, a1, xdot);
           xdot[6] = fp.f.vt_dot; xdot[7] = fp.f.alpha_dot; xdot[8] = fp.f.beta_dot;
           const float h = c.dt - 0.0f;
+          const bool frozen = PLAN && (badq || doneq);  // planning_env.py:162-166: s <- recent_s (u keeps filtering)
 #pragma unroll
-          for (int j = 0; j < 12; ++j) sq[j] = sq[j] + h * xdot[j];
+          for (int j = 0; j < 12; ++j) sq[j] = frozen ? sq[j] : sq[j] + h * xdot[j];
           stepq += 1;
           xa[(q1 ? kCoopPairs : 0) + lane] = sq[7];
           xb[(q1 ? kCoopPairs : 0) + lane] = sq[8];
         } else {
           const Verdict v = judge_state<false, TASK>(c, sq, tq, g, fp.f, stepq);
-          excq = v.exc; badq = v.bad; doneq = v.done;
+          excq |= v.exc; badq |= v.bad; doneq |= v.done;                           // OR-accumulated over the sub-steps
           rewq = v.rw + (float)(-200 * (int)badq + 200 * (int)doneq);
-          causesq = actq ? v.causes : 0;
+          causesq |= actq ? v.causes : 0;
         }
       }
       if (pass == 0) {
@@ -330,6 +379,7 @@ __global__ void __launch_bounds__(NW * 32, NW == 4 ? 2 : 1) f16_step_coop_kernel
         be = make_float2(xb[lane], xb[kCoopPairs + lane]);
       }
     }
+    }  // sub-steps
 
     if (owner) {
 #pragma unroll
@@ -342,6 +392,10 @@ __global__ void __launch_bounds__(NW * 32, NW == 4 ? 2 : 1) f16_step_coop_kernel
 #pragma unroll
         for (int j = 0; j < 3; ++j) p.tgt[(size_t)j * ld + row] = tq[j];
         p.reward[row] = rewq;
+        if constexpr (PLAN) {
+#pragma unroll
+          for (int j = 0; j < kPidRows; ++j) p.pid[(size_t)j * ld + row] = pid[j];
+        }
         p.step_count[row] = stepq;
         p.flags[row] = doneq ? 1 : 0;
         p.flags[ld + row] = badq ? 1 : 0;

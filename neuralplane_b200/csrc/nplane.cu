@@ -946,6 +946,61 @@ static int launch_env_step(np_env* env, const StepParams& p, cudaStream_t st) {
   }
 }
 
+// K1c (coop_step_kernel.cuh): populations of up to one wave of its CTAs, MLP aero back-end, no forced CTA shape
+static bool coop_eligible(const np_env* env, const StepParams& p) {
+  return env->coop_pairs > 0 && !env->block && !env->tables && p.pair_end - p.pair_begin <= env->coop_pairs;
+}
+template <bool PLAN>
+static int launch_coop(np_env* env, const StepParams& p, cudaStream_t st) {
+  const int npairs = p.pair_end - p.pair_begin;
+  if (npairs <= 0) return NP_OK;
+  const int smem = coop_smem_bytes(p.aero_bytes);
+  const int want = (npairs + kCoopPairs - 1) / kCoopPairs;
+  // eight warps while one CTA per SM covers the population (9 472 aircraft), four (two CTAs per SM) up to 18 944
+  const int nw = env->coop_warps ? env->coop_warps : (want <= env->num_sms ? 8 : 4);
+  const int per_sm = nw == 8 ? 1 : 2;
+  env->grid = want < env->num_sms * per_sm ? want : env->num_sms * per_sm;
+  if (env->coop_grid > 0 && env->grid > env->coop_grid) env->grid = env->coop_grid;
+  env->smem = smem;
+  env->last_block = nw * 32;
+  static int configured[64][8] = {};
+  auto launch = [&](auto kern, int t) -> int {
+    if (configured[env->device & 63][t] < smem) {
+      NP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      configured[env->device & 63][t] = smem;
+    }
+    // programmatic dependent launch: the CTAs may start (and stage the aero image) while the previous kernel of the stream drains
+    cudaLaunchConfig_t lc = {};
+    lc.gridDim = dim3(env->grid);
+    lc.blockDim = dim3(nw * 32);
+    lc.dynamicSmemBytes = smem;
+    lc.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    lc.attrs = at;
+    lc.numAttrs = env->pdl ? 1 : 0;
+    NP_CUDA(cudaLaunchKernelEx(&lc, kern, p));
+    return NP_OK;
+  };
+  if constexpr (PLAN) {   // PlanningEnv flies the tracking task (planning_env.py:33)
+    return nw == 8 ? launch(f16_step_coop_kernel<NP_TASK_TRACKING, 8, true>, 6) : launch(f16_step_coop_kernel<NP_TASK_TRACKING, 4, true>, 7);
+  } else {
+    if (nw == 8) {
+      switch (env->cfg.task) {
+        case NP_TASK_HEADING: return launch(f16_step_coop_kernel<NP_TASK_HEADING, 8>, 3);
+        case NP_TASK_CONTROL: return launch(f16_step_coop_kernel<NP_TASK_CONTROL, 8>, 4);
+        default: return launch(f16_step_coop_kernel<NP_TASK_TRACKING, 8>, 5);
+      }
+    }
+    switch (env->cfg.task) {
+      case NP_TASK_HEADING: return launch(f16_step_coop_kernel<NP_TASK_HEADING, 4>, 0);
+      case NP_TASK_CONTROL: return launch(f16_step_coop_kernel<NP_TASK_CONTROL, 4>, 1);
+      default: return launch(f16_step_coop_kernel<NP_TASK_TRACKING, 4>, 2);
+    }
+  }
+}
+
 // Block size of the MLP step for a range of `npairs` aircraft pairs.  384 threads (12 warps, 168 registers, no spills) is the
 // fastest shape per SM; 512 (16 warps at 128 registers, a few spills) runs at ~0.93 of its rate but covers a third more aircraft
 // per wave.  A persistent grid of 148 CTAs works in whole waves of 148 x BS pairs, so when the population is a small number
@@ -1243,51 +1298,7 @@ static int step_range_impl(np_env* env, const float* action_dev, const float* dr
       default: return fail(NP_EINVAL, "np_env_step: table back-end block size not compiled in (build with -DNPLANE_ALL_BLOCKS)");
     }
   }
-  if (env->coop_pairs > 0 && !env->block && p.pair_end - p.pair_begin <= env->coop_pairs) {   // K1c: the warps of a CTA share each pair's MLPs
-    const int npairs = p.pair_end - p.pair_begin;
-    if (npairs <= 0) return NP_OK;
-    const int smem = coop_smem_bytes(p.aero_bytes);
-    const int want = (npairs + kCoopPairs - 1) / kCoopPairs;
-    // eight warps while one CTA per SM covers the population (9 472 aircraft), four (two CTAs per SM) up to 18 944
-    const int nw = env->coop_warps ? env->coop_warps : (want <= env->num_sms ? 8 : 4);
-    const int per_sm = nw == 8 ? 1 : 2;
-    env->grid = want < env->num_sms * per_sm ? want : env->num_sms * per_sm;
-    if (env->coop_grid > 0 && env->grid > env->coop_grid) env->grid = env->coop_grid;
-    env->smem = smem;
-    env->last_block = nw * 32;
-    static int configured[64][6] = {};
-    auto launch = [&](auto kern, int t) -> int {
-      if (configured[env->device & 63][t] < smem) {
-        NP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        configured[env->device & 63][t] = smem;
-      }
-      // programmatic dependent launch: the CTAs may start (and stage the aero image) while the previous kernel of the stream drains
-      cudaLaunchConfig_t lc = {};
-      lc.gridDim = dim3(env->grid);
-      lc.blockDim = dim3(nw * 32);
-      lc.dynamicSmemBytes = smem;
-      lc.stream = st;
-      cudaLaunchAttribute at[1];
-      at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-      at[0].val.programmaticStreamSerializationAllowed = 1;
-      lc.attrs = at;
-      lc.numAttrs = env->pdl ? 1 : 0;
-      NP_CUDA(cudaLaunchKernelEx(&lc, kern, p));
-      return NP_OK;
-    };
-    if (nw == 8) {
-      switch (env->cfg.task) {
-        case NP_TASK_HEADING: return launch(f16_step_coop_kernel<NP_TASK_HEADING, 8>, 3);
-        case NP_TASK_CONTROL: return launch(f16_step_coop_kernel<NP_TASK_CONTROL, 8>, 4);
-        default: return launch(f16_step_coop_kernel<NP_TASK_TRACKING, 8>, 5);
-      }
-    }
-    switch (env->cfg.task) {
-      case NP_TASK_HEADING: return launch(f16_step_coop_kernel<NP_TASK_HEADING, 4>, 0);
-      case NP_TASK_CONTROL: return launch(f16_step_coop_kernel<NP_TASK_CONTROL, 4>, 1);
-      default: return launch(f16_step_coop_kernel<NP_TASK_TRACKING, 4>, 2);
-    }
-  }
+  if (coop_eligible(env, p)) return launch_coop<false>(env, p, st);   // K1c: the warps of a CTA share each pair's MLPs
   switch (pick_block(env, p.pair_end - p.pair_begin)) {
     case 128: return launch_env_step<128, 2>(env, p, st);   // two CTAs may share an SM (2 x 110 KB of shared memory)
 #ifdef NPLANE_ALL_BLOCKS
@@ -1396,9 +1407,15 @@ int np_env_plan_step(np_env* env, const float* action3_dev, int n_sub, const flo
   env->pid_started = true;
   env->step_index++;
   if (env->tables) return launch_step<384, 1, MODE_PLAN, true, NP_TASK_TRACKING>(env, p, (cudaStream_t)stream);
+  // train_tracking.sh flies 10 000 planning envs: K1c up to 18 944 aircraft, 128-thread CTAs up to 75 776 (latency bound, as the step)
+  if (coop_eligible(env, p)) return launch_coop<true>(env, p, (cudaStream_t)stream);
   // a strong-scaling shard (125 k aircraft = 1.1 waves of 148 x 384 pairs) runs in ONE wave of 512-thread CTAs (pick_block)
-  if (pick_block(env, p.pair_end - p.pair_begin) == 512) return launch_step<512, 1, MODE_PLAN, false, NP_TASK_TRACKING>(env, p, (cudaStream_t)stream);
-  return launch_step<384, 1, MODE_PLAN, false, NP_TASK_TRACKING>(env, p, (cudaStream_t)stream);
+  switch (pick_block(env, p.pair_end - p.pair_begin)) {
+    case 128: return launch_step<128, 2, MODE_PLAN, false, NP_TASK_TRACKING>(env, p, (cudaStream_t)stream);
+    case 512: return launch_step<512, 1, MODE_PLAN, false, NP_TASK_TRACKING>(env, p, (cudaStream_t)stream);
+    case 384: return launch_step<384, 1, MODE_PLAN, false, NP_TASK_TRACKING>(env, p, (cudaStream_t)stream);
+    default: return fail(NP_EINVAL, "np_env_plan_step: block size not compiled in for the planning step (128 / 384 / 512)");
+  }
 }
 
 int np_env_combat_step(np_env* env, const float* action_dev, int n_sub, const float* draws_dev, void* stream) {

@@ -44,8 +44,48 @@ def _push(env, orc, first):
     nv.check(nv.lib().np_env_set_pid_started(env._handle, 0 if first else 1), "np_env_set_pid_started")
 
 
+@pytest.fixture(params=["K1c", "K1"])
+def plan_kernel(request, monkeypatch):
+    """Planning populations up to 18 944 aircraft (train_tracking.sh: 10 000) run on K1c's PLAN instantiation by default; the
+    oracle tests at such sizes run once on it and once on K1's MODE_PLAN."""
+    if request.param == "K1":
+        monkeypatch.setenv("NPLANE_COOP_PAIRS", "0")
+    return request.param
+
+
+@pytest.mark.parametrize("n,n_sub", [(3000, 50), (10_001, 7), (63, 3), (18_944, 2)])
+def test_cooperative_planning_kernel_is_bit_identical(n, n_sub):
+    """K1c<PLAN> (coop_step_kernel.cuh) against K1<MODE_PLAN>: the same env steps -- PID stack, control lag, n_sub FDM sub-steps
+    with frozen terminated aircraft, episodic resets -- must agree in every output, the state, the controls, the controller
+    state and the counters, bit for bit."""
+    from neuralplane_b200 import PlanningEnv
+    kw = dict(num_envs=n, config="tracking", model="F16", random_seed=3, device="cuda:0", n_substeps=n_sub)
+    coop = PlanningEnv(**kw)
+    os.environ["NPLANE_COOP_PAIRS"] = "0"
+    try:
+        ref = PlanningEnv(**kw)
+    finally:
+        del os.environ["NPLANE_COOP_PAIRS"]
+    coop.reset(); ref.reset()
+    for k in range(1, 13):
+        a = _cuda(tapes.action_tape(3, k, n, 1.0, num_actions=3))
+        for x, y in zip(coop.step(a)[:5], ref.step(a)[:5]):
+            assert torch.equal(x, y), k
+        assert torch.equal(coop.pid_state, ref.pid_state), k
+        if k % 4 == 0:
+            for e in (coop, ref):
+                e.is_done[::7] = True
+                e.bad_done[3::64] = True
+    li, lr = coop.launch_info(), ref.launch_info()
+    assert li["block"] == (256 if n <= 148 * 64 else 128) and li["grid"] == (n + 63) // 64, li
+    assert lr["block"] == 128 and lr["grid"] == (n + 255) // 256, lr
+    assert torch.equal(coop.model.s, ref.model.s) and torch.equal(coop.model.u, ref.model.u)
+    assert torch.equal(coop.step_count, ref.step_count)
+    assert coop.termination_counters() == ref.termination_counters() and coop.termination_counters()["resets"] > 0
+
+
 @pytest.mark.parametrize("n_sub", [1, 5])
-def test_teacher_forced_substeps_vs_oracle(n_sub):
+def test_teacher_forced_substeps_vs_oracle(n_sub, plan_kernel):
     from oracle.planning_oracle import PlanningOracle
     n, seed, iters = 2048, 23, 40 if n_sub == 1 else 12
     env, orc = _env(n, n_sub), PlanningOracle(n)

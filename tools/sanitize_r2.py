@@ -62,6 +62,15 @@ m = MultipleCombatEnv(num_envs=500, random_seed=1, device=dev)
 m.reset()
 for k in range(3):
     m.step(torch.rand((m.n, 4), device=dev) - 0.5)
+for n_plan, var in ((513, None), (12_001, None), (513, "NPLANE_COOP_PAIRS")):   # K1c<PLAN> with 8 / 4 warps, K1<128, MODE_PLAN>
+    if var:
+        os.environ[var] = "0"
+    p = PlanningEnv(num_envs=n_plan, config="tracking", model="F16", random_seed=1, device=dev, n_substeps=3)
+    if var:
+        del os.environ[var]
+    p.reset()
+    for k in range(2):
+        p.step(torch.rand((n_plan, 3), device=dev) - 0.5)
 p = PlanningEnv(num_envs=513, config="tracking", model="F16_tables", random_seed=1, device=dev, n_substeps=3)
 p.reset()
 p.step(torch.rand((513, 3), device=dev) - 0.5)
