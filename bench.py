@@ -358,7 +358,20 @@ def side_small_n(dev, barrier, n=3000, K=200, W=20):
     return {"workload": f"F16 Heading task, ControlEnv, num_agents={n} (the reference's training population)",
             "us_per_step": ms * 1e3, "aircraft_steps_per_s": n / (ms * 1e-3), "how": "device-resident step under CUDA-graph replay",
             "e2e_us_per_step": e2e_us, "e2e_aircraft_steps_per_s": n / (e2e_us * 1e-6), "e2e_boundary": venv.boundary,
-            "launch": env.launch_info()}
+            "launch": env.launch_info(), "planning_10000_envs": side_plan_small(dev, barrier)}
+
+
+def side_plan_small(dev, barrier, n=10_000, K=20, W=5):
+    """scripts/train_tracking.sh: PlanningEnv at 10 000 envs, 50 FDM sub-steps per env step under the fused PID controller."""
+    import torch
+    from neuralplane_b200 import PlanningEnv
+    env = PlanningEnv(num_envs=n, config="tracking", random_seed=0, device=dev)
+    env.reset()
+    acts = [torch.rand((n, 3), device=dev) * 2 - 1 for _ in range(2)]
+    ms = timed_steps(lambda k: env.step(acts[k % 2]), K, W, barrier) / K
+    return {"workload": f"F16 Tracking task, PlanningEnv, fused PID low-level controller, num_agents={n} (the reference's training population)",
+            "sub_steps": env.n_substeps, "ms_per_env_step": ms, "us_per_fdm_substep": ms * 1e3 / env.n_substeps,
+            "fdm_steps_per_s": n * env.n_substeps / (ms * 1e-3), "launch": env.launch_info()}
 
 
 def main():

@@ -77,11 +77,6 @@ __device__ __forceinline__ void coop_static_for(F&& f) {
   }
 }
 static_assert(kCoopGroupK0[0] - kFirstAB2 == 0 && kCoopGroupK0[5] + 3 - kFirstAB2 == kNumAB2, "K1c: group table vs net enum");
-#ifdef NPLANE_COOP_ROLLED   // experiment: keep the two passes rolled (smaller code)
-#define NP_COOP_UNROLL_PASS _Pragma("unroll 1")
-#else
-#define NP_COOP_UNROLL_PASS
-#endif
 #ifdef NPLANE_COOP_TIMING   // debug build (tools/k1c_phases.py): per-warp clock stamps of CTA 0, left in the first obs rows
 #define NP_COOP_STAMP_INIT() __shared__ long long np_stamps[8][10]; long long* stamps = np_stamps[warp]; const long long t_start = clock64()
 #define NP_COOP_STAMP(i) do { if (lane == 0) stamps[i] = clock64() - t_start; } while (0)
@@ -293,7 +288,6 @@ __global__ void __launch_bounds__(NW * 32, NW == 4 ? 2 : 1) f16_step_coop_kernel
       __syncthreads();   // the new elevator of both aircraft; the verdict of the last sub-step has read its slots
       el = make_float2(xe[lane], xe[kCoopPairs + lane]);
     }
-    NP_COOP_UNROLL_PASS
     for (int pass = 0; pass < 2; ++pass) {
       const float2 adeg = make_float2(al.x * kR2D, al.y * kR2D);
       const float2 bdeg = make_float2(be.x * kR2D, be.y * kR2D);
