@@ -1418,6 +1418,16 @@ int np_env_plan_step(np_env* env, const float* action3_dev, int n_sub, const flo
   }
 }
 
+// K5 by population, as the step: 128-thread CTAs up to 75 776 aircraft (latency bound), 384, 512 where that saves a wave
+static int launch_combat(np_env* env, const StepParams& p, cudaStream_t st) {
+  switch (pick_block(env, p.pair_end - p.pair_begin)) {
+    case 128: return launch_step<128, 2, MODE_COMBAT>(env, p, st);
+    case 512: return launch_step<512, 1, MODE_COMBAT>(env, p, st);
+    case 384: return launch_step<384, 1, MODE_COMBAT>(env, p, st);
+    default: return fail(NP_EINVAL, "np_env_combat_step: block size not compiled in for the combat step (128 / 384 / 512)");
+  }
+}
+
 int np_env_combat_step(np_env* env, const float* action_dev, int n_sub, const float* draws_dev, void* stream) {
   if (!env || !env->bound) return fail(NP_ESTATE, "np_env_combat_step: env not bound");
   if (env->cfg.model != NP_MODEL_F16 || (env->cfg.n & 1)) return fail(NP_EINVAL, "np_env_combat_step: needs the F16 plug-in and an even population (pairs)");
@@ -1430,8 +1440,7 @@ int np_env_combat_step(np_env* env, const float* action_dev, int n_sub, const fl
   if (n_sub > 0) env->pid_started = true;
   env->step_index++;
   if (env->tables) return launch_step<384, 1, MODE_COMBAT, true>(env, p, (cudaStream_t)stream);
-  if (pick_block(env, p.pair_end - p.pair_begin) == 512) return launch_step<512, 1, MODE_COMBAT>(env, p, (cudaStream_t)stream);
-  return launch_step<384, 1, MODE_COMBAT>(env, p, (cudaStream_t)stream);
+  return launch_combat(env, p, (cudaStream_t)stream);
 }
 
 // Role-sharded combat step, local half: np_env_combat_step for a rank that holds ONE aircraft of every env (all egos or all
@@ -1449,8 +1458,7 @@ int np_env_combat_role_local(np_env* env, const float* action_dev, int n_sub, co
   if (n_sub > 0) env->pid_started = true;
   p.records = records_dev;
   env->step_index++;
-  if (pick_block(env, p.pair_end - p.pair_begin) == 512) return launch_step<512, 1, MODE_COMBAT>(env, p, (cudaStream_t)stream);
-  return launch_step<384, 1, MODE_COMBAT>(env, p, (cudaStream_t)stream);
+  return launch_combat(env, p, (cudaStream_t)stream);
 }
 
 // Role-sharded combat step, pair half (combat_pair_kernel): to be enqueued after a cross-device barrier that makes the

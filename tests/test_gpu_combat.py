@@ -295,6 +295,38 @@ def test_role_sharded_step_is_bit_identical_to_pair_sharded():
     assert cp["crash_or_shutdown"] == c0["crash_or_shutdown"] + c1["crash_or_shutdown"]
 
 
+def test_combat_cta_shape_is_bit_identical():
+    """Small combat populations run K5 with 128-thread CTAs (latency bound, like the step); the shape must not change a bit:
+    3 000 envs on the default dispatch against the 384-thread shape (NPLANE_BLOCK=384), with Crash / Shutdown / resets."""
+    import os
+    from neuralplane_b200 import SingleCombatEnv
+    E = 3000
+    kw = dict(num_envs=E, config="selfplay", random_seed=11, device="cuda:0")
+    small = SingleCombatEnv(**kw)
+    os.environ["NPLANE_BLOCK"] = "384"
+    try:
+        ref = SingleCombatEnv(**kw)
+    finally:
+        del os.environ["NPLANE_BLOCK"]
+    assert torch.equal(small.reset(), ref.reset())
+    for e in (small, ref):                     # a third of the pairs inside the crash radius / gun range
+        close = torch.arange(E, device="cuda") % 3 == 0
+        s = e.model.s
+        s[1::2][close, 0] = s[0::2][close, 0] + 150.0
+        s[1::2][close, 1] = s[0::2][close, 1]
+        s[1::2][close, 2] = s[0::2][close, 2] + 15.0
+        e.blood[1::18] = 0.4
+    g = torch.Generator(device="cuda").manual_seed(4)
+    for k in range(12):
+        a = torch.rand((2 * E, 4), device="cuda", generator=g) - 0.5
+        for x, y in zip(small.step(a)[:5], ref.step(a)[:5]):
+            assert torch.equal(x, y), k
+    assert small.launch_info()["block"] == 128 and ref.launch_info()["block"] == 384
+    assert torch.equal(small.model.s, ref.model.s) and torch.equal(small.blood, ref.blood)
+    c = small.termination_counters()
+    assert c == ref.termination_counters() and c["crash_or_shutdown"] > 0 and c["resets"] > 2 * E
+
+
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
 def test_role_sharded_step_two_ranks():
     """The same comparison across two processes / GPUs with both real exchanges (NVLink peer slabs; NCCL all-gather)."""
