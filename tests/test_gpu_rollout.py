@@ -120,3 +120,54 @@ def test_zero_copy_rollout_with_native_env():
     assert np.array_equal(buf.returns.cpu().numpy(), want)
     buf.after_update()
     assert torch.equal(buf.obs[0], buf.obs[-1])
+
+
+def test_whole_rollout_in_one_cuda_graph():
+    """The B200-idiomatic way to run the reference's training population (3 000 envs): the whole rollout -- a device policy,
+    env.step writing obs / reward in place, mask derivation, value / action inserts, for all T slots -- captured ONCE in a CUDA
+    graph and replayed per PPO iteration (env.advance_rng(T) inside the graph keeps the reset / noise streams moving).
+    Two replays, with compute_returns + after_update between them, must fill the buffer exactly like 2 x T eager steps."""
+    from neuralplane_b200 import ControlEnv
+    from neuralplane_b200.rollout import DeviceRolloutBuffer
+    T, N = 32, 3000
+    mk = lambda: ControlEnv(num_envs=N, config="heading", model="F16", random_seed=7, device="cuda:0")  # noqa: E731
+    W = torch.randn((22, 4), device="cuda", generator=torch.Generator(device="cuda").manual_seed(2)) * 8.0   # saturating: episodes end
+
+    def policy(obs):                       # a deterministic stand-in for the actor: any capturable torch code
+        x = obs.view(-1, 22)
+        return torch.tanh(x @ W), (x[:, :1] * 0.1).view(N, 1, 1)
+
+    def rollout(buf, env):
+        for t in range(T):
+            a, v = policy(buf.obs[t])
+            buf.step_env(env, a, None, v)
+
+    envs, bufs = [mk(), mk()], []
+    for env in envs:
+        buf = DeviceRolloutBuffer(_args(T, N), env.num_agents, env.observation_space, env.action_space, "cuda:0")
+        buf.attach(env)
+        env.reset()
+        bufs.append(buf)
+    (env_g, env_e), (buf_g, buf_e) = envs, bufs
+    # one warm-up rollout on both (first launches configure the kernels), then capture the graph on env_g
+    for env, buf in zip(envs, bufs):
+        rollout(buf, env)
+        buf.compute_returns(torch.zeros((N, 1, 1), device="cuda")); buf.after_update()
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        rollout(buf_g, env_g)
+        env_g.advance_rng(T)
+    assert buf_g.step == 0
+    for it in range(2):
+        g.replay()
+        rollout(buf_e, env_e)
+        for buf in bufs:
+            buf.compute_returns(torch.zeros((N, 1, 1), device="cuda"))
+        torch.cuda.synchronize()
+        for name in ("obs", "rewards", "masks", "bad_masks", "actions", "value_preds", "returns"):
+            assert torch.equal(getattr(buf_g, name), getattr(buf_e, name)), (it, name)
+        for buf in bufs:
+            buf.after_update()
+    assert torch.equal(env_g.model.s, env_e.model.s) and env_g.termination_counters() == env_e.termination_counters()
+    assert env_g.termination_counters()["resets"] > N + 100          # episodes ended and were reset inside the graph
