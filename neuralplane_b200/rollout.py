@@ -162,11 +162,12 @@ class DeviceRolloutBuffer:
                                        self.masks[t + 1].data_ptr(), self.bad_masks[t + 1].data_ptr(), self.reset_env.data_ptr(),
                                        torch.cuda.current_stream(self.device).cuda_stream)
         nv.check(st, "np_rollout_masks")
-        keep = (self.reset_env == 0).to(torch.float32).view(-1, 1, 1, 1)
-        if rnn_states_actor is not None:
-            self.rnn_states_actor[t + 1].copy_(rnn_states_actor.reshape(self.rnn_states_actor[t + 1].shape) * keep)
-        if rnn_states_critic is not None:
-            self.rnn_states_critic[t + 1].copy_(rnn_states_critic.reshape(self.rnn_states_critic[t + 1].shape) * keep)
+        if rnn_states_actor is not None or rnn_states_critic is not None:
+            keep = (self.reset_env == 0).to(torch.float32).view(-1, 1, 1, 1)
+            if rnn_states_actor is not None:
+                self.rnn_states_actor[t + 1].copy_(rnn_states_actor.reshape(self.rnn_states_actor[t + 1].shape) * keep)
+            if rnn_states_critic is not None:
+                self.rnn_states_critic[t + 1].copy_(rnn_states_critic.reshape(self.rnn_states_critic[t + 1].shape) * keep)
         self._put(self.actions[t], a)
         self._put(self.action_log_probs[t], action_log_probs)
         self._put(self.value_preds[t], value_preds)
