@@ -87,7 +87,7 @@ static_assert(kCoopGroupK0[0] - kFirstAB2 == 0 && kCoopGroupK0[5] + 3 - kFirstAB
 #define NP_COOP_STAMP_FLUSH() do { } while (0)
 #endif
 static int coop_smem_bytes(int aero_bytes) {
-  return aero_bytes + kNumSlots * kCoopPairs * 8 + kObsTileFloats * 4 + 6 * kCoopPairs * 4 + 16;
+  return aero_bytes + kNumSlots * kCoopPairs * 8 + kObsTileFloats * 4 + 12 * kCoopPairs * 4 + 16;
 }
 
 // PLAN = true: PlanningEnv.step (planning_env.py:144-177) -- K1's MODE_PLAN on the same CTA shape.  train_tracking.sh runs it
@@ -95,9 +95,14 @@ static int coop_smem_bytes(int aero_bytes) {
 // times per launch.  Warps 0 / 1 run their aircraft's controller and control lag at the top of every sub-step and publish the
 // new elevator deflection (the one control the nets see) through shared memory; state, controller state and flags stay in
 // their registers for the whole env step; the observation row is produced in the last sub-step only.
-template <int TASK, int NW, bool PLAN = false>
+// MODE_COMBAT: SingleCombatEnv.step / MultipleCombatEnv.step, pair-sharded (K1's MODE_COMBAT without p.records): the lane's two
+// aircraft are the duel.  Warps 0 / 1 run the attitude-demand controller per sub-step, exchange their new positions with the
+// (alpha, beta) hand-off for the Crash check, and after the last sub-step warp 1 hands its aircraft to warp 0, which produces
+// the pair's 15-D observations, rewards and blood exactly as K1's thread does (combat_outputs).
+template <int TASK, int NW, int MODE = MODE_STEP>
 __global__ void __launch_bounds__(NW * 32, NW == 4 ? 2 : 1) f16_step_coop_kernel(const __grid_constant__ StepParams p) {
   static_assert(NW == 4 || NW == 8, "K1c: four or eight warps");
+  constexpr bool PLAN = MODE == MODE_PLAN, COMBAT = MODE == MODE_COMBAT, SUBSTEPS = PLAN || COMBAT;
   constexpr int V = NW == 8 ? 1 : 0;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   float* blob = reinterpret_cast<float*>(smem_raw);
@@ -105,8 +110,9 @@ __global__ void __launch_bounds__(NW * 32, NW == 4 ? 2 : 1) f16_step_coop_kernel
   float* otile = reinterpret_cast<float*>(coef_all + kNumSlots * kCoopPairs);  // the CTA's 64 observation rows
   float* xa = otile + kObsTileFloats;                                        // [2][32]: alpha' of aircraft q of pair `lane`
   float* xb = xa + 2 * kCoopPairs;                                           // [2][32]: beta'
-  float* xe = xb + 2 * kCoopPairs;                                           // [2][32]: elevator after the control lag (PLAN)
-  uint64_t* bar = reinterpret_cast<uint64_t*>(xe + 2 * kCoopPairs);
+  float* xe = xb + 2 * kCoopPairs;                                           // [2][32]: elevator after the control lag (PLAN / COMBAT)
+  float* xp = xe + 2 * kCoopPairs;                                           // [2][3][32]: position after the Euler step (COMBAT: Crash)
+  uint64_t* bar = reinterpret_cast<uint64_t*>(xp + 6 * kCoopPairs);
 
   stage_aero_issue(blob, p.aero, (uint32_t)p.aero_bytes, bar);   // waited for below, behind the first state loads
   // Launched with programmatic stream serialisation: everything above (CTA start-up, the image copies: immutable data) may
@@ -134,7 +140,7 @@ __global__ void __launch_bounds__(NW * 32, NW == 4 ? 2 : 1) f16_step_coop_kernel
     const int prl = pr < pend ? pr : pend - 1;
     const bool act[2] = {pr < pend && 2 * pr < n, pr < pend && 2 * pr + 1 < n};
     const int idx[2] = {min(2 * prl, n - 1), min(2 * prl + 1, n - 1)};
-    const bool staged = __all_sync(0xffffffffu, act[1]) && ((reinterpret_cast<uintptr_t>(p.obs) & 15) == 0);
+    const bool staged = !COMBAT && __all_sync(0xffffffffu, act[1]) && ((reinterpret_cast<uintptr_t>(p.obs) & 15) == 0);
 
     // ---- load (every warp: both aircraft of the lane's pair) ---------------------------------------------------
     float s[2][12], u[2][4], tgt[2][3], a[2][4];
@@ -152,7 +158,7 @@ __global__ void __launch_bounds__(NW * 32, NW == 4 ? 2 : 1) f16_step_coop_kernel
     }
 #pragma unroll
     for (int j = 0; j < 3; ++j) {
-      const float2 v = reinterpret_cast<const float2*>(p.tgt + (size_t)j * ld)[prl];
+      const float2 v = COMBAT ? make_float2(0.f, 0.f) : reinterpret_cast<const float2*>(p.tgt + (size_t)j * ld)[prl];
       tgt[0][j] = v.x; tgt[1][j] = v.y;
     }
     {
@@ -174,7 +180,7 @@ __global__ void __launch_bounds__(NW * 32, NW == 4 ? 2 : 1) f16_step_coop_kernel
         if (ow == warp) coef2[(kFirstAB2 + k) * kCoopPairs] = reinterpret_cast<const float2*>(p.cache + (size_t)k * ld)[prl];
       });
     }
-    if constexpr (!PLAN) {
+    if constexpr (!SUBSTEPS) {
 #pragma unroll
       for (int q = 0; q < 2; ++q) {
         const float4 av = reinterpret_cast<const float4*>(p.action)[idx[q]];
@@ -191,12 +197,26 @@ __global__ void __launch_bounds__(NW * 32, NW == 4 ? 2 : 1) f16_step_coop_kernel
     const AeroTabs tabs = aero_tabs(blob, wb0);
     const float* c0 = blob + reinterpret_cast<const int32_t*>(blob)[kHdrC0];
 
-    // ---- episodic reset (env_base.py:83-97) -----------------------------------------------------------------------
+    // ---- episodic reset (env_base.py:83-97); COMBAT: env-level (singlecombat_env.py:207-238), either flag re-initialises the pair
+    float blood[2] = {0.f, 0.f};
+    if constexpr (COMBAT) {
+      const float2 bv = reinterpret_cast<const float2*>(p.blood)[prl];
+      blood[0] = bv.x; blood[1] = bv.y;
+      bool r = rst[0] || rst[1];
+      // MultipleCombat (multiplecombat_env.py:207-238): an env is TWO adjacent duels = two adjacent lanes; any flag resets all four
+      if (c.combat_pairs_per_env == 2) r |= __shfl_xor_sync(0xffffffffu, (int)r, 1) != 0;
+      rst[0] = rst[1] = r;
+    }
 #pragma unroll
     for (int q = 0; q < 2; ++q) {
       if (rst[q]) {
         const Draws r = reset_draws(p, idx[q], rng);
-        reset_aircraft(c, TASK, r, s[q], u[q], tgt[q]);
+        if constexpr (COMBAT) {
+          combat_reset_aircraft(c, r, s[q], u[q]);
+          blood[q] = 100.0f;
+        } else {
+          reset_aircraft(c, TASK, r, s[q], u[q], tgt[q]);
+        }
         steps[q] = 0;
       }
     }
@@ -221,8 +241,8 @@ __global__ void __launch_bounds__(NW * 32, NW == 4 ? 2 : 1) f16_step_coop_kernel
       });
     }
 
-    // ---- control lag (F16_model.py:52-57); PLAN: per sub-step, by the warp that flies the aircraft ---------------------
-    if constexpr (!PLAN) {
+    // ---- control lag (F16_model.py:52-57); PLAN / COMBAT: per sub-step, by the warp that flies the aircraft ---------------
+    if constexpr (!SUBSTEPS) {
 #pragma unroll
       for (int q = 0; q < 2; ++q) {
 #pragma unroll
@@ -252,7 +272,16 @@ __global__ void __launch_bounds__(NW * 32, NW == 4 ? 2 : 1) f16_step_coop_kernel
     float rewq = 0.0f;
     int causesq = 0;
     // planning step: targets from the high-level action (planning_env.py:146-152) and the controller state, owner warps only
-    float plan_tgt[3] = {0.f, 0.f, 0.f}, pid[PLAN ? kPidRows : 1];
+    float plan_tgt[3] = {0.f, 0.f, 0.f}, a_cmd[4] = {0.f, 0.f, 0.f, 0.f}, pid[SUBSTEPS ? kPidRows : 1];
+    if constexpr (COMBAT) {   // the caller's clamped 4-D action, kept for all sub-steps, and the controller state
+      if (owner) {
+        const float4 av = reinterpret_cast<const float4*>(p.action)[idxq];
+        a_cmd[0] = fminf(fmaxf(av.x, -1.0f), 1.0f); a_cmd[1] = fminf(fmaxf(av.y, -1.0f), 1.0f);
+        a_cmd[2] = fminf(fmaxf(av.z, -1.0f), 1.0f); a_cmd[3] = fminf(fmaxf(av.w, -1.0f), 1.0f);
+#pragma unroll
+        for (int j = 0; j < kPidRows; ++j) pid[j] = p.pid[(size_t)j * ld + idxq];
+      }
+    }
     if constexpr (PLAN) {
       if (owner) {
         float a3[3];
@@ -265,7 +294,7 @@ __global__ void __launch_bounds__(NW * 32, NW == 4 ? 2 : 1) f16_step_coop_kernel
         for (int j = 0; j < kPidRows; ++j) pid[j] = p.pid[(size_t)j * ld + idxq];
       }
     }
-    const int nsub = PLAN ? p.n_sub : 1;
+    const int nsub = SUBSTEPS ? p.n_sub : 1;
 
     if (!first_iter && threadIdx.x == 0) bulk_wait_read0();   // the tile may still be being read by the previous bulk store
     first_iter = false;
@@ -273,10 +302,11 @@ __global__ void __launch_bounds__(NW * 32, NW == 4 ? 2 : 1) f16_step_coop_kernel
     NP_COOP_STAMP(0);
 #pragma unroll 1
     for (int sub = 0; sub < nsub; ++sub) {
-    if constexpr (PLAN) {
+    if constexpr (SUBSTEPS) {
       if (owner) {   // the PID stack (ctrl_device.cuh) and the control lag of this FDM sub-step
         float a4[4];
-        pid_controller(sq, c.airspeed, c.dt, plan_tgt[0], plan_tgt[1], plan_tgt[2], pid, p.pid_first != 0 && sub == 0, a4);
+        if constexpr (PLAN) pid_controller(sq, c.airspeed, c.dt, plan_tgt[0], plan_tgt[1], plan_tgt[2], pid, p.pid_first != 0 && sub == 0, a4);
+        else combat_controller(sq, c.airspeed, c.dt, a_cmd, pid, p.pid_first != 0 && sub == 0, a4);
 #pragma unroll
         for (int j = 0; j < 4; ++j) a4[j] = fminf(fmaxf(a4[j], -1.0f), 1.0f);
         uq[0] = 0.9f * uq[0] + 0.1f * a4[0] * 0.225f * 76300.0f / DC(0.3048f);
@@ -317,7 +347,7 @@ __global__ void __launch_bounds__(NW * 32, NW == 4 ? 2 : 1) f16_step_coop_kernel
         g = make_trig(sq);
         tp = tfac_pow(sq[2]);
         alpha_coefs<kNumUsed - kFirstA1>(blob, tabs, seg, aq, a1);
-        if (pass == 1 && sub == nsub - 1) {   // the observation of the new state (env_base.py:103) needs no coefficient at all
+        if (!COMBAT && pass == 1 && sub == nsub - 1) {   // the observation of the new state (env_base.py:103) needs no coefficient at all
           float o[NP_NUM_OBS];
           make_obs(c, TASK, sq, uq, tq, g, eas2tas_of(tp), o);
           add_obs_noise(p, idxq, o, rng);
@@ -358,11 +388,26 @@ __global__ void __launch_bounds__(NW * 32, NW == 4 ? 2 : 1) f16_step_coop_kernel
           stepq += 1;
           xa[(q1 ? kCoopPairs : 0) + lane] = sq[7];
           xb[(q1 ? kCoopPairs : 0) + lane] = sq[8];
+          if constexpr (COMBAT) {
+#pragma unroll
+            for (int j = 0; j < 3; ++j) xp[((q1 ? 3 : 0) + j) * kCoopPairs + lane] = sq[j];
+          }
         } else {
-          const Verdict v = judge_state<false, TASK>(c, sq, tq, g, fp.f, stepq);
+          const Verdict v = judge_state<COMBAT, TASK>(c, sq, tq, g, fp.f, stepq);
           excq |= v.exc; badq |= v.bad; doneq |= v.done;                           // OR-accumulated over the sub-steps
           rewq = v.rw + (float)(-200 * (int)badq + 200 * (int)doneq);
           causesq |= actq ? v.causes : 0;
+          if constexpr (COMBAT) {   // pair conditions: Crash (crash.py:29-42) and Shutdown (shutdown.py:30-40); ego - enemy, as K1
+            const int po = (q1 ? 0 : 3) * kCoopPairs + lane;   // the partner's position after this sub-step
+            const float pn = xp[po], pe = xp[po + kCoopPairs], pa = xp[po + 2 * kCoopPairs];
+            const float dn0 = q1 ? pn - sq[0] : sq[0] - pn, de0 = q1 ? pe - sq[1] : sq[1] - pe, da0 = q1 ? pa - sq[2] : sq[2] - pa;
+            const bool crash = (dn0 * dn0 + de0 * de0 + da0 * da0) <= c.distance_limit * c.distance_limit;
+            const bool m1 = blood[0] <= 0.0f, m2 = blood[1] <= 0.0f;
+            const bool sd_done = m2 && !m1;
+            badq |= crash | m1;
+            doneq |= sd_done;
+            causesq |= actq ? (((int)(crash | m1) << 5) | ((int)sd_done << 6)) : 0;
+          }
         }
       }
       if (pass == 0) {
@@ -375,6 +420,23 @@ __global__ void __launch_bounds__(NW * 32, NW == 4 ? 2 : 1) f16_step_coop_kernel
     }
     }  // sub-steps
 
+    if constexpr (COMBAT) {   // warp 1 hands its final state to warp 0 (through the unused observation tile), which finishes the pair
+      if (warp == 1) {
+#pragma unroll
+        for (int j = 0; j < 12; ++j) otile[j * kCoopPairs + lane] = sq[j];
+      }
+      __syncthreads();
+      if (warp == 0) {
+        float sp[2][12], rw[2];
+#pragma unroll
+        for (int j = 0; j < 12; ++j) { sp[0][j] = sq[j]; sp[1][j] = otile[j * kCoopPairs + lane]; }
+        combat_outputs(p, sp, blood, rw, pr, act, nsub > 0);   // 15-D rows, rewards, blood (singlecombat_env.py:64-181,263-271)
+        if (act[0]) {
+          store_pair(p.blood, pr, make_float2(blood[0], blood[1]), act[1]);
+          store_pair(p.reward, pr, make_float2(rw[0], rw[1]), act[1]);
+        }
+      }
+    }
     if (owner) {
 #pragma unroll
       for (int w = 0; w < 7; ++w) count_cause1(p.counters, w, (causesq >> w) & 1);
@@ -383,10 +445,12 @@ __global__ void __launch_bounds__(NW * 32, NW == 4 ? 2 : 1) f16_step_coop_kernel
         for (int j = 0; j < 12; ++j) p.s[(size_t)j * ld + row] = sq[j];
 #pragma unroll
         for (int j = 0; j < 4; ++j) p.u[(size_t)j * ld + row] = uq[j];
+        if constexpr (!COMBAT) {
 #pragma unroll
-        for (int j = 0; j < 3; ++j) p.tgt[(size_t)j * ld + row] = tq[j];
-        p.reward[row] = rewq;
-        if constexpr (PLAN) {
+          for (int j = 0; j < 3; ++j) p.tgt[(size_t)j * ld + row] = tq[j];
+          p.reward[row] = rewq;
+        }
+        if constexpr (SUBSTEPS) {
 #pragma unroll
           for (int j = 0; j < kPidRows; ++j) p.pid[(size_t)j * ld + row] = pid[j];
         }

@@ -950,7 +950,7 @@ static int launch_env_step(np_env* env, const StepParams& p, cudaStream_t st) {
 static bool coop_eligible(const np_env* env, const StepParams& p) {
   return env->coop_pairs > 0 && !env->block && !env->tables && p.pair_end - p.pair_begin <= env->coop_pairs;
 }
-template <bool PLAN>
+template <int MODE>
 static int launch_coop(np_env* env, const StepParams& p, cudaStream_t st) {
   const int npairs = p.pair_end - p.pair_begin;
   if (npairs <= 0) return NP_OK;
@@ -963,7 +963,7 @@ static int launch_coop(np_env* env, const StepParams& p, cudaStream_t st) {
   if (env->coop_grid > 0 && env->grid > env->coop_grid) env->grid = env->coop_grid;
   env->smem = smem;
   env->last_block = nw * 32;
-  static int configured[64][8] = {};
+  static int configured[64][10] = {};
   auto launch = [&](auto kern, int t) -> int {
     if (configured[env->device & 63][t] < smem) {
       NP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -983,8 +983,10 @@ static int launch_coop(np_env* env, const StepParams& p, cudaStream_t st) {
     NP_CUDA(cudaLaunchKernelEx(&lc, kern, p));
     return NP_OK;
   };
-  if constexpr (PLAN) {   // PlanningEnv flies the tracking task (planning_env.py:33)
-    return nw == 8 ? launch(f16_step_coop_kernel<NP_TASK_TRACKING, 8, true>, 6) : launch(f16_step_coop_kernel<NP_TASK_TRACKING, 4, true>, 7);
+  if constexpr (MODE == MODE_PLAN) {   // PlanningEnv flies the tracking task (planning_env.py:33)
+    return nw == 8 ? launch(f16_step_coop_kernel<NP_TASK_TRACKING, 8, MODE_PLAN>, 6) : launch(f16_step_coop_kernel<NP_TASK_TRACKING, 4, MODE_PLAN>, 7);
+  } else if constexpr (MODE == MODE_COMBAT) {
+    return nw == 8 ? launch(f16_step_coop_kernel<NP_TASK_HEADING, 8, MODE_COMBAT>, 8) : launch(f16_step_coop_kernel<NP_TASK_HEADING, 4, MODE_COMBAT>, 9);
   } else {
     if (nw == 8) {
       switch (env->cfg.task) {
@@ -1298,7 +1300,7 @@ static int step_range_impl(np_env* env, const float* action_dev, const float* dr
       default: return fail(NP_EINVAL, "np_env_step: table back-end block size not compiled in (build with -DNPLANE_ALL_BLOCKS)");
     }
   }
-  if (coop_eligible(env, p)) return launch_coop<false>(env, p, st);   // K1c: the warps of a CTA share each pair's MLPs
+  if (coop_eligible(env, p)) return launch_coop<MODE_STEP>(env, p, st);   // K1c: the warps of a CTA share each pair's MLPs
   switch (pick_block(env, p.pair_end - p.pair_begin)) {
     case 128: return launch_env_step<128, 2>(env, p, st);   // two CTAs may share an SM (2 x 110 KB of shared memory)
 #ifdef NPLANE_ALL_BLOCKS
@@ -1408,7 +1410,7 @@ int np_env_plan_step(np_env* env, const float* action3_dev, int n_sub, const flo
   env->step_index++;
   if (env->tables) return launch_step<384, 1, MODE_PLAN, true, NP_TASK_TRACKING>(env, p, (cudaStream_t)stream);
   // train_tracking.sh flies 10 000 planning envs: K1c up to 18 944 aircraft, 128-thread CTAs up to 75 776 (latency bound, as the step)
-  if (coop_eligible(env, p)) return launch_coop<true>(env, p, (cudaStream_t)stream);
+  if (coop_eligible(env, p)) return launch_coop<MODE_PLAN>(env, p, (cudaStream_t)stream);
   // a strong-scaling shard (125 k aircraft = 1.1 waves of 148 x 384 pairs) runs in ONE wave of 512-thread CTAs (pick_block)
   switch (pick_block(env, p.pair_end - p.pair_begin)) {
     case 128: return launch_step<128, 2, MODE_PLAN, false, NP_TASK_TRACKING>(env, p, (cudaStream_t)stream);
@@ -1440,6 +1442,7 @@ int np_env_combat_step(np_env* env, const float* action_dev, int n_sub, const fl
   if (n_sub > 0) env->pid_started = true;
   env->step_index++;
   if (env->tables) return launch_step<384, 1, MODE_COMBAT, true>(env, p, (cudaStream_t)stream);
+  if (coop_eligible(env, p)) return launch_coop<MODE_COMBAT>(env, p, (cudaStream_t)stream);   // pair-sharded duels at small populations
   return launch_combat(env, p, (cudaStream_t)stream);
 }
 

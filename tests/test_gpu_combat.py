@@ -295,22 +295,29 @@ def test_role_sharded_step_is_bit_identical_to_pair_sharded():
     assert cp["crash_or_shutdown"] == c0["crash_or_shutdown"] + c1["crash_or_shutdown"]
 
 
-def test_combat_cta_shape_is_bit_identical():
-    """Small combat populations run K5 with 128-thread CTAs (latency bound, like the step); the shape must not change a bit:
-    3 000 envs on the default dispatch against the 384-thread shape (NPLANE_BLOCK=384), with Crash / Shutdown / resets."""
+@pytest.mark.parametrize("cls,E", [("single", 3000), ("single", 7001), ("multi", 1500)])
+def test_combat_kernel_shape_is_bit_identical(cls, E):
+    """Small combat populations run the pair-sharded step on K1c<MODE_COMBAT> (up to 18 944 aircraft) or on K5 with 128-thread
+    CTAs (latency bound, like the step).  Neither may change a bit: the default dispatch against K5 with 128-thread CTAs
+    (NPLANE_COOP_PAIRS=0) and against the 384-thread shape (NPLANE_BLOCK=384), 1-v-1 and 2-v-2, with Crash / Shutdown /
+    env-level resets occurring."""
     import os
-    from neuralplane_b200 import SingleCombatEnv
-    E = 3000
-    kw = dict(num_envs=E, config="selfplay", random_seed=11, device="cuda:0")
-    small = SingleCombatEnv(**kw)
-    os.environ["NPLANE_BLOCK"] = "384"
-    try:
-        ref = SingleCombatEnv(**kw)
-    finally:
-        del os.environ["NPLANE_BLOCK"]
-    assert torch.equal(small.reset(), ref.reset())
-    for e in (small, ref):                     # a third of the pairs inside the crash radius / gun range
-        close = torch.arange(E, device="cuda") % 3 == 0
+    from neuralplane_b200 import MultipleCombatEnv, SingleCombatEnv
+    mk = (lambda: SingleCombatEnv(num_envs=E, config="selfplay", random_seed=11, device="cuda:0")) if cls == "single" else \
+         (lambda: MultipleCombatEnv(num_envs=E, random_seed=11, device="cuda:0"))
+    envs = [mk()]
+    for var, val in (("NPLANE_COOP_PAIRS", "0"), ("NPLANE_BLOCK", "384")):
+        os.environ[var] = val
+        try:
+            envs.append(mk())
+        finally:
+            del os.environ[var]
+    coop, k128, k384 = envs
+    n = coop.n
+    o = [e.reset() for e in envs]
+    assert torch.equal(o[0], o[1]) and torch.equal(o[0], o[2])
+    for e in envs:                             # a third of the duels inside the crash radius / gun range, some nearly dead
+        close = torch.arange(n // 2, device="cuda") % 3 == 0
         s = e.model.s
         s[1::2][close, 0] = s[0::2][close, 0] + 150.0
         s[1::2][close, 1] = s[0::2][close, 1]
@@ -318,13 +325,21 @@ def test_combat_cta_shape_is_bit_identical():
         e.blood[1::18] = 0.4
     g = torch.Generator(device="cuda").manual_seed(4)
     for k in range(12):
-        a = torch.rand((2 * E, 4), device="cuda", generator=g) - 0.5
-        for x, y in zip(small.step(a)[:5], ref.step(a)[:5]):
-            assert torch.equal(x, y), k
-    assert small.launch_info()["block"] == 128 and ref.launch_info()["block"] == 384
-    assert torch.equal(small.model.s, ref.model.s) and torch.equal(small.blood, ref.blood)
-    c = small.termination_counters()
-    assert c == ref.termination_counters() and c["crash_or_shutdown"] > 0 and c["resets"] > 2 * E
+        a = torch.rand((n, 4), device="cuda", generator=g) - 0.5
+        r = [e.step(a) for e in envs]
+        for other in r[1:]:
+            for x, y in zip(r[0][:5], other[:5]):
+                assert torch.equal(x, y), k
+    li = coop.launch_info()
+    assert li["block"] == (256 if n <= 148 * 64 else 128) and li["grid"] == (n + 63) // 64, li
+    assert k128.launch_info()["block"] == 128 and k384.launch_info()["block"] == 384
+    for other in (k128, k384):
+        assert torch.equal(coop.model.s, other.model.s) and torch.equal(coop.model.u, other.model.u)
+        assert torch.equal(coop.blood, other.blood) and torch.equal(coop.ctrl_state, other.ctrl_state)
+        assert torch.equal(coop.step_count, other.step_count)
+        assert coop.termination_counters() == other.termination_counters()
+    c = coop.termination_counters()
+    assert c["crash_or_shutdown"] > 0 and c["resets"] > n
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")

@@ -74,6 +74,15 @@ for n_plan, var in ((513, None), (12_001, None), (513, "NPLANE_COOP_PAIRS")):   
 p = PlanningEnv(num_envs=513, config="tracking", model="F16_tables", random_seed=1, device=dev, n_substeps=3)
 p.reset()
 p.step(torch.rand((513, 3), device=dev) - 0.5)
+for E_c, var in ((300, None), (6001, None), (300, "NPLANE_COOP_PAIRS")):   # K1c<MODE_COMBAT> with 8 / 4 warps, K5 with 128-thread CTAs
+    if var:
+        os.environ[var] = "0"
+    c = SingleCombatEnv(num_envs=E_c, config="selfplay", random_seed=1, device=dev)
+    if var:
+        del os.environ[var]
+    c.reset()
+    for k in range(2):
+        c.step(torch.rand((2 * E_c, 4), device=dev) - 0.5)
 c = SingleCombatEnv(num_envs=300, config="selfplay", model="F16_tables", random_seed=1, device=dev)
 c.reset()
 c.step(torch.rand((600, 4), device=dev) - 0.5)
