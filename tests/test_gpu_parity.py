@@ -270,7 +270,7 @@ def test_single_step_random_envelope(dev, task):
     assert 0 < int(o_bad.sum()) < n and int(o_done.sum()) > 0      # the case exercises both branches
 
 
-def test_coef_cache_is_bit_identical(dev):
+def test_coef_cache_is_bit_identical(dev, step_kernel):
     """The (alpha,beta)-coefficient cache must not change a single bit of any output (200 steps with resets)."""
     n, seed = 512, 31
     e1, e2 = _env(n, "heading", use_coef_cache=True), _env(n, "heading", use_coef_cache=False)
