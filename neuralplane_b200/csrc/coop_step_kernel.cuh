@@ -1,5 +1,5 @@
-// K1c: BaseEnv.step for SMALL populations (the reference trains at 3 000 envs, scripts/train_heading.sh:13), where a step
-// is latency bound: its duration is one warp's pass through ~24 000 dependent instructions of K1, not a throughput.
+// K1c: BaseEnv.step -- and, by MODE, PlanningEnv.step and the pair-sharded combat step -- for SMALL populations (the reference
+// trains at 3 000 envs, scripts/train_heading.sh:13, and 10 000 planning envs, train_tracking.sh), where a step is latency bound: its duration is one warp's pass through ~24 000 dependent instructions of K1, not a throughput.
 // Included by nplane.cu after K1 (uses its StepParams, tile constants and device functions).
 //
 // The cure is to cut the pass, not to add aircraft: a CTA of NW = 4 or 8 warps flies 32 aircraft pairs (one pair per lane, as
@@ -222,7 +222,7 @@ __global__ void __launch_bounds__(NW * 32, NW == 4 ? 2 : 1) f16_step_coop_kernel
     }
     if (warp == 0) count_cause2(p.counters, 7, rst[0] && act[0], rst[1] && act[1]);
 
-    // ---- cache hit / reset constants / miss: the same decision in all four warps ------------------------------------
+    // ---- cache hit / reset constants / miss: the same decision in every warp ------------------------------------
     bool hit[2] = {rst[0], rst[1]};
     if (use_cache) {
       hit[0] |= __float_as_uint(ka.x) == __float_as_uint(s[0][7]) && __float_as_uint(kb.x) == __float_as_uint(s[0][8]);
