@@ -222,6 +222,18 @@ def run_reference(args, rank, world):
                                                "what": "the unmodified reference ControlEnv(device='cuda:0'): eager PyTorch on this B200"}
         except Exception as e:
             out["reference_cuda_eager"] = {"error": repr(e)[:300]}
+        # the population the reference itself trains at (scripts/train_heading.sh:13): our arm reports it under side.small_n_latency
+        try:
+            import torch
+            small = {"workload": "the unmodified reference ControlEnv, num_agents=3000 (scripts/train_heading.sh)", "steps": 20, "warmup": 3}
+            vs, es = time_reference_env(3000, "cpu", 3, 20, threads=os.cpu_count())
+            small["cpu"] = {"us_per_step": 1e6 * es / 20, "aircraft_steps_per_s": vs, "cores": os.cpu_count()}
+            if torch.cuda.is_available():
+                vs, es = time_reference_env(3000, "cuda:0", 3, 20)
+                small["cuda_eager"] = {"us_per_step": 1e6 * es / 20, "aircraft_steps_per_s": vs}
+            out["reference_small_n"] = small
+        except Exception as e:
+            out["reference_small_n"] = {"error": repr(e)[:300]}
     args.emit(out)
 
 
