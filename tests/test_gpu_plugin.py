@@ -178,6 +178,44 @@ def test_cooperative_small_population_kernel_is_bit_identical(config, n):
     assert coop.termination_counters()["resets"] > 0
 
 
+@pytest.mark.parametrize("env_name", ["control", "planning", "combat"])
+def test_cooperative_kernel_over_several_waves(env_name):
+    """The dispatch gives K1c at most one wave of CTAs, but its loop must also be right when a CTA flies several groups of 32
+    pairs (tile, coefficient slots and exchange rows reused across iterations): forced onto 45 001 / 40 000 aircraft
+    (NPLANE_COOP_PAIRS=10^8, four warps, 296 CTAs -> three iterations) against K1, bit for bit."""
+    import os
+    from neuralplane_b200 import ControlEnv, PlanningEnv, SingleCombatEnv
+    if env_name == "control":
+        n, A = 45_001, 4
+        mk = lambda: ControlEnv(num_envs=n, config="control", model="F16", random_seed=6, device="cuda:0")  # noqa: E731
+    elif env_name == "planning":
+        n, A = 45_001, 3
+        mk = lambda: PlanningEnv(num_envs=n, config="tracking", model="F16", random_seed=6, device="cuda:0", n_substeps=3)  # noqa: E731
+    else:
+        n, A = 40_000, 4
+        mk = lambda: SingleCombatEnv(num_envs=n // 2, config="selfplay", random_seed=6, device="cuda:0")  # noqa: E731
+    ref = mk()                                   # 45 001 aircraft: K1 / K4 / K5 with 128-thread CTAs
+    os.environ["NPLANE_COOP_PAIRS"] = "100000000"
+    try:
+        coop = mk()
+    finally:
+        del os.environ["NPLANE_COOP_PAIRS"]
+    assert torch.equal(coop.reset(), ref.reset())
+    for k in range(1, 9):
+        a = _cuda(tapes.action_tape(6, k, n, 1.0, num_actions=A)) if A == 3 else _cuda(tapes.action_tape(6, k, n, 1.0))
+        if env_name == "combat":
+            a = a * 0.5
+        for x, y in zip(coop.step(a)[:5], ref.step(a)[:5]):
+            assert torch.equal(x, y), k
+        if k % 3 == 0:
+            for e in (coop, ref):
+                e.is_done[::7] = True
+    li = coop.launch_info()
+    assert li["block"] == 128 and li["grid"] == 296 and ref.launch_info()["grid"] == (n + 255) // 256, (li, ref.launch_info())
+    assert torch.equal(coop.model.s, ref.model.s) and torch.equal(coop.model.u, ref.model.u)
+    assert coop.termination_counters() == ref.termination_counters()
+
+
 @pytest.mark.parametrize("n", [3000, 40_000])
 def test_cuda_graph_replay_equals_eager_loop(n):
     """A rollout loop captured in a CUDA graph: K1c (n = 3 000) is launched with programmatic stream serialisation (the next
